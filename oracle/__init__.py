@@ -1,0 +1,199 @@
+"""CPU oracle for the slideo hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this package, and only as the checker.  The product (``slideo_b200``) never imports it.
+
+Two tiers:
+  * ``liboracle.so``  -- plain-C restatement of OpenCV's ORB / brute-force k-NN / the reference's vote
+                         (orb_oracle.c, bf_oracle.c; each function cites the reference file:line it follows)
+  * ``cv2_oracle``    -- the same path through the real OpenCV (cv2 4.13.0), which is the third-party
+                         library the reference's arithmetic lives in (reference pins 4.5.2).  It pins the
+                         restatement; it is also the CPU baseline that bench.py times.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# reference ORB parameters: crates/matching-opencv/src/feature_extractor.rs:13-23
+ORB_REF = dict(nfeatures=2000, scale_factor=1.2, nlevels=8, edge_threshold=62, patch_size=62, fast_threshold=20)
+KNN_K = 30            # crates/matching-opencv/src/lib.rs:266
+VOTE_RATIO = 1.05     # crates/matching-opencv/src/lib.rs:275
+
+
+def build() -> str:
+    """Compile liboracle.so (gcc) if missing or stale."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        c_u8p = ctypes.POINTER(ctypes.c_uint8)
+        c_i32p = ctypes.POINTER(ctypes.c_int32)
+        c_f32p = ctypes.POINTER(ctypes.c_float)
+        ci, cf = ctypes.c_int, ctypes.c_float
+        L.orb_gray_from_bgr.argtypes = [c_u8p, ci, ci, ci, c_u8p]
+        L.orb_level_scale.argtypes = [ci, cf]
+        L.orb_level_scale.restype = cf
+        L.orb_level_size.argtypes = [ci, ci, ci, cf, c_i32p, c_i32p]
+        L.orb_level_quota.argtypes = [ci, ci, cf, c_i32p]
+        L.orb_resize_linear_exact.argtypes = [c_u8p, ci, ci, c_u8p, ci, ci]
+        L.orb_fast_score_map.argtypes = [c_u8p, ci, ci, ci, c_u8p]
+        L.orb_fast_nms.argtypes = [c_u8p, ci, ci, c_i32p, c_i32p, c_i32p, ci]
+        L.orb_fast_nms.restype = ci
+        L.orb_fast_atan2.argtypes = [cf, cf]
+        L.orb_fast_atan2.restype = cf
+        L.orb_blur7.argtypes = [c_u8p, ci, ci, c_u8p]
+        L.orb_pattern.argtypes = [ci, ci, c_i32p]
+        L.orb_detect_and_compute.argtypes = [c_u8p, ci, ci, ci, cf, ci, ci, ci, ci, c_i32p, c_f32p, c_u8p, ci]
+        L.orb_detect_and_compute.restype = ci
+        L.bf_knn_hamming.argtypes = [c_u8p, ci, c_u8p, ci, ci, c_i32p, c_i32p]
+        L.bf_knn_l2.argtypes = [c_f32p, ci, c_f32p, ci, ci, ci, c_i32p, c_f32p]
+        L.bf_vote.argtypes = [c_i32p, c_f32p, ci, ci, c_i32p, ci, c_i32p]
+        L.bf_vote.restype = ci
+        _LIB = L
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+# ----------------------------------------------------------------------------- ORB stages
+def gray_from_bgr(bgr: np.ndarray) -> np.ndarray:
+    bgr = _u8(bgr)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orb_gray_from_bgr(_p(bgr, ctypes.c_uint8), w, h, w * 3, _p(out, ctypes.c_uint8))
+    return out
+
+
+def level_sizes(w: int, h: int, nlevels: int = 8, scale_factor: float = 1.2):
+    out = []
+    for l in range(nlevels):
+        lw, lh = ctypes.c_int32(), ctypes.c_int32()
+        lib().orb_level_size(w, h, l, scale_factor, ctypes.byref(lw), ctypes.byref(lh))
+        out.append((lw.value, lh.value))
+    return out
+
+
+def level_quota(nfeatures: int = 2000, nlevels: int = 8, scale_factor: float = 1.2):
+    q = np.zeros(nlevels, np.int32)
+    lib().orb_level_quota(nfeatures, nlevels, scale_factor, _p(q, ctypes.c_int32))
+    return q.tolist()
+
+
+def resize_linear_exact(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = _u8(src)
+    out = np.empty((dh, dw), np.uint8)
+    lib().orb_resize_linear_exact(_p(src, ctypes.c_uint8), src.shape[1], src.shape[0], _p(out, ctypes.c_uint8), dw, dh)
+    return out
+
+
+def fast_score_map(img: np.ndarray, thr: int = 20) -> np.ndarray:
+    img = _u8(img)
+    out = np.empty_like(img)
+    lib().orb_fast_score_map(_p(img, ctypes.c_uint8), img.shape[1], img.shape[0], thr, _p(out, ctypes.c_uint8))
+    return out
+
+
+def fast_keypoints(img: np.ndarray, thr: int = 20):
+    """(x, y, score) after 3x3 NMS, raster order."""
+    sm = fast_score_map(img, thr)
+    cap = img.size // 4 + 16
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orb_fast_nms(_p(sm, ctypes.c_uint8), img.shape[1], img.shape[0], _p(xs, ctypes.c_int32),
+                           _p(ys, ctypes.c_int32), _p(sc, ctypes.c_int32), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def blur7(img: np.ndarray) -> np.ndarray:
+    img = _u8(img)
+    out = np.empty_like(img)
+    lib().orb_blur7(_p(img, ctypes.c_uint8), img.shape[1], img.shape[0], _p(out, ctypes.c_uint8))
+    return out
+
+
+def pattern(half: int = 31, npoints: int = 512) -> np.ndarray:
+    out = np.empty((npoints, 2), np.int32)
+    lib().orb_pattern(half, npoints, _p(out, ctypes.c_int32))
+    return out
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(lib().orb_fast_atan2(y, x))
+
+
+def orb_detect_and_compute(gray: np.ndarray, nfeatures=2000, scale_factor=1.2, nlevels=8, edge_threshold=62,
+                           patch_size=62, fast_threshold=20, cap=65536):
+    """Restated ORB on an 8-bit gray image.  Canonical order (octave, y, x).
+
+    Returns (kp_i [n,4] int32 {x_level,y_level,octave,score}, kp_f [n,4] f32 {pt.x,pt.y,size,angle}, desc [n,32] u8).
+    """
+    gray = _u8(gray)
+    h, w = gray.shape
+    kp_i = np.empty((cap, 4), np.int32)
+    kp_f = np.empty((cap, 4), np.float32)
+    desc = np.empty((cap, 32), np.uint8)
+    n = lib().orb_detect_and_compute(_p(gray, ctypes.c_uint8), w, h, nfeatures, scale_factor, nlevels,
+                                     edge_threshold, patch_size, fast_threshold, _p(kp_i, ctypes.c_int32),
+                                     _p(kp_f, ctypes.c_float), _p(desc, ctypes.c_uint8), cap)
+    if n < 0:
+        raise RuntimeError(f"orb oracle failed ({n})")
+    return kp_i[:n].copy(), kp_f[:n].copy(), desc[:n].copy()
+
+
+# ----------------------------------------------------------------------------- matcher + vote
+def bf_knn_hamming(q: np.ndarray, t: np.ndarray, k: int = KNN_K):
+    q, t = _u8(q), _u8(t)
+    idx = np.empty((len(q), k), np.int32)
+    dist = np.empty((len(q), k), np.int32)
+    lib().bf_knn_hamming(_p(q, ctypes.c_uint8), len(q), _p(t, ctypes.c_uint8), len(t), k, _p(idx, ctypes.c_int32),
+                         _p(dist, ctypes.c_int32))
+    return idx, dist
+
+
+def bf_knn_l2(q: np.ndarray, t: np.ndarray, k: int = KNN_K):
+    q = np.ascontiguousarray(q, np.float32)
+    t = np.ascontiguousarray(t, np.float32)
+    idx = np.empty((len(q), k), np.int32)
+    dist = np.empty((len(q), k), np.float32)
+    lib().bf_knn_l2(_p(q, ctypes.c_float), len(q), _p(t, ctypes.c_float), len(t), q.shape[1], k,
+                    _p(idx, ctypes.c_int32), _p(dist, ctypes.c_float))
+    return idx, dist
+
+
+def vote(idx: np.ndarray, dist: np.ndarray, page_offsets):
+    """Reference vote (lib.rs:268-282).  Returns (best_page or -1, votes_of_best, votes[P])."""
+    idx = np.ascontiguousarray(idx, np.int32)
+    dist = np.ascontiguousarray(dist, np.float32)
+    po = np.ascontiguousarray(page_offsets, np.int32)
+    votes = np.zeros(len(po) - 1, np.int32)
+    best = lib().bf_vote(_p(idx, ctypes.c_int32), _p(dist, ctypes.c_float), idx.shape[0], idx.shape[1],
+                         _p(po, ctypes.c_int32), len(po) - 1, _p(votes, ctypes.c_int32))
+    return best, (int(votes[best]) if best >= 0 else 0), votes
+
+
+def match_frame(frame_desc: np.ndarray, page_descs, k: int = KNN_K):
+    """Whole matcher stage for one frame: pooled BF k-NN + vote -> (best_page, votes, votes[P])."""
+    offs = np.zeros(len(page_descs) + 1, np.int32)
+    offs[1:] = np.cumsum([len(d) for d in page_descs])
+    pool = np.concatenate([_u8(d).reshape(-1, 32) for d in page_descs], 0) if offs[-1] else np.zeros((0, 32), np.uint8)
+    idx, dist = bf_knn_hamming(frame_desc, pool, k)
+    return vote(idx, dist.astype(np.float32), offs)
