@@ -1,0 +1,191 @@
+/*
+ * slideo_b200.h -- C ABI of libslideo_b200.so: the B200-native (sm_100a) replacement for the per-frame hot
+ * path of hediet/slideo's `crates/matching-opencv`.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, status codes instead of panics,
+ * no exception ever crosses it.  A Rust `matching-b200` crate binds these symbols 1:1 and
+ * implements the reference's traits `ImageVideoMatcher / VideoMatcher / VideoMatcherTask`
+ * (crates/matching/src/lib.rs:7-29) on top of them.  Every entry point cites the reference interface it replaces.
+ *
+ * Ownership  : the caller owns every buffer it passes; the library copies what it keeps.  The only interior
+ *              pointer ever returned is the `const char*` of slideo_b200_last_error (valid until the next call
+ *              on that ctx) and the device pointers of slideo_b200_pool_device_view (valid until the pool changes).
+ * Threading  : a ctx is NOT re-entrant: one in-flight call per ctx.  Different ctxs (one per GPU) may be driven
+ *              from different threads / processes.  (The reference keeps one ORB + one FLANN object per rayon
+ *              thread for the same reason: crates/matching-opencv/src/lib.rs:88-90,136.)
+ * Errors     : every function returns slideo_b200_status (0 = OK, negative = error).  The reference unwraps /
+ *              panics everywhere (lib.rs:95-101, feature_extractor.rs:24,40, flann.rs:16-46); a Rust binding maps
+ *              non-zero to panic!() to keep the trait signatures unchanged.
+ * No fallback: there is no CPU path.  Without a CUDA device slideo_b200_create fails with SLIDEO_B200_E_CUDA.
+ */
+#ifndef SLIDEO_B200_H
+#define SLIDEO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLIDEO_B200_ABI_VERSION 1
+
+typedef enum slideo_b200_status {
+    SLIDEO_B200_OK = 0,
+    SLIDEO_B200_E_INVALID_ARG = -1,
+    SLIDEO_B200_E_CUDA = -2,
+    SLIDEO_B200_E_OOM = -3,
+    SLIDEO_B200_E_NOTIMPL = -4,
+    SLIDEO_B200_E_STATE = -5,    /* call order violated (e.g. match before finalize_pool) */
+    SLIDEO_B200_E_CAPACITY = -6, /* an internal fixed capacity was exceeded; nothing was silently truncated */
+    SLIDEO_B200_E_INTERNAL = -7
+} slideo_b200_status;
+
+typedef enum slideo_b200_descriptor_kind {
+    SLIDEO_B200_DESC_ORB256 = 0, /* 32-byte binary descriptors, Hamming distance (the reference's path) */
+    SLIDEO_B200_DESC_SIFT128 = 1 /* 128-d float descriptors, L2 distance (north_star variant; not in the reference) */
+} slideo_b200_descriptor_kind;
+
+/* All algorithm parameters of the reference are hard-coded literals; they are collected here with those values
+ * as defaults (slideo_b200_default_config).
+ *   ORB       : crates/matching-opencv/src/feature_extractor.rs:13-23
+ *   knn_k     : crates/matching-opencv/src/lib.rs:266
+ *   vote_ratio: crates/matching-opencv/src/lib.rs:275 */
+typedef struct slideo_b200_config {
+    int32_t abi_version;     /* SLIDEO_B200_ABI_VERSION */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t nfeatures;       /* 2000 */
+    float scale_factor;      /* 1.2f */
+    int32_t nlevels;         /* 8 */
+    int32_t edge_threshold;  /* 62 */
+    int32_t patch_size;      /* 62 */
+    int32_t fast_threshold;  /* 20 */
+    int32_t knn_k;           /* 30 (1..32) */
+    float vote_ratio;        /* 1.05f */
+    int32_t descriptor_kind; /* slideo_b200_descriptor_kind */
+    int32_t max_batch;       /* frames processed per internal batch (default 32) */
+    int32_t keep_matches;    /* !=0: keep the k-NN rows of the last match call for slideo_b200_get_matches */
+    int32_t reserved[3];
+} slideo_b200_config;
+
+/* Hot-path output per frame: the head of the reference's ranking, lib.rs:268-295.
+ * best_slide = argmax over pages of the 1.05-ratio votes (ties -> lowest page index; -1 when nobody voted),
+ * votes = votes[best_slide], n_keypoints = ORB keypoints found in the frame (-1: capacity error on this frame). */
+typedef struct slideo_b200_frame_result {
+    int32_t best_slide;
+    int32_t votes;
+    int32_t n_keypoints;
+} slideo_b200_frame_result;
+
+/* One k-NN entry, field for field the reference's KeyedDMatch (crates/matching-opencv/src/flann.rs:51-59). */
+typedef struct slideo_b200_match {
+    int32_t query_idx; /* descriptor index within the frame (canonical order: octave, y, x) */
+    int32_t train_idx; /* descriptor index within the page */
+    int32_t source;    /* page index (position in add_page order == `images` order, lib.rs:259) */
+    float distance;    /* Hamming distance as float, like cv::DMatch */
+} slideo_b200_match;
+
+/* Device-time accounting of the last call(s) on a ctx, CUDA events on the ctx's own stream. */
+typedef struct slideo_b200_timings {
+    float ms_detect;         /* K1-K7 ORB extraction kernels */
+    float ms_knn;            /* K8 brute-force k-NN kernel(s) */
+    float ms_vote;           /* K9 vote + argmax (0 when fused into K8) */
+    float ms_h2d;            /* host->device copies issued by the library */
+    int64_t knn_pairs;       /* descriptor pairs evaluated by K8 */
+    int64_t knn_launches;    /* K8 launches */
+    int64_t kernel_launches; /* all kernel launches of the library */
+    int64_t frames;          /* frames processed */
+} slideo_b200_timings;
+
+typedef struct slideo_b200_ctx slideo_b200_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+/* Fills *cfg with the reference's literals (see slideo_b200_config). */
+int32_t slideo_b200_default_config(slideo_b200_config* cfg);
+/* Replaces OpenCVImageVideoMatcher::default() + the thread-local FeatureExtractor (lib.rs:33-35, 88-90). */
+int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_ctx);
+int32_t slideo_b200_destroy(slideo_b200_ctx* ctx);
+/* Human-readable text of the last error on this ctx ("" if none).  ctx may be NULL (global create errors). */
+const char* slideo_b200_last_error(const slideo_b200_ctx* ctx);
+const char* slideo_b200_version(void);
+
+/* ---- page pool  (replaces ProcessedImage::compute lib.rs:93-131 + FlannMatcher::new flann.rs:64-71) ------- */
+/* ORB-extracts one page given as the 8-bit gray that `imread(path, IMREAD_GRAYSCALE)` returns (lib.rs:98) and
+ * appends its descriptors to the pool.  Pages get consecutive indices in call order. */
+int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int32_t w, int32_t h, int32_t stride,
+                                   int32_t* out_n_keypoints);
+/* Appends a page whose descriptors were computed elsewhere (n x 32 bytes for ORB256, n x 128 floats for SIFT128). */
+int32_t slideo_b200_add_page_descriptors(slideo_b200_ctx* ctx, const void* desc, int32_t n);
+/* Concatenates the pages into the device-resident pool (flann.rs add + train; brute force has no index to build). */
+int32_t slideo_b200_finalize_pool(slideo_b200_ctx* ctx);
+int32_t slideo_b200_pool_info(const slideo_b200_ctx* ctx, int32_t* out_n_descriptors, int32_t* out_n_pages);
+/* Pool replication across GPUs (one ctx per GPU): export on the rank that built it, import on the others.
+ * Host variant: desc = n_desc*desc_bytes, page_offsets = n_pages+1 int32.  Either pointer may be NULL to skip. */
+int32_t slideo_b200_pool_export(const slideo_b200_ctx* ctx, void* desc, int32_t* page_offsets);
+int32_t slideo_b200_pool_import(slideo_b200_ctx* ctx, const void* desc, int32_t n_desc, const int32_t* page_offsets,
+                                int32_t n_pages);
+/* Device variant for an NCCL broadcast done by the host process (torch.distributed / ncclBroadcast): reserve a
+ * pool of the given geometry, expose its device buffers, then call slideo_b200_pool_commit once they are filled. */
+int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n_pages);
+int32_t slideo_b200_pool_device_view(slideo_b200_ctx* ctx, void** d_desc, size_t* desc_bytes, void** d_page_offsets,
+                                     size_t* offsets_bytes);
+int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx);
+
+/* ---- the per-frame hot path  (replaces match_images_with_frame lib.rs:249-295, head of the ranking) ------- */
+/* n BGR 8UC3 frames (what VideoCapture::retrieve yields, video_capture.rs:45-53), HOST memory, frame i at
+ * frames + i*frame_stride; rows `stride` bytes apart.  Copies to the device, extracts ORB, k-NN against the pool,
+ * votes, writes n results.  Pinned host memory (slideo_b200_host_alloc) makes the copies asynchronous. */
+int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h,
+                                      int32_t stride, size_t frame_stride, slideo_b200_frame_result* out);
+/* Same with frames already resident in device memory (HBM-resident throughput measurement). */
+int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d_frames, int32_t n, int32_t w,
+                                             int32_t h, int32_t stride, size_t frame_stride,
+                                             slideo_b200_frame_result* out);
+/* Match pre-extracted descriptors of n frames (frame i owns rows [frame_offsets[i], frame_offsets[i+1])). */
+int32_t slideo_b200_match_descriptors(slideo_b200_ctx* ctx, const void* desc, const int32_t* frame_offsets, int32_t n,
+                                      slideo_b200_frame_result* out);
+/* k-NN rows of frame `frame_i` of the last match call (needs cfg.keep_matches): n_query*k entries, row-major,
+ * each row ascending by (distance, pooled index) -- what FlannMatcher::knn_match returns (flann.rs:73-89). */
+int32_t slideo_b200_get_matches(slideo_b200_ctx* ctx, int32_t frame_i, slideo_b200_match* out, int32_t cap_rows,
+                                int32_t* out_rows);
+
+/* ---- stage-level entry points (parity tests, matcher sweeps) --------------------------------------------- */
+/* ORB::detectAndCompute (feature_extractor.rs:29-46) on one HOST image, channels = 1 (gray) or 3 (BGR).
+ * Canonical order (octave, y, x).  kp_i: n x 4 {x_level, y_level, octave, score}; kp_f: n x 4 {pt.x, pt.y, size,
+ * angle_deg}; desc: n x 32.  Any output pointer may be NULL. */
+int32_t slideo_b200_extract_orb(slideo_b200_ctx* ctx, const uint8_t* img, int32_t w, int32_t h, int32_t stride,
+                                int32_t channels, int32_t* kp_i, float* kp_f, uint8_t* desc, int32_t cap,
+                                int32_t* out_n);
+/* Intermediate images of the last extract/match call, image 0 of the batch: what = 0 pyramid level, 1 blurred
+ * level, 2 FAST candidates (packed score<<24|y<<12|x, unordered).  Tightly packed into `out`. */
+int32_t slideo_b200_debug_fetch(slideo_b200_ctx* ctx, int32_t what, int32_t level, void* out, size_t cap_bytes,
+                                int32_t* out_w, int32_t* out_h);
+/* BFMatcher(NORM_HAMMING).knnMatch semantics: k smallest by (distance, index), HOST buffers.
+ * idx/dist: nq x k int32, rows padded with -1 when nt < k. */
+int32_t slideo_b200_bf_knn_hamming(slideo_b200_ctx* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt,
+                                   int32_t k, int32_t* idx, int32_t* dist);
+/* Same on DEVICE buffers (q, t 16-byte aligned); keys_out: nq x k uint32 = dist<<23 | idx (0xFFFFFFFF = empty). */
+int32_t slideo_b200_bf_knn_hamming_device(slideo_b200_ctx* ctx, const void* d_q, int32_t nq, const void* d_t,
+                                          int32_t nt, int32_t k, void* d_keys_out);
+/* BFMatcher(NORM_L2).knnMatch: dist = sqrtf(sum (a-b)^2); bf16 tcgen05 cross term, exact for integer-valued
+ * descriptors (cv2 SIFT).  HOST buffers. */
+int32_t slideo_b200_bf_knn_l2(slideo_b200_ctx* ctx, const float* q, int32_t nq, const float* t, int32_t nt,
+                              int32_t dim, int32_t k, int32_t* idx, float* dist);
+
+/* Same on DEVICE buffers (fp32 q/t, 16-byte aligned; idx int32 nq x k, dist float nq x k). */
+int32_t slideo_b200_bf_knn_l2_device(slideo_b200_ctx* ctx, const void* d_q, int32_t nq, const void* d_t, int32_t nt,
+                                     int32_t dim, int32_t k, void* d_idx, void* d_dist);
+
+/* ---- utilities ------------------------------------------------------------------------------------------ */
+int32_t slideo_b200_host_alloc(void** out, size_t bytes); /* pinned host memory */
+int32_t slideo_b200_host_free(void* p);
+int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, int32_t reset);
+/* Integer-pipe micro-benchmark used as the K8 roofline denominator: which = 0 LOP3, 1 POPC, 2 the K8 inner-loop
+ * instruction mix; returns thread-level ops (or descriptor pairs for which=2) per second over the whole GPU. */
+int32_t slideo_b200_microbench(slideo_b200_ctx* ctx, int32_t which, double* out_per_second);
+int32_t slideo_b200_synchronize(slideo_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIDEO_B200_H */

@@ -1,0 +1,993 @@
+// api.cu -- the extern "C" boundary of libslideo_b200.so (include/slideo_b200.h) and the per-ctx host logic:
+// device-resident page pool, frame batching with double-buffered uploads, K1-K7 -> K8/K9 -> per-frame result.
+// Host-side counterpart of the reference's orchestration in crates/matching-opencv/src/lib.rs:37-64 (page pool),
+// lib.rs:249-295 (per-frame path) and flann.rs:64-89 (matcher); all arithmetic runs in the CUDA kernels of
+// orb.cu / knn_hamming.cu / knn_l2.cu.  There is no CPU fallback: without a device every entry point fails.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/slideo_b200.h"
+#include "common.cuh"
+#include "knn_l2.cuh"
+#include "orb.cuh"
+
+using namespace slideo;
+
+namespace {
+
+template <typename T>
+struct DevBuf {  // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw CudaError(e, std::string("cudaMalloc of ") + std::to_string(want * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
+        }
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kind = 0;  // 0 detect, 1 knn, 2 h2d
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct slideo_b200_ctx {
+    slideo_b200_config cfg{};
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    mutable std::string err;
+
+    // ---- page pool --------------------------------------------------------------------------------------
+    int desc_bytes = 32;                 // 32 (ORB256) or 512 (SIFT128 as float)
+    std::vector<uint8_t> h_pool;         // host staging until finalize
+    std::vector<int32_t> page_off{0};    // prefix offsets, size n_pages + 1
+    bool finalized = false;
+    DevBuf<uint8_t> d_pool;              // nt x 32 (ORB) / nt x 128 bf16 (SIFT)
+    DevBuf<float> d_pool_norm;           // SIFT: squared norms
+    DevBuf<uint16_t> d_page_of;          // nt
+    DevBuf<int32_t> d_page_off;          // n_pages + 1
+    int nt = 0, n_pages = 0;
+    bool reserved = false;               // pool_reserve called, waiting for commit
+
+    // ---- workspaces -------------------------------------------------------------------------------------
+    std::map<std::tuple<int, int, int>, std::unique_ptr<OrbExtractor>> extractors;
+    OrbExtractor* last_ext = nullptr;
+    DevBuf<uint8_t> d_frames[2];
+    DevBuf<uint8_t> d_img;               // single-image upload (pages, extract_orb)
+    DevBuf<uint32_t> d_scratch, d_partial, d_keys;
+    DevBuf<int32_t> d_votes, d_results, d_q_frame, d_idx, d_dist;
+    DevBuf<uint8_t> d_q;                 // uploaded query descriptors
+    DevBuf<uint8_t> d_t;                 // uploaded train descriptors (stage-level knn)
+    L2Workspace l2ws;
+    DevBuf<uint8_t> d_l2_pool;           // bf16 copy of the last bf_knn_l2_device pool
+    DevBuf<float> d_l2_norm;
+    int32_t* h_results = nullptr;        // pinned, max_batch x 3 x 2
+    size_t h_results_cap = 0;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+
+    // ---- kept matches of the last match call -------------------------------------------------------------
+    std::vector<uint32_t> kept_keys;     // total_q x k
+    std::vector<float> kept_l2;          // SIFT: distances
+    std::vector<int32_t> kept_l2_idx;
+    std::vector<int32_t> kept_frame_off{0};
+
+    // ---- timings ----------------------------------------------------------------------------------------
+    slideo_b200_timings tm{};
+    std::vector<EventPair> ev_pending, ev_free_list;
+
+    ~slideo_b200_ctx() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        extractors.clear();
+        for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (auto& e : ev_free_list) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (int i = 0; i < 2; ++i) {
+            if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
+            if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+        }
+        if (h_results) cudaFreeHost(h_results);
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+
+    // -------------------------------------------------------------------------------------------------------
+    EventPair begin_timing(int kind, cudaStream_t s) {
+        EventPair e;
+        if (!ev_free_list.empty()) {
+            e = ev_free_list.back();
+            ev_free_list.pop_back();
+        } else {
+            SLIDEO_CUDA(cudaEventCreate(&e.a));
+            SLIDEO_CUDA(cudaEventCreate(&e.b));
+        }
+        e.kind = kind;
+        SLIDEO_CUDA(cudaEventRecord(e.a, s));
+        return e;
+    }
+    void end_timing(EventPair e, cudaStream_t s) {
+        SLIDEO_CUDA(cudaEventRecord(e.b, s));
+        ev_pending.push_back(e);
+    }
+    void collect_timings() {  // after a synchronize
+        for (auto& e : ev_pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+                if (e.kind == 0) tm.ms_detect += ms;
+                else if (e.kind == 1) tm.ms_knn += ms;
+                else if (e.kind == 2) tm.ms_h2d += ms;
+                else tm.ms_vote += ms;
+            }
+            ev_free_list.push_back(e);
+        }
+        ev_pending.clear();
+    }
+
+    OrbExtractor& extractor(int w, int h, int cap) {
+        auto key = std::make_tuple(w, h, cap);
+        auto it = extractors.find(key);
+        if (it == extractors.end()) {
+            OrbConfig oc;
+            oc.nfeatures = cfg.nfeatures;
+            oc.scale_factor = cfg.scale_factor;
+            oc.nlevels = cfg.nlevels;
+            oc.edge_threshold = cfg.edge_threshold;
+            oc.patch_size = cfg.patch_size;
+            oc.fast_threshold = cfg.fast_threshold;
+            if (extractors.size() >= 8) {  // bounded cache of geometries
+                SLIDEO_CUDA(cudaStreamSynchronize(stream));
+                extractors.clear();
+                last_ext = nullptr;
+            }
+            it = extractors.emplace(key, std::make_unique<OrbExtractor>(oc, w, h, cap)).first;
+        }
+        last_ext = it->second.get();
+        return *it->second;
+    }
+
+    void require_orb() const {
+        if (cfg.descriptor_kind != SLIDEO_B200_DESC_ORB256) throw StateError("this entry point needs descriptor_kind ORB256");
+    }
+    void require_pool() const {
+        if (!finalized) throw StateError("page pool not finalized (call slideo_b200_finalize_pool / pool_import / pool_commit first)");
+    }
+
+    // uploads `n_img` images (host) into dst as tightly packed rows of row_bytes
+    void upload_images(uint8_t* dst, const uint8_t* src, int n_img, int row_bytes, int h, int stride, size_t frame_stride,
+                       cudaStream_t s) {
+        if (stride == row_bytes && frame_stride == (size_t)row_bytes * h) {
+            SLIDEO_CUDA(cudaMemcpyAsync(dst, src, (size_t)n_img * row_bytes * h, cudaMemcpyHostToDevice, s));
+        } else if (stride == row_bytes) {
+            SLIDEO_CUDA(cudaMemcpy2DAsync(dst, (size_t)row_bytes * h, src, frame_stride, (size_t)row_bytes * h, n_img,
+                                          cudaMemcpyHostToDevice, s));
+        } else {
+            for (int i = 0; i < n_img; ++i)
+                SLIDEO_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * row_bytes * h, row_bytes, src + (size_t)i * frame_stride, stride,
+                                              row_bytes, h, cudaMemcpyHostToDevice, s));
+        }
+    }
+
+    // K8 (+ fused K9) on nq device-resident query descriptors against the pool; fills d_results for n_frames
+    void knn_vote_hamming(const uint8_t* dq, int nq, const int32_t* d_qf, int n_frames, const int32_t* d_frame_nkp,
+                          bool want_keys) {
+        d_votes.reserve((size_t)n_frames * std::max(n_pages, 1));
+        d_results.reserve((size_t)n_frames * 3);
+        SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)n_frames * std::max(n_pages, 1) * 4, stream));
+        if (nq > 0) {
+            KnnPlan plan = knn_hamming_plan(nq, nt, cfg.knn_k, num_sms);
+            d_scratch.reserve(plan.scratch_bytes / 4);
+            if (plan.partial_bytes) d_partial.reserve(plan.partial_bytes / 4);
+            if (want_keys) d_keys.reserve((size_t)nq * cfg.knn_k);
+            VoteArgs va{d_qf, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio};
+            EventPair t = begin_timing(1, stream);
+            int nl = 0;
+            knn_hamming_launch(plan, dq, d_pool.p, want_keys ? d_keys.p : nullptr, d_scratch.p, d_partial.p, &va, stream, &nl);
+            end_timing(t, stream);
+            tm.knn_launches += nl;
+            tm.kernel_launches += nl;
+            tm.knn_pairs += (int64_t)nq * nt;
+        }
+        vote_argmax_launch(d_votes.p, n_frames, n_pages, d_frame_nkp, d_results.p, stream);
+        tm.kernel_launches += 1;
+    }
+
+    void ensure_host_results(size_t n) {
+        if (n <= h_results_cap) return;
+        if (h_results) cudaFreeHost(h_results);
+        h_results = nullptr;
+        SLIDEO_CUDA(cudaMallocHost(&h_results, n * 3 * sizeof(int32_t)));
+        h_results_cap = n;
+    }
+
+    void keep_batch_keys(int nq, const std::vector<int32_t>& frame_off_local) {
+        const size_t base = kept_keys.size();
+        kept_keys.resize(base + (size_t)nq * cfg.knn_k);
+        if (nq > 0)
+            SLIDEO_CUDA(cudaMemcpyAsync(kept_keys.data() + base, d_keys.p, (size_t)nq * cfg.knn_k * 4, cudaMemcpyDeviceToHost, stream));
+        const int32_t q0 = kept_frame_off.back();
+        for (size_t i = 1; i < frame_off_local.size(); ++i) kept_frame_off.push_back(q0 + frame_off_local[i]);
+        SLIDEO_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // the per-frame hot path on device-resident BGR frames (one batch <= max_batch)
+    void match_batch_device(const uint8_t* d_src, int nb, int w, int h, int stride, size_t frame_stride, int32_t* h_out) {
+        OrbExtractor& ex = extractor(w, h, cfg.max_batch);
+        EventPair t = begin_timing(0, stream);
+        int nl = 0;
+        const int total = ex.run(d_src, nb, stride, frame_stride, 3, stream, &nl);
+        end_timing(t, stream);
+        tm.kernel_launches += nl;
+        knn_vote_hamming(ex.d_desc(), total, ex.d_q_frame(), nb, ex.d_frame_nkp(), cfg.keep_matches != 0);
+        SLIDEO_CUDA(cudaMemcpyAsync(h_out, d_results.p, (size_t)nb * 3 * 4, cudaMemcpyDeviceToHost, stream));
+        if (cfg.keep_matches) {
+            std::vector<int32_t> fo(ex.h_frame_off().begin(), ex.h_frame_off().begin() + nb + 1);
+            keep_batch_keys(total, fo);
+        }
+        tm.frames += nb;
+    }
+
+    void reset_kept() {
+        kept_keys.clear();
+        kept_l2.clear();
+        kept_l2_idx.clear();
+        kept_frame_off.assign(1, 0);
+    }
+
+    void upload_pool_orb(const uint8_t* desc) {
+        d_pool.reserve((size_t)std::max(nt, 1) * 32 + 64);
+        d_page_of.reserve((size_t)std::max(nt, 1));
+        d_page_off.reserve((size_t)n_pages + 1);
+        if (nt > 0 && desc) SLIDEO_CUDA(cudaMemcpyAsync(d_pool.p, desc, (size_t)nt * 32, cudaMemcpyHostToDevice, stream));
+        build_page_of();
+    }
+    void build_page_of() {
+        std::vector<uint16_t> po((size_t)nt);
+        for (int p = 0; p < n_pages; ++p)
+            for (int i = page_off[p]; i < page_off[p + 1]; ++i) po[(size_t)i] = (uint16_t)p;
+        d_page_of.reserve((size_t)std::max(nt, 1));
+        d_page_off.reserve((size_t)n_pages + 1);
+        if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_page_of.p, po.data(), (size_t)nt * 2, cudaMemcpyHostToDevice, stream));
+        SLIDEO_CUDA(cudaMemcpyAsync(d_page_off.p, page_off.data(), ((size_t)n_pages + 1) * 4, cudaMemcpyHostToDevice, stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(stream));
+    }
+    void check_pool_limits(int64_t n_desc, int64_t pages) const {
+        if (n_desc > KNN_MAX_POOL) throw CapacityError("pool exceeds 8,388,608 descriptors");
+        if (pages > 65535) throw CapacityError("pool exceeds 65535 pages");
+    }
+};
+
+namespace {
+
+template <typename F>
+int32_t guarded(const slideo_b200_ctx* ctx, F&& f) {
+    std::string* err = ctx ? &ctx->err : &g_create_error;
+    try {
+        if (ctx) {
+            cudaError_t e = cudaSetDevice(ctx->device);
+            if (e != cudaSuccess) throw CudaError(e, std::string("cudaSetDevice failed: ") + cudaGetErrorString(e));
+        }
+        err->clear();
+        f();
+        return SLIDEO_B200_OK;
+    } catch (const ArgError& e) {
+        *err = e.what();
+        return SLIDEO_B200_E_INVALID_ARG;
+    } catch (const StateError& e) {
+        *err = e.what();
+        return SLIDEO_B200_E_STATE;
+    } catch (const CapacityError& e) {
+        *err = e.what();
+        return SLIDEO_B200_E_CAPACITY;
+    } catch (const NotImplError& e) {
+        *err = e.what();
+        return SLIDEO_B200_E_NOTIMPL;
+    } catch (const CudaError& e) {
+        *err = e.what();
+        cudaGetLastError();
+        return e.code == cudaErrorMemoryAllocation ? SLIDEO_B200_E_OOM : SLIDEO_B200_E_CUDA;
+    } catch (const std::bad_alloc&) {
+        *err = "host allocation failed";
+        return SLIDEO_B200_E_OOM;
+    } catch (const std::exception& e) {
+        *err = e.what();
+        return SLIDEO_B200_E_INTERNAL;
+    } catch (...) {
+        *err = "unknown exception";
+        return SLIDEO_B200_E_INTERNAL;
+    }
+}
+
+#define REQUIRE_CTX(ctx) \
+    if (!(ctx)) return SLIDEO_B200_E_INVALID_ARG
+
+void arg(bool ok, const char* what) {
+    if (!ok) throw ArgError(what);
+}
+
+}  // namespace
+
+// ===================================================================================================================
+extern "C" {
+
+int32_t slideo_b200_default_config(slideo_b200_config* cfg) {
+    if (!cfg) return SLIDEO_B200_E_INVALID_ARG;
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->abi_version = SLIDEO_B200_ABI_VERSION;
+    cfg->device = 0;
+    cfg->nfeatures = 2000;       // feature_extractor.rs:14
+    cfg->scale_factor = 1.2f;    // :15
+    cfg->nlevels = 8;            // :16
+    cfg->edge_threshold = 62;    // :17
+    cfg->patch_size = 62;        // :22
+    cfg->fast_threshold = 20;    // :23
+    cfg->knn_k = 30;             // lib.rs:266
+    cfg->vote_ratio = 1.05f;     // lib.rs:275
+    cfg->descriptor_kind = SLIDEO_B200_DESC_ORB256;
+    cfg->max_batch = 32;
+    cfg->keep_matches = 0;
+    return SLIDEO_B200_OK;
+}
+
+int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_ctx) {
+    if (out_ctx) *out_ctx = nullptr;
+    return guarded(nullptr, [&] {
+        arg(cfg && out_ctx, "cfg and out_ctx must not be NULL");
+        arg(cfg->abi_version == SLIDEO_B200_ABI_VERSION, "abi_version mismatch");
+        arg(cfg->knn_k >= 1 && cfg->knn_k <= KNN_MAX_K, "knn_k must be in 1..32");
+        arg(cfg->max_batch >= 1 && cfg->max_batch <= 1024, "max_batch must be in 1..1024");
+        arg(cfg->nfeatures >= 1 && cfg->nfeatures <= 4096, "nfeatures must be in 1..4096");
+        arg(cfg->nlevels >= 1 && cfg->nlevels <= ORB_MAX_LEVELS, "nlevels out of range");
+        arg(cfg->scale_factor > 1.0f && cfg->scale_factor <= 2.0f, "scale_factor must be in (1, 2]");
+        arg(cfg->edge_threshold >= 3 && cfg->edge_threshold < 1024, "edge_threshold out of range");
+        arg(cfg->patch_size >= 2 && cfg->patch_size / 2 <= 38, "patch_size out of range");
+        arg(cfg->fast_threshold >= 1 && cfg->fast_threshold < 255, "fast_threshold out of range");
+        arg(cfg->vote_ratio >= 1.0f && cfg->vote_ratio < 16.f, "vote_ratio out of range");
+        arg(cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256 || cfg->descriptor_kind == SLIDEO_B200_DESC_SIFT128,
+            "unknown descriptor_kind");
+        int n_dev = 0;
+        cudaError_t e = cudaGetDeviceCount(&n_dev);
+        if (e != cudaSuccess || n_dev == 0)
+            throw CudaError(e == cudaSuccess ? cudaErrorNoDevice : e,
+                            std::string("no CUDA device (libslideo_b200 has no CPU fallback): ") +
+                                cudaGetErrorString(e == cudaSuccess ? cudaErrorNoDevice : e));
+        arg(cfg->device >= 0 && cfg->device < n_dev, "device ordinal out of range");
+        SLIDEO_CUDA(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        SLIDEO_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major != 10)
+            throw CudaError(cudaErrorInvalidDevice, std::string("device is sm_") + std::to_string(prop.major) +
+                                                        std::to_string(prop.minor) + "; this library is built for sm_100a only");
+        std::unique_ptr<slideo_b200_ctx> c(new slideo_b200_ctx());
+        c->cfg = *cfg;
+        c->device = cfg->device;
+        c->num_sms = prop.multiProcessorCount;
+        c->desc_bytes = cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256 ? 32 : 512;
+        SLIDEO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SLIDEO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+            SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+        *out_ctx = c.release();
+    });
+}
+
+int32_t slideo_b200_destroy(slideo_b200_ctx* ctx) {
+    if (!ctx) return SLIDEO_B200_OK;
+    try {
+        delete ctx;
+    } catch (...) {
+        return SLIDEO_B200_E_INTERNAL;
+    }
+    return SLIDEO_B200_OK;
+}
+
+const char* slideo_b200_last_error(const slideo_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+const char* slideo_b200_version(void) { return "slideo_b200 0.1.0 (sm_100a, abi 1)"; }
+
+// ---- page pool ------------------------------------------------------------------------------------------------
+int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int32_t w, int32_t h, int32_t stride,
+                                   int32_t* out_n_keypoints) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        arg(px != nullptr, "px must not be NULL");
+        arg(stride >= w, "stride < w");
+        if (ctx->finalized || ctx->reserved) throw StateError("pool already finalized");
+        ctx->check_pool_limits((int64_t)ctx->page_off.back(), (int64_t)ctx->page_off.size());
+        OrbExtractor& ex = ctx->extractor(w, h, 1);
+        ctx->d_img.reserve((size_t)w * h);
+        ctx->upload_images(ctx->d_img.p, px, 1, w, h, stride, (size_t)stride * h, ctx->stream);
+        int nl = 0;
+        const int total = ex.run(ctx->d_img.p, 1, w, (size_t)w * h, 1, ctx->stream, &nl);
+        ctx->tm.kernel_launches += nl;
+        const size_t base = ctx->h_pool.size();
+        ctx->h_pool.resize(base + (size_t)total * 32);
+        if (total > 0)
+            SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_pool.data() + base, ex.d_desc(), (size_t)total * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->page_off.push_back(ctx->page_off.back() + total);
+        ctx->check_pool_limits((int64_t)ctx->page_off.back(), (int64_t)ctx->page_off.size() - 1);
+        if (out_n_keypoints) *out_n_keypoints = total;
+    });
+}
+
+int32_t slideo_b200_add_page_descriptors(slideo_b200_ctx* ctx, const void* desc, int32_t n) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(n >= 0, "n < 0");
+        arg(desc != nullptr || n == 0, "desc must not be NULL");
+        if (ctx->finalized || ctx->reserved) throw StateError("pool already finalized");
+        ctx->check_pool_limits((int64_t)ctx->page_off.back() + n, (int64_t)ctx->page_off.size());
+        const size_t base = ctx->h_pool.size();
+        ctx->h_pool.resize(base + (size_t)n * ctx->desc_bytes);
+        if (n) std::memcpy(ctx->h_pool.data() + base, desc, (size_t)n * ctx->desc_bytes);
+        ctx->page_off.push_back(ctx->page_off.back() + n);
+    });
+}
+
+static void finalize_from_host(slideo_b200_ctx* ctx) {
+    ctx->nt = ctx->page_off.back();
+    ctx->n_pages = (int)ctx->page_off.size() - 1;
+    if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) {
+        ctx->upload_pool_orb(ctx->h_pool.data());
+    } else {
+        ctx->d_t.reserve((size_t)std::max(ctx->nt, 1) * 512);
+        if (ctx->nt > 0)
+            SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_t.p, ctx->h_pool.data(), (size_t)ctx->nt * 512, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->d_pool.reserve((size_t)l2_rows_padded(ctx->nt) * 256 + 256);
+        ctx->d_pool_norm.reserve((size_t)l2_rows_padded(ctx->nt) + 64);
+        l2_prepare_launch((const float*)ctx->d_t.p, ctx->nt, 128, (uint16_t*)ctx->d_pool.p, ctx->d_pool_norm.p, ctx->stream);
+        ctx->build_page_of();
+    }
+    ctx->finalized = true;
+}
+
+int32_t slideo_b200_finalize_pool(slideo_b200_ctx* ctx) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (ctx->finalized) throw StateError("pool already finalized");
+        if (ctx->reserved) throw StateError("pool_reserve pending: call pool_commit");
+        finalize_from_host(ctx);
+    });
+}
+
+int32_t slideo_b200_pool_info(const slideo_b200_ctx* ctx, int32_t* out_n_descriptors, int32_t* out_n_pages) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (out_n_descriptors) *out_n_descriptors = ctx->page_off.back();
+        if (out_n_pages) *out_n_pages = (int32_t)ctx->page_off.size() - 1;
+    });
+}
+
+int32_t slideo_b200_pool_export(const slideo_b200_ctx* ctx, void* desc, int32_t* page_offsets) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (ctx->h_pool.size() != (size_t)ctx->page_off.back() * ctx->desc_bytes)
+            throw StateError("this ctx holds no host copy of the pool (it was imported through the device view)");
+        if (desc && !ctx->h_pool.empty()) std::memcpy(desc, ctx->h_pool.data(), ctx->h_pool.size());
+        if (page_offsets) std::memcpy(page_offsets, ctx->page_off.data(), ctx->page_off.size() * 4);
+    });
+}
+
+int32_t slideo_b200_pool_import(slideo_b200_ctx* ctx, const void* desc, int32_t n_desc, const int32_t* page_offsets,
+                                int32_t n_pages) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(n_desc >= 0 && n_pages >= 0, "negative size");
+        arg(page_offsets != nullptr, "page_offsets must not be NULL");
+        arg(desc != nullptr || n_desc == 0, "desc must not be NULL");
+        arg(page_offsets[0] == 0 && page_offsets[n_pages] == n_desc, "page_offsets must start at 0 and end at n_desc");
+        for (int p = 0; p < n_pages; ++p) arg(page_offsets[p] <= page_offsets[p + 1], "page_offsets must be non-decreasing");
+        ctx->check_pool_limits(n_desc, n_pages);
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->h_pool.assign((const uint8_t*)desc, (const uint8_t*)desc + (size_t)n_desc * ctx->desc_bytes);
+        ctx->page_off.assign(page_offsets, page_offsets + n_pages + 1);
+        ctx->reserved = false;
+        finalize_from_host(ctx);
+    });
+}
+
+int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n_pages) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        arg(n_desc >= 0 && n_pages >= 0, "negative size");
+        ctx->check_pool_limits(n_desc, n_pages);
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->finalized = false;
+        ctx->reserved = true;
+        ctx->nt = n_desc;
+        ctx->n_pages = n_pages;
+        ctx->h_pool.clear();
+        ctx->page_off.assign((size_t)n_pages + 1, 0);
+        ctx->d_pool.reserve((size_t)std::max(n_desc, 1) * 32 + 64);
+        ctx->d_page_off.reserve((size_t)n_pages + 1);
+    });
+}
+
+int32_t slideo_b200_pool_device_view(slideo_b200_ctx* ctx, void** d_desc, size_t* desc_bytes, void** d_page_offsets,
+                                     size_t* offsets_bytes) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        if (!ctx->finalized && !ctx->reserved) throw StateError("no device pool yet (finalize_pool or pool_reserve first)");
+        if (d_desc) *d_desc = ctx->d_pool.p;
+        if (desc_bytes) *desc_bytes = (size_t)ctx->nt * 32;
+        if (d_page_offsets) *d_page_offsets = ctx->d_page_off.p;
+        if (offsets_bytes) *offsets_bytes = ((size_t)ctx->n_pages + 1) * 4;
+    });
+}
+
+int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (!ctx->reserved) throw StateError("pool_commit without pool_reserve");
+        SLIDEO_CUDA(cudaDeviceSynchronize());  // the broadcast ran on a stream the library does not own
+        SLIDEO_CUDA(cudaMemcpy(ctx->page_off.data(), ctx->d_page_off.p, ((size_t)ctx->n_pages + 1) * 4, cudaMemcpyDeviceToHost));
+        if (ctx->page_off[0] != 0 || ctx->page_off[ctx->n_pages] != ctx->nt) throw ArgError("received page offsets do not match the reserved geometry");
+        for (int p = 0; p < ctx->n_pages; ++p)
+            if (ctx->page_off[p] > ctx->page_off[p + 1]) throw ArgError("received page offsets are not monotone");
+        ctx->build_page_of();
+        ctx->reserved = false;
+        ctx->finalized = true;
+    });
+}
+
+// ---- the per-frame hot path -----------------------------------------------------------------------------------
+int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h,
+                                      int32_t stride, size_t frame_stride, slideo_b200_frame_result* out) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        ctx->require_pool();
+        arg(n >= 0, "n < 0");
+        if (n == 0) return;
+        arg(frames && out, "frames/out must not be NULL");
+        arg(stride >= 3 * w, "stride < 3*w");
+        arg(frame_stride >= (size_t)stride * (h - 1) + (size_t)3 * w, "frame_stride too small");
+        ctx->reset_kept();
+        const int B = ctx->cfg.max_batch;
+        const size_t img_bytes = (size_t)3 * w * h;
+        const int n_batches = cdiv(n, B);
+        for (int i = 0; i < 2; ++i) ctx->d_frames[i].reserve((size_t)std::min(B, n) * img_bytes);
+        ctx->ensure_host_results((size_t)n);
+        auto issue_copy = [&](int b) {
+            const int buf = b & 1, f0 = b * B, nb = std::min(B, n - f0);
+            SLIDEO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));  // buffer consumed by batch b-2
+            EventPair t = ctx->begin_timing(2, ctx->copy_stream);
+            ctx->upload_images(ctx->d_frames[buf].p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride,
+                               ctx->copy_stream);
+            ctx->end_timing(t, ctx->copy_stream);
+            SLIDEO_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+        };
+        // ev_free events start "complete" (never recorded) -> first two waits fall through
+        issue_copy(0);
+        for (int b = 0; b < n_batches; ++b) {
+            const int buf = b & 1, f0 = b * B, nb = std::min(B, n - f0);
+            if (b + 1 < n_batches) issue_copy(b + 1);
+            SLIDEO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+            ctx->match_batch_device(ctx->d_frames[buf].p, nb, w, h, 3 * w, img_bytes, ctx->h_results + (size_t)f0 * 3);
+            SLIDEO_CUDA(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
+        }
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->collect_timings();
+        for (int i = 0; i < n; ++i) {
+            out[i].best_slide = ctx->h_results[3 * i];
+            out[i].votes = ctx->h_results[3 * i + 1];
+            out[i].n_keypoints = ctx->h_results[3 * i + 2];
+        }
+    });
+}
+
+int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d_frames, int32_t n, int32_t w, int32_t h,
+                                             int32_t stride, size_t frame_stride, slideo_b200_frame_result* out) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        ctx->require_pool();
+        arg(n >= 0, "n < 0");
+        if (n == 0) return;
+        arg(d_frames && out, "d_frames/out must not be NULL");
+        arg(stride >= 3 * w, "stride < 3*w");
+        ctx->reset_kept();
+        const int B = ctx->cfg.max_batch;
+        ctx->ensure_host_results((size_t)n);
+        for (int f0 = 0; f0 < n; f0 += B) {
+            const int nb = std::min(B, n - f0);
+            ctx->match_batch_device((const uint8_t*)d_frames + (size_t)f0 * frame_stride, nb, w, h, stride, frame_stride,
+                                    ctx->h_results + (size_t)f0 * 3);
+        }
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->collect_timings();
+        for (int i = 0; i < n; ++i) {
+            out[i].best_slide = ctx->h_results[3 * i];
+            out[i].votes = ctx->h_results[3 * i + 1];
+            out[i].n_keypoints = ctx->h_results[3 * i + 2];
+        }
+    });
+}
+
+int32_t slideo_b200_match_descriptors(slideo_b200_ctx* ctx, const void* desc, const int32_t* frame_offsets, int32_t n,
+                                      slideo_b200_frame_result* out) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_pool();
+        arg(n >= 0, "n < 0");
+        if (n == 0) return;
+        arg(frame_offsets && out, "frame_offsets/out must not be NULL");
+        arg(frame_offsets[0] == 0, "frame_offsets[0] must be 0");
+        for (int i = 0; i < n; ++i) arg(frame_offsets[i] <= frame_offsets[i + 1], "frame_offsets must be non-decreasing");
+        arg(desc != nullptr || frame_offsets[n] == 0, "desc must not be NULL");
+        ctx->reset_kept();
+        const int B = ctx->cfg.max_batch;
+        const bool orb = ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256;
+        ctx->ensure_host_results((size_t)n);
+        std::vector<int32_t> qf, nkp, fo;
+        for (int f0 = 0; f0 < n; f0 += B) {
+            const int nb = std::min(B, n - f0);
+            const int q0 = frame_offsets[f0], nq = frame_offsets[f0 + nb] - q0;
+            qf.resize((size_t)nq);
+            nkp.resize((size_t)nb);
+            fo.assign(1, 0);
+            for (int i = 0; i < nb; ++i) {
+                nkp[i] = frame_offsets[f0 + i + 1] - frame_offsets[f0 + i];
+                for (int j = frame_offsets[f0 + i] - q0; j < frame_offsets[f0 + i + 1] - q0; ++j) qf[(size_t)j] = i;
+                fo.push_back(frame_offsets[f0 + i + 1] - q0);
+            }
+            ctx->d_q.reserve((size_t)std::max(nq, 1) * ctx->desc_bytes);
+            ctx->d_q_frame.reserve((size_t)nq + nb + 1);
+            int32_t* d_nkp = ctx->d_q_frame.p + nq;
+            EventPair t = ctx->begin_timing(2, ctx->stream);
+            if (nq > 0) {
+                SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_q.p, (const uint8_t*)desc + (size_t)q0 * ctx->desc_bytes,
+                                            (size_t)nq * ctx->desc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+                SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_q_frame.p, qf.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+            }
+            SLIDEO_CUDA(cudaMemcpyAsync(d_nkp, nkp.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->end_timing(t, ctx->stream);
+            if (orb) {
+                ctx->knn_vote_hamming(ctx->d_q.p, nq, ctx->d_q_frame.p, nb, d_nkp, ctx->cfg.keep_matches != 0);
+            } else {
+                // SIFT128: tcgen05 L2 k-NN, then the same vote on (distance, index) rows
+                ctx->d_votes.reserve((size_t)nb * std::max(ctx->n_pages, 1));
+                ctx->d_results.reserve((size_t)nb * 3);
+                ctx->d_idx.reserve((size_t)std::max(nq, 1) * ctx->cfg.knn_k);
+                ctx->d_dist.reserve((size_t)std::max(nq, 1) * ctx->cfg.knn_k);
+                SLIDEO_CUDA(cudaMemsetAsync(ctx->d_votes.p, 0, (size_t)nb * std::max(ctx->n_pages, 1) * 4, ctx->stream));
+                if (nq > 0) {
+                    EventPair tk = ctx->begin_timing(1, ctx->stream);
+                    int nl = 0;
+                    l2_knn_launch(ctx->l2ws, (const float*)ctx->d_q.p, nq, (const uint16_t*)ctx->d_pool.p, ctx->d_pool_norm.p, ctx->nt,
+                                  ctx->cfg.knn_k, ctx->d_idx.p, (float*)ctx->d_dist.p, ctx->num_sms, ctx->stream, &nl);
+                    l2_vote_launch(ctx->d_idx.p, (const float*)ctx->d_dist.p, nq, ctx->cfg.knn_k, ctx->d_q_frame.p, ctx->d_page_of.p,
+                                   ctx->d_votes.p, ctx->n_pages, ctx->cfg.vote_ratio, ctx->stream);
+                    ctx->end_timing(tk, ctx->stream);
+                    ctx->tm.knn_launches += nl;
+                    ctx->tm.kernel_launches += nl + 1;
+                    ctx->tm.knn_pairs += (int64_t)nq * ctx->nt;
+                }
+                vote_argmax_launch(ctx->d_votes.p, nb, ctx->n_pages, d_nkp, ctx->d_results.p, ctx->stream);
+                ctx->tm.kernel_launches += 1;
+            }
+            SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_results + (size_t)f0 * 3, ctx->d_results.p, (size_t)nb * 3 * 4, cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+            if (ctx->cfg.keep_matches) {
+                if (orb) {
+                    ctx->keep_batch_keys(nq, fo);
+                } else {
+                    const size_t base = ctx->kept_l2.size();
+                    ctx->kept_l2.resize(base + (size_t)nq * ctx->cfg.knn_k);
+                    ctx->kept_l2_idx.resize(base + (size_t)nq * ctx->cfg.knn_k);
+                    if (nq > 0) {
+                        SLIDEO_CUDA(cudaMemcpyAsync(ctx->kept_l2.data() + base, ctx->d_dist.p, (size_t)nq * ctx->cfg.knn_k * 4,
+                                                    cudaMemcpyDeviceToHost, ctx->stream));
+                        SLIDEO_CUDA(cudaMemcpyAsync(ctx->kept_l2_idx.data() + base, ctx->d_idx.p, (size_t)nq * ctx->cfg.knn_k * 4,
+                                                    cudaMemcpyDeviceToHost, ctx->stream));
+                    }
+                    const int32_t qb = ctx->kept_frame_off.back();
+                    for (size_t i = 1; i < fo.size(); ++i) ctx->kept_frame_off.push_back(qb + fo[i]);
+                }
+            }
+            SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors are reused by the next batch
+            ctx->tm.frames += nb;
+        }
+        ctx->collect_timings();
+        for (int i = 0; i < n; ++i) {
+            out[i].best_slide = ctx->h_results[3 * i];
+            out[i].votes = ctx->h_results[3 * i + 1];
+            out[i].n_keypoints = ctx->h_results[3 * i + 2];
+        }
+    });
+}
+
+int32_t slideo_b200_get_matches(slideo_b200_ctx* ctx, int32_t frame_i, slideo_b200_match* out, int32_t cap_rows,
+                                int32_t* out_rows) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (!ctx->cfg.keep_matches) throw StateError("cfg.keep_matches was not set");
+        arg(frame_i >= 0 && frame_i + 1 < (int)ctx->kept_frame_off.size(), "frame_i out of range of the last match call");
+        const int q0 = ctx->kept_frame_off[frame_i], q1 = ctx->kept_frame_off[frame_i + 1], k = ctx->cfg.knn_k;
+        if (out_rows) *out_rows = q1 - q0;
+        if (!out) return;
+        arg(cap_rows >= q1 - q0, "cap_rows too small");
+        const bool orb = ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256;
+        for (int q = q0; q < q1; ++q)
+            for (int j = 0; j < k; ++j) {
+                slideo_b200_match& m = out[(size_t)(q - q0) * k + j];
+                int gi;
+                float dist;
+                if (orb) {
+                    const uint32_t key = ctx->kept_keys[(size_t)q * k + j];
+                    gi = key == KEY_EMPTY ? -1 : (int)(key & KEY_IDX_MASK);
+                    dist = (float)(key >> KEY_IDX_BITS);
+                } else {
+                    gi = ctx->kept_l2_idx[(size_t)q * k + j];
+                    dist = ctx->kept_l2[(size_t)q * k + j];
+                }
+                m.query_idx = q - q0;
+                if (gi < 0) {
+                    m.train_idx = -1;
+                    m.source = -1;
+                    m.distance = -1.f;
+                    continue;
+                }
+                const int page = (int)(std::upper_bound(ctx->page_off.begin(), ctx->page_off.end(), gi) - ctx->page_off.begin()) - 1;
+                m.source = page;
+                m.train_idx = gi - ctx->page_off[page];
+                m.distance = dist;
+            }
+    });
+}
+
+// ---- stage-level entry points -----------------------------------------------------------------------------------
+int32_t slideo_b200_extract_orb(slideo_b200_ctx* ctx, const uint8_t* img, int32_t w, int32_t h, int32_t stride, int32_t channels,
+                                int32_t* kp_i, float* kp_f, uint8_t* desc, int32_t cap, int32_t* out_n) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(img != nullptr, "img must not be NULL");
+        arg(channels == 1 || channels == 3, "channels must be 1 or 3");
+        arg(stride >= w * channels, "stride too small");
+        OrbExtractor& ex = ctx->extractor(w, h, 1);
+        ctx->d_img.reserve((size_t)w * h * channels);
+        ctx->upload_images(ctx->d_img.p, img, 1, w * channels, h, stride, (size_t)stride * h, ctx->stream);
+        int nl = 0;
+        EventPair t = ctx->begin_timing(0, ctx->stream);
+        const int total = ex.run(ctx->d_img.p, 1, w * channels, (size_t)w * h * channels, channels, ctx->stream, &nl);
+        ctx->end_timing(t, ctx->stream);
+        ctx->tm.kernel_launches += nl;
+        if (out_n) *out_n = total;
+        if (total > cap && (kp_i || kp_f || desc)) throw CapacityError("cap smaller than the number of keypoints");
+        if (total > 0) {
+            if (kp_i) SLIDEO_CUDA(cudaMemcpyAsync(kp_i, ex.d_kp_i(), (size_t)total * 16, cudaMemcpyDeviceToHost, ctx->stream));
+            if (kp_f) SLIDEO_CUDA(cudaMemcpyAsync(kp_f, ex.d_kp_f(), (size_t)total * 16, cudaMemcpyDeviceToHost, ctx->stream));
+            if (desc) SLIDEO_CUDA(cudaMemcpyAsync(desc, ex.d_desc(), (size_t)total * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->collect_timings();
+    });
+}
+
+int32_t slideo_b200_debug_fetch(slideo_b200_ctx* ctx, int32_t what, int32_t level, void* out, size_t cap_bytes, int32_t* out_w,
+                                int32_t* out_h) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        OrbExtractor* ex = ctx->last_ext;
+        if (!ex) throw StateError("no extract/match call yet");
+        arg(level >= 0 && level < ex->nlevels(), "level out of range");
+        const OrbLevelGeom& L = ex->level(level);
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (what == 0 || what == 1) {
+            if (out_w) *out_w = L.w;
+            if (out_h) *out_h = L.h;
+            if (!out) return;
+            arg(cap_bytes >= (size_t)L.w * L.h, "cap_bytes too small");
+            const uint8_t* src = (what == 0 ? ex->d_pyramid(0) : ex->d_blurred(0)) + L.img_off;
+            SLIDEO_CUDA(cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+        } else if (what == 2) {
+            int32_t cnt = 0;
+            SLIDEO_CUDA(cudaMemcpy(&cnt, ex->d_cand_count() + level, 4, cudaMemcpyDeviceToHost));
+            cnt = std::min(cnt, L.cand_cap);
+            if (out_w) *out_w = cnt;
+            if (out_h) *out_h = 1;
+            if (!out) return;
+            arg(cap_bytes >= (size_t)cnt * 4, "cap_bytes too small");
+            if (cnt) SLIDEO_CUDA(cudaMemcpy(out, ex->d_candidates(0) + L.cand_off, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+        } else {
+            throw ArgError("unknown `what`");
+        }
+    });
+}
+
+int32_t slideo_b200_bf_knn_hamming_device(slideo_b200_ctx* ctx, const void* d_q, int32_t nq, const void* d_t, int32_t nt, int32_t k,
+                                          void* d_keys_out) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(nq >= 0 && nt >= 0, "negative size");
+        arg(k >= 1 && k <= KNN_MAX_K, "k must be in 1..32");
+        arg(nt <= KNN_MAX_POOL, "nt exceeds 8,388,608");
+        if (nq == 0) return;
+        arg(d_q && d_keys_out && (d_t || nt == 0), "NULL buffer");
+        arg(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0, "device buffers must be 16-byte aligned");
+        KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
+        ctx->d_scratch.reserve(plan.scratch_bytes / 4);
+        if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
+        EventPair t = ctx->begin_timing(1, ctx->stream);
+        int nl = 0;
+        knn_hamming_launch(plan, d_q, d_t, (uint32_t*)d_keys_out, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
+        ctx->end_timing(t, ctx->stream);
+        ctx->tm.knn_launches += nl;
+        ctx->tm.kernel_launches += nl;
+        ctx->tm.knn_pairs += (int64_t)nq * nt;
+    });
+}
+
+int32_t slideo_b200_bf_knn_hamming(slideo_b200_ctx* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t k,
+                                   int32_t* idx, int32_t* dist) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(nq >= 0 && nt >= 0, "negative size");
+        arg(k >= 1 && k <= KNN_MAX_K, "k must be in 1..32");
+        arg(nt <= KNN_MAX_POOL, "nt exceeds 8,388,608");
+        if (nq == 0) return;
+        arg(q && idx && dist && (t || nt == 0), "NULL buffer");
+        ctx->d_q.reserve((size_t)nq * 32);
+        ctx->d_t.reserve((size_t)std::max(nt, 1) * 32);
+        ctx->d_keys.reserve((size_t)nq * k);
+        ctx->d_idx.reserve((size_t)nq * k);
+        ctx->d_dist.reserve((size_t)nq * k);
+        SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
+        if (nt) SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, ctx->stream));
+        KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
+        ctx->d_scratch.reserve(plan.scratch_bytes / 4);
+        if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
+        EventPair tk = ctx->begin_timing(1, ctx->stream);
+        int nl = 0;
+        knn_hamming_launch(plan, ctx->d_q.p, ctx->d_t.p, ctx->d_keys.p, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
+        ctx->end_timing(tk, ctx->stream);
+        keys_to_idx_dist_launch(ctx->d_keys.p, (size_t)nq * k, ctx->d_idx.p, ctx->d_dist.p, ctx->stream);
+        ctx->tm.knn_launches += nl;
+        ctx->tm.kernel_launches += nl + 1;
+        ctx->tm.knn_pairs += (int64_t)nq * nt;
+        SLIDEO_CUDA(cudaMemcpyAsync(idx, ctx->d_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SLIDEO_CUDA(cudaMemcpyAsync(dist, ctx->d_dist.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->collect_timings();
+    });
+}
+
+int32_t slideo_b200_bf_knn_l2(slideo_b200_ctx* ctx, const float* q, int32_t nq, const float* t, int32_t nt, int32_t dim, int32_t k,
+                              int32_t* idx, float* dist) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(nq >= 0 && nt >= 0, "negative size");
+        arg(dim == 128, "dim must be 128");
+        arg(k >= 1 && k <= KNN_MAX_K, "k must be in 1..32");
+        arg(nt <= (1 << 24), "nt exceeds 16,777,216");
+        if (nq == 0) return;
+        arg(q && idx && dist && (t || nt == 0), "NULL buffer");
+        ctx->d_q.reserve((size_t)nq * 512);
+        ctx->d_t.reserve((size_t)std::max(nt, 1) * 512);
+        DevBuf<uint8_t> tb;
+        DevBuf<float> tn;
+        tb.reserve((size_t)l2_rows_padded(nt) * 256 + 256);
+        tn.reserve((size_t)l2_rows_padded(nt) + 64);
+        ctx->d_idx.reserve((size_t)nq * k);
+        ctx->d_dist.reserve((size_t)nq * k);
+        SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_q.p, q, (size_t)nq * 512, cudaMemcpyHostToDevice, ctx->stream));
+        if (nt) SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_t.p, t, (size_t)nt * 512, cudaMemcpyHostToDevice, ctx->stream));
+        l2_prepare_launch((const float*)ctx->d_t.p, nt, 128, (uint16_t*)tb.p, tn.p, ctx->stream);
+        EventPair tk = ctx->begin_timing(1, ctx->stream);
+        int nl = 0;
+        l2_knn_launch(ctx->l2ws, (const float*)ctx->d_q.p, nq, (const uint16_t*)tb.p, tn.p, nt, k, ctx->d_idx.p, (float*)ctx->d_dist.p,
+                      ctx->num_sms, ctx->stream, &nl);
+        ctx->end_timing(tk, ctx->stream);
+        ctx->tm.knn_launches += nl;
+        ctx->tm.kernel_launches += nl + 1;
+        ctx->tm.knn_pairs += (int64_t)nq * nt;
+        SLIDEO_CUDA(cudaMemcpyAsync(idx, ctx->d_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SLIDEO_CUDA(cudaMemcpyAsync(dist, ctx->d_dist.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->collect_timings();
+    });
+}
+
+int32_t slideo_b200_bf_knn_l2_device(slideo_b200_ctx* ctx, const void* d_q, int32_t nq, const void* d_t, int32_t nt, int32_t dim,
+                                     int32_t k, void* d_idx, void* d_dist) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(nq >= 0 && nt >= 0, "negative size");
+        arg(dim == 128, "dim must be 128");
+        arg(k >= 1 && k <= KNN_MAX_K, "k must be in 1..32");
+        arg(nt <= (1 << 24), "nt exceeds 16,777,216");
+        if (nq == 0) return;
+        arg(d_q && d_idx && d_dist && (d_t || nt == 0), "NULL buffer");
+        arg(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0, "device buffers must be 16-byte aligned");
+        // bf16 copy + norms of the pool (outside the K10 timing bracket)
+        ctx->d_l2_pool.reserve((size_t)l2_rows_padded(nt) * 256 + 256);
+        ctx->d_l2_norm.reserve((size_t)l2_rows_padded(nt) + 64);
+        l2_prepare_launch((const float*)d_t, nt, 128, (uint16_t*)ctx->d_l2_pool.p, ctx->d_l2_norm.p, ctx->stream);
+        EventPair tk = ctx->begin_timing(1, ctx->stream);
+        int nl = 0;
+        l2_knn_launch(ctx->l2ws, (const float*)d_q, nq, (const uint16_t*)ctx->d_l2_pool.p, ctx->d_l2_norm.p, nt, k, (int32_t*)d_idx,
+                      (float*)d_dist, ctx->num_sms, ctx->stream, &nl);
+        ctx->end_timing(tk, ctx->stream);
+        ctx->tm.knn_launches += nl;
+        ctx->tm.kernel_launches += nl;
+        ctx->tm.knn_pairs += (int64_t)nq * nt;
+    });
+}
+
+// ---- utilities ------------------------------------------------------------------------------------------------
+int32_t slideo_b200_host_alloc(void** out, size_t bytes) {
+    if (!out) return SLIDEO_B200_E_INVALID_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaMallocHost failed: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? SLIDEO_B200_E_OOM : SLIDEO_B200_E_CUDA;
+    }
+    return SLIDEO_B200_OK;
+}
+
+int32_t slideo_b200_host_free(void* p) {
+    if (!p) return SLIDEO_B200_OK;
+    return cudaFreeHost(p) == cudaSuccess ? SLIDEO_B200_OK : SLIDEO_B200_E_CUDA;
+}
+
+int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, int32_t reset) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->collect_timings();
+        if (out) *out = ctx->tm;
+        if (reset) ctx->tm = slideo_b200_timings{};
+    });
+}
+
+int32_t slideo_b200_microbench(slideo_b200_ctx* ctx, int32_t which, double* out_per_second) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(which >= 0 && which <= 2, "which must be 0, 1 or 2");
+        arg(out_per_second != nullptr, "out_per_second must not be NULL");
+        *out_per_second = microbench_run(which, ctx->num_sms, ctx->stream);
+    });
+}
+
+int32_t slideo_b200_synchronize(slideo_b200_ctx* ctx) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->collect_timings();
+    });
+}
+
+}  // extern "C"

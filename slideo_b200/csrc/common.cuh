@@ -1,0 +1,69 @@
+// common.cuh -- shared declarations of libslideo_b200 (sm_100a only; no other backend, no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace slideo {
+
+struct CudaError : std::runtime_error {
+    cudaError_t code;
+    CudaError(cudaError_t c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct CapacityError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NotImplError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define SLIDEO_CUDA(expr)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            throw ::slideo::CudaError(_e, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +  \
+                                              __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- K8/K9: brute-force Hamming k-NN + vote (knn_hamming.cu) -------------------------------------------------
+// A k-NN entry is one uint32 key = distance << 23 | pooled index, so that integer order == the oracle's
+// (distance, pooled index) order.  0xFFFFFFFF = empty slot.
+constexpr int KEY_IDX_BITS = 23;
+constexpr uint32_t KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1;
+constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
+constexpr int KNN_MAX_K = 32;
+constexpr int KNN_MAX_POOL = 1 << KEY_IDX_BITS;  // 8,388,608 pooled descriptors (README.md:41 expects < 1000 slides)
+
+struct KnnPlan {
+    int nq = 0, nt = 0, k = 0;
+    int n_tiles = 0;     // query tiles
+    int n_splits = 0;    // pool splits
+    int split_len = 0;   // pooled descriptors per split (multiple of the smem chunk)
+    int grid = 0;        // persistent CTAs
+    size_t scratch_bytes = 0;  // candidate buffers (grid * tile * slots * 4)
+    size_t partial_bytes = 0;  // per-split partial rows when n_splits > 1
+};
+
+struct VoteArgs {            // fused K9: vote straight out of K8's final sort (n_splits == 1) or from vote kernel
+    const int32_t* q_frame;  // [nq] frame of each query row
+    const uint16_t* page_of; // [nt] page of each pooled descriptor
+    int32_t* votes;          // [n_frames][n_pages]
+    int n_pages;
+    float ratio;
+};
+
+KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms);
+// keys_out: [nq][k] uint32 (may be nullptr when vote != nullptr).  scratch/partial sized per plan.
+void knn_hamming_launch(const KnnPlan& plan, const void* d_q, const void* d_pool, uint32_t* d_keys_out,
+                        uint32_t* d_scratch, uint32_t* d_partial, const VoteArgs* vote, cudaStream_t stream,
+                        int* launches);
+// frame results from the vote table
+void vote_argmax_launch(const int32_t* d_votes, int n_frames, int n_pages, const int32_t* d_frame_nkp,
+                        int32_t* d_results /* n_frames x 3 */, cudaStream_t stream);
+void keys_to_idx_dist_launch(const uint32_t* d_keys, size_t n, int32_t* d_idx, int32_t* d_dist, cudaStream_t stream);
+double microbench_run(int which, int num_sms, cudaStream_t stream);
+
+}  // namespace slideo

@@ -1,0 +1,660 @@
+// orb.cu -- K1-K7: batched ORB feature extraction, bit-exact with OpenCV's ORB as the reference configures it
+// (crates/matching-opencv/src/feature_extractor.rs:12-46: ORB::create(2000, 1.2, 8, 62, 0, 2, FAST_SCORE, 62, 20)
+//  .detectAndCompute).  The algorithm is the one restated in oracle/orb_oracle.c; every
+// kernel below names the stage it implements.  All images of a batch share one geometry.
+//
+//   K1 gray_kernel      BGR -> gray (fixed point), level 0 of the pyramid
+//   K2 resize_kernel    INTER_LINEAR_EXACT 8.8 fixed-point chain, level l from level l-1
+//   K3 fast_kernel      FAST-9/16 score + 3x3 NMS + border(edgeThreshold) filter, all levels in one launch
+//   K4 select_kernel    retainBest(quota) with ties via a 256-bin score histogram, canonical (y, x) sort
+//      scan_kernel      keypoint offsets per (image, level); scatter_kernel writes keypoint records
+//   K6 blur_kernel      7x7 sigma-2 Gaussian, separable fp32 with OpenCV's exact fma order, all levels in one launch
+//   K5+K7 describe_kernel  intensity-centroid angle (fastAtan2) + 256-bit steered descriptor, one warp per keypoint
+#include "orb.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace slideo {
+
+namespace {
+
+constexpr int TILE_W = 64, TILE_H = 32;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct Geo {
+    int nlevels, total_tiles, edge, fast_thr, patch, half;
+    size_t pyr_img_bytes, cand_img_words, sel_img_words;
+    int umax[40];
+    OrbLevelGeom lv[ORB_MAX_LEVELS];
+};
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    // BORDER_REFLECT_101; n >= 2 in practice, loop handles far-out coordinates
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+// ---- K1 -----------------------------------------------------------------------------------------------------
+// cvtColor BGR2GRAY 8u: (B*3735 + G*19235 + R*9798 + 2^14) >> 15   
+__global__ void __launch_bounds__(128) gray_kernel(const uint8_t* __restrict__ src, int stride, size_t frame_stride,
+                                                   int channels, uint8_t* __restrict__ pyr, size_t pyr_img_bytes, int w,
+                                                   int h, int pitch) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, img = blockIdx.z;
+    if (x >= w) return;
+    const uint8_t* row = src + (size_t)img * frame_stride + (size_t)y * stride;
+    uint8_t g[4] = {0, 0, 0, 0};
+    if (channels == 3) {
+        const uint8_t* p = row + 3 * x;
+        if (x + 4 <= w && (((uintptr_t)p) & 3) == 0) {
+            const uint32_t* p32 = reinterpret_cast<const uint32_t*>(p);
+            const uint32_t a = __ldg(p32), b = __ldg(p32 + 1), c = __ldg(p32 + 2);
+            const uint32_t B0 = a & 255, G0 = (a >> 8) & 255, R0 = (a >> 16) & 255, B1 = a >> 24;
+            const uint32_t G1 = b & 255, R1 = (b >> 8) & 255, B2 = (b >> 16) & 255, G2 = b >> 24;
+            const uint32_t R2 = c & 255, B3 = (c >> 8) & 255, G3 = (c >> 16) & 255, R3 = c >> 24;
+            g[0] = (uint8_t)((B0 * 3735u + G0 * 19235u + R0 * 9798u + 16384u) >> 15);
+            g[1] = (uint8_t)((B1 * 3735u + G1 * 19235u + R1 * 9798u + 16384u) >> 15);
+            g[2] = (uint8_t)((B2 * 3735u + G2 * 19235u + R2 * 9798u + 16384u) >> 15);
+            g[3] = (uint8_t)((B3 * 3735u + G3 * 19235u + R3 * 9798u + 16384u) >> 15);
+        } else {
+            for (int i = 0; i < 4 && x + i < w; ++i)
+                g[i] = (uint8_t)(((uint32_t)p[3 * i] * 3735u + (uint32_t)p[3 * i + 1] * 19235u +
+                                  (uint32_t)p[3 * i + 2] * 9798u + 16384u) >> 15);
+        }
+    } else {
+        for (int i = 0; i < 4 && x + i < w; ++i) g[i] = row[x + i];
+    }
+    uchar4 o = make_uchar4(g[0], g[1], g[2], g[3]);
+    *reinterpret_cast<uchar4*>(pyr + (size_t)img * pyr_img_bytes + (size_t)y * pitch + x) = o;
+}
+
+// ---- K2 -----------------------------------------------------------------------------------------------------
+// resize INTER_LINEAR_EXACT, 8-bit: horizontal 8.8 fixed point then vertical, (v + 2^15) >> 16   
+// tables (host-built in double precision, identical to the oracle): xofs[dw], xc1[dw], yofs[dh], yc1[dh]
+__global__ void __launch_bounds__(128) resize_kernel(uint8_t* __restrict__ pyr, size_t pyr_img_bytes, size_t src_off,
+                                                     int sw, int sh, int spitch, size_t dst_off, int dw, int dh,
+                                                     int dpitch, const int32_t* __restrict__ tab) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, img = blockIdx.z;
+    if (x0 >= dw) return;
+    const int32_t* xofs = tab;
+    const int32_t* xc1 = tab + dw;
+    const int32_t* yofs = tab + 2 * dw;
+    const int32_t* yc1 = tab + 2 * dw + dh;
+    const int oy = __ldg(yofs + y), fy = __ldg(yc1 + y);
+    const uint8_t* base = pyr + (size_t)img * pyr_img_bytes;
+    const uint8_t* s0 = base + src_off + (size_t)oy * spitch;
+    const uint8_t* s1 = base + src_off + (size_t)min(oy + 1, sh - 1) * spitch;
+    uint8_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        if (x < dw) {
+            const int ox = __ldg(xofs + x), fx = __ldg(xc1 + x);
+            const int ox1 = min(ox + 1, sw - 1);
+            const uint32_t a = (uint32_t)s0[ox] * (uint32_t)(256 - fx) + (uint32_t)s0[ox1] * (uint32_t)fx;
+            const uint32_t b = (uint32_t)s1[ox] * (uint32_t)(256 - fx) + (uint32_t)s1[ox1] * (uint32_t)fx;
+            uint32_t v = (a * (uint32_t)(256 - fy) + b * (uint32_t)fy + (1u << 15)) >> 16;
+            o[i] = (uint8_t)min(v, 255u);
+        }
+    }
+    *reinterpret_cast<uchar4*>(pyr + (size_t)img * pyr_img_bytes + dst_off + (size_t)y * dpitch + x0) =
+        make_uchar4(o[0], o[1], o[2], o[3]);
+}
+
+// ---- K3 -----------------------------------------------------------------------------------------------------
+// FAST-9/16 (threshold t, nonmaxSuppression=true) restated: score = max over the 16 arcs of 9 contiguous circle
+// pixels of max(min(c - p), min(p - c)); corner iff score > t; response = score - 1; NMS strict > over 8 neighbours
+// (SURVEY A.4).  Then KeyPointsFilter::runByImageBorder(edgeThreshold) (A.5).
+__device__ __forceinline__ int fast_score(const uint8_t* sp, int pitch) {
+    // sp points at the centre pixel inside the shared tile
+    const int c = sp[0];
+    int d[16];
+    d[0] = c - sp[3 * pitch];      d[1] = c - sp[3 * pitch + 1];  d[2] = c - sp[2 * pitch + 2];  d[3] = c - sp[pitch + 3];
+    d[4] = c - sp[3];              d[5] = c - sp[-pitch + 3];     d[6] = c - sp[-2 * pitch + 2]; d[7] = c - sp[-3 * pitch + 1];
+    d[8] = c - sp[-3 * pitch];     d[9] = c - sp[-3 * pitch - 1]; d[10] = c - sp[-2 * pitch - 2]; d[11] = c - sp[-pitch - 3];
+    d[12] = c - sp[-3];            d[13] = c - sp[pitch - 3];     d[14] = c - sp[2 * pitch - 2]; d[15] = c - sp[3 * pitch - 1];
+    // "all nine brighter" is evaluated as a min-tree over e = -d rather than as -max(d): on sm_100a (CUDA 12.9) the
+    // max/negate form was observed to miscompile (scores too high next to strong edges); min-only trees are exact.
+    int e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = -d[k];
+    int a2[16], b2[16], a4[16], b4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { a2[k] = min(d[k], d[(k + 1) & 15]); b2[k] = min(e[k], e[(k + 1) & 15]); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { a4[k] = min(a2[k], a2[(k + 2) & 15]); b4[k] = min(b2[k], b2[(k + 2) & 15]); }
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int a9 = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);   // min over d[k..k+8]: all nine darker
+        const int b9 = min(min(b4[k], b4[(k + 4) & 15]), e[(k + 8) & 15]);   // min over -d[k..k+8]: all nine brighter
+        best = max(best, max(a9, b9));
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ pyr, const Geo* __restrict__ gp,
+                                                   uint32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+    constexpr int PW = TILE_W + 8, PH = TILE_H + 8;   // pixel tile incl. 4-px halo
+    constexpr int SW = TILE_W + 2, SH = TILE_H + 2;   // score tile incl. 1-px halo
+    __shared__ uint8_t s_px[PH][PW];
+    __shared__ uint8_t s_sc[SH][SW + 2];
+
+    const Geo& g = *gp;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].tile_base) ++l;
+    const OrbLevelGeom L = g.lv[l];
+    const int t = blockIdx.x - L.tile_base;
+    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    const int img = blockIdx.y;
+    const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
+
+    for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+        const int py = i / PW, px = i - py * PW;
+        const int gx = tx0 + px - 4, gy = ty0 + py - 4;
+        s_px[py][px] = (gx >= 0 && gx < L.w && gy >= 0 && gy < L.h) ? src[(size_t)gy * L.pitch + gx] : 0;
+    }
+    __syncthreads();
+
+    const int thr = g.fast_thr;
+    for (int i = threadIdx.x; i < SH * SW; i += blockDim.x) {
+        const int sy = i / SW, sx = i - sy * SW;
+        const int gx = tx0 + sx - 1, gy = ty0 + sy - 1;
+        int score = 0;
+        if (gx >= 3 && gx < L.w - 3 && gy >= 3 && gy < L.h - 3) {
+            const uint8_t* sp = &s_px[sy + 3][sx + 3];
+            const int c = sp[0];
+            const int p0 = sp[3 * PW], p4 = sp[3], p8 = sp[-3 * PW], p12 = sp[-3];
+            // any 9-arc contains two adjacent compass points -> exact necessary condition
+            const int hi = c + thr, lo = c - thr;
+            const bool b0 = p0 > hi, b4 = p4 > hi, b8 = p8 > hi, b12 = p12 > hi;
+            const bool k0 = p0 < lo, k4 = p4 < lo, k8 = p8 < lo, k12 = p12 < lo;
+            if ((b0 && b4) || (b4 && b8) || (b8 && b12) || (b12 && b0) || (k0 && k4) || (k4 && k8) || (k8 && k12) ||
+                (k12 && k0)) {
+                const int s = fast_score(sp, PW);
+                if (s > thr) score = s - 1;
+            }
+        }
+        s_sc[sy][sx] = (uint8_t)score;
+    }
+    __syncthreads();
+
+    const int e = g.edge;
+    for (int i = threadIdx.x; i < TILE_H * TILE_W; i += blockDim.x) {
+        const int y = i / TILE_W, x = i - y * TILE_W;
+        const int s = s_sc[y + 1][x + 1];
+        if (s == 0) continue;
+        const int gx = tx0 + x, gy = ty0 + y;
+        if (gx < e || gx >= L.w - e || gy < e || gy >= L.h - e) continue;
+        if (s > s_sc[y][x] && s > s_sc[y][x + 1] && s > s_sc[y][x + 2] && s > s_sc[y + 1][x] && s > s_sc[y + 1][x + 2] &&
+            s > s_sc[y + 2][x] && s > s_sc[y + 2][x + 1] && s > s_sc[y + 2][x + 2]) {
+            const int pos = atomicAdd(&cand_cnt[img * g.nlevels + l], 1);
+            if (pos < L.cand_cap)
+                cand[(size_t)img * g.cand_img_words + L.cand_off + pos] = ((uint32_t)s << 24) | ((uint32_t)gy << 12) | (uint32_t)gx;
+        }
+    }
+}
+
+// ---- K4 -----------------------------------------------------------------------------------------------------
+// KeyPointsFilter::retainBest(quota): keep everything >= the quota-th largest response (ties kept),
+// then canonical (y, x) order (A.9).  One CTA per (level, image).
+__global__ void __launch_bounds__(256) select_kernel(const Geo* __restrict__ gp, const uint32_t* __restrict__ cand,
+                                                     const int32_t* __restrict__ cand_cnt, uint32_t* __restrict__ sel,
+                                                     int32_t* __restrict__ sel_cnt, int32_t* __restrict__ flags) {
+    extern __shared__ uint32_t s_keys[];  // sel_cap entries
+    __shared__ int s_hist[256];
+    __shared__ int s_thr, s_n;
+    const Geo& g = *gp;
+    const int l = blockIdx.x, img = blockIdx.y;
+    const OrbLevelGeom L = g.lv[l];
+    int n = cand_cnt[img * g.nlevels + l];
+    if (n > L.cand_cap) {
+        if (threadIdx.x == 0) atomicOr(flags, 1);
+        n = L.cand_cap;
+    }
+    const uint32_t* c = cand + (size_t)img * g.cand_img_words + L.cand_off;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[c[i] >> 24], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int thr = 0;
+        if (n > L.quota) {
+            thr = 256;
+            int acc = 0;
+            for (int t = 255; t > 0 && L.quota > 0; --t) {
+                acc += s_hist[t];
+                if (acc >= L.quota) { thr = t; break; }
+            }
+        }
+        s_thr = thr;
+    }
+    __syncthreads();
+    const int thr = s_thr;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t v = c[i];
+        if ((int)(v >> 24) >= thr) {
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < L.sel_cap) s_keys[pos] = v;
+        }
+    }
+    __syncthreads();
+    int m = s_n;
+    if (m > L.sel_cap) {
+        if (threadIdx.x == 0) atomicOr(flags, 2);
+        m = L.sel_cap;
+    }
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    for (int i = m + threadIdx.x; i < p2; i += blockDim.x) s_keys[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    // bitonic sort on (y << 12 | x) = low 24 bits (padding sorts last)
+    for (int size = 2; size <= p2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const uint32_t a = s_keys[i], b = s_keys[j];
+                    const bool pa = a == 0xFFFFFFFFu, pb = b == 0xFFFFFFFFu;
+                    const uint32_t ka = pa ? 0xFFFFFFFFu : (a & 0xFFFFFFu), kb = pb ? 0xFFFFFFFFu : (b & 0xFFFFFFu);
+                    const bool up = (i & size) == 0;
+                    if ((ka > kb) == up) { s_keys[i] = b; s_keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    uint32_t* out = sel + (size_t)img * g.sel_img_words + L.sel_off;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) out[i] = s_keys[i];
+    if (threadIdx.x == 0) sel_cnt[img * g.nlevels + l] = m;
+}
+
+// exclusive scan of sel_cnt over (image, level) -> kp_off[n*nlevels + 1], frame_off[n + 1], frame_nkp[n]
+__global__ void __launch_bounds__(256) scan_kernel(const int32_t* __restrict__ sel_cnt, int n_img, int nlevels,
+                                                   int32_t* __restrict__ kp_off, int32_t* __restrict__ frame_off,
+                                                   int32_t* __restrict__ frame_nkp, const int32_t* __restrict__ flags,
+                                                   int32_t* __restrict__ h_out) {
+    __shared__ int s_tot[1024];
+    const int tid = threadIdx.x;
+    for (int f = tid; f < n_img; f += blockDim.x) {
+        int t = 0;
+        for (int l = 0; l < nlevels; ++l) t += sel_cnt[f * nlevels + l];
+        s_tot[f] = t;
+        frame_nkp[f] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int f = 0; f < n_img; ++f) {
+            frame_off[f] = acc;
+            h_out[2 + f] = acc;
+            int a2 = acc;
+            for (int l = 0; l < nlevels; ++l) { kp_off[f * nlevels + l] = a2; a2 += sel_cnt[f * nlevels + l]; }
+            acc += s_tot[f];
+        }
+        frame_off[n_img] = acc;
+        kp_off[n_img * nlevels] = acc;
+        h_out[2 + n_img] = acc;
+        h_out[0] = acc;
+        h_out[1] = flags[0];
+    }
+}
+
+// keypoint records in canonical order: kp_src[g] = img << 4 | level ... packed with the selected entry
+__global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp, const uint32_t* __restrict__ sel,
+                                                      const int32_t* __restrict__ sel_cnt,
+                                                      const int32_t* __restrict__ kp_off, uint32_t* __restrict__ kp_src,
+                                                      int32_t* __restrict__ q_frame, int32_t* __restrict__ kp_i,
+                                                      size_t kp_cap) {
+    const Geo& g = *gp;
+    const int l = blockIdx.x, img = blockIdx.y;
+    const OrbLevelGeom L = g.lv[l];
+    const int m = sel_cnt[img * g.nlevels + l], off = kp_off[img * g.nlevels + l];
+    const uint32_t* s = sel + (size_t)img * g.sel_img_words + L.sel_off;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const size_t o = (size_t)off + i;
+        if (o >= kp_cap) continue;
+        const uint32_t v = s[i];
+        kp_src[2 * o] = v;
+        kp_src[2 * o + 1] = ((uint32_t)img << 8) | (uint32_t)l;
+        q_frame[o] = img;
+        reinterpret_cast<int4*>(kp_i)[o] = make_int4((int)(v & 0xFFF), (int)((v >> 12) & 0xFFF), l, (int)(v >> 24));
+    }
+}
+
+// ---- K6 -----------------------------------------------------------------------------------------------------
+// GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) as ORB invokes it: the generic float separable filter
+// (row: acc = k0*p0; acc = fma(k_i, p_i, acc) left to right; column: acc = k3*r3; acc = fma(k_{3+j}, r_{3+j} + r_{3-j},
+// acc); round-half-even, saturate) -- SURVEY A.7.
+__global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+                                                   const Geo* __restrict__ gp) {
+    constexpr int PW = TILE_W + 8, PH = TILE_H + 6;  // 3-px halo (PW padded to a multiple of 4)
+    __shared__ uint8_t s_px[PH][PW];
+    __shared__ float s_row[PH][TILE_W + 1];
+
+    const Geo& g = *gp;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].tile_base) ++l;
+    const OrbLevelGeom L = g.lv[l];
+    const int t = blockIdx.x - L.tile_base;
+    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    const int img = blockIdx.y;
+    const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
+    uint8_t* dst = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
+
+    for (int i = threadIdx.x; i < PH * (TILE_W + 6); i += blockDim.x) {
+        const int py = i / (TILE_W + 6), px = i - py * (TILE_W + 6);
+        const int gx = reflect101(tx0 + px - 3, L.w), gy = reflect101(ty0 + py - 3, L.h);
+        s_px[py][px] = src[(size_t)gy * L.pitch + gx];
+    }
+    __syncthreads();
+    // getGaussianKernel(7, 2, CV_32F) as exact bit patterns
+    const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
+                k3 = __uint_as_float(0x3e5d4ae0u);
+    for (int i = threadIdx.x; i < PH * TILE_W; i += blockDim.x) {
+        const int py = i / TILE_W, x = i - py * TILE_W;
+        const uint8_t* p = &s_px[py][x];
+        float acc = __fmul_rn(k0, (float)p[0]);
+        acc = __fmaf_rn(k1, (float)p[1], acc);
+        acc = __fmaf_rn(k2, (float)p[2], acc);
+        acc = __fmaf_rn(k3, (float)p[3], acc);
+        acc = __fmaf_rn(k2, (float)p[4], acc);
+        acc = __fmaf_rn(k1, (float)p[5], acc);
+        acc = __fmaf_rn(k0, (float)p[6], acc);
+        s_row[py][x] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TILE_H * TILE_W; i += blockDim.x) {
+        const int y = i / TILE_W, x = i - y * TILE_W;
+        const int gx = tx0 + x, gy = ty0 + y;
+        if (gx >= L.w || gy >= L.h) continue;
+        float acc = __fmul_rn(k3, s_row[y + 3][x]);
+        acc = __fmaf_rn(k2, __fadd_rn(s_row[y + 4][x], s_row[y + 2][x]), acc);
+        acc = __fmaf_rn(k1, __fadd_rn(s_row[y + 5][x], s_row[y + 1][x]), acc);
+        acc = __fmaf_rn(k0, __fadd_rn(s_row[y + 6][x], s_row[y][x]), acc);
+        int v = __float2int_rn(acc);
+        dst[(size_t)gy * L.pitch + gx] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// ---- K5 + K7 ------------------------------------------------------------------------------------------------
+// cv::fastAtan2 (degrees), float products/sums evaluated without contraction
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float p1 = __uint_as_float(0x4265226fu), p3 = __uint_as_float(0xc19556eeu), p5 = __uint_as_float(0x410e9fbfu),
+                p7 = __uint_as_float(0xc0228ad9u);
+    const float eps = __uint_as_float(0x25800000u);  // (float)DBL_EPSILON
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+                                                       const Geo* __restrict__ gp, const uint32_t* __restrict__ kp_src, int total,
+                                                       const int8_t* __restrict__ pattern, float* __restrict__ kp_f,
+                                                       uint8_t* __restrict__ desc) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= total) return;
+    const uint32_t v = kp_src[2 * k], fl = kp_src[2 * k + 1];
+    const int x = v & 0xFFF, y = (v >> 12) & 0xFFF, l = fl & 0xFF, img = fl >> 8;
+    const Geo& g = *gp;
+    const OrbLevelGeom L = g.lv[l];
+    const uint8_t* im = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
+    const int half = g.half;
+
+    // K5: intensity centroid over the disc of radius `half` on the unblurred level
+    int m10 = 0, m01 = 0;
+    for (int vv = -half; vv <= half; ++vv) {
+        const int du = g.umax[vv < 0 ? -vv : vv];
+        const int yy = reflect101(y + vv, L.h);
+        const uint8_t* row = im + (size_t)yy * L.pitch;
+        for (int u = -half + lane; u <= half; u += 32) {
+            if (u >= -du && u <= du) {
+                const int val = row[reflect101(x + u, L.w)];
+                m10 += u * val;
+                m01 += vv * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(FULL, m10, o);
+        m01 += __shfl_xor_sync(FULL, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
+    if (lane == 0) reinterpret_cast<float4*>(kp_f)[k] = make_float4(ptx, pty, __fmul_rn((float)g.patch, L.scale), angle);
+
+    // K7: steered BRIEF on the blurred level (pattern = cv::RNG(0x34985739) points)
+    const uint8_t* bl = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
+    const int cx = __float2int_rn(__fmul_rn(ptx, L.inv_scale)), cy = __float2int_rn(__fmul_rn(pty, L.inv_scale));
+    const float th = __fmul_rn(angle, __uint_as_float(0x3c8efa35u));  // (float)(CV_PI / 180)
+    const float a = (float)cos((double)th), b = (float)sin((double)th);
+    const uint4* pat4 = reinterpret_cast<const uint4*>(pattern) + lane * 2;
+    const uint4 w0 = __ldg(pat4), w1 = __ldg(pat4 + 1);
+    const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    uint32_t byte = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        // word j holds the two points of bit j: (x0, y0, x1, y1) as int8
+        const uint32_t wv = words[j];
+        int val[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const float px = (float)(int)(int8_t)((wv >> (16 * t)) & 255), py = (float)(int)(int8_t)((wv >> (16 * t + 8)) & 255);
+            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            val[t] = bl[(size_t)reflect101(cy + iy, L.h) * L.pitch + reflect101(cx + ix, L.w)];
+        }
+        byte |= (uint32_t)(val[0] < val[1]) << j;
+    }
+    desc[(size_t)k * 32 + lane] = (uint8_t)byte;
+}
+
+// host-side restatement of the geometry helpers (same arithmetic as oracle/orb_oracle.c)
+int cv_round_f(float v) { return (int)lrintf(v); }
+int cv_round_d(double v) { return (int)lrint(v); }
+
+void build_axis_table(int src, int dst, int32_t* ofs, int32_t* c1) {
+    const double scale = (double)src / (double)dst;
+    for (int d = 0; d < dst; ++d) {
+        const double val = scale * (d + 0.5) - 0.5;
+        int o = (int)floor(val);
+        int f = cv_round_d((val - o) * 256.0);
+        if (o < 0) { o = 0; f = 0; }
+        else if (o >= src - 1) { o = src - 1; f = 0; }
+        ofs[d] = o;
+        c1[d] = f;
+    }
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : cfg_(cfg), w_(w), h_(h), batch_cap_(batch_cap) {
+    if (cfg.nlevels < 1 || cfg.nlevels > ORB_MAX_LEVELS) throw ArgError("nlevels out of range");
+    if (w > ORB_MAX_DIM || h > ORB_MAX_DIM || w < 16 || h < 16) throw ArgError("image size out of range (16..4095)");
+    if (batch_cap < 1 || batch_cap > 1024) throw ArgError("batch out of range (1..1024)");
+    if (cfg.patch_size / 2 > 38 || cfg.patch_size < 2) throw ArgError("patch_size out of range");
+    const int L = cfg.nlevels;
+    lv_.resize(L);
+    // quota per level (orb.cpp), SURVEY A.5
+    {
+        const float factor = (float)(1.0 / cfg.scale_factor);
+        float nd = cfg.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)L));
+        int sum = 0;
+        for (int l = 0; l < L - 1; ++l) { lv_[l].quota = cv_round_f(nd); sum += lv_[l].quota; nd *= factor; }
+        lv_[L - 1].quota = cfg.nfeatures - sum > 0 ? cfg.nfeatures - sum : 0;
+    }
+    size_t img_off = 0, cand_off = 0, sel_off = 0, tab_off = 0;
+    int tile_base = 0;
+    std::vector<int32_t> tables;
+    for (int l = 0; l < L; ++l) {
+        OrbLevelGeom& g = lv_[l];
+        g.scale = (float)pow((double)cfg.scale_factor, (double)l);
+        g.inv_scale = 1.f / g.scale;
+        g.w = cv_round_f((float)w * g.inv_scale);
+        g.h = cv_round_f((float)h * g.inv_scale);
+        if (g.w < 8 || g.h < 8) throw ArgError("image too small for the requested pyramid");
+        g.pitch = (int)align_up((size_t)g.w, 16);
+        g.img_off = img_off;
+        img_off += align_up((size_t)g.pitch * g.h, 256);
+        g.cand_cap = (g.w / 2 + 1) * (g.h / 2 + 1);  // strict 3x3 maxima: at most one per 2x2 block -> cannot overflow
+        g.cand_off = cand_off;
+        cand_off += (size_t)g.cand_cap;
+        g.sel_cap = next_pow2(g.quota * 2 > g.quota + 256 ? g.quota * 2 : g.quota + 256);
+        if (g.sel_cap > 8192) throw ArgError("nfeatures too large");
+        g.sel_off = sel_off;
+        sel_off += (size_t)g.sel_cap;
+        g.tiles_x = cdiv(g.w, TILE_W);
+        g.tiles_y = cdiv(g.h, TILE_H);
+        g.tile_base = tile_base;
+        tile_base += g.tiles_x * g.tiles_y;
+        g.tab_off = tab_off;
+        if (l > 0) {
+            tables.resize(tab_off + 2 * (size_t)(g.w + g.h));
+            build_axis_table(lv_[l - 1].w, g.w, tables.data() + tab_off, tables.data() + tab_off + g.w);
+            build_axis_table(lv_[l - 1].h, g.h, tables.data() + tab_off + 2 * g.w, tables.data() + tab_off + 2 * g.w + g.h);
+            tab_off += 2 * (size_t)(g.w + g.h);
+        }
+    }
+    total_tiles_ = tile_base;
+    pyr_img_bytes_ = img_off;
+    cand_img_words_ = cand_off;
+    sel_img_words_ = sel_off;
+    kp_cap_ = (size_t)batch_cap * sel_off;
+
+    const size_t B = (size_t)batch_cap;
+    SLIDEO_CUDA(cudaMalloc(&d_pyr_, B * pyr_img_bytes_));
+    SLIDEO_CUDA(cudaMalloc(&d_blur_, B * pyr_img_bytes_));
+    SLIDEO_CUDA(cudaMalloc(&d_cand_, B * cand_img_words_ * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_sel_, B * sel_img_words_ * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_cand_cnt_, B * L * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_sel_cnt_, B * L * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_kp_off_, (B * L + 1) * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_frame_off_, (B + 1) * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_frame_nkp_, B * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_flags_, 4));
+    SLIDEO_CUDA(cudaMalloc(&d_kp_src_, kp_cap_ * 8));
+    SLIDEO_CUDA(cudaMalloc(&d_q_frame_, kp_cap_ * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_kp_i_, kp_cap_ * 16));
+    SLIDEO_CUDA(cudaMalloc(&d_kp_f_, kp_cap_ * 16));
+    SLIDEO_CUDA(cudaMalloc(&d_desc_, kp_cap_ * 32));
+    SLIDEO_CUDA(cudaMalloc(&d_tables_, (tables.size() + 4) * 4));
+    if (!tables.empty())
+        SLIDEO_CUDA(cudaMemcpy(d_tables_, tables.data(), tables.size() * 4, cudaMemcpyHostToDevice));
+    SLIDEO_CUDA(cudaMallocHost(&h_pinned_, (B + 4) * 4));
+
+    // sampling pattern (A.8) and umax (A.6)
+    {
+        const int half = cfg.patch_size / 2;
+        int8_t pat[1024];
+        uint64_t s = 0x34985739u;
+        for (int i = 0; i < 1024; ++i) {
+            s = (uint64_t)(uint32_t)s * 4164903690u + (s >> 32);
+            pat[i] = (int8_t)(-half + (int)((uint32_t)s % (uint32_t)(2 * half + 1)));
+        }
+        SLIDEO_CUDA(cudaMalloc(&d_pattern_, 1024));
+        SLIDEO_CUDA(cudaMemcpy(d_pattern_, pat, 1024, cudaMemcpyHostToDevice));
+        int* umax = umax_;
+        memset(umax_, 0, sizeof umax_);
+        const int vmax = (int)floor(half * sqrt(2.0) / 2 + 1), vmin = (int)ceil(half * sqrt(2.0) / 2);
+        for (int v = 0; v <= vmax; ++v) umax[v] = cv_round_d(sqrt((double)half * half - (double)v * v));
+        for (int v = half, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+    {
+        Geo g;
+        memset(&g, 0, sizeof g);
+        g.nlevels = L; g.total_tiles = total_tiles_; g.edge = cfg_.edge_threshold; g.fast_thr = cfg_.fast_threshold;
+        g.patch = cfg_.patch_size; g.half = cfg_.patch_size / 2;
+        g.pyr_img_bytes = pyr_img_bytes_; g.cand_img_words = cand_img_words_; g.sel_img_words = sel_img_words_;
+        memcpy(g.umax, umax_, sizeof g.umax);
+        for (int l = 0; l < L; ++l) g.lv[l] = lv_[l];
+        SLIDEO_CUDA(cudaMalloc(&d_geom_, sizeof g));
+        SLIDEO_CUDA(cudaMemcpy(d_geom_, &g, sizeof g, cudaMemcpyHostToDevice));
+    }
+}
+
+OrbExtractor::~OrbExtractor() {
+    cudaFree(d_pyr_); cudaFree(d_blur_); cudaFree(d_cand_); cudaFree(d_sel_); cudaFree(d_cand_cnt_); cudaFree(d_sel_cnt_);
+    cudaFree(d_kp_off_); cudaFree(d_frame_off_); cudaFree(d_frame_nkp_); cudaFree(d_flags_); cudaFree(d_kp_src_);
+    cudaFree(d_q_frame_); cudaFree(d_kp_i_); cudaFree(d_kp_f_); cudaFree(d_desc_); cudaFree(d_tables_);
+    cudaFree(d_pattern_); cudaFree(d_geom_);
+    cudaFreeHost(h_pinned_);
+}
+
+int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
+                      int* launches) {
+    if (n < 1 || n > batch_cap_) throw ArgError("batch size out of range");
+    if (channels != 1 && channels != 3) throw ArgError("channels must be 1 or 3");
+    const int L = cfg_.nlevels;
+    const Geo* g = static_cast<const Geo*>(d_geom_);
+    int nl = 0;
+
+    SLIDEO_CUDA(cudaMemsetAsync(d_cand_cnt_, 0, (size_t)n * L * 4, stream));
+    SLIDEO_CUDA(cudaMemsetAsync(d_flags_, 0, 4, stream));
+    {
+        dim3 grid(cdiv(cdiv(w_, 4), 128), h_, n);
+        gray_kernel<<<grid, 128, 0, stream>>>(d_src, stride, frame_stride, channels, d_pyr_, pyr_img_bytes_, w_, h_, lv_[0].pitch);
+        ++nl;
+    }
+    for (int l = 1; l < L; ++l) {
+        const OrbLevelGeom &s = lv_[l - 1], &d = lv_[l];
+        dim3 grid(cdiv(cdiv(d.w, 4), 128), d.h, n);
+        resize_kernel<<<grid, 128, 0, stream>>>(d_pyr_, pyr_img_bytes_, s.img_off, s.w, s.h, s.pitch, d.img_off, d.w, d.h,
+                                                d.pitch, d_tables_ + d.tab_off);
+        ++nl;
+    }
+    fast_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, g, d_cand_, d_cand_cnt_);
+    ++nl;
+    {
+        int max_sel = 0;
+        for (int l = 0; l < L; ++l) max_sel = lv_[l].sel_cap > max_sel ? lv_[l].sel_cap : max_sel;
+        select_kernel<<<dim3(L, n), 256, (size_t)max_sel * 4, stream>>>(g, d_cand_, d_cand_cnt_, d_sel_, d_sel_cnt_, d_flags_);
+        ++nl;
+    }
+    int32_t* d_hout = nullptr;
+    SLIDEO_CUDA(cudaHostGetDevicePointer(&d_hout, h_pinned_, 0));
+    scan_kernel<<<1, 256, 0, stream>>>(d_sel_cnt_, n, L, d_kp_off_, d_frame_off_, d_frame_nkp_, d_flags_, d_hout);
+    ++nl;
+    scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_);
+    ++nl;
+    blur_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, d_blur_, g);
+    ++nl;
+    SLIDEO_CUDA(cudaGetLastError());
+    SLIDEO_CUDA(cudaStreamSynchronize(stream));   // total keypoints of the batch sizes the remaining launches
+    const int total = h_pinned_[0], flags = h_pinned_[1];
+    h_frame_off_.assign(h_pinned_ + 2, h_pinned_ + 2 + n + 1);
+    if (flags & 1) throw CapacityError("FAST candidate capacity exceeded on at least one image");
+    if (flags & 2) throw CapacityError("selected-keypoint capacity exceeded on at least one image");
+    if ((size_t)total > kp_cap_) throw CapacityError("keypoint capacity exceeded");
+    if (total > 0) {
+        describe_kernel<<<cdiv(total, 8), 256, 0, stream>>>(d_pyr_, d_blur_, g, d_kp_src_, total, d_pattern_, d_kp_f_, d_desc_);
+        ++nl;
+        SLIDEO_CUDA(cudaGetLastError());
+    }
+    if (launches) *launches += nl;
+    return total;
+}
+
+}  // namespace slideo

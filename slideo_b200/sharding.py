@@ -1,0 +1,98 @@
+"""Multi-GPU plumbing of the path: one process per GPU, frames sharded contiguously, the page-descriptor pool
+replicated once.  The reference has no distributed code at all; its only data parallelism is
+rayon over frames inside one process (crates/matching-opencv/src/lib.rs:174-221) with the page set shared read-only
+(`Arc<Vec<ProcessedImage>>`, lib.rs:134-137) -- the broadcast below is the multi-process equivalent of that Arc.
+
+No collective touches the per-frame data path.  `torch.distributed` is plumbing: NCCL (device pointers of the
+library's own pool buffers, zero-copy) on GPUs, gloo (host arrays) in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n units for `rank`: ceil(n / world) per rank (the last ranks may be short/empty)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    per = -(-n // world)
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+class _DevView:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def broadcast_pool_host(desc: Optional[np.ndarray], page_offsets: Optional[np.ndarray], src: int = 0, desc_width: int = 32,
+                        dtype=np.uint8):
+    """Replicates (desc [n, width], page_offsets [P+1]) from `src` to every rank through host tensors (any backend that
+    accepts CPU tensors, i.e. gloo).  Returns the arrays on every rank."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    hdr = torch.zeros(2, dtype=torch.int64)
+    if rank == src:
+        hdr[0], hdr[1] = len(desc), len(page_offsets) - 1
+    dist.broadcast(hdr, src)
+    n, p = int(hdr[0]), int(hdr[1])
+    t_off = torch.from_numpy(np.ascontiguousarray(page_offsets, np.int32)) if rank == src else torch.empty(p + 1, dtype=torch.int32)
+    dist.broadcast(t_off, src)
+    if rank == src:
+        t_desc = torch.from_numpy(np.ascontiguousarray(desc, dtype).reshape(n, desc_width))
+    else:
+        t_desc = torch.from_numpy(np.empty((n, desc_width), dtype))
+    if n:
+        dist.broadcast(t_desc, src)
+    return t_desc.numpy(), t_off.numpy()
+
+
+def broadcast_pool_device(ctx, src: int = 0) -> None:
+    """ORB256 pools: ONE NCCL broadcast of the pooled descriptors straight between the library's device buffers
+    (plus the tiny page-offset table and a two-word header).  On return every rank's ctx holds the finalized pool."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+    if rank == src:
+        n, p = ctx.pool_info()
+        hdr[0], hdr[1] = n, p
+    dist.broadcast(hdr, src)
+    n, p = int(hdr[0].item()), int(hdr[1].item())
+    if rank != src:
+        ctx.pool_reserve(n, p)
+    d_desc, desc_bytes, d_off, off_bytes = ctx.pool_device_view()
+    t_off = torch.as_tensor(_DevView(d_off, off_bytes), device=dev)
+    dist.broadcast(t_off, src)
+    if desc_bytes:
+        t_desc = torch.as_tensor(_DevView(d_desc, desc_bytes), device=dev)
+        dist.broadcast(t_desc, src)                   # the one payload collective of the whole job
+    torch.cuda.synchronize()
+    if rank != src:
+        ctx.pool_commit()
+
+
+def gather_results(local: np.ndarray, n_total: int, world: Optional[int] = None) -> Optional[np.ndarray]:
+    """Concatenates the per-rank (best_slide, votes, n_keypoints) rows in rank order on rank 0 (host side, after the
+    timed region; results are 12 B/frame)."""
+    import torch
+    import torch.distributed as dist
+    world = world or dist.get_world_size()
+    rank = dist.get_rank()
+    per = -(-n_total // world)
+    buf = np.full((per, 3), -2, np.int32)
+    buf[:len(local)] = local
+    t = torch.from_numpy(buf)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    outs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, outs, dst=0)
+    if rank != 0:
+        return None
+    return np.concatenate([o.cpu().numpy() for o in outs])[:n_total]

@@ -1,0 +1,79 @@
+"""The N>1 host logic on CPU: world_size-2 gloo processes shard frames contiguously, replicate the pool with a
+broadcast, match their shard (here with the oracle standing in for the GPU -- tests may use it as the checker) and
+rank 0 gathers rows identical to the single-process result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from slideo_b200 import sharding
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 8, 9, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            assert max(hi - lo for lo, hi in spans) == -(-n // world) or n == 0
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_frames, out_path):
+    import torch.distributed as dist
+    import oracle
+    import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pages = None
+        if rank == 0:
+            pages = [synth.hamming_pool(n, seed=400 + i, dup_frac=0.02) for i, n in enumerate((120, 0, 90, 200))]
+            desc = np.concatenate(pages)
+            offs = np.zeros(len(pages) + 1, np.int32)
+            offs[1:] = np.cumsum([len(p) for p in pages])
+        else:
+            desc = offs = None
+        desc, offs = sharding.broadcast_pool_host(desc, offs, src=0)
+        page_descs = [desc[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+        lo, hi = sharding.shard_range(n_frames, rank, world)
+        local = []
+        for f in range(lo, hi):
+            q = synth.hamming_queries(desc, 40 + f, seed=500 + f, near_frac=0.8)
+            best, votes, _ = oracle.match_frame(q, page_descs)
+            local.append((best, votes, len(q)))
+        local = np.array(local, np.int32).reshape(-1, 3)
+        allr = sharding.gather_results(local, n_frames)
+        if rank == 0:
+            np.save(out_path, allr)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [7, 8])
+def test_two_rank_run_equals_single_process(tmp_path, n_frames):
+    import torch.multiprocessing as mp
+    import oracle
+    import synth
+    out = str(tmp_path / "gathered.npy")
+    mp.spawn(_worker, args=(2, _free_port(), n_frames, out), nprocs=2, join=True)
+    got = np.load(out)
+    pages = [synth.hamming_pool(n, seed=400 + i, dup_frac=0.02) for i, n in enumerate((120, 0, 90, 200))]
+    desc = np.concatenate(pages)
+    want = []
+    for f in range(n_frames):
+        q = synth.hamming_queries(desc, 40 + f, seed=500 + f, near_frac=0.8)
+        best, votes, _ = oracle.match_frame(q, pages)
+        want.append((best, votes, len(q)))
+    assert np.array_equal(got, np.array(want, np.int32))
