@@ -95,6 +95,8 @@ typedef struct slideo_b200_timings {
     int64_t knn_launches;    /* K8 launches */
     int64_t kernel_launches; /* all kernel launches of the library */
     int64_t frames;          /* frames processed */
+    float ms_total;          /* whole match_* calls, first enqueue to last result on the ctx stream */
+    float reserved0;
 } slideo_b200_timings;
 
 typedef struct slideo_b200_ctx slideo_b200_ctx;

@@ -66,6 +66,8 @@ struct slideo_b200_ctx {
     std::vector<int32_t> page_off{0};    // prefix offsets, size n_pages + 1
     bool finalized = false;
     DevBuf<uint8_t> d_pool;              // nt x 32 (ORB) / nt x 128 bf16 (SIFT)
+    DevBuf<uint8_t> d_pool48;            // ORB: the 48 B expanded rows K8 streams (knn_pool_expand_launch)
+    DevBuf<uint8_t> d_t48;               // expanded copy of a caller-provided pool (stage-level k-NN)
     DevBuf<float> d_pool_norm;           // SIFT: squared norms
     DevBuf<uint16_t> d_page_of;          // nt
     DevBuf<int32_t> d_page_off;          // n_pages + 1
@@ -139,6 +141,7 @@ struct slideo_b200_ctx {
                 if (e.kind == 0) tm.ms_detect += ms;
                 else if (e.kind == 1) tm.ms_knn += ms;
                 else if (e.kind == 2) tm.ms_h2d += ms;
+                else if (e.kind == 4) tm.ms_total += ms;
                 else tm.ms_vote += ms;
             }
             ev_free_list.push_back(e);
@@ -204,7 +207,7 @@ struct slideo_b200_ctx {
             VoteArgs va{d_qf, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio};
             EventPair t = begin_timing(1, stream);
             int nl = 0;
-            knn_hamming_launch(plan, dq, d_pool.p, want_keys ? d_keys.p : nullptr, d_scratch.p, d_partial.p, &va, stream, &nl);
+            knn_hamming_launch(plan, dq, d_pool48.p, want_keys ? d_keys.p : nullptr, d_scratch.p, d_partial.p, &va, stream, &nl);
             end_timing(t, stream);
             tm.knn_launches += nl;
             tm.kernel_launches += nl;
@@ -271,6 +274,11 @@ struct slideo_b200_ctx {
         d_page_off.reserve((size_t)n_pages + 1);
         if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_page_of.p, po.data(), (size_t)nt * 2, cudaMemcpyHostToDevice, stream));
         SLIDEO_CUDA(cudaMemcpyAsync(d_page_off.p, page_off.data(), ((size_t)n_pages + 1) * 4, cudaMemcpyHostToDevice, stream));
+        if (cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) {
+            d_pool48.reserve(knn_pool_expanded_bytes(nt) + 64);
+            knn_pool_expand_launch(d_pool.p, nt, d_pool48.p, stream);
+            tm.kernel_launches += nt > 0 ? 1 : 0;
+        }
         SLIDEO_CUDA(cudaStreamSynchronize(stream));
     }
     void check_pool_limits(int64_t n_desc, int64_t pages) const {
@@ -571,6 +579,7 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
         arg(stride >= 3 * w, "stride < 3*w");
         arg(frame_stride >= (size_t)stride * (h - 1) + (size_t)3 * w, "frame_stride too small");
         ctx->reset_kept();
+        EventPair t_total = ctx->begin_timing(4, ctx->stream);
         const int B = ctx->cfg.max_batch;
         const size_t img_bytes = (size_t)3 * w * h;
         const int n_batches = cdiv(n, B);
@@ -594,6 +603,7 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
             ctx->match_batch_device(ctx->d_frames[buf].p, nb, w, h, 3 * w, img_bytes, ctx->h_results + (size_t)f0 * 3);
             SLIDEO_CUDA(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
         }
+        ctx->end_timing(t_total, ctx->stream);
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
         ctx->collect_timings();
@@ -616,6 +626,7 @@ int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d
         arg(d_frames && out, "d_frames/out must not be NULL");
         arg(stride >= 3 * w, "stride < 3*w");
         ctx->reset_kept();
+        EventPair t_total = ctx->begin_timing(4, ctx->stream);
         const int B = ctx->cfg.max_batch;
         ctx->ensure_host_results((size_t)n);
         for (int f0 = 0; f0 < n; f0 += B) {
@@ -623,6 +634,7 @@ int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d
             ctx->match_batch_device((const uint8_t*)d_frames + (size_t)f0 * frame_stride, nb, w, h, stride, frame_stride,
                                     ctx->h_results + (size_t)f0 * 3);
         }
+        ctx->end_timing(t_total, ctx->stream);
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->collect_timings();
         for (int i = 0; i < n; ++i) {
@@ -645,6 +657,7 @@ int32_t slideo_b200_match_descriptors(slideo_b200_ctx* ctx, const void* desc, co
         for (int i = 0; i < n; ++i) arg(frame_offsets[i] <= frame_offsets[i + 1], "frame_offsets must be non-decreasing");
         arg(desc != nullptr || frame_offsets[n] == 0, "desc must not be NULL");
         ctx->reset_kept();
+        EventPair t_total = ctx->begin_timing(4, ctx->stream);
         const int B = ctx->cfg.max_batch;
         const bool orb = ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256;
         ctx->ensure_host_results((size_t)n);
@@ -717,6 +730,8 @@ int32_t slideo_b200_match_descriptors(slideo_b200_ctx* ctx, const void* desc, co
             SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors are reused by the next batch
             ctx->tm.frames += nb;
         }
+        ctx->end_timing(t_total, ctx->stream);
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->collect_timings();
         for (int i = 0; i < n; ++i) {
             out[i].best_slide = ctx->h_results[3 * i];
@@ -837,9 +852,11 @@ int32_t slideo_b200_bf_knn_hamming_device(slideo_b200_ctx* ctx, const void* d_q,
         KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
         ctx->d_scratch.reserve(plan.scratch_bytes / 4);
         if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
+        ctx->d_t48.reserve(plan.pool_bytes + 64);
+        knn_pool_expand_launch(d_t, nt, ctx->d_t48.p, ctx->stream);   // once per pool in the frame path; per call here
         EventPair t = ctx->begin_timing(1, ctx->stream);
         int nl = 0;
-        knn_hamming_launch(plan, d_q, d_t, (uint32_t*)d_keys_out, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
+        knn_hamming_launch(plan, d_q, ctx->d_t48.p, (uint32_t*)d_keys_out, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
         ctx->end_timing(t, ctx->stream);
         ctx->tm.knn_launches += nl;
         ctx->tm.kernel_launches += nl;
@@ -866,9 +883,11 @@ int32_t slideo_b200_bf_knn_hamming(slideo_b200_ctx* ctx, const uint8_t* q, int32
         KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
         ctx->d_scratch.reserve(plan.scratch_bytes / 4);
         if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
+        ctx->d_t48.reserve(plan.pool_bytes + 64);
+        knn_pool_expand_launch(ctx->d_t.p, nt, ctx->d_t48.p, ctx->stream);
         EventPair tk = ctx->begin_timing(1, ctx->stream);
         int nl = 0;
-        knn_hamming_launch(plan, ctx->d_q.p, ctx->d_t.p, ctx->d_keys.p, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
+        knn_hamming_launch(plan, ctx->d_q.p, ctx->d_t48.p, ctx->d_keys.p, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
         ctx->end_timing(tk, ctx->stream);
         keys_to_idx_dist_launch(ctx->d_keys.p, (size_t)nq * k, ctx->d_idx.p, ctx->d_dist.p, ctx->stream);
         ctx->tm.knn_launches += nl;

@@ -39,12 +39,15 @@ constexpr int KNN_MAX_POOL = 1 << KEY_IDX_BITS;  // 8,388,608 pooled descriptors
 
 struct KnnPlan {
     int nq = 0, nt = 0, k = 0;
-    int n_tiles = 0;     // query tiles
-    int n_splits = 0;    // pool splits
-    int split_len = 0;   // pooled descriptors per split (multiple of the smem chunk)
-    int grid = 0;        // persistent CTAs
-    size_t scratch_bytes = 0;  // candidate buffers (grid * tile * slots * 4)
-    size_t partial_bytes = 0;  // per-split partial rows when n_splits > 1
+    int qr = 8, tile = 1024;   // queries per thread (4 or 8) and per tile (128 threads x qr)
+    int n_tiles = 0;           // query tiles
+    int n_chunks = 0;          // pool chunks per tile
+    int max_seg = 1;           // max CTAs sharing one tile (stream-K); > 1 -> partial rows + merge kernel
+    long long total_units = 0; // n_tiles * n_chunks, divided evenly over the grid
+    int grid = 0;              // persistent CTAs
+    size_t scratch_bytes = 0;  // candidate buffers
+    size_t partial_bytes = 0;  // per-segment partial rows (0 when every tile has one segment)
+    size_t pool_bytes = 0;     // expanded pool (48 B rows)
 };
 
 struct VoteArgs {            // fused K9: vote straight out of K8's final sort (n_splits == 1) or from vote kernel
@@ -56,8 +59,11 @@ struct VoteArgs {            // fused K9: vote straight out of K8's final sort (
 };
 
 KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms);
+// 32 B descriptors -> the 48 B rows K8 streams ({w0..w7, w0^w1^w2, w3^w4^w5, w0^..^w6, 0}); once per pool
+size_t knn_pool_expanded_bytes(int nt);
+void knn_pool_expand_launch(const void* d_pool32, int nt, void* d_pool48, cudaStream_t stream);
 // keys_out: [nq][k] uint32 (may be nullptr when vote != nullptr).  scratch/partial sized per plan.
-void knn_hamming_launch(const KnnPlan& plan, const void* d_q, const void* d_pool, uint32_t* d_keys_out,
+void knn_hamming_launch(const KnnPlan& plan, const void* d_q, const void* d_pool48, uint32_t* d_keys_out,
                         uint32_t* d_scratch, uint32_t* d_partial, const VoteArgs* vote, cudaStream_t stream,
                         int* launches);
 // frame results from the vote table

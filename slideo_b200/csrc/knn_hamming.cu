@@ -4,17 +4,27 @@
 // crates/matching-opencv/src/lib.rs:266) with the exact semantics LSH approximates == cv2.BFMatcher(NORM_HAMMING)
 // .knnMatch: the k smallest by (distance, pooled index), and the vote loop lib.rs:268-282.
 //
-// Design (integer-pipe bound, not HBM bound: the pool is <= 32 MB and lives in the 126 MB L2):
-//   * every thread owns QR=4 query descriptors in registers for a whole pass over (a split of) the pool;
-//   * the pool is streamed through shared memory in 8 KB chunks by 1-D TMA bulk copies (cp.async.bulk +
-//     mbarrier, 3 stages); all lanes read the same pooled descriptor (LDS.128 broadcast);
-//   * distance = popcount of 8 xor-ed words through a carry-save adder tree: 14 LOP3 + 4 POPC per pair instead of
-//     8 LOP3 + 8 POPC, which balances the ALU pipe against the quarter-rate POPC pipe;
-//   * selection is exact: key = dist << 23 | index is compared against the thread's running k-th best key; the
-//     rare survivors are appended to a 64-slot per-query candidate buffer (L2-resident scratch) that is compacted
-//     by a warp-cooperative 64-key bitonic sort whenever it fills up; the final sort emits rows in oracle order;
-//   * small query counts split the pool across CTAs (partial rows + a merge kernel);
+// Design (integer-pipe bound, not HBM bound: the pool is <= 48 MB and lives in the 126 MB L2).  The ncu capture of the
+// first version (profiles/k8_r1_summary.md) showed the ALU pipe 84 % busy at 24.8 ALU ops per pair; this version
+// spends 13 LOP3 + 1 ISETP on the ALU pipe, 4 POPC on the XU pipe and 3 IMAD on the FMA pipe per pair:
+//   * every thread owns QR query descriptors in registers for a whole pass over its share of the pool;
+//   * the pool is pre-expanded once to 48 B rows {w0..w7, w0^w1^w2, w3^w4^w5, w0^..^w6, 0} and streamed through shared
+//     memory in 12 KB chunks by 1-D TMA bulk copies (cp.async.bulk + mbarrier, 3 stages); all lanes read the same
+//     row (LDS.128 broadcast);
+//   * distance = popcount of the 8 xor-ed words through a carry-save adder tree whose sum bits come straight from the
+//     pre-xor-ed words (s1 = q012^p012, s2 = q345^p345, s3 = q0..6^p0..6) and whose carries use the
+//     "two inputs + sum" form, so x2, x5, x6 are never materialised;
+//   * selection is exact: a pair survives iff dist < the distance of the thread's running k-th best (strict '<' is
+//     exact because the pool is scanned in increasing index order, like the oracle's insertion); survivors are rare,
+//     a warp vote per pooled row skips the append code entirely when no lane has one; appended keys
+//     (dist << 23 | index) go to a 64-slot per-query buffer (L2-resident scratch) that a warp-cooperative 64-key
+//     bitonic sort cuts back to the k best whenever it fills up; the final sort emits rows in oracle order;
+//   * work is split stream-K style: the (query tile x pool chunk) units are divided evenly over the persistent grid,
+//     so every CTA does the same amount of work whatever the shape; tiles covered by several CTAs go through
+//     partial rows + a merge kernel;
 //   * K9 (vote, lib.rs:270-282) is fused into the final sort: lane m holds neighbour m of the row.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace slideo {
@@ -22,12 +32,11 @@ namespace slideo {
 namespace {
 
 constexpr int KNN_THREADS = 128;
-constexpr int KNN_QR = 4;
-constexpr int KNN_TILE = KNN_THREADS * KNN_QR;  // queries per work item
-constexpr int KNN_SLOTS = 64;                   // candidate keys per query
-constexpr int KNN_CHUNK = 256;                  // pooled descriptors per smem stage (8 KB)
+constexpr int KNN_QR_MAX = 8;                    // queries per thread: 4 or 8 (template parameter of K8)
+constexpr int KNN_SLOTS = 64;                    // candidate keys per query
+constexpr int KNN_CHUNK = 256;                   // pooled descriptors per smem stage (12 KB of 48 B rows)
+constexpr int KNN_ROW_U4 = 3;                    // uint4 per expanded pool row
 constexpr int KNN_STAGES = 3;
-constexpr int KNN_GROUP = 8;                    // pooled descriptors between overflow checks
 constexpr int KNN_CTAS_PER_SM = 4;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -95,15 +104,20 @@ __device__ __forceinline__ void warp_sort64(uint32_t& k0, uint32_t& k1, int lane
 
 struct KnnParams {
     const uint4* q;
-    const uint4* pool;
-    uint32_t* keys_out;   // [nq][k] (n_splits == 1) -- may be null
-    uint32_t* partial;    // [nq][n_splits][k] (n_splits > 1)
-    uint32_t* scratch;    // [grid][KNN_TILE][KNN_SLOTS]
-    int nq, nt, k, n_tiles, n_splits, split_len;
-    VoteArgs vote;        // vote.votes == nullptr -> no fused vote
+    const uint4* pool;    // expanded rows, KNN_ROW_U4 uint4 each
+    uint32_t* keys_out;   // [nq][k] -- may be null
+    uint32_t* partial;    // [n_tiles][max_seg][tile][k]
+    uint32_t* scratch;    // [grid][tile][KNN_SLOTS]
+    int nq, nt, k, n_tiles, n_chunks, max_seg, tile;
+    long long total_units;  // n_tiles * n_chunks
+    VoteArgs vote;          // vote.votes == nullptr -> no fused vote
 };
 
-// Row emission shared by K8 (n_splits == 1) and the merge kernel: lane m < k holds neighbour m (sorted).
+// stream-K bookkeeping: CTA b owns units [U*b/G, U*(b+1)/G); cta_of(u) = the CTA that owns unit u
+__device__ __host__ __forceinline__ long long unit_begin(long long U, int G, int b) { return U * b / G; }
+__device__ __host__ __forceinline__ int cta_of(long long U, int G, long long u) { return (int)(((u + 1) * G + U - 1) / U - 1); }
+
+// Row emission shared by K8 (single-segment tiles) and the merge kernel: lane m < k holds neighbour m (sorted).
 __device__ __forceinline__ void emit_row(uint32_t key, int lane, int q, int k, uint32_t* keys_out, const VoteArgs& v) {
     if (keys_out != nullptr && lane < k) keys_out[(size_t)q * k + lane] = key;
     if (v.votes != nullptr) {
@@ -119,9 +133,25 @@ __device__ __forceinline__ void emit_row(uint32_t key, int lane, int q, int k, u
     }
 }
 
+// pool rows 32 B -> 48 B {w0..w7, w0^w1^w2, w3^w4^w5, w0^..^w6, 0}
+__global__ void __launch_bounds__(256) pool_expand_kernel(const uint4* __restrict__ src, int nt, uint4* __restrict__ dst) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nt) return;
+    const uint4 a = __ldg(src + 2 * (size_t)j), b = __ldg(src + 2 * (size_t)j + 1);
+    const uint32_t p012 = a.x ^ a.y ^ a.z, p345 = a.w ^ b.x ^ b.y;
+    dst[3 * (size_t)j] = a;
+    dst[3 * (size_t)j + 1] = b;
+    dst[3 * (size_t)j + 2] = make_uint4(p012, p345, p012 ^ p345 ^ b.z, 0u);
+}
+
+template <int KNN_QR>
 __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kernel(const KnnParams P) {
-    __shared__ __align__(128) uint4 s_pool[KNN_STAGES][KNN_CHUNK * 2];
-    __shared__ __align__(8) uint64_t s_full[KNN_STAGES];
+    constexpr int KNN_TILE = KNN_THREADS * KNN_QR;
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    uint4* s_pool = reinterpret_cast<uint4*>(s_raw);                                   // [STAGES][CHUNK * ROW_U4]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_raw + (size_t)KNN_STAGES * KNN_CHUNK * KNN_ROW_U4 * 16);
+    int* s_cnt = reinterpret_cast<int*>(s_full + KNN_STAGES);                          // [KNN_TILE] candidate counts (compaction, final sort)
+    uint32_t* s_taud = reinterpret_cast<uint32_t*>(s_cnt + KNN_TILE);                  // [KNN_TILE] thresholds handed back by the compaction
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -132,27 +162,38 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
 
     uint32_t* my_scratch = P.scratch + (size_t)blockIdx.x * KNN_TILE * KNN_SLOTS;
     uint32_t gchunk = 0;  // chunks consumed so far by this CTA (stage = gchunk % STAGES, parity from gchunk / STAGES)
-    const int n_items = P.n_tiles * P.n_splits;
+    const int G = gridDim.x;
+    long long u = unit_begin(P.total_units, G, blockIdx.x);
+    const long long u_end = unit_begin(P.total_units, G, blockIdx.x + 1);
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int tile = item / P.n_splits, split = item - tile * P.n_splits;
+    while (u < u_end) {
+        const int tile = (int)(u / P.n_chunks);
+        const int c0 = (int)(u - (long long)tile * P.n_chunks);
+        const int c1 = (int)min((long long)P.n_chunks, c0 + (u_end - u));
+        const int n_chunks = c1 - c0;
+        u += n_chunks;
         const int qbase = tile * KNN_TILE;
-        const int t0 = split * P.split_len;
-        const int t1 = min(P.nt, t0 + P.split_len);
-        const int n_chunks = (t1 - t0 + KNN_CHUNK - 1) / KNN_CHUNK;
+        const int t0 = c0 * KNN_CHUNK;
+        const int t1 = min(P.nt, c1 * KNN_CHUNK);
+        const long long tile_u0 = (long long)tile * P.n_chunks;
+        const int first_cta = cta_of(P.total_units, G, tile_u0);
+        const int n_seg = cta_of(P.total_units, G, tile_u0 + P.n_chunks - 1) - first_cta + 1;
+        const int seg = blockIdx.x - first_cta;
 
         // producer prologue
         if (tid == 0) {
             for (int c = 0; c < min(n_chunks, KNN_STAGES); ++c) {
                 const int s = (gchunk + c) % KNN_STAGES;
                 const int n = min(KNN_CHUNK, t1 - (t0 + c * KNN_CHUNK));
-                mbar_expect_tx(&s_full[s], (uint32_t)n * 32u);
-                bulk_g2s(&s_pool[s][0], P.pool + (size_t)(t0 + c * KNN_CHUNK) * 2, (uint32_t)n * 32u, &s_full[s]);
+                mbar_expect_tx(&s_full[s], (uint32_t)n * 48u);
+                bulk_g2s(s_pool + (size_t)s * KNN_CHUNK * KNN_ROW_U4, P.pool + (size_t)(t0 + c * KNN_CHUNK) * KNN_ROW_U4, (uint32_t)n * 48u,
+                         &s_full[s]);
             }
         }
 
-        // this thread's queries
-        uint32_t qw[KNN_QR][8], q012[KNN_QR], q345[KNN_QR], tau[KNN_QR];
+        // this thread's queries: words 0,1,3,4,7 individually + the three pre-xor-ed sums
+        uint32_t q0[KNN_QR], q1[KNN_QR], q3[KNN_QR], q4[KNN_QR], q7[KNN_QR], q012[KNN_QR], q345[KNN_QR], q06[KNN_QR];
+        uint32_t taud[KNN_QR];   // distance of the running k-th best (strict '<' admits a pair)
         int cnt[KNN_QR];
 #pragma unroll
         for (int i = 0; i < KNN_QR; ++i) {
@@ -162,131 +203,165 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
                 a = __ldg(P.q + (size_t)q * 2);
                 b = __ldg(P.q + (size_t)q * 2 + 1);
             }
-            qw[i][0] = a.x; qw[i][1] = a.y; qw[i][2] = a.z; qw[i][3] = a.w;
-            qw[i][4] = b.x; qw[i][5] = b.y; qw[i][6] = b.z; qw[i][7] = b.w;
+            q0[i] = a.x; q1[i] = a.y; q3[i] = a.w; q4[i] = b.x; q7[i] = b.w;
             q012[i] = a.x ^ a.y ^ a.z;
             q345[i] = a.w ^ b.x ^ b.y;
-            tau[i] = q < P.nq ? KEY_EMPTY : 0u;  // dummy queries never push
+            q06[i] = q012[i] ^ q345[i] ^ b.z;
+            taud[i] = q < P.nq ? 512u : 0u;  // dummy queries never admit anything
             cnt[i] = 0;
         }
 
-        auto compact = [&](int i) {
-            // warp-cooperative: every lane whose buffer i is nearly full gets it sorted and cut to the k best
-            unsigned need = __ballot_sync(FULL, cnt[i] > KNN_SLOTS - KNN_GROUP);
-            while (need) {
-                const int L = __ffs(need) - 1;
-                need &= need - 1;
-                uint32_t* buf = my_scratch + (size_t)(warp * 32 + L + i * KNN_THREADS) * KNN_SLOTS;
-                const int n = __shfl_sync(FULL, cnt[i], L);
-                uint32_t k0 = lane < n ? __ldcg(buf + lane) : KEY_EMPTY;
-                uint32_t k1 = lane + 32 < n ? __ldcg(buf + lane + 32) : KEY_EMPTY;
-                warp_sort64(k0, k1, lane);
-                if (lane < P.k) buf[lane] = k0;
-                const uint32_t kth = __shfl_sync(FULL, k0, P.k - 1);
-                if (lane == L) {
-                    tau[i] = kth;
-                    cnt[i] = min(n, P.k);
+        // distances of this thread's QR queries to one expanded pool row {a, b, e}
+        auto distances = [&](const uint4& a, const uint4& b, const uint4& e, uint32_t (&dist)[KNN_QR]) {
+#pragma unroll
+            for (int i = 0; i < KNN_QR; ++i) {
+                const uint32_t x0 = q0[i] ^ a.x, x1 = q1[i] ^ a.y;
+                const uint32_t s1 = q012[i] ^ e.x;                  // x0 ^ x1 ^ x2
+                const uint32_t c1 = lop3<LUT_CARRY>(x0, x1, s1);    // maj(x0, x1, x2)
+                const uint32_t x3 = q3[i] ^ a.w, x4 = q4[i] ^ b.x;
+                const uint32_t s2 = q345[i] ^ e.y;                  // x3 ^ x4 ^ x5
+                const uint32_t c2 = lop3<LUT_CARRY>(x3, x4, s2);    // maj(x3, x4, x5)
+                const uint32_t s3 = q06[i] ^ e.z;                   // s1 ^ s2 ^ x6            (weight 1)
+                const uint32_t c3 = lop3<LUT_CARRY>(s1, s2, s3);    // maj(s1, s2, x6)         (weight 2)
+                const uint32_t x7 = q7[i] ^ b.w;                    //                         (weight 1)
+                const uint32_t s5 = lop3<LUT_XOR3>(c1, c2, c3);     //                         (weight 2)
+                const uint32_t c5 = lop3<LUT_MAJ>(c1, c2, c3);      //                         (weight 4)
+                dist[i] = (uint32_t)__popc(s3) + (uint32_t)__popc(x7) + 2u * (uint32_t)__popc(s5) + 4u * (uint32_t)__popc(c5);
+            }
+        };
+
+        // warp-cooperative compaction of every candidate buffer of this warp that is (nearly) full: sort its keys,
+        // keep the k best, tighten the owner's threshold.  State goes through shared memory so that ONE copy of the
+        // sort serves all QR buffers of a lane.
+        auto compact_all = [&]() {
+#pragma unroll
+            for (int i = 0; i < KNN_QR; ++i) s_cnt[tid + i * KNN_THREADS] = cnt[i];
+            __syncwarp();
+#pragma unroll 1
+            for (int i = 0; i < KNN_QR; ++i) {
+                const int base_row = warp * 32 + i * KNN_THREADS;
+                unsigned need = __ballot_sync(FULL, s_cnt[base_row + lane] >= KNN_SLOTS - 1);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    uint32_t* buf = my_scratch + (size_t)(base_row + L) * KNN_SLOTS;
+                    const int n = s_cnt[base_row + L];
+                    uint32_t k0 = lane < n ? __ldcg(buf + lane) : KEY_EMPTY;
+                    uint32_t k1 = lane + 32 < n ? __ldcg(buf + lane + 32) : KEY_EMPTY;
+                    warp_sort64(k0, k1, lane);
+                    if (lane < P.k) buf[lane] = k0;
+                    const uint32_t kth = __shfl_sync(FULL, k0, P.k - 1);
+                    if (lane == L) {
+                        s_taud[base_row + L] = kth == KEY_EMPTY ? 512u : (kth >> KEY_IDX_BITS);
+                        s_cnt[base_row + L] = min(n, P.k);
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < KNN_QR; ++i) {
+                if (cnt[i] >= KNN_SLOTS - 1) {
+                    cnt[i] = s_cnt[tid + i * KNN_THREADS];
+                    taud[i] = s_taud[tid + i * KNN_THREADS];
                 }
             }
-            __syncwarp();
         };
 
         for (int c = 0; c < n_chunks; ++c, ++gchunk) {
             const int s = gchunk % KNN_STAGES;
             const int n = min(KNN_CHUNK, t1 - (t0 + c * KNN_CHUNK));
             mbar_wait(&s_full[s], (gchunk / KNN_STAGES) & 1);
-            const uint4* sp = &s_pool[s][0];
+            const uint4* sp = s_pool + (size_t)s * KNN_CHUNK * KNN_ROW_U4;
             const uint32_t gbase = (uint32_t)(t0 + c * KNN_CHUNK);
 
-            auto process = [&](int j) {
-                const uint4 a = sp[2 * j], b = sp[2 * j + 1];
-                const uint32_t p012 = a.x ^ a.y ^ a.z, p345 = a.w ^ b.x ^ b.y;
-                const uint32_t gidx = gbase + (uint32_t)j;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int nb = min(32, n - j0);
+                // fast path: 32 rows, no selection work at all -- a lane only remembers WHICH rows held a survivor
+                uint32_t mask = 0;
+#pragma unroll 2
+                for (int r = 0; r < nb; ++r) {
+                    const uint4* row = sp + 3 * (j0 + r);
+                    uint32_t dist[KNN_QR];
+                    distances(row[0], row[1], row[2], dist);
+                    bool hit = false;
 #pragma unroll
-                for (int i = 0; i < KNN_QR; ++i) {
-                    const uint32_t x0 = qw[i][0] ^ a.x, x1 = qw[i][1] ^ a.y;
-                    const uint32_t s1 = q012[i] ^ p012;                 // x0 ^ x1 ^ x2
-                    const uint32_t c1 = lop3<LUT_CARRY>(x0, x1, s1);    // maj(x0, x1, x2)
-                    const uint32_t x3 = qw[i][3] ^ a.w, x4 = qw[i][4] ^ b.x;
-                    const uint32_t s2 = q345[i] ^ p345;                 // x3 ^ x4 ^ x5
-                    const uint32_t c2 = lop3<LUT_CARRY>(x3, x4, s2);
-                    const uint32_t x6 = qw[i][6] ^ b.z, x7 = qw[i][7] ^ b.w;
-                    const uint32_t s3 = lop3<LUT_XOR3>(s1, s2, x6);     // weight 1
-                    const uint32_t c3 = lop3<LUT_MAJ>(s1, s2, x6);      // weight 2
-                    const uint32_t s5 = lop3<LUT_XOR3>(c1, c2, c3);     // weight 2
-                    const uint32_t c5 = lop3<LUT_MAJ>(c1, c2, c3);      // weight 4
-                    const uint32_t ones = __popc(s3) + __popc(x7);
-                    const uint32_t key = (ones << KEY_IDX_BITS) + ((uint32_t)__popc(s5) << (KEY_IDX_BITS + 1)) +
-                                         ((uint32_t)__popc(c5) << (KEY_IDX_BITS + 2)) + gidx;
-                    if (key < tau[i]) {
-                        my_scratch[(size_t)(tid + i * KNN_THREADS) * KNN_SLOTS + cnt[i]] = key;
-                        ++cnt[i];
+                    for (int i = 0; i < KNN_QR; ++i) hit |= dist[i] < taud[i];
+                    if (hit) mask |= 1u << r;
+                }
+                // slow path (rare after the first few hundred rows of a segment): every lane revisits its own flagged
+                // rows, lowest first, and appends the survivors; buffers are compacted cooperatively when one fills up
+                while (__any_sync(FULL, mask != 0)) {
+                    bool full = false;
+                    if (mask != 0) {
+                        const int r = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint4* row = sp + 3 * (j0 + r);
+                        uint32_t dist[KNN_QR];
+                        distances(row[0], row[1], row[2], dist);
+                        const uint32_t gidx = gbase + (uint32_t)(j0 + r);
+#pragma unroll
+                        for (int i = 0; i < KNN_QR; ++i) {
+                            if (dist[i] < taud[i]) {
+                                my_scratch[(size_t)(tid + i * KNN_THREADS) * KNN_SLOTS + cnt[i]] = (dist[i] << KEY_IDX_BITS) | gidx;
+                                ++cnt[i];
+                                full |= cnt[i] >= KNN_SLOTS - 1;
+                            }
+                        }
                     }
+                    if (__any_sync(FULL, full)) compact_all();
                 }
-            };
-            auto check = [&]() {
-                bool need = false;
-#pragma unroll
-                for (int i = 0; i < KNN_QR; ++i) need |= cnt[i] > KNN_SLOTS - KNN_GROUP;
-                if (__any_sync(FULL, need)) {
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < KNN_QR; ++i) compact(i);
-                }
-            };
-
-            int j = 0;
-            for (; j + KNN_GROUP <= n; j += KNN_GROUP) {
-#pragma unroll
-                for (int jj = 0; jj < KNN_GROUP; ++jj) process(j + jj);
-                check();
-            }
-            if (j < n) {
-                for (; j < n; ++j) process(j);
-                check();
             }
 
             __syncthreads();  // every warp is done with stage s
             if (tid == 0 && c + KNN_STAGES < n_chunks) {
                 const int cn = c + KNN_STAGES;
                 const int nn = min(KNN_CHUNK, t1 - (t0 + cn * KNN_CHUNK));
-                mbar_expect_tx(&s_full[s], (uint32_t)nn * 32u);
-                bulk_g2s(&s_pool[s][0], P.pool + (size_t)(t0 + cn * KNN_CHUNK) * 2, (uint32_t)nn * 32u, &s_full[s]);
+                mbar_expect_tx(&s_full[s], (uint32_t)nn * 48u);
+                bulk_g2s(s_pool + (size_t)s * KNN_CHUNK * KNN_ROW_U4, P.pool + (size_t)(t0 + cn * KNN_CHUNK) * KNN_ROW_U4, (uint32_t)nn * 48u,
+                         &s_full[s]);
             }
         }
 
-        // final sort + emission: 4 x 32 rows per warp, one row at a time, lane m <- neighbour m
-        __syncwarp();
+        // final sort + emission: QR x 32 rows per warp, one row at a time, lane m <- neighbour m
 #pragma unroll
+        for (int i = 0; i < KNN_QR; ++i) s_cnt[tid + i * KNN_THREADS] = cnt[i];
+        __syncwarp();
+#pragma unroll 1
         for (int i = 0; i < KNN_QR; ++i) {
+#pragma unroll 1
             for (int L = 0; L < 32; ++L) {
-                const int q = qbase + warp * 32 + L + i * KNN_THREADS;
+                const int row = warp * 32 + L + i * KNN_THREADS;
+                const int q = qbase + row;
                 if (q >= P.nq) break;  // warp-uniform
-                const uint32_t* buf = my_scratch + (size_t)(warp * 32 + L + i * KNN_THREADS) * KNN_SLOTS;
-                const int n = __shfl_sync(FULL, cnt[i], L);
+                const uint32_t* buf = my_scratch + (size_t)row * KNN_SLOTS;
+                const int n = s_cnt[row];
                 uint32_t k0 = lane < n ? __ldcg(buf + lane) : KEY_EMPTY;
                 uint32_t k1 = lane + 32 < n ? __ldcg(buf + lane + 32) : KEY_EMPTY;
                 warp_sort64(k0, k1, lane);
-                if (P.n_splits == 1) {
+                if (n_seg == 1) {
                     emit_row(k0, lane, q, P.k, P.keys_out, P.vote);
                 } else if (lane < P.k) {
-                    P.partial[((size_t)q * P.n_splits + split) * P.k + lane] = k0;
+                    P.partial[(((size_t)tile * P.max_seg + seg) * KNN_TILE + row) * P.k + lane] = k0;
                 }
             }
         }
-        __syncthreads();  // scratch + smem stages are reused by the next item
+        __syncthreads();  // scratch + smem stages are reused by the next segment
     }
 }
 
-// merge of per-split partial rows: one warp per query
-__global__ void __launch_bounds__(128) knn_merge_kernel(const uint32_t* __restrict__ partial, int nq, int n_splits, int k,
-                                                        uint32_t* keys_out, const VoteArgs vote) {
+// merge of the per-segment partial rows of multi-segment tiles: one warp per query
+__global__ void __launch_bounds__(128) knn_merge_kernel(const uint32_t* __restrict__ partial, int nq, int k, int n_chunks, int max_seg,
+                                                        long long total_units, int G, int KNN_TILE, uint32_t* keys_out, const VoteArgs vote) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
+    const int tile = q / KNN_TILE, row = q - tile * KNN_TILE;
+    const long long tile_u0 = (long long)tile * n_chunks;
+    const int n_seg = cta_of(total_units, G, tile_u0 + n_chunks - 1) - cta_of(total_units, G, tile_u0) + 1;
+    if (n_seg == 1) return;  // emitted by K8 itself
     uint32_t k0 = KEY_EMPTY;
-    for (int s = 0; s < n_splits; ++s) {
-        uint32_t k1 = lane < k ? partial[((size_t)q * n_splits + s) * k + lane] : KEY_EMPTY;
+    for (int s = 0; s < n_seg; ++s) {
+        uint32_t k1 = lane < k ? partial[(((size_t)tile * max_seg + s) * KNN_TILE + row) * k + lane] : KEY_EMPTY;
         warp_sort64(k0, k1, lane);
     }
     emit_row(k0, lane, q, k, keys_out, vote);
@@ -326,7 +401,9 @@ __global__ void keys_to_idx_dist_kernel(const uint32_t* __restrict__ keys, size_
 // ---- integer-pipe micro-benchmarks: the roofline denominators for K8 ------------------------------------------
 template <int WHICH>
 __global__ void __launch_bounds__(256) microbench_kernel(uint32_t* out, int iters) {
-    uint32_t a = threadIdx.x * 2654435761u + 1u, b = blockIdx.x * 40503u + 7u, c = a ^ 0x9E3779B9u, d = b + 0x7F4A7C15u;
+    // every chain is lane-dependent: warp-uniform values would be moved to the uniform datapath (UPOPC / ULOP3)
+    const uint32_t t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 1u;
+    uint32_t a = t0, b = t0 * 40503u + 7u, c = a ^ 0x9E3779B9u, d = b + 0x7F4A7C15u;
     uint32_t e = a + 11u, f = b ^ 0x1234567u, g = c + 5u, h = d ^ 0xABCDEFu;
     if (WHICH == 0) {  // 8 independent LOP3 chains
         for (int i = 0; i < iters; ++i) {
@@ -336,58 +413,65 @@ __global__ void __launch_bounds__(256) microbench_kernel(uint32_t* out, int iter
                 e = lop3<LUT_MAJ>(e, f, g); f = lop3<LUT_CARRY>(f, g, h); g = lop3<LUT_XOR3>(g, h, a); h = lop3<LUT_MAJ>(h, a, b);
             }
         }
-    } else {  // 8 independent POPC chains (popc feeds an xor to keep the chain alive on another pipe)
+    } else {  // 8 independent POPC chains (each popc feeds an IMAD on the FMA pipe, so only POPC loads the XU pipe)
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                a = __popc(a) + 0x55555u; b = __popc(b) + 0x33333u; c = __popc(c) + 0x77777u; d = __popc(d) + 0x11111u;
-                e = __popc(e) + 0x5a5a5u; f = __popc(f) + 0x3c3c3u; g = __popc(g) + 0x69696u; h = __popc(h) + 0x0f0f1u;
+                a = __popc(a) * 0x55555u; b = __popc(b) * 0x33333u; c = __popc(c) * 0x77777u; d = __popc(d) * 0x11111u;
+                e = __popc(e) * 0x5a5a5u; f = __popc(f) * 0x3c3c3u; g = __popc(g) * 0x69696u; h = __popc(h) * 0x0f0f1u;
             }
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
 }
 
-// which = 2: the K8 inner-loop instruction mix (14 LOP3 + 4 POPC + key assembly + compare per pair, 4 queries per
-// thread) with no memory traffic and no selection -- the achievable ceiling of this formulation in pairs/s.
+// which = 2: the K8 inner-loop instruction mix (13 LOP3 + 4 POPC + 3 IMAD + 1 ISETP per pair, QR queries per thread)
+// with no memory traffic and no selection -- the achievable ceiling of this formulation in pairs/s.
 __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) microbench_mix_kernel(uint32_t* out, int iters) {
-    uint32_t qw[KNN_QR][8], q012[KNN_QR], q345[KNN_QR], best[KNN_QR];
+    constexpr int KNN_QR = KNN_QR_MAX;
+    uint32_t q0[KNN_QR], q1[KNN_QR], q3[KNN_QR], q4[KNN_QR], q7[KNN_QR], q012[KNN_QR], q345[KNN_QR], q06[KNN_QR], best[KNN_QR];
     uint32_t seed = threadIdx.x * 2654435761u + blockIdx.x * 40503u + 1u;
 #pragma unroll
     for (int i = 0; i < KNN_QR; ++i) {
+        uint32_t w[8];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { seed = seed * 1664525u + 1013904223u; qw[i][w] = seed; }
-        q012[i] = qw[i][0] ^ qw[i][1] ^ qw[i][2];
-        q345[i] = qw[i][3] ^ qw[i][4] ^ qw[i][5];
-        best[i] = KEY_EMPTY;
+        for (int j = 0; j < 8; ++j) { seed = seed * 1664525u + 1013904223u; w[j] = seed; }
+        q0[i] = w[0]; q1[i] = w[1]; q3[i] = w[3]; q4[i] = w[4]; q7[i] = w[7];
+        q012[i] = w[0] ^ w[1] ^ w[2];
+        q345[i] = w[3] ^ w[4] ^ w[5];
+        q06[i] = q012[i] ^ q345[i] ^ w[6];
+        best[i] = (seed >> 27) + 1u;   // 1..32: unknown to the compiler, practically never beaten by a random 256-bit distance
     }
     uint4 a = make_uint4(seed, seed * 3u, seed * 5u, seed * 7u), b = make_uint4(seed * 11u, seed * 13u, seed * 17u, seed * 19u);
+    uint4 e = make_uint4(seed * 23u, seed * 29u, seed * 31u, 0u);
+    uint32_t hits = 0;
     for (int it = 0; it < iters; ++it) {
-        const uint32_t p012 = a.x ^ a.y ^ a.z, p345 = a.w ^ b.x ^ b.y;
+        bool hit = false;
 #pragma unroll
         for (int i = 0; i < KNN_QR; ++i) {
-            const uint32_t x0 = qw[i][0] ^ a.x, x1 = qw[i][1] ^ a.y;
-            const uint32_t s1 = q012[i] ^ p012;
+            const uint32_t x0 = q0[i] ^ a.x, x1 = q1[i] ^ a.y;
+            const uint32_t s1 = q012[i] ^ e.x;
             const uint32_t c1 = lop3<LUT_CARRY>(x0, x1, s1);
-            const uint32_t x3 = qw[i][3] ^ a.w, x4 = qw[i][4] ^ b.x;
-            const uint32_t s2 = q345[i] ^ p345;
+            const uint32_t x3 = q3[i] ^ a.w, x4 = q4[i] ^ b.x;
+            const uint32_t s2 = q345[i] ^ e.y;
             const uint32_t c2 = lop3<LUT_CARRY>(x3, x4, s2);
-            const uint32_t x6 = qw[i][6] ^ b.z, x7 = qw[i][7] ^ b.w;
-            const uint32_t s3 = lop3<LUT_XOR3>(s1, s2, x6);
-            const uint32_t c3 = lop3<LUT_MAJ>(s1, s2, x6);
+            const uint32_t s3 = q06[i] ^ e.z;
+            const uint32_t c3 = lop3<LUT_CARRY>(s1, s2, s3);
+            const uint32_t x7 = q7[i] ^ b.w;
             const uint32_t s5 = lop3<LUT_XOR3>(c1, c2, c3);
             const uint32_t c5 = lop3<LUT_MAJ>(c1, c2, c3);
-            const uint32_t ones = __popc(s3) + __popc(x7);
-            const uint32_t key = (ones << KEY_IDX_BITS) + ((uint32_t)__popc(s5) << (KEY_IDX_BITS + 1)) +
-                                 ((uint32_t)__popc(c5) << (KEY_IDX_BITS + 2)) + (uint32_t)it;
-            if (key < best[i]) best[i] = key;
+            const uint32_t dist = (uint32_t)__popc(s3) + (uint32_t)__popc(x7) + 2u * (uint32_t)__popc(s5) + 4u * (uint32_t)__popc(c5);
+            hit |= dist < best[i];
         }
-        // next "pooled descriptor": a cheap dependent update (2 IMAD-class ops per pooled descriptor, amortised over 4 pairs)
-        a.x = a.x * 1664525u + best[0];
+        if (__any_sync(FULL, hit)) ++hits;   // data dependent, practically never taken after the first iterations
+        if (hits > 1000000u) best[0] += 1u;
+        // next "pooled row": a cheap dependent update (IMAD-class ops, amortised over QR pairs)
+        a.x = a.x * 1664525u + hits;
         b.w = b.w * 22695477u + a.x;
-        uint32_t t = a.x; a.x = a.y; a.y = a.z; a.z = a.w; a.w = b.x; b.x = b.y; b.y = b.z; b.z = b.w; b.w = t;
+        e.x = e.x * 69069u + b.w;
+        uint32_t t = a.x; a.x = a.y; a.y = a.z; a.z = a.w; a.w = b.x; b.x = b.y; b.y = b.z; b.z = b.w; b.w = e.y; e.y = e.z; e.z = e.x; e.x = t;
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = best[0] ^ best[1] ^ best[2] ^ best[3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = best[0] ^ best[1] ^ hits;
 }
 
 }  // namespace
@@ -396,55 +480,71 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) microbench_mix_k
 KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms) {
     KnnPlan p;
     p.nq = nq; p.nt = nt; p.k = k;
+    // queries per thread: 8 amortises the pooled-row loads best, 4 gives twice as many tiles -> fewer, longer stream-K
+    // segments per tile (every segment re-warms its selection thresholds from scratch)
+    const long long target0 = (long long)num_sms * KNN_CTAS_PER_SM;
+    p.qr = (long long)cdiv(nq, KNN_THREADS * 8) * 2 >= target0 * 3 ? 8 : 4;
+    if (const char* e = getenv("SLIDEO_KNN_QR")) { if (atoi(e) == 4 || atoi(e) == 8) p.qr = atoi(e); }
+    const int KNN_TILE = KNN_THREADS * p.qr;
+    p.tile = KNN_TILE;
     p.n_tiles = cdiv(nq, KNN_TILE);
-    const int chunks = cdiv(nt > 0 ? nt : 1, KNN_CHUNK);
-    const int target = num_sms * KNN_CTAS_PER_SM;
-    // choose the number of pool splits: fill the machine for several waves while keeping splits long enough
-    // that the per-item final sort (~ one pass over 350 pooled descriptors) stays a small fraction
-    int best_ns = 1;
-    double best_eff = -1.0;
-    const int max_ns = chunks < 256 ? chunks : 256;
-    for (int ns = 1; ns <= max_ns; ++ns) {
-        const int len_chunks = cdiv(chunks, ns);
-        const int real_ns = cdiv(chunks, len_chunks);
-        if (real_ns != ns) continue;
-        const long items = (long)p.n_tiles * ns;
-        const int grid = (int)(items < target ? items : target);
-        const long waves = (items + grid - 1) / grid;
-        double eff = (double)items / (double)(waves * target);
-        const double len = (double)len_chunks * KNN_CHUNK;
-        eff *= len / (len + 350.0);
-        if (eff > best_eff * 1.02) { best_eff = eff; best_ns = ns; }
-    }
-    p.n_splits = best_ns;
-    p.split_len = cdiv(chunks, best_ns) * KNN_CHUNK;
-    const long items = (long)p.n_tiles * p.n_splits;
-    p.grid = (int)(items < target ? items : target);
+    p.n_chunks = cdiv(nt > 0 ? nt : 1, KNN_CHUNK);
+    p.total_units = (long long)p.n_tiles * p.n_chunks;
+    const long long target = (long long)num_sms * KNN_CTAS_PER_SM;
+    p.grid = (int)(p.total_units < target ? p.total_units : target);
     if (p.grid < 1) p.grid = 1;
+    p.max_seg = 1;
+    for (int t = 0; t < p.n_tiles; ++t) {
+        const long long u0 = (long long)t * p.n_chunks;
+        const int n_seg = cta_of(p.total_units, p.grid, u0 + p.n_chunks - 1) - cta_of(p.total_units, p.grid, u0) + 1;
+        if (n_seg > p.max_seg) p.max_seg = n_seg;
+    }
     p.scratch_bytes = (size_t)p.grid * KNN_TILE * KNN_SLOTS * sizeof(uint32_t);
-    p.partial_bytes = p.n_splits > 1 ? (size_t)nq * p.n_splits * k * sizeof(uint32_t) : 0;
+    p.partial_bytes = p.max_seg > 1 ? (size_t)p.n_tiles * p.max_seg * KNN_TILE * k * sizeof(uint32_t) : 0;
+    p.pool_bytes = (size_t)(nt > 0 ? nt : 1) * KNN_ROW_U4 * 16;
     return p;
 }
 
-void knn_hamming_launch(const KnnPlan& plan, const void* d_q, const void* d_pool, uint32_t* d_keys_out,
+size_t knn_pool_expanded_bytes(int nt) { return (size_t)(nt > 0 ? nt : 1) * KNN_ROW_U4 * 16; }
+
+void knn_pool_expand_launch(const void* d_pool32, int nt, void* d_pool48, cudaStream_t stream) {
+    if (nt <= 0) return;
+    pool_expand_kernel<<<cdiv(nt, 256), 256, 0, stream>>>((const uint4*)d_pool32, nt, (uint4*)d_pool48);
+    SLIDEO_CUDA(cudaGetLastError());
+}
+
+void knn_hamming_launch(const KnnPlan& plan, const void* d_q, const void* d_pool48, uint32_t* d_keys_out,
                         uint32_t* d_scratch, uint32_t* d_partial, const VoteArgs* vote, cudaStream_t stream,
                         int* launches) {
     if (plan.nq <= 0) return;
     KnnParams P;
     P.q = (const uint4*)d_q;
-    P.pool = (const uint4*)d_pool;
+    P.pool = (const uint4*)d_pool48;
     P.keys_out = d_keys_out;
     P.partial = d_partial;
     P.scratch = d_scratch;
     P.nq = plan.nq; P.nt = plan.nt; P.k = plan.k;
-    P.n_tiles = plan.n_tiles; P.n_splits = plan.n_splits; P.split_len = plan.split_len;
+    P.n_tiles = plan.n_tiles; P.n_chunks = plan.n_chunks; P.max_seg = plan.max_seg; P.total_units = plan.total_units;
+    P.tile = plan.tile;
     if (vote) P.vote = *vote;
     else P.vote = VoteArgs{nullptr, nullptr, nullptr, 0, 0.f};
-    knn_hamming_kernel<<<plan.grid, KNN_THREADS, 0, stream>>>(P);
+    const size_t smem = (size_t)KNN_STAGES * KNN_CHUNK * KNN_ROW_U4 * 16 + KNN_STAGES * sizeof(uint64_t) + 2 * plan.tile * sizeof(int);
+    static bool configured = false;
+    if (!configured) {
+        const int max_smem = (int)((size_t)KNN_STAGES * KNN_CHUNK * KNN_ROW_U4 * 16 + KNN_STAGES * sizeof(uint64_t) + 2 * KNN_THREADS * KNN_QR_MAX * sizeof(int));
+        SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    if (plan.qr == 8) knn_hamming_kernel<8><<<plan.grid, KNN_THREADS, smem, stream>>>(P);
+    else knn_hamming_kernel<4><<<plan.grid, KNN_THREADS, smem, stream>>>(P);
     SLIDEO_CUDA(cudaGetLastError());
     if (launches) ++*launches;
-    if (plan.n_splits > 1) {
-        knn_merge_kernel<<<cdiv(plan.nq, 4), 128, 0, stream>>>(d_partial, plan.nq, plan.n_splits, plan.k, d_keys_out, P.vote);
+    if (plan.max_seg > 1) {
+        knn_merge_kernel<<<cdiv(plan.nq, 4), 128, 0, stream>>>(d_partial, plan.nq, plan.k, plan.n_chunks, plan.max_seg, plan.total_units,
+                                                              plan.grid, plan.tile, d_keys_out, P.vote);
         SLIDEO_CUDA(cudaGetLastError());
         if (launches) ++*launches;
     }
@@ -488,7 +588,7 @@ double microbench_run(int which, int num_sms, cudaStream_t stream) {
     cudaEventDestroy(e1);
     cudaFree(d_out);
     // which 0/1: thread-level ops per second; which 2: descriptor pairs per second
-    const double ops = which == 2 ? (double)blocks * threads * (double)iters * KNN_QR : (double)blocks * threads * (double)iters * 64.0;
+    const double ops = which == 2 ? (double)blocks * threads * (double)iters * KNN_QR_MAX : (double)blocks * threads * (double)iters * 64.0;
     return ops / (best * 1e-3);
 }
 

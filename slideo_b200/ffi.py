@@ -43,7 +43,7 @@ class Match(ctypes.Structure):
 class Timings(ctypes.Structure):
     _fields_ = [("ms_detect", c_f32), ("ms_knn", c_f32), ("ms_vote", c_f32), ("ms_h2d", c_f32),
                 ("knn_pairs", ctypes.c_int64), ("knn_launches", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
-                ("frames", ctypes.c_int64)]
+                ("frames", ctypes.c_int64), ("ms_total", c_f32), ("reserved0", c_f32)]
 
 
 # name -> (restype, argtypes); every symbol include/slideo_b200.h declares
