@@ -68,7 +68,7 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_pool;              // nt x 32 (ORB) / nt x 128 bf16 (SIFT)
     DevBuf<uint8_t> d_pool48;            // ORB: the 48 B expanded rows K8 streams (knn_pool_expand_launch)
     DevBuf<uint8_t> d_t48;               // expanded copy of a caller-provided pool (stage-level k-NN)
-    DevBuf<float> d_pool_norm;           // SIFT: squared norms
+    DevBuf<uint8_t> d_pool_tail;         // SIFT: bf16 norm tails of the pool (knn_l2.cu)
     DevBuf<uint16_t> d_page_of;          // nt
     DevBuf<int32_t> d_page_off;          // n_pages + 1
     int nt = 0, n_pages = 0;
@@ -84,8 +84,7 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_q;                 // uploaded query descriptors
     DevBuf<uint8_t> d_t;                 // uploaded train descriptors (stage-level knn)
     L2Workspace l2ws;
-    DevBuf<uint8_t> d_l2_pool;           // bf16 copy of the last bf_knn_l2_device pool
-    DevBuf<float> d_l2_norm;
+    DevBuf<uint8_t> d_l2_pool, d_l2_tail; // bf16 operands of a caller-provided pool (stage-level L2 k-NN)
     int32_t* h_results = nullptr;        // pinned, max_batch x 3 x 2
     size_t h_results_cap = 0;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -467,9 +466,10 @@ static void finalize_from_host(slideo_b200_ctx* ctx) {
         ctx->d_t.reserve((size_t)std::max(ctx->nt, 1) * 512);
         if (ctx->nt > 0)
             SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_t.p, ctx->h_pool.data(), (size_t)ctx->nt * 512, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->d_pool.reserve((size_t)l2_rows_padded(ctx->nt) * 256 + 256);
-        ctx->d_pool_norm.reserve((size_t)l2_rows_padded(ctx->nt) + 64);
-        l2_prepare_launch((const float*)ctx->d_t.p, ctx->nt, 128, (uint16_t*)ctx->d_pool.p, ctx->d_pool_norm.p, ctx->stream);
+        ctx->d_pool.reserve(l2_main_bytes(ctx->nt));
+        ctx->d_pool_tail.reserve(l2_tail_bytes(ctx->nt));
+        l2_prepare_launch((const float*)ctx->d_t.p, ctx->nt, false, ctx->d_pool.p, ctx->d_pool_tail.p, ctx->stream);
+        ctx->tm.kernel_launches += 1;
         ctx->build_page_of();
     }
     ctx->finalized = true;
@@ -696,7 +696,7 @@ int32_t slideo_b200_match_descriptors(slideo_b200_ctx* ctx, const void* desc, co
                 if (nq > 0) {
                     EventPair tk = ctx->begin_timing(1, ctx->stream);
                     int nl = 0;
-                    l2_knn_launch(ctx->l2ws, (const float*)ctx->d_q.p, nq, (const uint16_t*)ctx->d_pool.p, ctx->d_pool_norm.p, ctx->nt,
+                    l2_knn_launch(ctx->l2ws, (const float*)ctx->d_q.p, nq, ctx->d_pool.p, ctx->d_pool_tail.p, ctx->nt,
                                   ctx->cfg.knn_k, ctx->d_idx.p, (float*)ctx->d_dist.p, ctx->num_sms, ctx->stream, &nl);
                     l2_vote_launch(ctx->d_idx.p, (const float*)ctx->d_dist.p, nq, ctx->cfg.knn_k, ctx->d_q_frame.p, ctx->d_page_of.p,
                                    ctx->d_votes.p, ctx->n_pages, ctx->cfg.vote_ratio, ctx->stream);
@@ -912,18 +912,16 @@ int32_t slideo_b200_bf_knn_l2(slideo_b200_ctx* ctx, const float* q, int32_t nq, 
         arg(q && idx && dist && (t || nt == 0), "NULL buffer");
         ctx->d_q.reserve((size_t)nq * 512);
         ctx->d_t.reserve((size_t)std::max(nt, 1) * 512);
-        DevBuf<uint8_t> tb;
-        DevBuf<float> tn;
-        tb.reserve((size_t)l2_rows_padded(nt) * 256 + 256);
-        tn.reserve((size_t)l2_rows_padded(nt) + 64);
+        ctx->d_l2_pool.reserve(l2_main_bytes(nt));
+        ctx->d_l2_tail.reserve(l2_tail_bytes(nt));
         ctx->d_idx.reserve((size_t)nq * k);
         ctx->d_dist.reserve((size_t)nq * k);
         SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_q.p, q, (size_t)nq * 512, cudaMemcpyHostToDevice, ctx->stream));
         if (nt) SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_t.p, t, (size_t)nt * 512, cudaMemcpyHostToDevice, ctx->stream));
-        l2_prepare_launch((const float*)ctx->d_t.p, nt, 128, (uint16_t*)tb.p, tn.p, ctx->stream);
+        l2_prepare_launch((const float*)ctx->d_t.p, nt, false, ctx->d_l2_pool.p, ctx->d_l2_tail.p, ctx->stream);
         EventPair tk = ctx->begin_timing(1, ctx->stream);
         int nl = 0;
-        l2_knn_launch(ctx->l2ws, (const float*)ctx->d_q.p, nq, (const uint16_t*)tb.p, tn.p, nt, k, ctx->d_idx.p, (float*)ctx->d_dist.p,
+        l2_knn_launch(ctx->l2ws, (const float*)ctx->d_q.p, nq, ctx->d_l2_pool.p, ctx->d_l2_tail.p, nt, k, ctx->d_idx.p, (float*)ctx->d_dist.p,
                       ctx->num_sms, ctx->stream, &nl);
         ctx->end_timing(tk, ctx->stream);
         ctx->tm.knn_launches += nl;
@@ -948,12 +946,12 @@ int32_t slideo_b200_bf_knn_l2_device(slideo_b200_ctx* ctx, const void* d_q, int3
         arg(d_q && d_idx && d_dist && (d_t || nt == 0), "NULL buffer");
         arg(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0, "device buffers must be 16-byte aligned");
         // bf16 copy + norms of the pool (outside the K10 timing bracket)
-        ctx->d_l2_pool.reserve((size_t)l2_rows_padded(nt) * 256 + 256);
-        ctx->d_l2_norm.reserve((size_t)l2_rows_padded(nt) + 64);
-        l2_prepare_launch((const float*)d_t, nt, 128, (uint16_t*)ctx->d_l2_pool.p, ctx->d_l2_norm.p, ctx->stream);
+        ctx->d_l2_pool.reserve(l2_main_bytes(nt));
+        ctx->d_l2_tail.reserve(l2_tail_bytes(nt));
+        l2_prepare_launch((const float*)d_t, nt, false, ctx->d_l2_pool.p, ctx->d_l2_tail.p, ctx->stream);
         EventPair tk = ctx->begin_timing(1, ctx->stream);
         int nl = 0;
-        l2_knn_launch(ctx->l2ws, (const float*)d_q, nq, (const uint16_t*)ctx->d_l2_pool.p, ctx->d_l2_norm.p, nt, k, (int32_t*)d_idx,
+        l2_knn_launch(ctx->l2ws, (const float*)d_q, nq, ctx->d_l2_pool.p, ctx->d_l2_tail.p, nt, k, (int32_t*)d_idx,
                       (float*)d_dist, ctx->num_sms, ctx->stream, &nl);
         ctx->end_timing(tk, ctx->stream);
         ctx->tm.knn_launches += nl;

@@ -1,20 +1,555 @@
-// knn_l2.cu -- K10 (placeholder until the tcgen05 kernel lands): every entry point reports NOTIMPL.
+// knn_l2.cu -- K10: exact brute-force L2 k-NN (k <= 32) of 128-d float descriptors on the 5th-gen tensor cores.
+//
+// The SIFT variant of the hot path (BASELINE.json north_star; not in the reference itself -- SURVEY.md D5/a10): the
+// semantics are cv2.BFMatcher(NORM_L2).knnMatch = the k smallest by (sqrtf(sum (a-b)^2), pooled index), rows ascending.
+//
+// d^2 = |q|^2 + |t|^2 - 2 q.t is evaluated ENTIRELY inside one bf16 GEMM with K = 128 + 16:
+//     A (queries, M side)  row = [ -2*q (128) | 1, 1, 1, qn_hi, qn_mid, qn_lo, 0 x 10 ]
+//     B (pool,    N side)  row = [    t (128) | tn_hi, tn_mid, tn_lo, 1, 1, 1, 0 x 10 ]
+// where the squared norms are split into three bf16 pieces (24 significant bits).  For integer-valued descriptors
+// (cv2 SIFT emits integers 0..255: exactly representable in bf16, every product and partial sum an integer < 2^24)
+// the fp32 accumulator in TMEM holds the exact squared distance, so sqrtf() of it is cv2's distance bit for bit.
+//
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
+//     warp 0      TMA producer      cp.async.bulk.tensor.2d (SWIZZLE_128B main blocks, SWIZZLE_32B norm tail) + mbarriers
+//     warp 1      MMA issuer        tcgen05.mma.cta_group::1.kind::f16, M = 128 queries x N = 256 pooled rows, 9 K-steps,
+//                                   fp32 accumulators in TMEM (2 x 256 columns = all 512), tcgen05.commit -> mbarriers
+//     warps 2-5   epilogue group 0  tcgen05.ld.32x32b.x32: thread = query row, 32 pooled columns per load; the epilogue of
+//     warps 6-9   epilogue group 1  a pair is ONE fp32 compare against the row's running k-th distance; survivors are
+//                                   appended as 64-bit keys (d2 bits << 32 | index) to a 128-slot per-(group,row) buffer in
+//                                   L2 scratch, compacted by a warp-cooperative 128-key bitonic sort when it fills up
+// The two groups drain alternate pool tiles (TMEM buffer = tile parity) so the tensor pipe never waits for one epilogue;
+// at the end of a work item both lists are merged and the row is emitted in oracle order.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <string>
+
 #include "knn_l2.cuh"
 
 namespace slideo {
 
+namespace {
+
+constexpr int L2_DIM = 128;
+constexpr int L2_TAIL = 16;
+constexpr int L2_BM = 128;              // queries per tile (TMEM lanes)
+constexpr int L2_BN = 256;              // pooled descriptors per tile (TMEM columns)
+constexpr int L2_STAGES = 2;            // B stages in shared memory
+constexpr int L2_THREADS = 320;
+constexpr int L2_SLOTS = 128;           // candidate keys per (group, row)
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint64_t KEY64_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+constexpr uint32_t A_MAIN_BYTES = L2_BM * 128;   // one 64-wide K block of the query tile (SW128: 128 B per row)
+constexpr uint32_t A_TAIL_BYTES = L2_BM * 32;
+constexpr uint32_t B_MAIN_BYTES = L2_BN * 128;
+constexpr uint32_t B_TAIL_BYTES = L2_BN * 32;
+constexpr uint32_t A_BYTES = 2 * A_MAIN_BYTES + A_TAIL_BYTES;   // 36 KB
+constexpr uint32_t B_BYTES = 2 * B_MAIN_BYTES + B_TAIL_BYTES;   // 72 KB
+constexpr uint32_t SMEM_OPERANDS = A_BYTES + L2_STAGES * B_BYTES;   // 180 KB
+constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 256 + 1024;          // + barriers/tmem ptr + alignment slack
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
+// version 1 << 46 | layout << 61.  layout: 2 = SWIZZLE_128B (8 rows x 128 B atoms, SBO 1024), 6 = SWIZZLE_32B (8 x 32 B, SBO 256)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)layout << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L2_BN >> 3) << 17) | ((uint32_t)(L2_BM >> 4) << 24);
+
+// 128-key ascending bitonic sort of 64-bit keys across a warp: position p = r * 32 + lane, r = 0..3
+__device__ __forceinline__ void warp_sort128(uint64_t (&k)[4], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if ((r & rs) == 0) {
+                        const int p = r * 32;   // lane bits do not matter for size >= 64
+                        const bool up = size == 128 ? true : ((p & size) == 0);
+                        const uint64_t a = k[r], b = k[r | rs];
+                        const bool sw = up ? (a > b) : (a < b);
+                        k[r] = sw ? b : a;
+                        k[r | rs] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int p = r * 32 + lane;
+                    const uint64_t o = __shfl_xor_sync(FULL, k[r], stride);
+                    const bool lower = (lane & stride) == 0;
+                    const bool up = size == 128 ? true : ((p & size) == 0);
+                    const uint64_t mn = k[r] < o ? k[r] : o, mx = k[r] < o ? o : k[r];
+                    k[r] = (lower == up) ? mn : mx;
+                }
+            }
+        }
+    }
+}
+
+struct L2Params {
+    int nq, nt, k;
+    int n_mtiles, n_ntiles, n_splits;
+    uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
+    uint64_t* partial;     // [nq][n_splits][k]   (n_splits > 1)
+    int32_t* idx_out;      // [nq][k]
+    float* dist_out;       // [nq][k]
+};
+
+__device__ __forceinline__ void emit_l2_row(uint64_t key, int lane, int q, int k, int32_t* idx_out, float* dist_out) {
+    if (lane < k) {
+        const bool ok = key != KEY64_EMPTY;
+        const float d2 = fmaxf(__uint_as_float((uint32_t)(key >> 32)), 0.f);
+        idx_out[(size_t)q * k + lane] = ok ? (int32_t)(uint32_t)key : -1;
+        dist_out[(size_t)q * k + lane] = ok ? sqrtf(d2) : -1.f;
+    }
+}
+
+__global__ void __launch_bounds__(L2_THREADS, 1)
+knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_tail,
+              const __grid_constant__ CUtensorMap tm_t_main, const __grid_constant__ CUtensorMap tm_t_tail, const L2Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                          // [main0 | main1 | tail]
+    uint8_t* sB = smem + A_BYTES;                // [stage][main0 | main1 | tail]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;                 // [L2_STAGES]
+    uint64_t* b_empty = bars + 4;                // [L2_STAGES]
+    uint64_t* acc_full = bars + 6;               // [2]
+    uint64_t* acc_empty = bars + 8;              // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < L2_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int n_items = P.n_mtiles * P.n_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0, bcount = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
+                const int j0 = (int)((long long)P.n_ntiles * sp / P.n_splits), j1 = (int)((long long)P.n_ntiles * (sp + 1) / P.n_splits);
+                mbar_wait(a_empty, (it & 1) ^ 1);      // MMAs of the previous item no longer read A
+                mbar_expect_tx(a_full, A_BYTES);
+                tma_load_2d(sA, &tm_q_main, 0, mt * L2_BM, a_full);
+                tma_load_2d(sA + A_MAIN_BYTES, &tm_q_main, 64, mt * L2_BM, a_full);
+                tma_load_2d(sA + 2 * A_MAIN_BYTES, &tm_q_tail, 0, mt * L2_BM, a_full);
+                for (int j = j0; j < j1; ++j, ++bcount) {
+                    const int s = bcount % L2_STAGES;
+                    mbar_wait(&b_empty[s], ((bcount / L2_STAGES) & 1) ^ 1);
+                    uint8_t* dst = sB + (size_t)s * B_BYTES;
+                    mbar_expect_tx(&b_full[s], B_BYTES);
+                    tma_load_2d(dst, &tm_t_main, 0, j * L2_BN, &b_full[s]);
+                    tma_load_2d(dst + B_MAIN_BYTES, &tm_t_main, 64, j * L2_BN, &b_full[s]);
+                    tma_load_2d(dst + 2 * B_MAIN_BYTES, &tm_t_tail, 0, j * L2_BN, &b_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0, bcount = 0, acc_use[2] = {0, 0};
+            const uint32_t a0 = smem_u32(sA), a1 = a0 + A_MAIN_BYTES, at = a0 + 2 * A_MAIN_BYTES;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
+                const int j0 = (int)((long long)P.n_ntiles * sp / P.n_splits), j1 = (int)((long long)P.n_ntiles * (sp + 1) / P.n_splits);
+                mbar_wait(a_full, it & 1);
+                for (int j = j0; j < j1; ++j, ++bcount) {
+                    const int b = (j - j0) & 1;
+                    const int s = bcount % L2_STAGES;
+                    mbar_wait(&acc_empty[b], (acc_use[b] & 1) ^ 1);   // epilogue drained this TMEM buffer
+                    ++acc_use[b];
+                    mbar_wait(&b_full[s], (bcount / L2_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t b0 = smem_u32(sB + (size_t)s * B_BYTES), b1 = b0 + B_MAIN_BYTES, bt = b0 + 2 * B_MAIN_BYTES;
+                    const uint32_t d = tmem_base + (uint32_t)b * L2_BN;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_bf16(d, smem_desc(a0 + kk * 32, 1024, 2), smem_desc(b0 + kk * 32, 1024, 2), IDESC, kk > 0);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_bf16(d, smem_desc(a1 + kk * 32, 1024, 2), smem_desc(b1 + kk * 32, 1024, 2), IDESC, 1);
+                    tc_mma_bf16(d, smem_desc(at, 256, 6), smem_desc(bt, 256, 6), IDESC, 1);
+                    tc_commit(&b_empty[s]);        // smem stage reusable once these MMAs have read it
+                    tc_commit(&acc_full[b]);       // accumulator ready for the epilogue
+                }
+                tc_commit(a_empty);
+            }
+        }
+    } else {
+        // ===================== epilogue groups =====================
+        const int g = (warp - 2) >> 2;               // 0: even tiles, 1: odd tiles
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;         // query row within the tile
+        uint64_t* my_buf = P.scratch + (((size_t)blockIdx.x * 2 + g) * L2_BM + row) * L2_SLOTS;
+        const uint32_t taddr_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * L2_BN;
+        uint32_t acc_seen = 0;
+
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
+            const int j0 = (int)((long long)P.n_ntiles * sp / P.n_splits), j1 = (int)((long long)P.n_ntiles * (sp + 1) / P.n_splits);
+            const int q = mt * L2_BM + row;
+            float tau = q < P.nq ? __int_as_float(0x7F800000) : -1.f;   // +inf / never
+            int cnt = 0;
+
+            auto compact = [&](bool force) {
+                // warp-cooperative: lanes whose buffer is nearly full (all lanes at the end of an item) get it sorted and
+                // cut to the k best; at the end of an item the list length is published in slot 32 (k <= 32) for the merge
+                unsigned need = force ? FULL : __ballot_sync(FULL, cnt > L2_SLOTS - 32);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    uint64_t* buf = my_buf + ((ptrdiff_t)L - lane) * L2_SLOTS;
+                    const int n = __shfl_sync(FULL, cnt, L);
+                    uint64_t kk[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) kk[r] = r * 32 + lane < n ? __ldcg(buf + r * 32 + lane) : KEY64_EMPTY;
+                    warp_sort128(kk, lane);
+                    if (lane < P.k) buf[lane] = kk[0];
+                    if (force && lane == 0) buf[32] = (uint64_t)min(n, P.k);
+                    const uint64_t kth = __shfl_sync(FULL, kk[0], P.k - 1);
+                    if (lane == L) {
+                        if (kth != KEY64_EMPTY) tau = __uint_as_float((uint32_t)(kth >> 32));
+                        cnt = min(n, P.k);
+                    }
+                }
+                __syncwarp();
+            };
+
+            for (int j = j0 + g; j < j1; j += 2) {
+                mbar_wait(&acc_full[g], acc_seen & 1);
+                ++acc_seen;
+                tc_fence_after();
+                const int col0 = j * L2_BN;
+#pragma unroll 1
+                for (int c = 0; c < L2_BN; c += 32) {
+                    uint32_t v[32];
+                    tc_ld32(taddr_base + (uint32_t)c, v);
+                    bool hit = false;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) hit |= __uint_as_float(v[i]) < tau;
+                    if (hit) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (__uint_as_float(v[i]) < tau) {
+                                my_buf[cnt] = ((uint64_t)v[i] << 32) | (uint32_t)(col0 + c + i);
+                                ++cnt;
+                            }
+                        }
+                    }
+                    if (__any_sync(FULL, cnt > L2_SLOTS - 32)) {
+                        __syncwarp();
+                        compact(false);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[g]);
+            }
+
+            // end of item: every list sorted and cut to k, then group 0 merges both lists of a row and emits it
+            __syncwarp();
+            compact(true);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (g == 0) {
+                const uint64_t* base0 = P.scratch + (((size_t)blockIdx.x * 2 + 0) * L2_BM + quarter * 32) * L2_SLOTS;
+                const uint64_t* base1 = P.scratch + (((size_t)blockIdx.x * 2 + 1) * L2_BM + quarter * 32) * L2_SLOTS;
+                // every list holds its min(cnt, k) best keys, sorted, with the length published in slot 32 by compact(true)
+                for (int L = 0; L < 32; ++L) {
+                    const int qq = mt * L2_BM + quarter * 32 + L;
+                    if (qq >= P.nq) break;   // warp-uniform
+                    const int n0 = (int)__ldcg(base0 + (size_t)L * L2_SLOTS + 32);
+                    const int n1 = (int)__ldcg(base1 + (size_t)L * L2_SLOTS + 32);
+                    uint64_t kk[4];
+                    kk[0] = lane < n0 ? __ldcg(base0 + (size_t)L * L2_SLOTS + lane) : KEY64_EMPTY;
+                    kk[1] = lane < n1 ? __ldcg(base1 + (size_t)L * L2_SLOTS + lane) : KEY64_EMPTY;
+                    kk[2] = KEY64_EMPTY;
+                    kk[3] = KEY64_EMPTY;
+                    warp_sort128(kk, lane);
+                    if (P.n_splits == 1) emit_l2_row(kk[0], lane, qq, P.k, P.idx_out, P.dist_out);
+                    else if (lane < P.k) P.partial[((size_t)qq * P.n_splits + sp) * P.k + lane] = kk[0];
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// merge of per-split partial rows: one warp per query
+__global__ void __launch_bounds__(128) l2_merge_kernel(const uint64_t* __restrict__ partial, int nq, int n_splits, int k, int32_t* idx_out,
+                                                       float* dist_out) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    uint64_t kk[4] = {KEY64_EMPTY, KEY64_EMPTY, KEY64_EMPTY, KEY64_EMPTY};
+    for (int s = 0; s < n_splits; ++s) {
+        kk[1] = lane < k ? partial[((size_t)q * n_splits + s) * k + lane] : KEY64_EMPTY;
+        kk[2] = KEY64_EMPTY;
+        kk[3] = KEY64_EMPTY;
+        warp_sort128(kk, lane);
+    }
+    emit_l2_row(kk[0], lane, q, k, idx_out, dist_out);
+}
+
+// fp32 rows -> bf16 GEMM operands.  One warp per row, 4 elements per lane.
+//   queries: main = bf16(-2 x), tail = [1, 1, 1, n_hi, n_mid, n_lo, 0...]
+//   pool   : main = bf16(x),    tail = [n_hi, n_mid, n_lo, 1, 1, 1, 0...];  padding rows: main 0, n_hi = +inf
+// n = sum of squares of the ROUNDED values, split into three bf16 pieces (exact to 24 bits).
+__global__ void __launch_bounds__(256) l2_prepare_kernel(const float* __restrict__ src, int n, int n_pad, int is_query,
+                                                         __nv_bfloat16* __restrict__ out_main, __nv_bfloat16* __restrict__ out_tail) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_pad) return;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * L2_DIM) + lane);
+    const float sc = is_query ? -2.f : 1.f;
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(sc * x.x), b1 = __float2bfloat16_rn(sc * x.y), b2 = __float2bfloat16_rn(sc * x.z),
+                        b3 = __float2bfloat16_rn(sc * x.w);
+    const float inv = is_query ? -0.5f : 1.f;
+    const float r0 = __bfloat162float(b0) * inv, r1 = __bfloat162float(b1) * inv, r2 = __bfloat162float(b2) * inv, r3 = __bfloat162float(b3) * inv;
+    float nn = __fmaf_rn(r3, r3, __fmaf_rn(r2, r2, __fmaf_rn(r1, r1, __fmul_rn(r0, r0))));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(FULL, nn, o);
+    __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(out_main + (size_t)row * L2_DIM) + lane * 2;
+    m2[0] = __nv_bfloat162(b0, b1);
+    m2[1] = __nv_bfloat162(b2, b3);
+    if (lane < L2_TAIL) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(nn);
+        const float e1 = nn - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(e1);
+        const float e2 = e1 - __bfloat162float(mid);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(e2);
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+        __nv_bfloat16 v = zero;
+        if (is_query) {
+            if (lane < 3) v = one;
+            else if (lane == 3) v = hi;
+            else if (lane == 4) v = mid;
+            else if (lane == 5) v = lo;
+        } else {
+            if (row >= n) v = lane == 0 ? __ushort_as_bfloat16((unsigned short)0x7F80) : (lane >= 3 && lane < 6 ? one : zero);   // +inf norm
+            else if (lane == 0) v = hi;
+            else if (lane == 1) v = mid;
+            else if (lane == 2) v = lo;
+            else if (lane < 6) v = one;
+        }
+        out_tail[(size_t)row * L2_TAIL + lane] = v;
+    }
+}
+
+// the reference vote (lib.rs:270-282) on float rows: one warp per query
+__global__ void __launch_bounds__(128) l2_vote_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dist, int nq, int k,
+                                                      const int32_t* __restrict__ q_frame, const uint16_t* __restrict__ page_of,
+                                                      int32_t* __restrict__ votes, int n_pages, float ratio) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int i = lane < k ? idx[(size_t)q * k + lane] : -1;
+    const float d = lane < k ? dist[(size_t)q * k + lane] : 0.f;
+    const float best = __shfl_sync(FULL, d, 0);
+    const int i0 = __shfl_sync(FULL, i, 0);
+    if (i0 >= 0 && i >= 0 && d < __fmul_rn(best, ratio)) atomicAdd(&votes[(size_t)q_frame[q] * n_pages + page_of[i]], 1);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SLIDEO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !p) throw CudaError(cudaErrorNotSupported, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+CUtensorMap make_map(const void* base, int inner, int rows, int box_inner, int box_rows, CUtensorMapSwizzle sw) {
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError(cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return tm;
+}
+
+void grow(void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    SLIDEO_CUDA(cudaMalloc(p, want));
+    *cap = want;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
 L2Workspace::~L2Workspace() {
-    if (d_qb) cudaFree(d_qb);
-    if (d_qn) cudaFree(d_qn);
+    if (d_q_main) cudaFree(d_q_main);
+    if (d_q_tail) cudaFree(d_q_tail);
+    if (d_scratch) cudaFree(d_scratch);
     if (d_part) cudaFree(d_part);
 }
-int l2_rows_padded(int n) { return (n + 255) / 256 * 256; }
-void l2_prepare_launch(const float*, int, int, uint16_t*, float*, cudaStream_t) { throw NotImplError("SIFT128/L2 path not implemented yet"); }
-void l2_knn_launch(L2Workspace&, const float*, int, const uint16_t*, const float*, int, int, int32_t*, float*, int, cudaStream_t, int*) {
-    throw NotImplError("SIFT128/L2 path not implemented yet");
+
+int l2_rows_padded(int n) { return (std::max(n, 1) + L2_BN - 1) / L2_BN * L2_BN; }
+size_t l2_main_bytes(int n) { return (size_t)l2_rows_padded(n) * L2_DIM * 2; }
+size_t l2_tail_bytes(int n) { return (size_t)l2_rows_padded(n) * L2_TAIL * 2; }
+
+void l2_prepare_launch(const float* d_src, int n, bool is_query, void* d_main, void* d_tail, cudaStream_t stream) {
+    const int n_pad = l2_rows_padded(n);
+    l2_prepare_kernel<<<cdiv(n_pad, 8), 256, 0, stream>>>(d_src, n, n_pad, is_query ? 1 : 0, (__nv_bfloat16*)d_main, (__nv_bfloat16*)d_tail);
+    SLIDEO_CUDA(cudaGetLastError());
 }
-void l2_vote_launch(const int32_t*, const float*, int, int, const int32_t*, const uint16_t*, int32_t*, int, float, cudaStream_t) {
-    throw NotImplError("SIFT128/L2 path not implemented yet");
+
+void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool_main, const void* d_pool_tail, int nt, int k,
+                   int32_t* d_idx, float* d_dist, int num_sms, cudaStream_t stream, int* launches) {
+    if (nq <= 0) return;
+    // queries -> bf16 operands
+    grow(&ws.d_q_main, &ws.q_main_cap, l2_main_bytes(nq));
+    grow(&ws.d_q_tail, &ws.q_tail_cap, l2_tail_bytes(nq));
+    l2_prepare_launch(d_q, nq, true, ws.d_q_main, ws.d_q_tail, stream);
+    if (launches) ++*launches;
+
+    L2Params P;
+    P.nq = nq; P.nt = nt; P.k = k;
+    P.n_mtiles = cdiv(nq, L2_BM);
+    P.n_ntiles = l2_rows_padded(nt) / L2_BN;
+    // pool splits only when there are too few query tiles to fill the machine
+    int ns = 1;
+    if (P.n_mtiles < num_sms) ns = std::min(P.n_ntiles, std::max(1, num_sms / P.n_mtiles));
+    P.n_splits = ns;
+    const int grid = std::min(P.n_mtiles * ns, num_sms);
+    grow(&ws.d_scratch, &ws.scratch_cap, (size_t)grid * 2 * L2_BM * L2_SLOTS * 8);
+    if (ns > 1) grow(&ws.d_part, &ws.part_cap, (size_t)nq * ns * k * 8);
+    P.scratch = (uint64_t*)ws.d_scratch;
+    P.partial = (uint64_t*)ws.d_part;
+    P.idx_out = d_idx;
+    P.dist_out = d_dist;
+
+    const int q_pad = l2_rows_padded(nq), t_pad = l2_rows_padded(nt);
+    const CUtensorMap tq_main = make_map(ws.d_q_main, L2_DIM, q_pad, 64, L2_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    const CUtensorMap tq_tail = make_map(ws.d_q_tail, L2_TAIL, q_pad, L2_TAIL, L2_BM, CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMap tt_main = make_map(d_pool_main, L2_DIM, t_pad, 64, L2_BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    const CUtensorMap tt_tail = make_map(d_pool_tail, L2_TAIL, t_pad, L2_TAIL, L2_BN, CU_TENSOR_MAP_SWIZZLE_32B);
+
+    static bool configured = false;
+    if (!configured) {
+        SLIDEO_CUDA(cudaFuncSetAttribute(knn_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+        configured = true;
+    }
+    knn_l2_kernel<<<grid, L2_THREADS, SMEM_TOTAL, stream>>>(tq_main, tq_tail, tt_main, tt_tail, P);
+    SLIDEO_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    if (ns > 1) {
+        l2_merge_kernel<<<cdiv(nq, 4), 128, 0, stream>>>((const uint64_t*)ws.d_part, nq, ns, k, d_idx, d_dist);
+        SLIDEO_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+}
+
+void l2_vote_launch(const int32_t* d_idx, const float* d_dist, int nq, int k, const int32_t* d_q_frame, const uint16_t* d_page_of,
+                    int32_t* d_votes, int n_pages, float ratio, cudaStream_t stream) {
+    if (nq <= 0) return;
+    l2_vote_kernel<<<cdiv(nq, 4), 128, 0, stream>>>(d_idx, d_dist, nq, k, d_q_frame, d_page_of, d_votes, n_pages, ratio);
+    SLIDEO_CUDA(cudaGetLastError());
 }
 
 }  // namespace slideo
