@@ -23,6 +23,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
 
@@ -49,7 +51,7 @@ constexpr uint32_t B_TAIL_BYTES = L2_BN * 32;
 constexpr uint32_t A_BYTES = 2 * A_MAIN_BYTES + A_TAIL_BYTES;   // 36 KB
 constexpr uint32_t B_BYTES = 2 * B_MAIN_BYTES + B_TAIL_BYTES;   // 72 KB
 constexpr uint32_t SMEM_OPERANDS = A_BYTES + L2_STAGES * B_BYTES;   // 180 KB
-constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 256 + 1024;          // + barriers/tmem ptr + alignment slack
+constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 128 + 2 * L2_BM * 4 + 1024;   // + barriers/tmem ptr + tau exchange + alignment slack
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,8 +106,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
 // version 1 << 46 | layout << 61.  layout: 2 = SWIZZLE_128B (8 rows x 128 B atoms, SBO 1024), 6 = SWIZZLE_32B (8 x 32 B, SBO 256)
@@ -154,6 +156,7 @@ __device__ __forceinline__ void warp_sort128(uint64_t (&k)[4], int lane) {
 struct L2Params {
     int nq, nt, k;
     int n_mtiles, n_ntiles, n_splits;
+    int dbg;               // developer switch (SLIDEO_L2_DEBUG): 1 = epilogue skips the TMEM drain, 2 = drains but never selects
     uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
     uint64_t* partial;     // [nq][n_splits][k]   (n_splits > 1)
     int32_t* idx_out;      // [nq][k]
@@ -184,6 +187,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     uint64_t* acc_full = bars + 6;               // [2]
     uint64_t* acc_empty = bars + 8;              // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 12);   // [2][L2_BM]: running k-th distance of each (group, row) list
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -194,6 +198,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < 2 * L2_BM; i += L2_THREADS) s_tau[i] = __int_as_float(0x7F800000);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -292,7 +297,10 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                     if (force && lane == 0) buf[32] = (uint64_t)min(n, P.k);
                     const uint64_t kth = __shfl_sync(FULL, kk[0], P.k - 1);
                     if (lane == L) {
-                        if (kth != KEY64_EMPTY) tau = __uint_as_float((uint32_t)(kth >> 32));
+                        if (kth != KEY64_EMPTY) {
+                            tau = __uint_as_float((uint32_t)(kth >> 32));
+                            s_tau[g * L2_BM + row] = tau;   // the other group may prune against it (non-strictly)
+                        }
                         cnt = min(n, P.k);
                     }
                 }
@@ -304,25 +312,59 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 ++acc_seen;
                 tc_fence_after();
                 const int col0 = j * L2_BN;
+                // effective threshold: own k-th distance (strict) or the other group's (non-strict: an equal distance
+                // with a smaller index could still displace its k-th entry), whichever is tighter
+                float thr = tau;
+                {
+                    const float other = s_tau[(g ^ 1) * L2_BM + row];
+                    if (other < thr) thr = fminf(thr, nextafterf(other, __int_as_float(0x7F800000)));
+                }
+                const int n_chunks = P.dbg == 1 ? 0 : L2_BN / 32;
+                uint32_t va[32], vb[32];
+                if (n_chunks) tc_ld32(taddr_base, va);
 #pragma unroll 1
-                for (int c = 0; c < L2_BN; c += 32) {
-                    uint32_t v[32];
-                    tc_ld32(taddr_base + (uint32_t)c, v);
-                    bool hit = false;
+                for (int c = 0; c < n_chunks; c += 2) {
+                    // software pipeline: the next 32 columns are in flight while these are compared
+                    tc_ld_wait();
+                    tc_ld32(taddr_base + (uint32_t)(c + 1) * 32, vb);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) hit |= __uint_as_float(v[i]) < tau;
-                    if (hit) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (__uint_as_float(v[i]) < tau) {
-                                my_buf[cnt] = ((uint64_t)v[i] << 32) | (uint32_t)(col0 + c + i);
-                                ++cnt;
-                            }
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t (&v)[32] = half == 0 ? va : vb;
+                        if (half == 1) {
+                            tc_ld_wait();
+                            if (c + 2 < n_chunks) tc_ld32(taddr_base + (uint32_t)(c + 2) * 32, va);
                         }
-                    }
-                    if (__any_sync(FULL, cnt > L2_SLOTS - 32)) {
-                        __syncwarp();
-                        compact(false);
+                        // fast path: one compare per pair, four group predicates
+                        bool h0 = false, h1 = false, h2 = false, h3 = false;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            h0 |= __uint_as_float(v[i]) < thr;
+                            h1 |= __uint_as_float(v[8 + i]) < thr;
+                            h2 |= __uint_as_float(v[16 + i]) < thr;
+                            h3 |= __uint_as_float(v[24 + i]) < thr;
+                        }
+                        if (P.dbg == 2) { h0 = h0 && v[0] == 0x12345678u; h1 = h2 = h3 = false; }
+                        if (h0 | h1 | h2 | h3) {
+                            const uint32_t cbase = (uint32_t)(col0 + (c + half) * 32);
+                            auto append8 = [&](int o) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    if (__uint_as_float(v[o + i]) < thr) {
+                                        my_buf[cnt] = ((uint64_t)v[o + i] << 32) | (cbase + (uint32_t)(o + i));
+                                        ++cnt;
+                                    }
+                                }
+                            };
+                            if (h0) append8(0);
+                            if (h1) append8(8);
+                            if (h2) append8(16);
+                            if (h3) append8(24);
+                        }
+                        if (__any_sync(FULL, cnt > L2_SLOTS - 32)) {
+                            __syncwarp();
+                            compact(false);
+                            thr = fminf(thr, tau);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -334,6 +376,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
             __syncwarp();
             compact(true);
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            s_tau[g * L2_BM + row] = __int_as_float(0x7F800000);   // next item starts unpruned (nobody reads it until the 2nd barrier)
             if (g == 0) {
                 const uint64_t* base0 = P.scratch + (((size_t)blockIdx.x * 2 + 0) * L2_BM + quarter * 32) * L2_SLOTS;
                 const uint64_t* base1 = P.scratch + (((size_t)blockIdx.x * 2 + 1) * L2_BM + quarter * 32) * L2_SLOTS;
@@ -523,6 +566,7 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.partial = (uint64_t*)ws.d_part;
     P.idx_out = d_idx;
     P.dist_out = d_dist;
+    P.dbg = getenv("SLIDEO_L2_DEBUG") ? atoi(getenv("SLIDEO_L2_DEBUG")) : 0;
 
     const int q_pad = l2_rows_padded(nq), t_pad = l2_rows_padded(nt);
     const CUtensorMap tq_main = make_map(ws.d_q_main, L2_DIM, q_pad, 64, L2_BM, CU_TENSOR_MAP_SWIZZLE_128B);
