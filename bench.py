@@ -206,8 +206,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (configs[1]: 1000)")
     ap.add_argument("--pages", type=int, default=50, help="slide pages in the pool (configs[1]: 50)")
-    ap.add_argument("--max-batch", type=int, default=148,
-                    help="frames per internal batch; 148 x ~2040 keypoints = 590 K8 query tiles for the 592 resident CTAs")
+    ap.add_argument("--max-batch", type=int, default=64,
+                    help="frames per detection batch (K8 runs on chunks of the pooled query stream, independent of this)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

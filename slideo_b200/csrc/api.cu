@@ -77,7 +77,8 @@ struct slideo_b200_ctx {
     // ---- workspaces -------------------------------------------------------------------------------------
     std::map<std::tuple<int, int, int>, std::unique_ptr<OrbExtractor>> extractors;
     OrbExtractor* last_ext = nullptr;
-    DevBuf<uint8_t> d_frames[2];
+    static constexpr int N_STAGING = 4;  // frame staging buffers (uploads run this many batches ahead)
+    DevBuf<uint8_t> d_frames[N_STAGING];
     DevBuf<uint8_t> d_img;               // single-image upload (pages, extract_orb)
     DevBuf<uint32_t> d_scratch, d_partial, d_keys;
     DevBuf<int32_t> d_votes, d_results, d_q_frame, d_idx, d_dist;
@@ -87,7 +88,7 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_l2_pool, d_l2_tail; // bf16 operands of a caller-provided pool (stage-level L2 k-NN)
     int32_t* h_results = nullptr;        // pinned, max_batch x 3 x 2
     size_t h_results_cap = 0;
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy[N_STAGING] = {}, ev_free[N_STAGING] = {};
 
     // ---- kept matches of the last match call -------------------------------------------------------------
     std::vector<uint32_t> kept_keys;     // total_q x k
@@ -106,7 +107,7 @@ struct slideo_b200_ctx {
         extractors.clear();
         for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto& e : ev_free_list) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < N_STAGING; ++i) {
             if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
             if (ev_free[i]) cudaEventDestroy(ev_free[i]);
         }
@@ -234,21 +235,82 @@ struct slideo_b200_ctx {
         SLIDEO_CUDA(cudaStreamSynchronize(stream));
     }
 
-    // the per-frame hot path on device-resident BGR frames (one batch <= max_batch)
-    void match_batch_device(const uint8_t* d_src, int nb, int w, int h, int stride, size_t frame_stride, int32_t* h_out) {
+    // ---- the per-frame hot path, decoupled: detection appends descriptors of many batches to one query stream, K8 then
+    //      runs over that stream in chunks of exactly (resident CTAs x tile) queries, whatever the frame boundaries ----
+    DevBuf<uint8_t> d_qs_desc;           // query stream: descriptors
+    DevBuf<int32_t> d_qs_frame;          // frame (within the super-batch) of each query
+    DevBuf<int32_t> d_qs_nkp;            // keypoints per frame
+    int qs_total = 0, qs_frames = 0;
+    size_t qs_cap = 0;
+    static constexpr int SUPER_BATCH = 2048;   // frames per query stream (bounds the stream buffers)
+
+    size_t kp_per_frame_cap(int w, int h) { return extractor(w, h, cfg.max_batch).kp_cap() / (size_t)cfg.max_batch; }
+
+    void stream_begin(int n_frames, int w, int h) {
+        qs_cap = (size_t)n_frames * kp_per_frame_cap(w, h);
+        d_qs_desc.reserve(qs_cap * 32 + 64);
+        d_qs_frame.reserve(qs_cap + 64);
+        d_qs_nkp.reserve((size_t)n_frames + 64);
+        qs_total = 0;
+        qs_frames = 0;
+        qs_matched = 0;
+        const int np = std::max(n_pages, 1);
+        d_votes.reserve((size_t)n_frames * np);
+        d_results.reserve((size_t)n_frames * 3);
+        if (cfg.keep_matches) d_keys.reserve(qs_cap * cfg.knn_k);
+        SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)n_frames * np * 4, stream));
+    }
+    // K1-K7 on nb device-resident frames, appended to the query stream
+    void stream_detect(const uint8_t* d_src, int nb, int w, int h, int stride, size_t frame_stride) {
         OrbExtractor& ex = extractor(w, h, cfg.max_batch);
+        OrbExtractor::Sink sink{d_qs_desc.p + (size_t)qs_total * 32, d_qs_frame.p + qs_total, d_qs_nkp.p + qs_frames, qs_frames,
+                                qs_cap - (size_t)qs_total};
         EventPair t = begin_timing(0, stream);
         int nl = 0;
-        const int total = ex.run(d_src, nb, stride, frame_stride, 3, stream, &nl);
+        const int total = ex.run(d_src, nb, stride, frame_stride, 3, stream, &nl, &sink);
         end_timing(t, stream);
         tm.kernel_launches += nl;
-        knn_vote_hamming(ex.d_desc(), total, ex.d_q_frame(), nb, ex.d_frame_nkp(), cfg.keep_matches != 0);
-        SLIDEO_CUDA(cudaMemcpyAsync(h_out, d_results.p, (size_t)nb * 3 * 4, cudaMemcpyDeviceToHost, stream));
-        if (cfg.keep_matches) {
-            std::vector<int32_t> fo(ex.h_frame_off().begin(), ex.h_frame_off().begin() + nb + 1);
-            keep_batch_keys(total, fo);
-        }
+        qs_total += total;
+        qs_frames += nb;
         tm.frames += nb;
+    }
+    // K8 + K9 over the part of the stream that is ready: whole chunks of (resident CTAs x tile) queries while detection is
+    // still appending (flush = false), everything that is left at the end (flush = true)
+    int qs_matched = 0;
+    void stream_match_ready(bool flush) {
+        const bool want_keys = cfg.keep_matches != 0;
+        const int chunk = num_sms * 4 * 512;   // one full wave of K8 tiles (QR = 4): every CTA owns exactly one tile
+        VoteArgs va{nullptr, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio};
+        while (qs_total - qs_matched >= chunk || (flush && qs_total > qs_matched)) {
+            const int q0 = qs_matched, nq = std::min(chunk, qs_total - q0);
+            KnnPlan plan = knn_hamming_plan(nq, nt, cfg.knn_k, num_sms);
+            d_scratch.reserve(plan.scratch_bytes / 4);
+            if (plan.partial_bytes) d_partial.reserve(plan.partial_bytes / 4);
+            va.q_frame = d_qs_frame.p + q0;
+            EventPair t = begin_timing(1, stream);
+            int nl = 0;
+            knn_hamming_launch(plan, d_qs_desc.p + (size_t)q0 * 32, d_pool48.p, want_keys ? d_keys.p + (size_t)q0 * cfg.knn_k : nullptr,
+                               d_scratch.p, d_partial.p, &va, stream, &nl);
+            end_timing(t, stream);
+            tm.knn_launches += 1;
+            tm.kernel_launches += nl;
+            tm.knn_pairs += (int64_t)nq * nt;
+            qs_matched += nq;
+        }
+    }
+    // per-frame argmax + results of the finished stream into h_out
+    void stream_finish(int32_t* h_out) {
+        stream_match_ready(true);
+        vote_argmax_launch(d_votes.p, qs_frames, n_pages, d_qs_nkp.p, d_results.p, stream);
+        tm.kernel_launches += 1;
+        SLIDEO_CUDA(cudaMemcpyAsync(h_out, d_results.p, (size_t)qs_frames * 3 * 4, cudaMemcpyDeviceToHost, stream));
+        if (cfg.keep_matches) {
+            std::vector<int32_t> nkp((size_t)qs_frames), fo(1, 0);
+            SLIDEO_CUDA(cudaMemcpyAsync(nkp.data(), d_qs_nkp.p, (size_t)qs_frames * 4, cudaMemcpyDeviceToHost, stream));
+            SLIDEO_CUDA(cudaStreamSynchronize(stream));
+            for (int f = 0; f < qs_frames; ++f) fo.push_back(fo.back() + nkp[f]);
+            keep_batch_keys(qs_total, fo);
+        }
     }
 
     void reset_kept() {
@@ -394,7 +456,7 @@ int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_
         c->desc_bytes = cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256 ? 32 : 512;
         SLIDEO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         SLIDEO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < slideo_b200_ctx::N_STAGING; ++i) {
             SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
             SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
         }
@@ -582,26 +644,34 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
         EventPair t_total = ctx->begin_timing(4, ctx->stream);
         const int B = ctx->cfg.max_batch;
         const size_t img_bytes = (size_t)3 * w * h;
-        const int n_batches = cdiv(n, B);
-        for (int i = 0; i < 2; ++i) ctx->d_frames[i].reserve((size_t)std::min(B, n) * img_bytes);
+        constexpr int NBUF = slideo_b200_ctx::N_STAGING;
+        for (int i = 0; i < NBUF; ++i) ctx->d_frames[i].reserve((size_t)std::min(B, n) * img_bytes);
         ctx->ensure_host_results((size_t)n);
-        auto issue_copy = [&](int b) {
-            const int buf = b & 1, f0 = b * B, nb = std::min(B, n - f0);
-            SLIDEO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));  // buffer consumed by batch b-2
-            EventPair t = ctx->begin_timing(2, ctx->copy_stream);
-            ctx->upload_images(ctx->d_frames[buf].p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride,
-                               ctx->copy_stream);
-            ctx->end_timing(t, ctx->copy_stream);
-            SLIDEO_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
-        };
-        // ev_free events start "complete" (never recorded) -> first two waits fall through
-        issue_copy(0);
-        for (int b = 0; b < n_batches; ++b) {
-            const int buf = b & 1, f0 = b * B, nb = std::min(B, n - f0);
-            if (b + 1 < n_batches) issue_copy(b + 1);
-            SLIDEO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
-            ctx->match_batch_device(ctx->d_frames[buf].p, nb, w, h, 3 * w, img_bytes, ctx->h_results + (size_t)f0 * 3);
-            SLIDEO_CUDA(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
+        for (int s0 = 0; s0 < n; s0 += slideo_b200_ctx::SUPER_BATCH) {
+            const int ns = std::min(slideo_b200_ctx::SUPER_BATCH, n - s0);
+            const int n_batches = cdiv(ns, B);
+            ctx->stream_begin(ns, w, h);
+            auto issue_copy = [&](int b) {
+                const int buf = b % NBUF, f0 = s0 + b * B, nb = std::min(B, s0 + ns - f0);
+                SLIDEO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));  // detection of batch b - NBUF is done
+                EventPair t = ctx->begin_timing(2, ctx->copy_stream);
+                ctx->upload_images(ctx->d_frames[buf].p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride,
+                                   ctx->copy_stream);
+                ctx->end_timing(t, ctx->copy_stream);
+                SLIDEO_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+            };
+            // uploads run NBUF batches ahead on the copy stream; K8 chunks are interleaved with detection on the compute
+            // stream, so the DMA engine keeps filling staging buffers while K8 owns the SMs
+            for (int b = 0; b < std::min(NBUF, n_batches); ++b) issue_copy(b);
+            for (int b = 0; b < n_batches; ++b) {
+                const int buf = b % NBUF, f0 = s0 + b * B, nb = std::min(B, s0 + ns - f0);
+                SLIDEO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+                ctx->stream_detect(ctx->d_frames[buf].p, nb, w, h, 3 * w, img_bytes);
+                SLIDEO_CUDA(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
+                if (b + NBUF < n_batches) issue_copy(b + NBUF);
+                ctx->stream_match_ready(false);
+            }
+            ctx->stream_finish(ctx->h_results + (size_t)s0 * 3);
         }
         ctx->end_timing(t_total, ctx->stream);
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -629,10 +699,15 @@ int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d
         EventPair t_total = ctx->begin_timing(4, ctx->stream);
         const int B = ctx->cfg.max_batch;
         ctx->ensure_host_results((size_t)n);
-        for (int f0 = 0; f0 < n; f0 += B) {
-            const int nb = std::min(B, n - f0);
-            ctx->match_batch_device((const uint8_t*)d_frames + (size_t)f0 * frame_stride, nb, w, h, stride, frame_stride,
-                                    ctx->h_results + (size_t)f0 * 3);
+        for (int s0 = 0; s0 < n; s0 += slideo_b200_ctx::SUPER_BATCH) {
+            const int ns = std::min(slideo_b200_ctx::SUPER_BATCH, n - s0);
+            ctx->stream_begin(ns, w, h);
+            for (int f0 = s0; f0 < s0 + ns; f0 += B) {
+                const int nb = std::min(B, s0 + ns - f0);
+                ctx->stream_detect((const uint8_t*)d_frames + (size_t)f0 * frame_stride, nb, w, h, stride, frame_stride);
+                ctx->stream_match_ready(false);
+            }
+            ctx->stream_finish(ctx->h_results + (size_t)s0 * 3);
         }
         ctx->end_timing(t_total, ctx->stream);
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));

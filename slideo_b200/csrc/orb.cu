@@ -137,10 +137,12 @@ __device__ __forceinline__ int fast_score(const uint8_t* sp, int pitch) {
 
 __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ pyr, const Geo* __restrict__ gp,
                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
-    constexpr int PW = TILE_W + 8, PH = TILE_H + 8;   // pixel tile incl. 4-px halo
+    constexpr int PW = TILE_W + 8, PH = TILE_H + 8;   // pixel tile incl. 4-px halo (72 x 40, rows are 18 words)
     constexpr int SW = TILE_W + 2, SH = TILE_H + 2;   // score tile incl. 1-px halo
-    __shared__ uint8_t s_px[PH][PW];
+    __shared__ __align__(16) uint8_t s_px[PH][PW];
     __shared__ uint8_t s_sc[SH][SW + 2];
+    __shared__ uint16_t s_list[SH * SW];               // positions that pass the cheap necessary test
+    __shared__ int s_n;
 
     const Geo& g = *gp;
     int l = 0;
@@ -151,33 +153,56 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ p
     const int img = blockIdx.y;
     const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
 
-    for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
-        const int py = i / PW, px = i - py * PW;
-        const int gx = tx0 + px - 4, gy = ty0 + py - 4;
-        s_px[py][px] = (gx >= 0 && gx < L.w && gy >= 0 && gy < L.h) ? src[(size_t)gy * L.pitch + gx] : 0;
+    if (threadIdx.x == 0) s_n = 0;
+    // tile load, one 32-bit word (4 pixels) per thread and step: tx0 - 4 and the level pitch are multiples of 4, and the
+    // level rows are padded to 16 B inside the allocation, so whole words inside [0, pitch) are always readable
+    for (int i = threadIdx.x; i < PH * (PW / 4); i += blockDim.x) {
+        const int py = i / (PW / 4), pw = i - py * (PW / 4);
+        const int gx = tx0 + pw * 4 - 4, gy = ty0 + py - 4;
+        uint32_t w = 0;
+        if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch) w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gy * L.pitch + gx));
+        reinterpret_cast<uint32_t*>(&s_px[py][0])[pw] = w;
     }
     __syncthreads();
 
+    // pass 1: the exact necessary condition (any 9-arc contains two adjacent compass points) on every position;
+    // survivors are compacted into s_list so that the expensive score runs on dense warps
     const int thr = g.fast_thr;
-    for (int i = threadIdx.x; i < SH * SW; i += blockDim.x) {
-        const int sy = i / SW, sx = i - sy * SW;
-        const int gx = tx0 + sx - 1, gy = ty0 + sy - 1;
-        int score = 0;
-        if (gx >= 3 && gx < L.w - 3 && gy >= 3 && gy < L.h - 3) {
-            const uint8_t* sp = &s_px[sy + 3][sx + 3];
-            const int c = sp[0];
-            const int p0 = sp[3 * PW], p4 = sp[3], p8 = sp[-3 * PW], p12 = sp[-3];
-            // any 9-arc contains two adjacent compass points -> exact necessary condition
-            const int hi = c + thr, lo = c - thr;
-            const bool b0 = p0 > hi, b4 = p4 > hi, b8 = p8 > hi, b12 = p12 > hi;
-            const bool k0 = p0 < lo, k4 = p4 < lo, k8 = p8 < lo, k12 = p12 < lo;
-            if ((b0 && b4) || (b4 && b8) || (b8 && b12) || (b12 && b0) || (k0 && k4) || (k4 && k8) || (k8 && k12) ||
-                (k12 && k0)) {
-                const int s = fast_score(sp, PW);
-                if (s > thr) score = s - 1;
+    for (int i0 = 0; i0 < SH * SW; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool pass = false;
+        if (i < SH * SW) {
+            const int sy = i / SW, sx = i - sy * SW;
+            const int gx = tx0 + sx - 1, gy = ty0 + sy - 1;
+            s_sc[sy][sx] = 0;
+            if (gx >= 3 && gx < L.w - 3 && gy >= 3 && gy < L.h - 3) {
+                const uint8_t* sp = &s_px[sy + 3][sx + 3];
+                const int c = sp[0];
+                const int p0 = sp[3 * PW], p4 = sp[3], p8 = sp[-3 * PW], p12 = sp[-3];
+                const int hi = c + thr, lo = c - thr;
+                const bool b0 = p0 > hi, b4 = p4 > hi, b8 = p8 > hi, b12 = p12 > hi;
+                const bool k0 = p0 < lo, k4 = p4 < lo, k8 = p8 < lo, k12 = p12 < lo;
+                pass = (b0 && b4) || (b4 && b8) || (b8 && b12) || (b12 && b0) || (k0 && k4) || (k4 && k8) || (k8 && k12) || (k12 && k0);
             }
         }
-        s_sc[sy][sx] = (uint8_t)score;
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (m) {
+            int base = 0;
+            const int lane = threadIdx.x & 31;
+            if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+            base = __shfl_sync(FULL, base, 0);
+            if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+
+    // pass 2: full FAST score on the survivors only
+    const int n_list = s_n;
+    for (int j = threadIdx.x; j < n_list; j += blockDim.x) {
+        const int i = s_list[j];
+        const int sy = i / SW, sx = i - sy * SW;
+        const int s = fast_score(&s_px[sy + 3][sx + 3], PW);
+        if (s > thr) s_sc[sy][sx] = (uint8_t)(s - 1);
     }
     __syncthreads();
 
@@ -276,7 +301,7 @@ __global__ void __launch_bounds__(256) select_kernel(const Geo* __restrict__ gp,
 __global__ void __launch_bounds__(256) scan_kernel(const int32_t* __restrict__ sel_cnt, int n_img, int nlevels,
                                                    int32_t* __restrict__ kp_off, int32_t* __restrict__ frame_off,
                                                    int32_t* __restrict__ frame_nkp, const int32_t* __restrict__ flags,
-                                                   int32_t* __restrict__ h_out) {
+                                                   int32_t* __restrict__ h_out, int32_t* __restrict__ frame_nkp2) {
     __shared__ int s_tot[1024];
     const int tid = threadIdx.x;
     for (int f = tid; f < n_img; f += blockDim.x) {
@@ -284,6 +309,7 @@ __global__ void __launch_bounds__(256) scan_kernel(const int32_t* __restrict__ s
         for (int l = 0; l < nlevels; ++l) t += sel_cnt[f * nlevels + l];
         s_tot[f] = t;
         frame_nkp[f] = t;
+        if (frame_nkp2) frame_nkp2[f] = t;
     }
     __syncthreads();
     if (tid == 0) {
@@ -308,7 +334,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp
                                                       const int32_t* __restrict__ sel_cnt,
                                                       const int32_t* __restrict__ kp_off, uint32_t* __restrict__ kp_src,
                                                       int32_t* __restrict__ q_frame, int32_t* __restrict__ kp_i,
-                                                      size_t kp_cap) {
+                                                      size_t kp_cap, int32_t* __restrict__ q_frame2, int frame_base, size_t cap2) {
     const Geo& g = *gp;
     const int l = blockIdx.x, img = blockIdx.y;
     const OrbLevelGeom L = g.lv[l];
@@ -321,6 +347,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp
         kp_src[2 * o] = v;
         kp_src[2 * o + 1] = ((uint32_t)img << 8) | (uint32_t)l;
         q_frame[o] = img;
+        if (q_frame2 && o < cap2) q_frame2[o] = frame_base + img;
         reinterpret_cast<int4*>(kp_i)[o] = make_int4((int)(v & 0xFFF), (int)((v >> 12) & 0xFFF), l, (int)(v >> 24));
     }
 }
@@ -331,9 +358,10 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp
 // acc); round-half-even, saturate) -- SURVEY A.7.
 __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
                                                    const Geo* __restrict__ gp) {
-    constexpr int PW = TILE_W + 8, PH = TILE_H + 6;  // 3-px halo (PW padded to a multiple of 4)
-    __shared__ uint8_t s_px[PH][PW];
-    __shared__ float s_row[PH][TILE_W + 1];
+    constexpr int PH = TILE_H + 6;            // 3-px halo above and below
+    constexpr int PWW = (TILE_W + 8) / 4;     // 18 words per row: columns tx0-4 .. tx0+67 (the filter needs tx0-3 .. tx0+66)
+    __shared__ uint32_t s_px[PH][PWW];
+    __shared__ float4 s_row[PH][TILE_W / 4];
 
     const Geo& g = *gp;
     int l = 0;
@@ -345,38 +373,71 @@ __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ p
     const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
     uint8_t* dst = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
 
-    for (int i = threadIdx.x; i < PH * (TILE_W + 6); i += blockDim.x) {
-        const int py = i / (TILE_W + 6), px = i - py * (TILE_W + 6);
-        const int gx = reflect101(tx0 + px - 3, L.w), gy = reflect101(ty0 + py - 3, L.h);
-        s_px[py][px] = src[(size_t)gy * L.pitch + gx];
+    // tile load, 4 pixels per thread and step: whole words where they lie inside the image, reflected bytes at the borders
+    for (int i = threadIdx.x; i < PH * PWW; i += blockDim.x) {
+        const int py = i / PWW, pw = i - py * PWW;
+        const int gx = tx0 - 4 + 4 * pw, gy = reflect101(ty0 + py - 3, L.h);
+        const uint8_t* row = src + (size_t)gy * L.pitch;
+        uint32_t w;
+        if (gx >= 0 && gx + 3 < L.w) {
+            w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+        } else {
+            w = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
+                ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
+        }
+        s_px[py][pw] = w;
     }
     __syncthreads();
     // getGaussianKernel(7, 2, CV_32F) as exact bit patterns
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
-    for (int i = threadIdx.x; i < PH * TILE_W; i += blockDim.x) {
-        const int py = i / TILE_W, x = i - py * TILE_W;
-        const uint8_t* p = &s_px[py][x];
-        float acc = __fmul_rn(k0, (float)p[0]);
-        acc = __fmaf_rn(k1, (float)p[1], acc);
-        acc = __fmaf_rn(k2, (float)p[2], acc);
-        acc = __fmaf_rn(k3, (float)p[3], acc);
-        acc = __fmaf_rn(k2, (float)p[4], acc);
-        acc = __fmaf_rn(k1, (float)p[5], acc);
-        acc = __fmaf_rn(k0, (float)p[6], acc);
-        s_row[py][x] = acc;
+    // row pass: 4 outputs per thread from 3 words (12 pixels: outputs x..x+3 use smem columns x+1 .. x+10)
+    for (int i = threadIdx.x; i < PH * (TILE_W / 4); i += blockDim.x) {
+        const int py = i / (TILE_W / 4), x4 = i - py * (TILE_W / 4);
+        const uint32_t w0 = s_px[py][x4], w1 = s_px[py][x4 + 1], w2 = s_px[py][x4 + 2];
+        float p[12];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            p[b] = (float)((w0 >> (8 * b)) & 255u);
+            p[4 + b] = (float)((w1 >> (8 * b)) & 255u);
+            p[8 + b] = (float)((w2 >> (8 * b)) & 255u);
+        }
+        float o[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float acc = __fmul_rn(k0, p[b + 1]);
+            acc = __fmaf_rn(k1, p[b + 2], acc);
+            acc = __fmaf_rn(k2, p[b + 3], acc);
+            acc = __fmaf_rn(k3, p[b + 4], acc);
+            acc = __fmaf_rn(k2, p[b + 5], acc);
+            acc = __fmaf_rn(k1, p[b + 6], acc);
+            acc = __fmaf_rn(k0, p[b + 7], acc);
+            o[b] = acc;
+        }
+        s_row[py][x4] = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < TILE_H * TILE_W; i += blockDim.x) {
-        const int y = i / TILE_W, x = i - y * TILE_W;
-        const int gx = tx0 + x, gy = ty0 + y;
+    // column pass: 4 outputs per thread, one 32-bit store (bytes beyond the level width stay inside the row padding)
+    for (int i = threadIdx.x; i < TILE_H * (TILE_W / 4); i += blockDim.x) {
+        const int y = i / (TILE_W / 4), x4 = i - y * (TILE_W / 4);
+        const int gx = tx0 + 4 * x4, gy = ty0 + y;
         if (gx >= L.w || gy >= L.h) continue;
-        float acc = __fmul_rn(k3, s_row[y + 3][x]);
-        acc = __fmaf_rn(k2, __fadd_rn(s_row[y + 4][x], s_row[y + 2][x]), acc);
-        acc = __fmaf_rn(k1, __fadd_rn(s_row[y + 5][x], s_row[y + 1][x]), acc);
-        acc = __fmaf_rn(k0, __fadd_rn(s_row[y + 6][x], s_row[y][x]), acc);
-        int v = __float2int_rn(acc);
-        dst[(size_t)gy * L.pitch + gx] = (uint8_t)min(max(v, 0), 255);
+        const float4 r0 = s_row[y][x4], r1 = s_row[y + 1][x4], r2 = s_row[y + 2][x4], r3 = s_row[y + 3][x4], r4 = s_row[y + 4][x4],
+                     r5 = s_row[y + 5][x4], r6 = s_row[y + 6][x4];
+        const float c0[4] = {r0.x, r0.y, r0.z, r0.w}, c1[4] = {r1.x, r1.y, r1.z, r1.w}, c2[4] = {r2.x, r2.y, r2.z, r2.w},
+                    c3[4] = {r3.x, r3.y, r3.z, r3.w}, c4[4] = {r4.x, r4.y, r4.z, r4.w}, c5[4] = {r5.x, r5.y, r5.z, r5.w},
+                    c6[4] = {r6.x, r6.y, r6.z, r6.w};
+        uint32_t out = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float acc = __fmul_rn(k3, c3[b]);
+            acc = __fmaf_rn(k2, __fadd_rn(c4[b], c2[b]), acc);
+            acc = __fmaf_rn(k1, __fadd_rn(c5[b], c1[b]), acc);
+            acc = __fmaf_rn(k0, __fadd_rn(c6[b], c0[b]), acc);
+            const int v = __float2int_rn(acc);
+            out |= (uint32_t)min(max(v, 0), 255) << (8 * b);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
     }
 }
 
@@ -604,7 +665,7 @@ OrbExtractor::~OrbExtractor() {
 }
 
 int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
-                      int* launches) {
+                      int* launches, const Sink* sink) {
     if (n < 1 || n > batch_cap_) throw ArgError("batch size out of range");
     if (channels != 1 && channels != 3) throw ArgError("channels must be 1 or 3");
     const int L = cfg_.nlevels;
@@ -635,9 +696,10 @@ int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stri
     }
     int32_t* d_hout = nullptr;
     SLIDEO_CUDA(cudaHostGetDevicePointer(&d_hout, h_pinned_, 0));
-    scan_kernel<<<1, 256, 0, stream>>>(d_sel_cnt_, n, L, d_kp_off_, d_frame_off_, d_frame_nkp_, d_flags_, d_hout);
+    scan_kernel<<<1, 256, 0, stream>>>(d_sel_cnt_, n, L, d_kp_off_, d_frame_off_, d_frame_nkp_, d_flags_, d_hout, sink ? sink->frame_nkp : nullptr);
     ++nl;
-    scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_);
+    scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_,
+                                                   sink ? sink->q_frame : nullptr, sink ? sink->frame_base : 0, sink ? sink->cap : 0);
     ++nl;
     blur_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, d_blur_, g);
     ++nl;
@@ -648,8 +710,10 @@ int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stri
     if (flags & 1) throw CapacityError("FAST candidate capacity exceeded on at least one image");
     if (flags & 2) throw CapacityError("selected-keypoint capacity exceeded on at least one image");
     if ((size_t)total > kp_cap_) throw CapacityError("keypoint capacity exceeded");
+    if (sink && (size_t)total > sink->cap) throw CapacityError("descriptor sink capacity exceeded");
     if (total > 0) {
-        describe_kernel<<<cdiv(total, 8), 256, 0, stream>>>(d_pyr_, d_blur_, g, d_kp_src_, total, d_pattern_, d_kp_f_, d_desc_);
+        describe_kernel<<<cdiv(total, 8), 256, 0, stream>>>(d_pyr_, d_blur_, g, d_kp_src_, total, d_pattern_, d_kp_f_,
+                                                           sink ? sink->desc : d_desc_);
         ++nl;
         SLIDEO_CUDA(cudaGetLastError());
     }

@@ -48,8 +48,18 @@ public:
 
     // Runs the whole extractor on n device images (channels 1 or 3).  Returns the total keypoint count of the
     // batch (one small D2H + stream sync after the selection stage).  Throws CapacityError on overflow.
+    // `sink` (optional) redirects the per-keypoint outputs a matcher needs into caller-owned arrays, so that several
+    // batches can be appended back to back: descriptors to sink->desc, the frame of each keypoint (+ frame_base) to
+    // sink->q_frame, the per-frame keypoint counts to sink->frame_nkp.
+    struct Sink {
+        uint8_t* desc;       // [.. x 32], this batch starts at element 0
+        int32_t* q_frame;    // [..]
+        int32_t* frame_nkp;  // [n]
+        int frame_base;
+        size_t cap;          // keypoints the arrays can hold
+    };
     int run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
-            int* launches);
+            int* launches, const Sink* sink = nullptr);
 
     // results of the last run (device pointers; canonical order frame, octave, y, x)
     const uint8_t* d_desc() const { return d_desc_; }          // total x 32
