@@ -57,7 +57,7 @@ thread_local std::string g_create_error;
 struct slideo_b200_ctx {
     slideo_b200_config cfg{};
     int device = 0, num_sms = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, knn_stream = nullptr;   // extraction | uploads | K8 of the frame path
     mutable std::string err;
 
     // ---- page pool --------------------------------------------------------------------------------------
@@ -89,6 +89,7 @@ struct slideo_b200_ctx {
     int32_t* h_results = nullptr;        // pinned, max_batch x 3 x 2
     size_t h_results_cap = 0;
     cudaEvent_t ev_copy[N_STAGING] = {}, ev_free[N_STAGING] = {};
+    cudaEvent_t ev_detect = nullptr;     // extraction of everything appended to the query stream so far is done
 
     // ---- kept matches of the last match call -------------------------------------------------------------
     std::vector<uint32_t> kept_keys;     // total_q x k
@@ -104,6 +105,7 @@ struct slideo_b200_ctx {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (knn_stream) cudaStreamSynchronize(knn_stream);
         extractors.clear();
         for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto& e : ev_free_list) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -114,6 +116,8 @@ struct slideo_b200_ctx {
         if (h_results) cudaFreeHost(h_results);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (knn_stream) cudaStreamDestroy(knn_stream);
+        if (ev_detect) cudaEventDestroy(ev_detect);
     }
 
     // -------------------------------------------------------------------------------------------------------
@@ -225,14 +229,15 @@ struct slideo_b200_ctx {
         h_results_cap = n;
     }
 
-    void keep_batch_keys(int nq, const std::vector<int32_t>& frame_off_local) {
+    void keep_batch_keys(int nq, const std::vector<int32_t>& frame_off_local, cudaStream_t st = nullptr) {
+        if (!st) st = stream;
         const size_t base = kept_keys.size();
         kept_keys.resize(base + (size_t)nq * cfg.knn_k);
         if (nq > 0)
-            SLIDEO_CUDA(cudaMemcpyAsync(kept_keys.data() + base, d_keys.p, (size_t)nq * cfg.knn_k * 4, cudaMemcpyDeviceToHost, stream));
+            SLIDEO_CUDA(cudaMemcpyAsync(kept_keys.data() + base, d_keys.p, (size_t)nq * cfg.knn_k * 4, cudaMemcpyDeviceToHost, st));
         const int32_t q0 = kept_frame_off.back();
         for (size_t i = 1; i < frame_off_local.size(); ++i) kept_frame_off.push_back(q0 + frame_off_local[i]);
-        SLIDEO_CUDA(cudaStreamSynchronize(stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(st));
     }
 
     // ---- the per-frame hot path, decoupled: detection appends descriptors of many batches to one query stream, K8 then
@@ -247,6 +252,7 @@ struct slideo_b200_ctx {
     size_t kp_per_frame_cap(int w, int h) { return extractor(w, h, cfg.max_batch).kp_cap() / (size_t)cfg.max_batch; }
 
     void stream_begin(int n_frames, int w, int h) {
+        SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));   // K8 of a previous stream no longer reads the buffers reused below
         qs_cap = (size_t)n_frames * kp_per_frame_cap(w, h);
         d_qs_desc.reserve(qs_cap * 32 + 64);
         d_qs_frame.reserve(qs_cap + 64);
@@ -258,7 +264,7 @@ struct slideo_b200_ctx {
         d_votes.reserve((size_t)n_frames * np);
         d_results.reserve((size_t)n_frames * 3);
         if (cfg.keep_matches) d_keys.reserve(qs_cap * cfg.knn_k);
-        SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)n_frames * np * 4, stream));
+        SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)n_frames * np * 4, knn_stream));
     }
     // K1-K7 on nb device-resident frames, appended to the query stream
     void stream_detect(const uint8_t* d_src, int nb, int w, int h, int stride, size_t frame_stride) {
@@ -269,6 +275,7 @@ struct slideo_b200_ctx {
         int nl = 0;
         const int total = ex.run(d_src, nb, stride, frame_stride, 3, stream, &nl, &sink);
         end_timing(t, stream);
+        SLIDEO_CUDA(cudaEventRecord(ev_detect, stream));
         tm.kernel_launches += nl;
         qs_total += total;
         qs_frames += nb;
@@ -277,21 +284,27 @@ struct slideo_b200_ctx {
     // K8 + K9 over the part of the stream that is ready: whole chunks of (resident CTAs x tile) queries while detection is
     // still appending (flush = false), everything that is left at the end (flush = true)
     int qs_matched = 0;
+    static constexpr int FRAME_PATH_CTAS = 3;   // K8 CTAs per SM in the frame path: the 4th slot's registers are left to K1-K7
     void stream_match_ready(bool flush) {
         const bool want_keys = cfg.keep_matches != 0;
-        const int chunk = num_sms * 4 * 512;   // one full wave of K8 tiles (QR = 4): every CTA owns exactly one tile
+        const int chunk = num_sms * FRAME_PATH_CTAS * KNN_TILE_QUERIES;   // one full wave of K8 tiles: every CTA owns one tile
         VoteArgs va{nullptr, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio};
+        bool waited = false;
         while (qs_total - qs_matched >= chunk || (flush && qs_total > qs_matched)) {
+            if (!waited) {
+                SLIDEO_CUDA(cudaStreamWaitEvent(knn_stream, ev_detect, 0));   // the queries of this chunk have been written
+                waited = true;
+            }
             const int q0 = qs_matched, nq = std::min(chunk, qs_total - q0);
-            KnnPlan plan = knn_hamming_plan(nq, nt, cfg.knn_k, num_sms);
+            KnnPlan plan = knn_hamming_plan(nq, nt, cfg.knn_k, num_sms, FRAME_PATH_CTAS);
             d_scratch.reserve(plan.scratch_bytes / 4);
             if (plan.partial_bytes) d_partial.reserve(plan.partial_bytes / 4);
             va.q_frame = d_qs_frame.p + q0;
-            EventPair t = begin_timing(1, stream);
+            EventPair t = begin_timing(1, knn_stream);
             int nl = 0;
             knn_hamming_launch(plan, d_qs_desc.p + (size_t)q0 * 32, d_pool48.p, want_keys ? d_keys.p + (size_t)q0 * cfg.knn_k : nullptr,
-                               d_scratch.p, d_partial.p, &va, stream, &nl);
-            end_timing(t, stream);
+                               d_scratch.p, d_partial.p, &va, knn_stream, &nl);
+            end_timing(t, knn_stream);
             tm.knn_launches += 1;
             tm.kernel_launches += nl;
             tm.knn_pairs += (int64_t)nq * nt;
@@ -301,15 +314,16 @@ struct slideo_b200_ctx {
     // per-frame argmax + results of the finished stream into h_out
     void stream_finish(int32_t* h_out) {
         stream_match_ready(true);
-        vote_argmax_launch(d_votes.p, qs_frames, n_pages, d_qs_nkp.p, d_results.p, stream);
+        SLIDEO_CUDA(cudaStreamWaitEvent(knn_stream, ev_detect, 0));   // frame_nkp of the last batch (and the empty-stream case)
+        vote_argmax_launch(d_votes.p, qs_frames, n_pages, d_qs_nkp.p, d_results.p, knn_stream);
         tm.kernel_launches += 1;
-        SLIDEO_CUDA(cudaMemcpyAsync(h_out, d_results.p, (size_t)qs_frames * 3 * 4, cudaMemcpyDeviceToHost, stream));
+        SLIDEO_CUDA(cudaMemcpyAsync(h_out, d_results.p, (size_t)qs_frames * 3 * 4, cudaMemcpyDeviceToHost, knn_stream));
         if (cfg.keep_matches) {
             std::vector<int32_t> nkp((size_t)qs_frames), fo(1, 0);
-            SLIDEO_CUDA(cudaMemcpyAsync(nkp.data(), d_qs_nkp.p, (size_t)qs_frames * 4, cudaMemcpyDeviceToHost, stream));
-            SLIDEO_CUDA(cudaStreamSynchronize(stream));
+            SLIDEO_CUDA(cudaMemcpyAsync(nkp.data(), d_qs_nkp.p, (size_t)qs_frames * 4, cudaMemcpyDeviceToHost, knn_stream));
+            SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
             for (int f = 0; f < qs_frames; ++f) fo.push_back(fo.back() + nkp[f]);
-            keep_batch_keys(qs_total, fo);
+            keep_batch_keys(qs_total, fo, knn_stream);
         }
     }
 
@@ -432,7 +446,7 @@ int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_
         arg(cfg->scale_factor > 1.0f && cfg->scale_factor <= 2.0f, "scale_factor must be in (1, 2]");
         arg(cfg->edge_threshold >= 3 && cfg->edge_threshold < 1024, "edge_threshold out of range");
         arg(cfg->patch_size >= 2 && cfg->patch_size / 2 <= 38, "patch_size out of range");
-        arg(cfg->fast_threshold >= 1 && cfg->fast_threshold < 255, "fast_threshold out of range");
+        arg(cfg->fast_threshold >= 1 && cfg->fast_threshold <= 126, "fast_threshold must be in 1..126");
         arg(cfg->vote_ratio >= 1.0f && cfg->vote_ratio < 16.f, "vote_ratio out of range");
         arg(cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256 || cfg->descriptor_kind == SLIDEO_B200_DESC_SIFT128,
             "unknown descriptor_kind");
@@ -456,6 +470,8 @@ int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_
         c->desc_bytes = cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256 ? 32 : 512;
         SLIDEO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         SLIDEO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        SLIDEO_CUDA(cudaStreamCreateWithFlags(&c->knn_stream, cudaStreamNonBlocking));
+        SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_detect, cudaEventDisableTiming));
         for (int i = 0; i < slideo_b200_ctx::N_STAGING; ++i) {
             SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
             SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
@@ -673,7 +689,8 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
             }
             ctx->stream_finish(ctx->h_results + (size_t)s0 * 3);
         }
-        ctx->end_timing(t_total, ctx->stream);
+        ctx->end_timing(t_total, ctx->knn_stream);
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->knn_stream));
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
         ctx->collect_timings();
@@ -709,7 +726,8 @@ int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d
             }
             ctx->stream_finish(ctx->h_results + (size_t)s0 * 3);
         }
-        ctx->end_timing(t_total, ctx->stream);
+        ctx->end_timing(t_total, ctx->knn_stream);
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->knn_stream));
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->collect_timings();
         for (int i = 0; i < n; ++i) {
@@ -1058,6 +1076,7 @@ int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, 
     return guarded(ctx, [&] {
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->knn_stream));
         ctx->collect_timings();
         if (out) *out = ctx->tm;
         if (reset) ctx->tm = slideo_b200_timings{};

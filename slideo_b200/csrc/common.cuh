@@ -58,7 +58,10 @@ struct VoteArgs {            // fused K9: vote straight out of K8's final sort (
     float ratio;
 };
 
-KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms);
+// ctas_per_sm: resident K8 CTAs per SM (1..4, 0 = 4).  3 leaves a quarter of the register file to kernels of another
+// stream (the frame path overlaps ORB extraction with K8 that way) at a ~4 % cost in K8 throughput.
+KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms, int ctas_per_sm = 0);
+constexpr int KNN_TILE_QUERIES = 512;   // queries per K8 tile at 4 queries per thread
 // 32 B descriptors -> the 48 B rows K8 streams ({w0..w7, w0^w1^w2, w3^w4^w5, w0^..^w6, 0}); once per pool
 size_t knn_pool_expanded_bytes(int nt);
 void knn_pool_expand_launch(const void* d_pool32, int nt, void* d_pool48, cudaStream_t stream);

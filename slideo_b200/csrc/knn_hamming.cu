@@ -477,12 +477,14 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) microbench_mix_k
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms) {
+KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms, int ctas_per_sm_req) {
     KnnPlan p;
     p.nq = nq; p.nt = nt; p.k = k;
     // queries per thread: 8 amortises the pooled-row loads best, 4 gives twice as many tiles -> fewer, longer stream-K
     // segments per tile (every segment re-warms its selection thresholds from scratch)
-    const long long target0 = (long long)num_sms * KNN_CTAS_PER_SM;
+    int ctas_per_sm = ctas_per_sm_req >= 1 && ctas_per_sm_req <= KNN_CTAS_PER_SM ? ctas_per_sm_req : KNN_CTAS_PER_SM;
+    if (const char* e = getenv("SLIDEO_KNN_CTAS")) { if (atoi(e) >= 1 && atoi(e) <= KNN_CTAS_PER_SM) ctas_per_sm = atoi(e); }
+    const long long target0 = (long long)num_sms * ctas_per_sm;
     p.qr = (long long)cdiv(nq, KNN_THREADS * 8) * 2 >= target0 * 3 ? 8 : 4;
     if (const char* e = getenv("SLIDEO_KNN_QR")) { if (atoi(e) == 4 || atoi(e) == 8) p.qr = atoi(e); }
     const int KNN_TILE = KNN_THREADS * p.qr;
@@ -490,7 +492,7 @@ KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms) {
     p.n_tiles = cdiv(nq, KNN_TILE);
     p.n_chunks = cdiv(nt > 0 ? nt : 1, KNN_CHUNK);
     p.total_units = (long long)p.n_tiles * p.n_chunks;
-    const long long target = (long long)num_sms * KNN_CTAS_PER_SM;
+    const long long target = target0;
     p.grid = (int)(p.total_units < target ? p.total_units : target);
     if (p.grid < 1) p.grid = 1;
     p.max_seg = 1;

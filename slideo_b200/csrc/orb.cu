@@ -135,13 +135,20 @@ __device__ __forceinline__ int fast_score(const uint8_t* sp, int pitch) {
     return best;
 }
 
+// byte flags (0x80 per byte) of the bytes of x that are > thr, for thr < 127:  k127 = (127 - thr) * 0x01010101
+__device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k127) {
+    return (((x & 0x7F7F7F7Fu) + k127) | x) & 0x80808080u;
+}
+
 __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ pyr, const Geo* __restrict__ gp,
                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
-    constexpr int PW = TILE_W + 8, PH = TILE_H + 8;   // pixel tile incl. 4-px halo (72 x 40, rows are 18 words)
-    constexpr int SW = TILE_W + 2, SH = TILE_H + 2;   // score tile incl. 1-px halo
-    __shared__ __align__(16) uint8_t s_px[PH][PW];
-    __shared__ uint8_t s_sc[SH][SW + 2];
-    __shared__ uint16_t s_list[SH * SW];               // positions that pass the cheap necessary test
+    // pixel tile: 40 rows x 20 words = columns tx0-8 .. tx0+71; score tile: 34 rows x 72 columns = tx0-4 .. tx0+67, i.e. the
+    // 64 x 32 pixels of the tile plus the halo the 3x3 NMS needs, rounded to whole words so every thread handles 4 pixels
+    constexpr int PH = TILE_H + 8, PWW = (TILE_W + 16) / 4, PWB = PWW * 4;
+    constexpr int SH = TILE_H + 2, SWW = (TILE_W + 8) / 4, SWB = SWW * 4;
+    __shared__ __align__(16) uint32_t s_px[PH][PWW];
+    __shared__ __align__(16) uint8_t s_sc[SH][SWB + 8];
+    __shared__ uint16_t s_list[SH * SWB];              // (row << 7 | col) of the positions that pass the cheap necessary test
     __shared__ int s_n;
 
     const Geo& g = *gp;
@@ -154,70 +161,73 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ p
     const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
 
     if (threadIdx.x == 0) s_n = 0;
-    // tile load, one 32-bit word (4 pixels) per thread and step: tx0 - 4 and the level pitch are multiples of 4, and the
-    // level rows are padded to 16 B inside the allocation, so whole words inside [0, pitch) are always readable
-    for (int i = threadIdx.x; i < PH * (PW / 4); i += blockDim.x) {
-        const int py = i / (PW / 4), pw = i - py * (PW / 4);
-        const int gx = tx0 + pw * 4 - 4, gy = ty0 + py - 4;
+    // tile load, one 32-bit word (4 pixels) per thread and step: tx0 and the level pitch are multiples of 4 and the level
+    // rows are padded to 16 B inside the allocation, so whole words inside [0, pitch) are always readable
+    for (int i = threadIdx.x; i < PH * PWW; i += blockDim.x) {
+        const int py = i / PWW, pw = i - py * PWW;
+        const int gx = tx0 - 8 + pw * 4, gy = ty0 - 4 + py;
         uint32_t w = 0;
         if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch) w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gy * L.pitch + gx));
-        reinterpret_cast<uint32_t*>(&s_px[py][0])[pw] = w;
+        s_px[py][pw] = w;
     }
+    for (int i = threadIdx.x; i < SH * (SWB + 8) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(&s_sc[0][0])[i] = 0;
     __syncthreads();
 
-    // pass 1: the exact necessary condition (any 9-arc contains two adjacent compass points) on every position;
-    // survivors are compacted into s_list so that the expensive score runs on dense warps
+    // pass 1, 4 pixels per thread: a corner needs two ADJACENT compass points (N,E,S,W at distance 3) on the same side of the
+    // centre by more than thr (any 9-arc contains two adjacent compass points); the test below drops the "same side"
+    // part -- (|N-c| > thr or |S-c| > thr) and (|E-c| > thr or |W-c| > thr) -- so it is a superset, evaluated with
+    // VABSDIFF4 on packed bytes.  Survivors are compacted into s_list so that the exact score runs on dense warps.
     const int thr = g.fast_thr;
-    for (int i0 = 0; i0 < SH * SW; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        bool pass = false;
-        if (i < SH * SW) {
-            const int sy = i / SW, sx = i - sy * SW;
-            const int gx = tx0 + sx - 1, gy = ty0 + sy - 1;
-            s_sc[sy][sx] = 0;
-            if (gx >= 3 && gx < L.w - 3 && gy >= 3 && gy < L.h - 3) {
-                const uint8_t* sp = &s_px[sy + 3][sx + 3];
-                const int c = sp[0];
-                const int p0 = sp[3 * PW], p4 = sp[3], p8 = sp[-3 * PW], p12 = sp[-3];
-                const int hi = c + thr, lo = c - thr;
-                const bool b0 = p0 > hi, b4 = p4 > hi, b8 = p8 > hi, b12 = p12 > hi;
-                const bool k0 = p0 < lo, k4 = p4 < lo, k8 = p8 < lo, k12 = p12 < lo;
-                pass = (b0 && b4) || (b4 && b8) || (b8 && b12) || (b12 && b0) || (k0 && k4) || (k4 && k8) || (k8 && k12) || (k12 && k0);
+    const uint32_t k127 = (uint32_t)(127 - thr) * 0x01010101u;
+    const bool interior = tx0 - 4 >= 3 && tx0 + TILE_W + 4 <= L.w - 3 && ty0 - 1 >= 3 && ty0 + TILE_H + 1 <= L.h - 3;
+    for (int i = threadIdx.x; i < SH * SWW; i += blockDim.x) {
+        const int r = i / SWW, wq = i - r * SWW + 1;      // score row r <-> pixel row r + 3; score word wq - 1 <-> pixel word wq
+        const uint32_t C = s_px[r + 3][wq], Wm = s_px[r + 3][wq - 1], Wp = s_px[r + 3][wq + 1], U = s_px[r][wq], D = s_px[r + 6][wq];
+        const uint32_t Lw = __byte_perm(Wm, C, 0x4321), Rw = __byte_perm(C, Wp, 0x6543);
+        uint32_t f = (bytes_gt(__vabsdiffu4(U, C), k127) | bytes_gt(__vabsdiffu4(D, C), k127)) &
+                     (bytes_gt(__vabsdiffu4(Lw, C), k127) | bytes_gt(__vabsdiffu4(Rw, C), k127));
+        if (f != 0 && !interior) {   // FAST is only defined 3 pixels inside the level
+            const int gy = ty0 - 1 + r;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int gx = tx0 - 8 + wq * 4 + b;
+                if (!(gx >= 3 && gx < L.w - 3 && gy >= 3 && gy < L.h - 3)) f &= ~(0x80u << (8 * b));
             }
         }
-        const unsigned m = __ballot_sync(FULL, pass);
-        if (m) {
-            int base = 0;
-            const int lane = threadIdx.x & 31;
-            if (lane == 0) base = atomicAdd(&s_n, __popc(m));
-            base = __shfl_sync(FULL, base, 0);
-            if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        if (f != 0) {
+            int pos = atomicAdd(&s_n, __popc(f));
+            const int c0 = (wq - 1) * 4;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (f & (0x80u << (8 * b))) s_list[pos++] = (uint16_t)((r << 7) | (c0 + b));
         }
     }
     __syncthreads();
 
-    // pass 2: full FAST score on the survivors only
+    // pass 2: exact FAST score on the survivors only
     const int n_list = s_n;
     for (int j = threadIdx.x; j < n_list; j += blockDim.x) {
-        const int i = s_list[j];
-        const int sy = i / SW, sx = i - sy * SW;
-        const int s = fast_score(&s_px[sy + 3][sx + 3], PW);
-        if (s > thr) s_sc[sy][sx] = (uint8_t)(s - 1);
+        const int code = s_list[j], r = code >> 7, c = code & 127;
+        const uint8_t* sp = reinterpret_cast<const uint8_t*>(&s_px[r + 3][0]) + (c + 4);
+        const int sc = fast_score(sp, PWB);
+        if (sc > thr) s_sc[r][c] = (uint8_t)(sc - 1);
     }
     __syncthreads();
 
+    // pass 3: 3x3 non-maximum suppression + border filter, again only where a score can be non-zero
     const int e = g.edge;
-    for (int i = threadIdx.x; i < TILE_H * TILE_W; i += blockDim.x) {
-        const int y = i / TILE_W, x = i - y * TILE_W;
-        const int s = s_sc[y + 1][x + 1];
-        if (s == 0) continue;
-        const int gx = tx0 + x, gy = ty0 + y;
+    for (int j = threadIdx.x; j < n_list; j += blockDim.x) {
+        const int code = s_list[j], r = code >> 7, c = code & 127;
+        if (r < 1 || r > TILE_H || c < 4 || c >= TILE_W + 4) continue;   // halo positions belong to the neighbouring tiles
+        const int sc = s_sc[r][c];
+        if (sc == 0) continue;
+        const int gx = tx0 - 4 + c, gy = ty0 - 1 + r;
         if (gx < e || gx >= L.w - e || gy < e || gy >= L.h - e) continue;
-        if (s > s_sc[y][x] && s > s_sc[y][x + 1] && s > s_sc[y][x + 2] && s > s_sc[y + 1][x] && s > s_sc[y + 1][x + 2] &&
-            s > s_sc[y + 2][x] && s > s_sc[y + 2][x + 1] && s > s_sc[y + 2][x + 2]) {
+        if (sc > s_sc[r - 1][c - 1] && sc > s_sc[r - 1][c] && sc > s_sc[r - 1][c + 1] && sc > s_sc[r][c - 1] && sc > s_sc[r][c + 1] &&
+            sc > s_sc[r + 1][c - 1] && sc > s_sc[r + 1][c] && sc > s_sc[r + 1][c + 1]) {
             const int pos = atomicAdd(&cand_cnt[img * g.nlevels + l], 1);
             if (pos < L.cand_cap)
-                cand[(size_t)img * g.cand_img_words + L.cand_off + pos] = ((uint32_t)s << 24) | ((uint32_t)gy << 12) | (uint32_t)gx;
+                cand[(size_t)img * g.cand_img_words + L.cand_off + pos] = ((uint32_t)sc << 24) | ((uint32_t)gy << 12) | (uint32_t)gx;
         }
     }
 }
