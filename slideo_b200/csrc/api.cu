@@ -3,6 +3,8 @@
 // Host-side counterpart of the reference's orchestration in crates/matching-opencv/src/lib.rs:37-64 (page pool),
 // lib.rs:249-295 (per-frame path) and flann.rs:64-89 (matcher); all arithmetic runs in the CUDA kernels of
 // orb.cu / knn_hamming.cu / knn_l2.cu.  There is no CPU fallback: without a device every entry point fails.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -284,7 +286,7 @@ struct slideo_b200_ctx {
     // K8 + K9 over the part of the stream that is ready: whole chunks of (resident CTAs x tile) queries while detection is
     // still appending (flush = false), everything that is left at the end (flush = true)
     int qs_matched = 0;
-    static constexpr int FRAME_PATH_CTAS = 3;   // K8 CTAs per SM in the frame path: the 4th slot's registers are left to K1-K7
+    int FRAME_PATH_CTAS = getenv("SLIDEO_FRAME_CTAS") ? atoi(getenv("SLIDEO_FRAME_CTAS")) : 4;   // K8 CTAs per SM in the frame path (measured: 4 beats 3 + more K1-K7 overlap, profiles/r1_frame_ctas.txt)
     void stream_match_ready(bool flush) {
         const bool want_keys = cfg.keep_matches != 0;
         const int chunk = num_sms * FRAME_PATH_CTAS * KNN_TILE_QUERIES;   // one full wave of K8 tiles: every CTA owns one tile
