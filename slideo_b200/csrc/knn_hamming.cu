@@ -76,6 +76,12 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
     return r;
 }
+// integer multiply-add pinned to the FMA pipe (IMAD), also for multiplier 1
+__device__ __forceinline__ int imad(int a, int b, int c) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 constexpr int LUT_XOR3 = 0x96;  // a ^ b ^ c
 constexpr int LUT_MAJ = 0xE8;   // majority(a, b, c)
 constexpr int LUT_CARRY = 0xD4; // majority(a, b, a ^ b ^ c): carry of a full adder given two inputs and the sum
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
         // this thread's queries: words 0,1,3,4,7 individually + the three pre-xor-ed sums
         uint32_t q0[KNN_QR], q1[KNN_QR], q3[KNN_QR], q4[KNN_QR], q7[KNN_QR], q012[KNN_QR], q345[KNN_QR], q06[KNN_QR];
         uint32_t taud[KNN_QR];   // distance of the running k-th best (strict '<' admits a pair)
+        int ntaud2[KNN_QR];      // -2 * taud, the addend of the margin chain
         int cnt[KNN_QR];
 #pragma unroll
         for (int i = 0; i < KNN_QR; ++i) {
@@ -208,11 +215,14 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
             q345[i] = a.w ^ b.x ^ b.y;
             q06[i] = q012[i] ^ q345[i] ^ b.z;
             taud[i] = q < P.nq ? 512u : 0u;  // dummy queries never admit anything
+            ntaud2[i] = -2 * (int)taud[i];
             cnt[i] = 0;
         }
 
-        // distances of this thread's QR queries to one expanded pool row {a, b, e}
-        auto distances = [&](const uint4& a, const uint4& b, const uint4& e, uint32_t (&dist)[KNN_QR]) {
+        // margins of this thread's QR queries against one expanded pool row {a, b, e}: margin = 2 * (distance - taud), negative
+        // iff the pair beats the running k-th distance.  The sums run as integer multiply-adds (FMA pipe): the ALU pipe is
+        // the bottleneck and keeps only the 13 logic ops of the carry-save tree per pair.
+        auto margins = [&](const uint4& a, const uint4& b, const uint4& e, int (&mg)[KNN_QR]) {
 #pragma unroll
             for (int i = 0; i < KNN_QR; ++i) {
                 const uint32_t x0 = q0[i] ^ a.x, x1 = q1[i] ^ a.y;
@@ -226,7 +236,11 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
                 const uint32_t x7 = q7[i] ^ b.w;                    //                         (weight 1)
                 const uint32_t s5 = lop3<LUT_XOR3>(c1, c2, c3);     //                         (weight 2)
                 const uint32_t c5 = lop3<LUT_MAJ>(c1, c2, c3);      //                         (weight 4)
-                dist[i] = (uint32_t)__popc(s3) + (uint32_t)__popc(x7) + 2u * (uint32_t)__popc(s5) + 4u * (uint32_t)__popc(c5);
+                // 2 * (distance - taud): every multiplier differs from 1, so ptxas keeps the chain on the FMA pipe (IMAD)
+                int m = imad(__popc(x7), 2, ntaud2[i]);
+                m = imad(__popc(s3), 2, m);
+                m = imad(__popc(s5), 4, m);
+                mg[i] = imad(__popc(c5), 8, m);
             }
         };
 
@@ -263,6 +277,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
                 if (cnt[i] >= KNN_SLOTS - 1) {
                     cnt[i] = s_cnt[tid + i * KNN_THREADS];
                     taud[i] = s_taud[tid + i * KNN_THREADS];
+                    ntaud2[i] = -2 * (int)taud[i];
                 }
             }
         };
@@ -281,12 +296,12 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
 #pragma unroll 2
                 for (int r = 0; r < nb; ++r) {
                     const uint4* row = sp + 3 * (j0 + r);
-                    uint32_t dist[KNN_QR];
-                    distances(row[0], row[1], row[2], dist);
-                    bool hit = false;
+                    int mg[KNN_QR];
+                    margins(row[0], row[1], row[2], mg);
+                    int any = mg[0];
 #pragma unroll
-                    for (int i = 0; i < KNN_QR; ++i) hit |= dist[i] < taud[i];
-                    if (hit) mask |= 1u << r;
+                    for (int i = 1; i < KNN_QR; ++i) any |= mg[i];   // sign bit set iff some margin is negative
+                    if (any < 0) mask |= 1u << r;
                 }
                 // slow path (rare after the first few hundred rows of a segment): every lane revisits its own flagged
                 // rows, lowest first, and appends the survivors; buffers are compacted cooperatively when one fills up
@@ -296,13 +311,14 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) knn_hamming_kern
                         const int r = __ffs(mask) - 1;
                         mask &= mask - 1;
                         const uint4* row = sp + 3 * (j0 + r);
-                        uint32_t dist[KNN_QR];
-                        distances(row[0], row[1], row[2], dist);
+                        int mg[KNN_QR];
+                        margins(row[0], row[1], row[2], mg);
                         const uint32_t gidx = gbase + (uint32_t)(j0 + r);
 #pragma unroll
                         for (int i = 0; i < KNN_QR; ++i) {
-                            if (dist[i] < taud[i]) {
-                                my_scratch[(size_t)(tid + i * KNN_THREADS) * KNN_SLOTS + cnt[i]] = (dist[i] << KEY_IDX_BITS) | gidx;
+                            if (mg[i] < 0) {
+                                const uint32_t dist = (uint32_t)((mg[i] >> 1) + (int)taud[i]);
+                                my_scratch[(size_t)(tid + i * KNN_THREADS) * KNN_SLOTS + cnt[i]] = (dist << KEY_IDX_BITS) | gidx;
                                 ++cnt[i];
                                 full |= cnt[i] >= KNN_SLOTS - 1;
                             }
@@ -446,7 +462,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) microbench_mix_k
     uint4 e = make_uint4(seed * 23u, seed * 29u, seed * 31u, 0u);
     uint32_t hits = 0;
     for (int it = 0; it < iters; ++it) {
-        bool hit = false;
+        int any = 0;
 #pragma unroll
         for (int i = 0; i < KNN_QR; ++i) {
             const uint32_t x0 = q0[i] ^ a.x, x1 = q1[i] ^ a.y;
@@ -460,9 +476,12 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS_PER_SM) microbench_mix_k
             const uint32_t x7 = q7[i] ^ b.w;
             const uint32_t s5 = lop3<LUT_XOR3>(c1, c2, c3);
             const uint32_t c5 = lop3<LUT_MAJ>(c1, c2, c3);
-            const uint32_t dist = (uint32_t)__popc(s3) + (uint32_t)__popc(x7) + 2u * (uint32_t)__popc(s5) + 4u * (uint32_t)__popc(c5);
-            hit |= dist < best[i];
+            int m = imad(__popc(x7), 2, -2 * (int)best[i]);
+            m = imad(__popc(s3), 2, m);
+            m = imad(__popc(s5), 4, m);
+            any |= imad(__popc(c5), 8, m);
         }
+        const bool hit = any < 0;
         if (__any_sync(FULL, hit)) ++hits;   // data dependent, practically never taken after the first iterations
         if (hits > 1000000u) best[0] += 1u;
         // next "pooled row": a cheap dependent update (IMAD-class ops, amortised over QR pairs)
