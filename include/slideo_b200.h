@@ -65,7 +65,8 @@ typedef struct slideo_b200_config {
     int32_t descriptor_kind; /* slideo_b200_descriptor_kind */
     int32_t max_batch;       /* frames processed per internal batch (default 32) */
     int32_t keep_matches;    /* !=0: keep the k-NN rows of the last match call for slideo_b200_get_matches */
-    int32_t reserved[3];
+    int32_t geometric_verification; /* !=0: match_frames_* also runs the RANSAC gate (lib.rs:284-333), see slideo_b200_get_verification */
+    int32_t reserved[2];
 } slideo_b200_config;
 
 /* Hot-path output per frame: the head of the reference's ranking, lib.rs:268-295.
@@ -96,8 +97,24 @@ typedef struct slideo_b200_timings {
     int64_t kernel_launches; /* all kernel launches of the library */
     int64_t frames;          /* frames processed */
     float ms_total;          /* whole match_* calls, first enqueue to last result on the ctx stream */
-    float reserved0;
+    float ms_verify;         /* K12 geometric verification */
 } slideo_b200_timings;
+
+/* Geometric verification of one frame (lib.rs:284-333): the (<= 40) slides with most votes in
+ * ranking order (ties -> lower page index) with their RANSAC rating = inlier count of
+ * estimateAffinePartial2D(slide keypoints -> frame keypoints, RANSAC, 3.0, 2000, 0.99, 10) (image_utils.rs:45-60), and the
+ * (<= 10) survivors of `sort by rating; truncate(10); retain(rating > 50 && rating / best > 0.2)` in that order. */
+#define SLIDEO_B200_TOP_SLIDES 40
+#define SLIDEO_B200_TOP_RATED 10
+typedef struct slideo_b200_verify_result {
+    int32_t n_candidates;
+    int32_t n_survivors;
+    int32_t cand_page[SLIDEO_B200_TOP_SLIDES];
+    int32_t cand_votes[SLIDEO_B200_TOP_SLIDES];
+    int32_t cand_rating[SLIDEO_B200_TOP_SLIDES];
+    int32_t survivor_page[SLIDEO_B200_TOP_RATED];
+    int32_t survivor_rating[SLIDEO_B200_TOP_RATED];
+} slideo_b200_verify_result;
 
 typedef struct slideo_b200_ctx slideo_b200_ctx;
 
@@ -118,6 +135,9 @@ int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int3
                                    int32_t* out_n_keypoints);
 /* Appends a page whose descriptors were computed elsewhere (n x 32 bytes for ORB256, n x 128 floats for SIFT128). */
 int32_t slideo_b200_add_page_descriptors(slideo_b200_ctx* ctx, const void* desc, int32_t n);
+/* Like add_page_descriptors, plus the KeyPoint.pt of every descriptor (n x 2 floats, level-0 coordinates): needed by the
+ * geometric verification when the page features were extracted elsewhere.  ORB256 only. */
+int32_t slideo_b200_add_page_features(slideo_b200_ctx* ctx, const void* desc, const float* pt_xy, int32_t n);
 /* Concatenates the pages into the device-resident pool (flann.rs add + train; brute force has no index to build). */
 int32_t slideo_b200_finalize_pool(slideo_b200_ctx* ctx);
 int32_t slideo_b200_pool_info(const slideo_b200_ctx* ctx, int32_t* out_n_descriptors, int32_t* out_n_pages);
@@ -150,6 +170,10 @@ int32_t slideo_b200_match_descriptors(slideo_b200_ctx* ctx, const void* desc, co
  * each row ascending by (distance, pooled index) -- what FlannMatcher::knn_match returns (flann.rs:73-89). */
 int32_t slideo_b200_get_matches(slideo_b200_ctx* ctx, int32_t frame_i, slideo_b200_match* out, int32_t cap_rows,
                                 int32_t* out_rows);
+
+/* Verification records of frames [frame0, frame0 + n) of the last match_frames_* call (needs cfg.geometric_verification and
+ * pages added through add_page_gray8 / add_page_features). */
+int32_t slideo_b200_get_verification(slideo_b200_ctx* ctx, int32_t frame0, int32_t n, slideo_b200_verify_result* out);
 
 /* ---- stage-level entry points (parity tests, matcher sweeps) --------------------------------------------- */
 /* ORB::detectAndCompute (feature_extractor.rs:29-46) on one HOST image, channels = 1 (gray) or 3 (BGR).

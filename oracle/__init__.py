@@ -30,7 +30,7 @@ VOTE_RATIO = 1.05     # crates/matching-opencv/src/lib.rs:275
 def build() -> str:
     """Compile liboracle.so (gcc) if missing or stale."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c", "ransac_oracle.c")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -63,6 +63,12 @@ def lib() -> ctypes.CDLL:
         L.bf_knn_l2.argtypes = [c_f32p, ci, c_f32p, ci, ci, ci, c_i32p, c_f32p]
         L.bf_vote.argtypes = [c_i32p, c_f32p, ci, ci, c_i32p, ci, c_i32p]
         L.bf_vote.restype = ci
+        c_dp = ctypes.POINTER(ctypes.c_double)
+        L.ransac_affine_partial.argtypes = [c_f32p, c_f32p, ci, ctypes.c_double, ci, ctypes.c_double, ci, c_u8p, c_dp, c_i32p]
+        L.ransac_affine_partial.restype = ci
+        L.ransac_sample_sequence.argtypes = [ci, ci, c_i32p]
+        L.ransac_update_num_iters.argtypes = [ctypes.c_double, ctypes.c_double, ci, ci]
+        L.ransac_update_num_iters.restype = ci
         _LIB = L
     return _LIB
 
@@ -197,3 +203,53 @@ def match_frame(frame_desc: np.ndarray, page_descs, k: int = KNN_K):
     pool = np.concatenate([_u8(d).reshape(-1, 32) for d in page_descs], 0) if offs[-1] else np.zeros((0, 32), np.uint8)
     idx, dist = bf_knn_hamming(frame_desc, pool, k)
     return vote(idx, dist.astype(np.float32), offs)
+
+
+# ----------------------------------------------------------------------------- geometric verification (lib.rs:284-333)
+RANSAC_THRESHOLD, RANSAC_MAX_ITERS, RANSAC_CONFIDENCE = 3.0, 2000, 0.99   # image_utils.rs:52
+TOP_SLIDES, TOP_RATED, MIN_RATING, MIN_RATING_FRACTION = 40, 10, 50.0, 0.2  # lib.rs:295, 330, 333
+
+
+def ransac_affine_partial(pts_from: np.ndarray, pts_to: np.ndarray):
+    """cv::estimateAffinePartial2D(from, to, inliers, RANSAC, 3.0, 2000, 0.99, 10) -> (rating, mask, ransac_model[6], iters)."""
+    a = np.ascontiguousarray(pts_from, np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(pts_to, np.float32).reshape(-1, 2)
+    n = len(a)
+    mask = np.zeros(max(n, 1), np.uint8)
+    model = np.zeros(6, np.float64)
+    it = ctypes.c_int32()
+    good = lib().ransac_affine_partial(_p(a, ctypes.c_float), _p(b, ctypes.c_float), n, RANSAC_THRESHOLD, RANSAC_MAX_ITERS,
+                                       RANSAC_CONFIDENCE, 0, _p(mask, ctypes.c_uint8), _p(model, ctypes.c_double), ctypes.byref(it))
+    return good, mask[:n].copy(), model, it.value
+
+
+def verify_frame(idx: np.ndarray, dist: np.ndarray, page_offsets, frame_pts: np.ndarray, pool_pts: np.ndarray):
+    """The reference's ranking + geometric gate for one frame (lib.rs:268-333) on exact k-NN rows.
+
+    idx/dist: [nq, k] rows (oracle order); frame_pts [nq, 2], pool_pts [Nt, 2] keypoint coordinates (KeyPoint.pt).
+    Returns dict(cand=[(page, votes, rating)] in ranking order (<= 40), survivors=[(page, rating)] (<= 10)).
+    Ties (votes, rating) resolve to the lower page index (the reference's HashMap order is arbitrary)."""
+    po = np.ascontiguousarray(page_offsets, np.int64)
+    npages = len(po) - 1
+    by_page = [[] for _ in range(npages)]
+    dist = np.asarray(dist, np.float32)
+    for q in range(idx.shape[0]):
+        if idx[q, 0] < 0:
+            continue
+        lim = np.float32(dist[q, 0]) * np.float32(VOTE_RATIO)
+        for j in range(idx.shape[1]):
+            g = idx[q, j]
+            if g >= 0 and dist[q, j] < lim:
+                by_page[int(np.searchsorted(po, g, side="right") - 1)].append((q, int(g)))
+    order = sorted((p for p in range(npages) if by_page[p]), key=lambda p: (-len(by_page[p]), p))[:TOP_SLIDES]
+    cand = []
+    for p in order:
+        m = by_page[p]
+        fr = pool_pts[[g for _, g in m]]          # slide keypoints  (lib.rs:299)
+        to = frame_pts[[q for q, _ in m]]         # frame keypoints  (lib.rs:300)
+        rating, _, _, _ = ransac_affine_partial(fr, to)
+        cand.append((p, len(m), rating))
+    ranked = sorted(cand, key=lambda c: -c[2])[:TOP_RATED]       # stable: ties keep the vote order (Rust sort_by is stable)
+    best = float(ranked[0][2]) if ranked else 0.0
+    surv = [(p, r) for p, _, r in ranked if r > MIN_RATING and (float(r) / best if best else 0.0) > MIN_RATING_FRACTION]
+    return dict(cand=cand, survivors=surv)

@@ -103,6 +103,14 @@ class Context:
         a = self._desc_array(desc)
         self._ck(self._lib.slideo_b200_add_page_descriptors(self._h, _ptr(a), len(a)))
 
+    def add_page_features(self, desc, pts) -> None:
+        """Descriptors + KeyPoint.pt (n x 2 float32, level-0 coordinates) of a page extracted elsewhere."""
+        a = self._desc_array(desc)
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        if len(p) != len(a):
+            raise ValueError("desc and pts disagree")
+        self._ck(self._lib.slideo_b200_add_page_features(self._h, _ptr(a), _ptr(p), len(a)))
+
     def finalize_pool(self) -> None:
         self._ck(self._lib.slideo_b200_finalize_pool(self._h))
 
@@ -152,8 +160,8 @@ class Context:
             frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape
         res = (ffi.FrameResult * max(n, 1))()
-        self._ck(self._lib.slideo_b200_match_frames_bgr8(self._h, _ptr(frames), n, w, h, frames.strides[1],
-                                                         frames.strides[0] if n else 0, res))
+        frame_stride = frames.strides[0] if n > 1 else frames.strides[1] * h   # a length-1 axis may carry any stride
+        self._ck(self._lib.slideo_b200_match_frames_bgr8(self._h, _ptr(frames), n, w, h, frames.strides[1], frame_stride, res))
         return self._results(res, n)
 
     def match_frames_bgr8_ptr(self, host_ptr: int, n: int, w: int, h: int, stride: Optional[int] = None,
@@ -191,6 +199,17 @@ class Context:
         out = np.empty((rows.value, self.k), dt)
         if rows.value:
             self._ck(self._lib.slideo_b200_get_matches(self._h, frame_i, _ptr(out), rows.value, ctypes.byref(rows)))
+        return out
+
+    def get_verification(self, frame0: int, n: int):
+        """RANSAC gate records of frames [frame0, frame0+n) of the last match_frames call (cfg.geometric_verification)."""
+        res = (ffi.VerifyResult * max(n, 1))()
+        self._ck(self._lib.slideo_b200_get_verification(self._h, frame0, n, res))
+        out = []
+        for i in range(n):
+            r = res[i]
+            out.append(dict(cand=[(r.cand_page[j], r.cand_votes[j], r.cand_rating[j]) for j in range(r.n_candidates)],
+                            survivors=[(r.survivor_page[j], r.survivor_rating[j]) for j in range(r.n_survivors)]))
         return out
 
     # ---- stage-level entry points ------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "knn_l2.cuh"
 #include "orb.cuh"
+#include "verify.cuh"
 
 using namespace slideo;
 
@@ -66,6 +67,9 @@ struct slideo_b200_ctx {
     int desc_bytes = 32;                 // 32 (ORB256) or 512 (SIFT128 as float)
     std::vector<uint8_t> h_pool;         // host staging until finalize
     std::vector<int32_t> page_off{0};    // prefix offsets, size n_pages + 1
+    std::vector<float> h_pool_pt;        // KeyPoint.pt of every pooled descriptor (x, y); empty when a page came without points
+    bool pool_pts_valid = true;
+    DevBuf<float2> d_pool_pt;
     bool finalized = false;
     DevBuf<uint8_t> d_pool;              // nt x 32 (ORB) / nt x 128 bf16 (SIFT)
     DevBuf<uint8_t> d_pool48;            // ORB: the 48 B expanded rows K8 streams (knn_pool_expand_launch)
@@ -148,6 +152,7 @@ struct slideo_b200_ctx {
                 else if (e.kind == 1) tm.ms_knn += ms;
                 else if (e.kind == 2) tm.ms_h2d += ms;
                 else if (e.kind == 4) tm.ms_total += ms;
+                else if (e.kind == 5) tm.ms_verify += ms;
                 else tm.ms_vote += ms;
             }
             ev_free_list.push_back(e);
@@ -247,6 +252,11 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_qs_desc;           // query stream: descriptors
     DevBuf<int32_t> d_qs_frame;          // frame (within the super-batch) of each query
     DevBuf<int32_t> d_qs_nkp;            // keypoints per frame
+    DevBuf<float2> d_qs_pt;              // KeyPoint.pt of each query (geometric verification)
+    DevBuf<int32_t> d_v_cand_page, d_v_cand_votes, d_v_n_cand, d_v_rating, d_v_q0;
+    DevBuf<uint8_t> d_v_corr;
+    DevBuf<VerifyRecord> d_v_out;
+    std::vector<VerifyRecord> verify_results;   // one per frame of the last match_frames_* call
     int qs_total = 0, qs_frames = 0;
     size_t qs_cap = 0;
     static constexpr int SUPER_BATCH = 2048;   // frames per query stream (bounds the stream buffers)
@@ -259,20 +269,21 @@ struct slideo_b200_ctx {
         d_qs_desc.reserve(qs_cap * 32 + 64);
         d_qs_frame.reserve(qs_cap + 64);
         d_qs_nkp.reserve((size_t)n_frames + 64);
+        if (cfg.geometric_verification) d_qs_pt.reserve(qs_cap + 64);
         qs_total = 0;
         qs_frames = 0;
         qs_matched = 0;
         const int np = std::max(n_pages, 1);
         d_votes.reserve((size_t)n_frames * np);
         d_results.reserve((size_t)n_frames * 3);
-        if (cfg.keep_matches) d_keys.reserve(qs_cap * cfg.knn_k);
+        if (cfg.keep_matches || cfg.geometric_verification) d_keys.reserve(qs_cap * cfg.knn_k);
         SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)n_frames * np * 4, knn_stream));
     }
     // K1-K7 on nb device-resident frames, appended to the query stream
     void stream_detect(const uint8_t* d_src, int nb, int w, int h, int stride, size_t frame_stride) {
         OrbExtractor& ex = extractor(w, h, cfg.max_batch);
-        OrbExtractor::Sink sink{d_qs_desc.p + (size_t)qs_total * 32, d_qs_frame.p + qs_total, d_qs_nkp.p + qs_frames, qs_frames,
-                                qs_cap - (size_t)qs_total};
+        OrbExtractor::Sink sink{d_qs_desc.p + (size_t)qs_total * 32, d_qs_frame.p + qs_total, d_qs_nkp.p + qs_frames,
+                                cfg.geometric_verification ? d_qs_pt.p + qs_total : nullptr, qs_frames, qs_cap - (size_t)qs_total};
         EventPair t = begin_timing(0, stream);
         int nl = 0;
         const int total = ex.run(d_src, nb, stride, frame_stride, 3, stream, &nl, &sink);
@@ -288,7 +299,7 @@ struct slideo_b200_ctx {
     int qs_matched = 0;
     int FRAME_PATH_CTAS = getenv("SLIDEO_FRAME_CTAS") ? atoi(getenv("SLIDEO_FRAME_CTAS")) : 4;   // K8 CTAs per SM in the frame path (measured: 4 beats 3 + more K1-K7 overlap, profiles/r1_frame_ctas.txt)
     void stream_match_ready(bool flush) {
-        const bool want_keys = cfg.keep_matches != 0;
+        const bool want_keys = cfg.keep_matches != 0 || cfg.geometric_verification != 0;
         const int chunk = num_sms * FRAME_PATH_CTAS * KNN_TILE_QUERIES;   // one full wave of K8 tiles: every CTA owns one tile
         VoteArgs va{nullptr, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio};
         bool waited = false;
@@ -320,16 +331,48 @@ struct slideo_b200_ctx {
         vote_argmax_launch(d_votes.p, qs_frames, n_pages, d_qs_nkp.p, d_results.p, knn_stream);
         tm.kernel_launches += 1;
         SLIDEO_CUDA(cudaMemcpyAsync(h_out, d_results.p, (size_t)qs_frames * 3 * 4, cudaMemcpyDeviceToHost, knn_stream));
-        if (cfg.keep_matches) {
-            std::vector<int32_t> nkp((size_t)qs_frames), fo(1, 0);
+        std::vector<int32_t> fo(1, 0);
+        if (cfg.keep_matches || cfg.geometric_verification) {
+            std::vector<int32_t> nkp((size_t)qs_frames);
             SLIDEO_CUDA(cudaMemcpyAsync(nkp.data(), d_qs_nkp.p, (size_t)qs_frames * 4, cudaMemcpyDeviceToHost, knn_stream));
             SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
             for (int f = 0; f < qs_frames; ++f) fo.push_back(fo.back() + nkp[f]);
-            keep_batch_keys(qs_total, fo, knn_stream);
         }
+        if (cfg.geometric_verification) verify_stream(fo);
+        if (cfg.keep_matches) keep_batch_keys(qs_total, fo, knn_stream);
+    }
+
+    // K12 on the frames of the finished stream (lib.rs:284-333); appends one record per frame to verify_results
+    void verify_stream(const std::vector<int32_t>& frame_q0) {
+        if (!pool_pts_valid) throw StateError("geometric verification needs the keypoint coordinates of every page (add_page_gray8 / add_page_features)");
+        const size_t F = (size_t)qs_frames;
+        d_v_cand_page.reserve(F * VERIFY_TOP_SLIDES);
+        d_v_cand_votes.reserve(F * VERIFY_TOP_SLIDES);
+        d_v_rating.reserve(F * VERIFY_TOP_SLIDES);
+        d_v_n_cand.reserve(F + 1);
+        d_v_q0.reserve(F + 1);
+        d_v_out.reserve(F + 1);
+        d_v_corr.reserve(verify_corr_bytes((long long)qs_total * cfg.knn_k));
+        SLIDEO_CUDA(cudaMemcpyAsync(d_v_q0.p, frame_q0.data(), (F + 1) * 4, cudaMemcpyHostToDevice, knn_stream));
+        VerifyArgs a;
+        a.n_frames = qs_frames; a.n_pages = n_pages; a.k = cfg.knn_k; a.ratio = cfg.vote_ratio;
+        a.d_votes = d_votes.p; a.d_keys = d_keys.p; a.d_frame_q0 = d_v_q0.p; a.d_page_of = d_page_of.p;
+        a.d_frame_pt = d_qs_pt.p; a.d_pool_pt = d_pool_pt.p;
+        a.d_cand_page = d_v_cand_page.p; a.d_cand_votes = d_v_cand_votes.p; a.d_n_cand = d_v_n_cand.p; a.d_rating = d_v_rating.p;
+        a.d_corr = d_v_corr.p; a.d_out = d_v_out.p;
+        EventPair t = begin_timing(5, knn_stream);
+        int nl = 0;
+        verify_launch(a, knn_stream, &nl);
+        end_timing(t, knn_stream);
+        tm.kernel_launches += nl;
+        const size_t base = verify_results.size();
+        verify_results.resize(base + F);
+        SLIDEO_CUDA(cudaMemcpyAsync(verify_results.data() + base, d_v_out.p, F * sizeof(VerifyRecord), cudaMemcpyDeviceToHost, knn_stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
     }
 
     void reset_kept() {
+        verify_results.clear();
         kept_keys.clear();
         kept_l2.clear();
         kept_l2_idx.clear();
@@ -351,6 +394,11 @@ struct slideo_b200_ctx {
         d_page_off.reserve((size_t)n_pages + 1);
         if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_page_of.p, po.data(), (size_t)nt * 2, cudaMemcpyHostToDevice, stream));
         SLIDEO_CUDA(cudaMemcpyAsync(d_page_off.p, page_off.data(), ((size_t)n_pages + 1) * 4, cudaMemcpyHostToDevice, stream));
+        pool_pts_valid = pool_pts_valid && h_pool_pt.size() == (size_t)nt * 2;
+        if (pool_pts_valid) {
+            d_pool_pt.reserve((size_t)std::max(nt, 1));
+            if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_pool_pt.p, h_pool_pt.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, stream));
+        }
         if (cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) {
             d_pool48.reserve(knn_pool_expanded_bytes(nt) + 64);
             knn_pool_expand_launch(d_pool.p, nt, d_pool48.p, stream);
@@ -514,9 +562,16 @@ int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int3
         ctx->tm.kernel_launches += nl;
         const size_t base = ctx->h_pool.size();
         ctx->h_pool.resize(base + (size_t)total * 32);
-        if (total > 0)
+        std::vector<float> kpf((size_t)total * 4);
+        if (total > 0) {
             SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_pool.data() + base, ex.d_desc(), (size_t)total * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            SLIDEO_CUDA(cudaMemcpyAsync(kpf.data(), ex.d_kp_f(), (size_t)total * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < total; ++i) {   // KeyPoint.pt of the slide keypoints (lib.rs:299)
+            ctx->h_pool_pt.push_back(kpf[(size_t)i * 4]);
+            ctx->h_pool_pt.push_back(kpf[(size_t)i * 4 + 1]);
+        }
         ctx->page_off.push_back(ctx->page_off.back() + total);
         ctx->check_pool_limits((int64_t)ctx->page_off.back(), (int64_t)ctx->page_off.size() - 1);
         if (out_n_keypoints) *out_n_keypoints = total;
@@ -533,6 +588,23 @@ int32_t slideo_b200_add_page_descriptors(slideo_b200_ctx* ctx, const void* desc,
         const size_t base = ctx->h_pool.size();
         ctx->h_pool.resize(base + (size_t)n * ctx->desc_bytes);
         if (n) std::memcpy(ctx->h_pool.data() + base, desc, (size_t)n * ctx->desc_bytes);
+        ctx->page_off.push_back(ctx->page_off.back() + n);
+        if (n) ctx->pool_pts_valid = false;   // no keypoint coordinates for this page: geometric verification unavailable
+    });
+}
+
+int32_t slideo_b200_add_page_features(slideo_b200_ctx* ctx, const void* desc, const float* pt_xy, int32_t n) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        arg(n >= 0, "n < 0");
+        arg((desc != nullptr && pt_xy != nullptr) || n == 0, "desc / pt_xy must not be NULL");
+        if (ctx->finalized || ctx->reserved) throw StateError("pool already finalized");
+        ctx->check_pool_limits((int64_t)ctx->page_off.back() + n, (int64_t)ctx->page_off.size());
+        const size_t base = ctx->h_pool.size();
+        ctx->h_pool.resize(base + (size_t)n * 32);
+        if (n) std::memcpy(ctx->h_pool.data() + base, desc, (size_t)n * 32);
+        ctx->h_pool_pt.insert(ctx->h_pool_pt.end(), pt_xy, pt_xy + (size_t)n * 2);
         ctx->page_off.push_back(ctx->page_off.back() + n);
     });
 }
@@ -594,6 +666,8 @@ int32_t slideo_b200_pool_import(slideo_b200_ctx* ctx, const void* desc, int32_t 
         ctx->check_pool_limits(n_desc, n_pages);
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->h_pool.assign((const uint8_t*)desc, (const uint8_t*)desc + (size_t)n_desc * ctx->desc_bytes);
+        ctx->h_pool_pt.clear();
+        ctx->pool_pts_valid = n_desc == 0;
         ctx->page_off.assign(page_offsets, page_offsets + n_pages + 1);
         ctx->reserved = false;
         finalize_from_host(ctx);
@@ -612,6 +686,8 @@ int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n
         ctx->nt = n_desc;
         ctx->n_pages = n_pages;
         ctx->h_pool.clear();
+        ctx->h_pool_pt.clear();
+        ctx->pool_pts_valid = n_desc == 0;
         ctx->page_off.assign((size_t)n_pages + 1, 0);
         ctx->d_pool.reserve((size_t)std::max(n_desc, 1) * 32 + 64);
         ctx->d_page_off.reserve((size_t)n_pages + 1);
@@ -872,6 +948,17 @@ int32_t slideo_b200_get_matches(slideo_b200_ctx* ctx, int32_t frame_i, slideo_b2
                 m.train_idx = gi - ctx->page_off[page];
                 m.distance = dist;
             }
+    });
+}
+
+int32_t slideo_b200_get_verification(slideo_b200_ctx* ctx, int32_t frame0, int32_t n, slideo_b200_verify_result* out) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (!ctx->cfg.geometric_verification) throw StateError("cfg.geometric_verification was not set");
+        arg(frame0 >= 0 && n >= 0 && (size_t)frame0 + (size_t)n <= ctx->verify_results.size(), "frame range outside the last match call");
+        arg(out != nullptr || n == 0, "out must not be NULL");
+        static_assert(sizeof(slideo_b200_verify_result) == sizeof(VerifyRecord), "ABI struct and kernel record must agree");
+        if (n) std::memcpy(out, ctx->verify_results.data() + frame0, (size_t)n * sizeof(VerifyRecord));
     });
 }
 

@@ -476,7 +476,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 __global__ void __launch_bounds__(256) describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                                                        const Geo* __restrict__ gp, const uint32_t* __restrict__ kp_src, int total,
                                                        const int8_t* __restrict__ pattern, float* __restrict__ kp_f,
-                                                       uint8_t* __restrict__ desc) {
+                                                       uint8_t* __restrict__ desc, float2* __restrict__ pt_out) {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (k >= total) return;
@@ -508,7 +508,10 @@ __global__ void __launch_bounds__(256) describe_kernel(const uint8_t* __restrict
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
     const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
-    if (lane == 0) reinterpret_cast<float4*>(kp_f)[k] = make_float4(ptx, pty, __fmul_rn((float)g.patch, L.scale), angle);
+    if (lane == 0) {
+        reinterpret_cast<float4*>(kp_f)[k] = make_float4(ptx, pty, __fmul_rn((float)g.patch, L.scale), angle);
+        if (pt_out) pt_out[k] = make_float2(ptx, pty);
+    }
 
     // K7: steered BRIEF on the blurred level (pattern = cv::RNG(0x34985739) points)
     const uint8_t* bl = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
@@ -723,7 +726,7 @@ int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stri
     if (sink && (size_t)total > sink->cap) throw CapacityError("descriptor sink capacity exceeded");
     if (total > 0) {
         describe_kernel<<<cdiv(total, 8), 256, 0, stream>>>(d_pyr_, d_blur_, g, d_kp_src_, total, d_pattern_, d_kp_f_,
-                                                           sink ? sink->desc : d_desc_);
+                                                           sink ? sink->desc : d_desc_, sink ? sink->pt : nullptr);
         ++nl;
         SLIDEO_CUDA(cudaGetLastError());
     }

@@ -55,6 +55,7 @@ public:
         uint8_t* desc;       // [.. x 32], this batch starts at element 0
         int32_t* q_frame;    // [..]
         int32_t* frame_nkp;  // [n]
+        float2* pt;          // [..] KeyPoint.pt (may be null)
         int frame_base;
         size_t cap;          // keypoints the arrays can hold
     };

@@ -1,0 +1,305 @@
+// verify.cu -- K12: geometric verification of the per-frame candidates.
+//
+// Replaces the middle of match_images_with_frame (crates/matching-opencv/src/lib.rs:284-333): slides ranked by votes,
+// take(40) -> per candidate `estimate_affine_partial_2d(slide kp -> frame kp, RANSAC, 3.0, 2000, 0.99, 10)`
+// (image_utils.rs:45-60) -> rating = inlier count -> sort by rating, truncate(10), retain(rating > 50 && rating/best > 0.2).
+// The algorithm restated is OpenCV's RANSACPointSetRegistrator::run with AffinePartial2DEstimatorCallback as pinned in
+// oracle/ransac_oracle.c: cv::RNG((uint64)-1) sample sequence (a pure function of the correspondence count), closed-form
+// similarity through two correspondences in double, fp32 residuals evaluated without contraction, adaptive iteration count.
+// All hypotheses of a chunk are evaluated in parallel (one warp per hypothesis); the sequential best-so-far / niters logic is
+// replayed over the chunk by one thread, so the result is identical to the sequential loop.
+// Compiled with -fmad=false: no floating-point contraction anywhere in this file.
+#include "verify.cuh"
+
+#include <float.h>
+
+namespace slideo {
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int V_THREADS = 256;
+constexpr int V_WARPS = V_THREADS / 32;
+constexpr int V_SMEM_PTS = 2560;          // correspondences staged in shared memory (float4 each = 40 KB)
+constexpr int V_CHUNK = 32;               // hypotheses per round (4 per warp)
+
+// ---- A: candidates = the 40 pages with most votes (ties -> lower page index) ---------------------------------------
+__global__ void __launch_bounds__(128) select_candidates_kernel(const int32_t* __restrict__ votes, int n_pages, int32_t* __restrict__ cand_page,
+                                                                int32_t* __restrict__ cand_votes, int32_t* __restrict__ n_cand) {
+    __shared__ unsigned long long s_best[4];
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t* v = votes + (size_t)f * n_pages;
+    // key = votes << 32 | (0xFFFFFFFF - page): unique per page, so round r simply takes the largest key below round r-1's
+    unsigned long long prev = ~0ull;
+    int n = 0;
+    for (int r = 0; r < VERIFY_TOP_SLIDES; ++r) {
+        unsigned long long best = 0;
+        for (int p = threadIdx.x; p < n_pages; p += blockDim.x) {
+            const int vv = v[p];
+            if (vv > 0) {
+                const unsigned long long key = ((unsigned long long)(uint32_t)vv << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+                if (key < prev && key > best) best = key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) s_best[warp] = best;
+        __syncthreads();
+        best = s_best[0];
+        for (int w = 1; w < 4; ++w) best = s_best[w] > best ? s_best[w] : best;
+        __syncthreads();
+        if (best == 0) break;
+        if (threadIdx.x == 0) {
+            cand_page[(size_t)f * VERIFY_TOP_SLIDES + r] = (int32_t)(0xFFFFFFFFu - (uint32_t)best);
+            cand_votes[(size_t)f * VERIFY_TOP_SLIDES + r] = (int32_t)(best >> 32);
+        }
+        prev = best;
+        n = r + 1;
+    }
+    if (threadIdx.x == 0) n_cand[f] = n;
+}
+
+// ---- B: ordered correspondence lists: the voting matches of (frame, candidate page) in (query, rank) order ------------
+__global__ void __launch_bounds__(V_THREADS) gather_matches_kernel(const uint32_t* __restrict__ keys, int k, const int32_t* __restrict__ frame_q0,
+                                                                   const uint16_t* __restrict__ page_of, const int32_t* __restrict__ cand_page,
+                                                                   const int32_t* __restrict__ cand_votes, const int32_t* __restrict__ n_cand, float ratio,
+                                                                   uint2* __restrict__ corr) {
+    __shared__ int s_warp[V_WARPS];
+    __shared__ int s_base;
+    const int c = blockIdx.x, f = blockIdx.y;
+    if (c >= n_cand[f]) return;
+    const int page = cand_page[(size_t)f * VERIFY_TOP_SLIDES + c];
+    const int q0 = frame_q0[f], q1 = frame_q0[f + 1];
+    const long long e0 = (long long)q0 * k, e1 = (long long)q1 * k;
+    // the lists of one frame are packed back to back into the frame's own key range [q0 * k, q1 * k): a frame casts at most
+    // one vote per k-NN entry, so the candidates' vote counts sum to no more than that
+    long long off0 = e0;
+    for (int cc = 0; cc < c; ++cc) off0 += cand_votes[(size_t)f * VERIFY_TOP_SLIDES + cc];
+    uint2* out = corr + off0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (long long e = e0 + threadIdx.x; e - threadIdx.x < e1; e += V_THREADS) {
+        bool take = false;
+        uint32_t key = KEY_EMPTY;
+        int q = 0;
+        if (e < e1) {
+            q = (int)(e / k);
+            key = keys[e];
+            const uint32_t best = keys[(long long)q * k];
+            if (key != KEY_EMPTY) {
+                const float d = (float)(key >> KEY_IDX_BITS), b = (float)(best >> KEY_IDX_BITS);
+                take = d < __fmul_rn(b, ratio) && page_of[key & KEY_IDX_MASK] == (uint16_t)page;   // lib.rs:275
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, take);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (take) out[off + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)q, key & KEY_IDX_MASK);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < V_WARPS; ++w) t += s_warp[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- C: RANSAC rating of one (frame, candidate) ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rng_next(unsigned long long& s) {
+    s = (unsigned long long)(uint32_t)s * 4164903690ull + (uint32_t)(s >> 32);
+    return (uint32_t)s;
+}
+
+// RANSACUpdateNumIters(confidence, ep, 2, max_iters)
+__device__ int update_num_iters(double p, double ep, int max_iters) {
+    p = fmax(p, 0.); p = fmin(p, 1.);
+    ep = fmax(ep, 0.); ep = fmin(ep, 1.);
+    double num = fmax(1. - p, DBL_MIN);
+    double denom = 1. - (1. - ep) * (1. - ep);   // std::pow(1 - ep, 2): correctly rounded square
+    if (denom < DBL_MIN) return 0;
+    num = log(num);
+    denom = log(denom);
+    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : __double2int_rn(num / denom);
+}
+
+__global__ void __launch_bounds__(V_THREADS) ransac_kernel(const uint2* __restrict__ corr, const int32_t* __restrict__ frame_q0, int k,
+                                                           const int32_t* __restrict__ cand_votes, const int32_t* __restrict__ n_cand,
+                                                           const float2* __restrict__ frame_pt, const float2* __restrict__ pool_pt,
+                                                           float thr, int max_iters, double confidence, int32_t* __restrict__ rating) {
+    extern __shared__ __align__(16) uint8_t v_smem[];
+    float4* s_pts = reinterpret_cast<float4*>(v_smem);                                        // [V_SMEM_PTS] (fx, fy, tx, ty)
+    uint2* s_pairs = reinterpret_cast<uint2*>(v_smem + (size_t)V_SMEM_PTS * sizeof(float4));  // [max_iters] sample indices
+    __shared__ int s_good[V_CHUNK];
+    __shared__ int s_state[3];   // niters, max_good, done
+
+    const int c = blockIdx.x, f = blockIdx.y;
+    if (c >= n_cand[f]) {
+        if (threadIdx.x == 0) rating[(size_t)f * VERIFY_TOP_SLIDES + c] = 0;
+        return;
+    }
+    const int n = cand_votes[(size_t)f * VERIFY_TOP_SLIDES + c];
+    long long off0 = (long long)frame_q0[f] * k;
+    for (int cc = 0; cc < c; ++cc) off0 += cand_votes[(size_t)f * VERIFY_TOP_SLIDES + cc];
+    const uint2* list = corr + off0;
+    int32_t* out = rating + (size_t)f * VERIFY_TOP_SLIDES + c;
+    if (n < 2) {          // fewer than modelPoints correspondences: no model, no inliers
+        if (threadIdx.x == 0) *out = 0;
+        return;
+    }
+    if (n == 2) {         // count == modelPoints: the model through both points, every point an inlier
+        if (threadIdx.x == 0) *out = 2;
+        return;
+    }
+    const bool in_smem = n <= V_SMEM_PTS;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < n; i += V_THREADS) {
+            const uint2 m = list[i];
+            const float2 to = frame_pt[m.x], fr = pool_pt[m.y];
+            s_pts[i] = make_float4(fr.x, fr.y, to.x, to.y);
+        }
+    }
+    if (threadIdx.x == 0) {
+        // the sample sequence of cv::RNG((uint64)-1): two distinct indices per iteration (getSubset; checkSubset never
+        // rejects a 2-point sample), a pure function of n
+        unsigned long long s = 0xFFFFFFFFFFFFFFFFull;
+        for (int it = 0; it < max_iters; ++it) {
+            const uint32_t i0 = rng_next(s) % (uint32_t)n;
+            uint32_t i1;
+            do { i1 = rng_next(s) % (uint32_t)n; } while (i1 == i0);
+            s_pairs[it] = make_uint2(i0, i1);
+        }
+        s_state[0] = max_iters > 1 ? max_iters : 1;
+        s_state[1] = 0;
+        s_state[2] = 0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float t = (float)((double)thr * (double)thr);
+    auto point = [&](int i) -> float4 {
+        if (in_smem) return s_pts[i];
+        const uint2 m = list[i];
+        const float2 to = frame_pt[m.x], fr = pool_pt[m.y];
+        return make_float4(fr.x, fr.y, to.x, to.y);
+    };
+
+    for (int it0 = 0; ; it0 += V_CHUNK) {
+        const int niters = s_state[0];
+        if (it0 >= niters) break;
+        for (int h = warp; h < V_CHUNK; h += V_WARPS) {
+            const int it = it0 + h;
+            int good = 0;
+            if (it < niters) {
+                const uint2 pr = s_pairs[it];
+                const float4 p0 = point((int)pr.x), p1 = point((int)pr.y);
+                // AffinePartial2DEstimatorCallback::runKernel (double, closed form)
+                const double x1 = p0.x, y1 = p0.y, x2 = p1.x, y2 = p1.y, X1 = p0.z, Y1 = p0.w, X2 = p1.z, Y2 = p1.w;
+                const double d = 1. / ((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+                const double S0 = d * ((X1 - X2) * (x1 - x2) + (Y1 - Y2) * (y1 - y2));
+                const double S1 = d * ((Y1 - Y2) * (x1 - x2) - (X1 - X2) * (y1 - y2));
+                const double S2 = d * ((Y1 - Y2) * (x1 * y2 - x2 * y1) - (X1 * y2 - X2 * y1) * (y1 - y2) - (X1 * x2 - X2 * x1) * (x1 - x2));
+                const double S3 = d * (-(X1 - X2) * (x1 * y2 - x2 * y1) - (Y1 * x2 - Y2 * x1) * (x1 - x2) - (Y1 * y2 - Y2 * y1) * (y1 - y2));
+                const float F0 = (float)S0, F1 = (float)(-S1), F2 = (float)S2, F3 = (float)S1, F4 = (float)S0, F5 = (float)S3;
+                // Affine2DEstimatorCallback::computeError + findInliers (fp32, no contraction, err <= thr^2)
+                for (int i = lane; i < n; i += 32) {
+                    const float4 p = point(i);
+                    const float a = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F0, p.x), __fmul_rn(F1, p.y)), F2), p.z);
+                    const float b = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F3, p.x), __fmul_rn(F4, p.y)), F5), p.w);
+                    const float e = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+                    good += e <= t ? 1 : 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(FULL, good, o);
+            }
+            if (lane == 0) s_good[h] = good;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // replay of the sequential loop over this chunk: a hypothesis only counts if the loop would still be running
+            int ni = s_state[0], mg = s_state[1];
+            for (int h = 0; h < V_CHUNK; ++h) {
+                const int it = it0 + h;
+                if (it >= ni) break;
+                const int good = s_good[h];
+                if (good > (mg > 1 ? mg : 1)) {
+                    mg = good;
+                    ni = update_num_iters(confidence, (double)(n - good) / n, ni);
+                }
+            }
+            s_state[0] = ni;
+            s_state[1] = mg;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s_state[1];
+}
+
+// ---- D: gates (lib.rs:329-333): stable sort by rating, truncate(10), retain(rating > 50 && rating / best > 0.2) -----------
+__global__ void __launch_bounds__(128) gate_kernel(const int32_t* __restrict__ cand_page, const int32_t* __restrict__ cand_votes,
+                                                   const int32_t* __restrict__ rating, const int32_t* __restrict__ n_cand, int n_frames,
+                                                   VerifyRecord* __restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    VerifyRecord r;
+    const int n = n_cand[f];
+    r.n_candidates = n;
+    int order[VERIFY_TOP_SLIDES];
+    for (int i = 0; i < VERIFY_TOP_SLIDES; ++i) {
+        r.cand_page[i] = i < n ? cand_page[(size_t)f * VERIFY_TOP_SLIDES + i] : -1;
+        r.cand_votes[i] = i < n ? cand_votes[(size_t)f * VERIFY_TOP_SLIDES + i] : 0;
+        r.cand_rating[i] = i < n ? rating[(size_t)f * VERIFY_TOP_SLIDES + i] : 0;
+        order[i] = i;
+    }
+    for (int i = 1; i < n; ++i) {   // stable insertion sort, descending rating
+        const int o = order[i];
+        int j = i - 1;
+        while (j >= 0 && r.cand_rating[order[j]] < r.cand_rating[o]) { order[j + 1] = order[j]; --j; }
+        order[j + 1] = o;
+    }
+    const int top = n < VERIFY_TOP_RATED ? n : VERIFY_TOP_RATED;
+    const double best = top > 0 ? (double)r.cand_rating[order[0]] : 0.0;
+    int ns = 0;
+    for (int i = 0; i < VERIFY_TOP_RATED; ++i) { r.survivor_page[i] = -1; r.survivor_rating[i] = 0; }
+    for (int i = 0; i < top; ++i) {
+        const double v = (double)r.cand_rating[order[i]];
+        if (v > 50.0 && v / best > 0.2) {
+            r.survivor_page[ns] = r.cand_page[order[i]];
+            r.survivor_rating[ns] = r.cand_rating[order[i]];
+            ++ns;
+        }
+    }
+    r.n_survivors = ns;
+    out[f] = r;
+}
+
+}  // namespace
+
+size_t verify_corr_bytes(long long total_entries) { return (size_t)(total_entries > 0 ? total_entries : 1) * sizeof(uint2); }
+
+void verify_launch(const VerifyArgs& a, cudaStream_t stream, int* launches) {
+    if (a.n_frames <= 0) return;
+    select_candidates_kernel<<<a.n_frames, 128, 0, stream>>>(a.d_votes, a.n_pages, a.d_cand_page, a.d_cand_votes, a.d_n_cand);
+    gather_matches_kernel<<<dim3(VERIFY_TOP_SLIDES, a.n_frames), V_THREADS, 0, stream>>>(a.d_keys, a.k, a.d_frame_q0, a.d_page_of, a.d_cand_page,
+                                                                                     a.d_cand_votes, a.d_n_cand, a.ratio, (uint2*)a.d_corr);
+    const size_t smem = (size_t)V_SMEM_PTS * sizeof(float4) + (size_t)VERIFY_MAX_ITERS * sizeof(uint2);
+    static bool configured = false;
+    if (!configured) {
+        SLIDEO_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    ransac_kernel<<<dim3(VERIFY_TOP_SLIDES, a.n_frames), V_THREADS, smem, stream>>>((const uint2*)a.d_corr, a.d_frame_q0, a.k, a.d_cand_votes,
+                                                                                  a.d_n_cand, a.d_frame_pt, a.d_pool_pt, 3.0f, VERIFY_MAX_ITERS,
+                                                                                  0.99, a.d_rating);
+    gate_kernel<<<cdiv(a.n_frames, 128), 128, 0, stream>>>(a.d_cand_page, a.d_cand_votes, a.d_rating, a.d_n_cand, a.n_frames, a.d_out);
+    SLIDEO_CUDA(cudaGetLastError());
+    if (launches) *launches += 4;
+}
+
+}  // namespace slideo

@@ -1,0 +1,35 @@
+// verify.cuh -- K12: geometric verification (top-40 slides by votes -> RANSAC similarity rating -> gates), lib.rs:284-333.
+#pragma once
+#include "common.cuh"
+
+namespace slideo {
+
+constexpr int VERIFY_TOP_SLIDES = 40;    // lib.rs:295  take(40)
+constexpr int VERIFY_TOP_RATED = 10;     // lib.rs:330  truncate(10)
+constexpr int VERIFY_MAX_ITERS = 2000;   // image_utils.rs:52
+
+// one per frame; layout == slideo_b200_verify_result (include/slideo_b200.h)
+struct VerifyRecord {
+    int32_t n_candidates, n_survivors;
+    int32_t cand_page[VERIFY_TOP_SLIDES], cand_votes[VERIFY_TOP_SLIDES], cand_rating[VERIFY_TOP_SLIDES];
+    int32_t survivor_page[VERIFY_TOP_RATED], survivor_rating[VERIFY_TOP_RATED];
+};
+
+struct VerifyArgs {
+    int n_frames, n_pages, k;
+    float ratio;
+    const int32_t* d_votes;       // [n_frames][n_pages]
+    const uint32_t* d_keys;       // k-NN rows of the frames' queries: [total_q][k]
+    const int32_t* d_frame_q0;    // [n_frames + 1] first query of each frame
+    const uint16_t* d_page_of;    // [Nt]
+    const float2* d_frame_pt;     // [total_q] KeyPoint.pt of the frame keypoints
+    const float2* d_pool_pt;      // [Nt] KeyPoint.pt of the pooled (slide) keypoints
+    int32_t *d_cand_page, *d_cand_votes, *d_n_cand, *d_rating;   // workspaces: [n_frames][40] x3, [n_frames]
+    void* d_corr;                 // verify_corr_bytes(total_q * k)
+    VerifyRecord* d_out;          // [n_frames]
+};
+
+size_t verify_corr_bytes(long long total_entries);
+void verify_launch(const VerifyArgs& a, cudaStream_t stream, int* launches);
+
+}  // namespace slideo

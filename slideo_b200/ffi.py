@@ -28,7 +28,7 @@ class Config(ctypes.Structure):
     _fields_ = [("abi_version", c_i32), ("device", c_i32), ("nfeatures", c_i32), ("scale_factor", c_f32),
                 ("nlevels", c_i32), ("edge_threshold", c_i32), ("patch_size", c_i32), ("fast_threshold", c_i32),
                 ("knn_k", c_i32), ("vote_ratio", c_f32), ("descriptor_kind", c_i32), ("max_batch", c_i32),
-                ("keep_matches", c_i32), ("reserved", c_i32 * 3)]
+                ("keep_matches", c_i32), ("geometric_verification", c_i32), ("reserved", c_i32 * 2)]
 
 
 class FrameResult(ctypes.Structure):
@@ -40,10 +40,19 @@ class Match(ctypes.Structure):
     _fields_ = [("query_idx", c_i32), ("train_idx", c_i32), ("source", c_i32), ("distance", c_f32)]
 
 
+TOP_SLIDES, TOP_RATED = 40, 10
+
+
+class VerifyResult(ctypes.Structure):
+    """slideo_b200_verify_result: RANSAC gate of one frame (lib.rs:284-333)."""
+    _fields_ = [("n_candidates", c_i32), ("n_survivors", c_i32), ("cand_page", c_i32 * TOP_SLIDES), ("cand_votes", c_i32 * TOP_SLIDES),
+                ("cand_rating", c_i32 * TOP_SLIDES), ("survivor_page", c_i32 * TOP_RATED), ("survivor_rating", c_i32 * TOP_RATED)]
+
+
 class Timings(ctypes.Structure):
     _fields_ = [("ms_detect", c_f32), ("ms_knn", c_f32), ("ms_vote", c_f32), ("ms_h2d", c_f32),
                 ("knn_pairs", ctypes.c_int64), ("knn_launches", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
-                ("frames", ctypes.c_int64), ("ms_total", c_f32), ("reserved0", c_f32)]
+                ("frames", ctypes.c_int64), ("ms_total", c_f32), ("ms_verify", c_f32)]
 
 
 # name -> (restype, argtypes); every symbol include/slideo_b200.h declares
@@ -55,6 +64,7 @@ SYMBOLS = {
     "slideo_b200_version": (ctypes.c_char_p, []),
     "slideo_b200_add_page_gray8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32p]),
     "slideo_b200_add_page_descriptors": (c_i32, [c_vp, c_vp, c_i32]),
+    "slideo_b200_add_page_features": (c_i32, [c_vp, c_vp, c_vp, c_i32]),
     "slideo_b200_finalize_pool": (c_i32, [c_vp]),
     "slideo_b200_pool_info": (c_i32, [c_vp, c_i32p, c_i32p]),
     "slideo_b200_pool_export": (c_i32, [c_vp, c_vp, c_vp]),
@@ -67,6 +77,7 @@ SYMBOLS = {
     "slideo_b200_match_frames_bgr8_device": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_vp]),
     "slideo_b200_match_descriptors": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp]),
     "slideo_b200_get_matches": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32p]),
+    "slideo_b200_get_verification": (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     "slideo_b200_extract_orb": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32p]),
     "slideo_b200_debug_fetch": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_sz, c_i32p, c_i32p]),
     "slideo_b200_bf_knn_hamming": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),

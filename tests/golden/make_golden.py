@@ -109,3 +109,31 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_ransac_golden():
+    """tests/golden/ransac.npz: cv2.estimateAffinePartial2D (RANSAC, 3.0, 2000, 0.99, 10) inlier masks -- the call of
+    crates/matching-opencv/src/image_utils.rs:52 -- on seeded correspondence sets."""
+    rng = np.random.default_rng(77)
+    sets = {}
+    for i, (n, frac, sig) in enumerate([(3, 1.0, 0.5), (7, 0.6, 1.0), (60, 0.3, 2.0), (200, 0.05, 2.0), (200, 0.0, 1.0),
+                                        (1500, 0.4, 1.5), (2500, 0.9, 2.5), (40, 0.5, 3.0)]):
+        fr = rng.uniform(0, 2000, (n, 2)).astype(np.float32)
+        s = rng.uniform(0.9, 1.1)
+        a = rng.uniform(-0.05, 0.05)
+        R = np.array([[s * np.cos(a), -s * np.sin(a)], [s * np.sin(a), s * np.cos(a)]])
+        to = (fr @ R.T + rng.uniform(-20, 20, 2)).astype(np.float32)
+        out = rng.random(n) > frac
+        to[out] = rng.uniform(0, 2000, (int(out.sum()), 2)).astype(np.float32)
+        to += rng.normal(0, sig, to.shape).astype(np.float32)
+        M, inl = cv2.estimateAffinePartial2D(fr, to, method=cv2.RANSAC, ransacReprojThreshold=3.0, maxIters=2000, confidence=0.99,
+                                             refineIters=10)
+        sets[f"from{i}"] = fr
+        sets[f"to{i}"] = to
+        sets[f"mask{i}"] = inl.ravel().astype(np.uint8) if inl is not None else np.zeros(n, np.uint8)
+    sets["n_sets"] = np.array([8])
+    np.savez_compressed(os.path.join(HERE, "ransac.npz"), **sets)
+
+
+if __name__ == "__main__":
+    make_ransac_golden()

@@ -1,0 +1,68 @@
+"""K12 parity: the RANSAC gate (lib.rs:284-333) on the GPU == the oracle pipeline (exact k-NN rows -> 1.05 votes grouped by
+slide in (query, rank) order -> top-40 -> oracle/ransac_oracle.c, itself pinned against cv2.estimateAffinePartial2D ->
+sort / truncate(10) / retain gates) on the same seeded pages and frames."""
+import numpy as np
+import pytest
+
+import oracle
+import synth
+
+pytestmark = pytest.mark.gpu
+
+NPAGES, NFRAMES = 7, 8
+
+
+@pytest.fixture(scope="module")
+def scene():
+    pages = [synth.make_page(p) for p in range(NPAGES)]
+    frames = np.stack([synth.make_frame(f, NPAGES, pages) for f in range(NFRAMES)])
+    feats = [oracle.orb_detect_and_compute(p) for p in pages]
+    page_desc = [f[2] for f in feats]
+    pool_pts = np.concatenate([f[1][:, :2] for f in feats])
+    offs = np.zeros(NPAGES + 1, np.int32)
+    offs[1:] = np.cumsum([len(d) for d in page_desc])
+    pool = np.concatenate(page_desc)
+    expect = []
+    for f in frames:
+        ki, kf, d = oracle.orb_detect_and_compute(oracle.gray_from_bgr(f))
+        idx, dist = oracle.bf_knn_hamming(d, pool, 30)
+        expect.append(oracle.verify_frame(idx, dist.astype(np.float32), offs, kf[:, :2], pool_pts))
+    return pages, frames, feats, expect
+
+
+@pytest.mark.parametrize("via_features", [False, True])
+def test_verification_equals_oracle(scene, via_features):
+    import slideo_b200
+    pages, frames, feats, expect = scene
+    with slideo_b200.Context(slideo_b200.default_config(geometric_verification=1, max_batch=3)) as c:
+        for p, (ki, kf, d) in zip(pages, feats):
+            if via_features:
+                c.add_page_features(d, kf[:, :2])
+            else:
+                c.add_page_gray8(p)
+        c.finalize_pool()
+        res = c.match_frames_bgr8(frames)
+        got = c.get_verification(0, NFRAMES)
+        t = c.timings()
+    assert t["ms_verify"] > 0
+    for f in range(NFRAMES):
+        assert got[f]["cand"] == [tuple(int(v) for v in x) for x in expect[f]["cand"]], f"frame {f} candidates"
+        assert got[f]["survivors"] == [tuple(int(v) for v in x) for x in expect[f]["survivors"]], f"frame {f} survivors"
+        # the head of the vote ranking is the hot path's (best_slide, votes)
+        if got[f]["cand"]:
+            assert (res[f, 0], res[f, 1]) == got[f]["cand"][0][:2]
+        truth = synth.frame_truth(f, NPAGES)
+        if truth >= 0:
+            assert got[f]["survivors"] and got[f]["survivors"][0][0] == truth     # the shown page passes the gate, first
+        else:
+            assert not got[f]["survivors"]                                         # clutter frames: nothing passes
+
+
+def test_verification_needs_points():
+    import slideo_b200
+    with slideo_b200.Context(slideo_b200.default_config(geometric_verification=1)) as c:
+        c.add_page_descriptors(synth.hamming_pool(100, seed=3))
+        c.finalize_pool()
+        with pytest.raises(slideo_b200.SlideoError) as e:
+            c.match_frames_bgr8(synth.make_frame(0, 1)[None])
+        assert e.value.status == slideo_b200.ffi.E_STATE
