@@ -352,6 +352,34 @@ def main():
         except Exception:
             pass
 
+    # ---- extra (rank 0, N=1): the same step with the RANSAC gate of lib.rs:284-333 switched on ----
+    verify_detail = None
+    if rank == 0 and world == 1:
+        try:
+            vctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=args.max_batch, geometric_verification=1))
+            for p in range(args.pages):
+                vctx.add_page_gray8(pages[p])
+            vctx.finalize_pool()
+            vctx.match_frames_bgr8_device(dev.data_ptr(), args.frames, FRAME_W, FRAME_H)
+            vctx.timings(reset=True)
+            t0 = time.perf_counter()
+            rv = vctx.match_frames_bgr8_device(dev.data_ptr(), args.frames, FRAME_W, FRAME_H)
+            dtv = time.perf_counter() - t0
+            tmv = vctx.timings(reset=True)
+            ver = vctx.get_verification(0, args.frames)
+            import synth as _synth
+            good = 0
+            for i in range(args.frames):
+                tr = _synth.frame_truth(f_lo + i, args.pages)
+                sv = ver[i]["survivors"]
+                good += int((tr < 0 and not sv) or (tr >= 0 and bool(sv) and sv[0][0] == tr))
+            verify_detail = {"frames_per_s": args.frames / dtv, "ms_verify_per_step": tmv["ms_verify"], "ms_per_step": 1e3 * dtv,
+                             "gate_decisions_matching_ground_truth": good, "frames": args.frames,
+                             "same_vote_results": bool(np.array_equal(rv, res_dev))}
+            vctx.close()
+        except Exception as ex:  # the extra must never break the contract line
+            verify_detail = {"error": str(ex)}
+
     if rank == 0:
         parity = None
         if cpu_results is not None:
@@ -372,7 +400,8 @@ def main():
                        "ms_knn_per_step": tm_dev["ms_knn"] / args.steps, "pool_descriptors": pool_n, "pool_pages": pool_pages,
                        "pool_build_s": t_pool, "keypoints_per_frame": float(np.mean(res_dev[:, 2])),
                        "frames_with_truth_match": int(sum(1 for i in range(args.frames) if _truth_ok(res_dev, f_lo + i, i, args.pages))),
-                       "cpu_sample_matches_gpu": parity, "descriptor_pairs_per_s": pairs * world / t_dev},
+                       "cpu_sample_matches_gpu": parity, "descriptor_pairs_per_s": pairs * world / t_dev,
+                       "with_geometric_verification": verify_detail},
         }
         print(json.dumps(line), flush=True)
     pin.close()

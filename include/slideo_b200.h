@@ -152,6 +152,10 @@ int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n
 int32_t slideo_b200_pool_device_view(slideo_b200_ctx* ctx, void** d_desc, size_t* desc_bytes, void** d_page_offsets,
                                      size_t* offsets_bytes);
 int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx);
+/* Device buffer of the pooled keypoint coordinates (n_desc x 2 floats; geometric verification).  On the rank that built the
+ * pool: *has_points tells whether every page came with coordinates.  On a reserved ctx: the buffer to receive them into;
+ * call with received != 0 after filling it (before pool_commit) to declare the coordinates valid. */
+int32_t slideo_b200_pool_points_device_view(slideo_b200_ctx* ctx, void** d_pt, size_t* bytes, int32_t* has_points, int32_t received);
 
 /* ---- the per-frame hot path  (replaces match_images_with_frame lib.rs:249-295, head of the ranking) ------- */
 /* n BGR 8UC3 frames (what VideoCapture::retrieve yields, video_capture.rs:45-53), HOST memory, frame i at

@@ -141,6 +141,12 @@ class Context:
                                                         ctypes.byref(ob)))
         return d.value or 0, db.value, o.value or 0, ob.value
 
+    def pool_points_device_view(self, received: bool = False):
+        """(d_pt ptr, bytes, has_points) of the pooled keypoint coordinates (geometric verification across GPUs)."""
+        d, b, h = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int32()
+        self._ck(self._lib.slideo_b200_pool_points_device_view(self._h, ctypes.byref(d), ctypes.byref(b), ctypes.byref(h), int(received)))
+        return d.value or 0, b.value, bool(h.value)
+
     def pool_commit(self) -> None:
         self._ck(self._lib.slideo_b200_pool_commit(self._h))
 

@@ -69,6 +69,7 @@ struct slideo_b200_ctx {
     std::vector<int32_t> page_off{0};    // prefix offsets, size n_pages + 1
     std::vector<float> h_pool_pt;        // KeyPoint.pt of every pooled descriptor (x, y); empty when a page came without points
     bool pool_pts_valid = true;
+    bool pts_received = false;           // a reserved pool got its coordinates through pool_points_device_view
     DevBuf<float2> d_pool_pt;
     bool finalized = false;
     DevBuf<uint8_t> d_pool;              // nt x 32 (ORB) / nt x 128 bf16 (SIFT)
@@ -395,7 +396,7 @@ struct slideo_b200_ctx {
         if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_page_of.p, po.data(), (size_t)nt * 2, cudaMemcpyHostToDevice, stream));
         SLIDEO_CUDA(cudaMemcpyAsync(d_page_off.p, page_off.data(), ((size_t)n_pages + 1) * 4, cudaMemcpyHostToDevice, stream));
         pool_pts_valid = pool_pts_valid && h_pool_pt.size() == (size_t)nt * 2;
-        if (pool_pts_valid) {
+        if (pool_pts_valid && !pts_received) {
             d_pool_pt.reserve((size_t)std::max(nt, 1));
             if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_pool_pt.p, h_pool_pt.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, stream));
         }
@@ -688,6 +689,7 @@ int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n
         ctx->h_pool.clear();
         ctx->h_pool_pt.clear();
         ctx->pool_pts_valid = n_desc == 0;
+        ctx->pts_received = false;
         ctx->page_off.assign((size_t)n_pages + 1, 0);
         ctx->d_pool.reserve((size_t)std::max(n_desc, 1) * 32 + 64);
         ctx->d_page_off.reserve((size_t)n_pages + 1);
@@ -707,6 +709,21 @@ int32_t slideo_b200_pool_device_view(slideo_b200_ctx* ctx, void** d_desc, size_t
     });
 }
 
+int32_t slideo_b200_pool_points_device_view(slideo_b200_ctx* ctx, void** d_pt, size_t* bytes, int32_t* has_points, int32_t received) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        if (!ctx->finalized && !ctx->reserved) throw StateError("no device pool yet (finalize_pool or pool_reserve first)");
+        if (ctx->reserved) {
+            ctx->d_pool_pt.reserve((size_t)std::max(ctx->nt, 1));
+            if (received) ctx->pts_received = true;
+        }
+        if (d_pt) *d_pt = ctx->d_pool_pt.p;
+        if (bytes) *bytes = (size_t)ctx->nt * 8;
+        if (has_points) *has_points = ctx->reserved ? (ctx->pts_received ? 1 : 0) : (ctx->pool_pts_valid ? 1 : 0);
+    });
+}
+
 int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
@@ -716,7 +733,9 @@ int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx) {
         if (ctx->page_off[0] != 0 || ctx->page_off[ctx->n_pages] != ctx->nt) throw ArgError("received page offsets do not match the reserved geometry");
         for (int p = 0; p < ctx->n_pages; ++p)
             if (ctx->page_off[p] > ctx->page_off[p + 1]) throw ArgError("received page offsets are not monotone");
-        ctx->build_page_of();
+        const bool got_pts = ctx->pts_received;
+        ctx->build_page_of();              // (no host copy of the coordinates on this rank: the device copy filled by the caller stays)
+        if (got_pts) ctx->pool_pts_valid = true;
         ctx->reserved = false;
         ctx->finalized = true;
     });

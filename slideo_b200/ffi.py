@@ -73,6 +73,7 @@ SYMBOLS = {
     "slideo_b200_pool_device_view": (c_i32, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_sz), ctypes.POINTER(c_vp),
                                              ctypes.POINTER(c_sz)]),
     "slideo_b200_pool_commit": (c_i32, [c_vp]),
+    "slideo_b200_pool_points_device_view": (c_i32, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_sz), c_i32p, c_i32]),
     "slideo_b200_match_frames_bgr8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_vp]),
     "slideo_b200_match_frames_bgr8_device": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_vp]),
     "slideo_b200_match_descriptors": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp]),

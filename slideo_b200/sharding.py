@@ -59,12 +59,12 @@ def broadcast_pool_device(ctx, src: int = 0) -> None:
     import torch.distributed as dist
     rank = dist.get_rank()
     dev = torch.device("cuda", torch.cuda.current_device())
-    hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+    hdr = torch.zeros(3, dtype=torch.int64, device=dev)
     if rank == src:
         n, p = ctx.pool_info()
-        hdr[0], hdr[1] = n, p
+        hdr[0], hdr[1], hdr[2] = n, p, int(ctx.pool_points_device_view()[2])
     dist.broadcast(hdr, src)
-    n, p = int(hdr[0].item()), int(hdr[1].item())
+    n, p, has_pts = int(hdr[0].item()), int(hdr[1].item()), bool(hdr[2].item())
     if rank != src:
         ctx.pool_reserve(n, p)
     d_desc, desc_bytes, d_off, off_bytes = ctx.pool_device_view()
@@ -73,6 +73,11 @@ def broadcast_pool_device(ctx, src: int = 0) -> None:
     if desc_bytes:
         t_desc = torch.as_tensor(_DevView(d_desc, desc_bytes), device=dev)
         dist.broadcast(t_desc, src)                   # the one payload collective of the whole job
+        if has_pts:                                   # keypoint coordinates, only needed by the geometric verification
+            d_pt, pt_bytes, _ = ctx.pool_points_device_view()
+            dist.broadcast(torch.as_tensor(_DevView(d_pt, pt_bytes), device=dev), src)
+            if rank != src:
+                ctx.pool_points_device_view(received=True)
     torch.cuda.synchronize()
     if rank != src:
         ctx.pool_commit()

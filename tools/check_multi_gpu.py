@@ -1,0 +1,31 @@
+"""N-rank check (torchrun): pool built on rank 0, replicated by the NCCL broadcast (descriptors + keypoint coordinates); every
+rank matches + verifies the SAME frames; results must be byte-identical across ranks and equal to rank 0's own."""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import slideo_b200, synth
+from slideo_b200 import sharding
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+NP, NF = 6, 8
+ctx = slideo_b200.Context(slideo_b200.default_config(device=local, geometric_verification=1, keep_matches=1))
+pages = [synth.make_page(p) for p in range(NP)]
+if rank == 0:
+    for p in pages:
+        ctx.add_page_gray8(p)
+    ctx.finalize_pool()
+sharding.broadcast_pool_device(ctx, src=0)
+frames = np.stack([synth.make_frame(f, NP, pages) for f in range(NF)])
+res = ctx.match_frames_bgr8(frames)
+ver = ctx.get_verification(0, NF)
+flat = np.array([[len(v["cand"]), len(v["survivors"])] + [x for c in v["cand"] for x in c] + [0] * (3 * (40 - len(v["cand"]))) for v in ver], np.int32)
+t = torch.from_numpy(np.concatenate([res.reshape(NF, -1), flat], axis=1)).cuda()
+outs = [torch.empty_like(t) for _ in range(world)]
+dist.all_gather(outs, t)
+if rank == 0:
+    same = all(torch.equal(outs[0], o) for o in outs)
+    print("ranks agree:", same, "| frame results:", res[:, :2].tolist(), "| survivors:", [v["survivors"] for v in ver])
+    assert same
+dist.destroy_process_group()
