@@ -179,6 +179,18 @@ int32_t slideo_b200_get_matches(slideo_b200_ctx* ctx, int32_t frame_i, slideo_b2
  * pages added through add_page_gray8 / add_page_features). */
 int32_t slideo_b200_get_verification(slideo_b200_ctx* ctx, int32_t frame0, int32_t n, slideo_b200_verify_result* out);
 
+/* ---- changed-frame prefilter  (replaces MarkSimilarIter video_capture.rs:60-103 + image_utils.rs:8-27) -------------- */
+/* For n consecutive SAMPLED frames (HOST, BGR 8UC3): similarity of each frame's small image (resize INTER_AREA to the
+ * ~300x400-area size) to the previous sampled frame's, and changed = similarity < 0.98.  The first frame after a reset
+ * (reset != 0, or the first call on a ctx, or a geometry change) has similarity 0 and is changed; otherwise the chain
+ * continues from the last frame of the previous call.  out_changed: n bytes (0/1); out_similarity: n floats (may be NULL). */
+int32_t slideo_b200_mark_changed_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h, int32_t stride,
+                                      size_t frame_stride, int32_t reset, uint8_t* out_changed, float* out_similarity);
+/* Same with frames resident in device memory. */
+int32_t slideo_b200_mark_changed_bgr8_device(slideo_b200_ctx* ctx, const void* d_frames, int32_t n, int32_t w, int32_t h,
+                                             int32_t stride, size_t frame_stride, int32_t reset, uint8_t* out_changed,
+                                             float* out_similarity);
+
 /* ---- stage-level entry points (parity tests, matcher sweeps) --------------------------------------------- */
 /* ORB::detectAndCompute (feature_extractor.rs:29-46) on one HOST image, channels = 1 (gray) or 3 (BGR).
  * Canonical order (octave, y, x).  kp_i: n x 4 {x_level, y_level, octave, score}; kp_f: n x 4 {pt.x, pt.y, size,

@@ -30,7 +30,7 @@ VOTE_RATIO = 1.05     # crates/matching-opencv/src/lib.rs:275
 def build() -> str:
     """Compile liboracle.so (gcc) if missing or stale."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c", "ransac_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c", "ransac_oracle.c", "area_oracle.c")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -69,6 +69,10 @@ def lib() -> ctypes.CDLL:
         L.ransac_sample_sequence.argtypes = [ci, ci, c_i32p]
         L.ransac_update_num_iters.argtypes = [ctypes.c_double, ctypes.c_double, ci, ci]
         L.ransac_update_num_iters.restype = ci
+        L.area_small_size.argtypes = [ci, ci, c_i32p, c_i32p]
+        L.area_resize_u8.argtypes = [c_u8p, ci, ci, ci, ci, c_u8p, ci, ci, ci]
+        L.area_similarity.argtypes = [c_u8p, c_u8p, ci, ci, ci]
+        L.area_similarity.restype = cf
         _LIB = L
     return _LIB
 
@@ -253,3 +257,43 @@ def verify_frame(idx: np.ndarray, dist: np.ndarray, page_offsets, frame_pts: np.
     best = float(ranked[0][2]) if ranked else 0.0
     surv = [(p, r) for p, _, r in ranked if r > MIN_RATING and (float(r) / best if best else 0.0) > MIN_RATING_FRACTION]
     return dict(cand=cand, survivors=surv)
+
+
+# ----------------------------------------------------------------------------- changed-frame prefilter (video_capture.rs:60-103)
+CHANGED_THRESHOLD = np.float32(0.98)   # video_capture.rs:98
+
+
+def small_size(w: int, h: int):
+    sw, sh = ctypes.c_int32(), ctypes.c_int32()
+    lib().area_small_size(w, h, ctypes.byref(sw), ctypes.byref(sh))
+    return sw.value, sh.value
+
+
+def to_small_image(img: np.ndarray) -> np.ndarray:
+    """image_utils.rs:8-19: cv::resize(img, small_size, INTER_AREA) for 8-bit images (1 or 3 interleaved channels)."""
+    img = _u8(img)
+    h, w = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    dw, dh = small_size(w, h)
+    out = np.empty((dh, dw) if img.ndim == 2 else (dh, dw, cn), np.uint8)
+    lib().area_resize_u8(_p(img, ctypes.c_uint8), w, h, img.strides[0], cn, _p(out, ctypes.c_uint8), dw, dh, 0)
+    return out
+
+
+def similarity(a: np.ndarray, b: np.ndarray) -> np.float32:
+    """image_utils.rs:21-27."""
+    a, b = _u8(a), _u8(b)
+    cn = 1 if a.ndim == 2 else a.shape[2]
+    return np.float32(lib().area_similarity(_p(a, ctypes.c_uint8), _p(b, ctypes.c_uint8), a.shape[1], a.shape[0], cn))
+
+
+def mark_similar(frames):
+    """MarkSimilarIter: (changed[n], similarity[n]) for consecutive sampled frames."""
+    last, ch, sims = None, [], []
+    for f in frames:
+        small = to_small_image(f)
+        s = similarity(last, small) if last is not None else np.float32(0.0)
+        last = small
+        sims.append(s)
+        ch.append(bool(s < CHANGED_THRESHOLD))
+    return np.array(ch, bool), np.array(sims, np.float32)

@@ -207,6 +207,24 @@ class Context:
             self._ck(self._lib.slideo_b200_get_matches(self._h, frame_i, _ptr(out), rows.value, ctypes.byref(rows)))
         return out
 
+    def mark_changed_bgr8(self, frames: np.ndarray, reset: bool = False):
+        """MarkSimilarIter (video_capture.rs:60-103) on consecutive SAMPLED frames [n, h, w, 3] (HOST): (changed bool[n], similarity f32[n])."""
+        if frames.ndim == 3:
+            frames = frames[None]
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w, _ = frames.shape
+        ch = np.zeros(max(n, 1), np.uint8)
+        sim = np.zeros(max(n, 1), np.float32)
+        self._ck(self._lib.slideo_b200_mark_changed_bgr8(self._h, _ptr(frames), n, w, h, 3 * w, 3 * w * h, int(reset), _ptr(ch), _ptr(sim)))
+        return ch[:n].astype(bool), sim[:n]
+
+    def mark_changed_bgr8_device(self, dev_ptr: int, n: int, w: int, h: int, reset: bool = False):
+        ch = np.zeros(max(n, 1), np.uint8)
+        sim = np.zeros(max(n, 1), np.float32)
+        self._ck(self._lib.slideo_b200_mark_changed_bgr8_device(self._h, ctypes.c_void_p(dev_ptr), n, w, h, 3 * w, 3 * w * h, int(reset),
+                                                                _ptr(ch), _ptr(sim)))
+        return ch[:n].astype(bool), sim[:n]
+
     def get_verification(self, frame0: int, n: int):
         """RANSAC gate records of frames [frame0, frame0+n) of the last match_frames call (cfg.geometric_verification)."""
         res = (ffi.VerifyResult * max(n, 1))()

@@ -3,6 +3,7 @@
 // Host-side counterpart of the reference's orchestration in crates/matching-opencv/src/lib.rs:37-64 (page pool),
 // lib.rs:249-295 (per-frame path) and flann.rs:64-89 (matcher); all arithmetic runs in the CUDA kernels of
 // orb.cu / knn_hamming.cu / knn_l2.cu.  There is no CPU fallback: without a device every entry point fails.
+#include <math.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -17,6 +18,7 @@
 #include "common.cuh"
 #include "knn_l2.cuh"
 #include "orb.cuh"
+#include "prefilter.cuh"
 #include "verify.cuh"
 
 using namespace slideo;
@@ -258,6 +260,12 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_v_corr;
     DevBuf<VerifyRecord> d_v_out;
     std::vector<VerifyRecord> verify_results;   // one per frame of the last match_frames_* call
+
+    // ---- changed-frame prefilter (K13) --------------------------------------------------------------------
+    AreaTables area;
+    DevBuf<uint8_t> d_small;                    // [batch + 1] small images: slot 0 = last frame of the previous batch
+    DevBuf<unsigned long long> d_sumsq;
+    bool have_prev_small = false;
     int qs_total = 0, qs_frames = 0;
     size_t qs_cap = 0;
     static constexpr int SUPER_BATCH = 2048;   // frames per query stream (bounds the stream buffers)
@@ -978,6 +986,99 @@ int32_t slideo_b200_get_verification(slideo_b200_ctx* ctx, int32_t frame0, int32
         arg(out != nullptr || n == 0, "out must not be NULL");
         static_assert(sizeof(slideo_b200_verify_result) == sizeof(VerifyRecord), "ABI struct and kernel record must agree");
         if (n) std::memcpy(out, ctx->verify_results.data() + frame0, (size_t)n * sizeof(VerifyRecord));
+    });
+}
+
+}  // extern "C"
+
+namespace {
+
+// MarkSimilarIter over n frames; frames are fetched batch by batch through `get_batch(f0, nb)` which returns a device pointer to
+// nb packed frames (row stride `stride`, frame stride `frame_stride`) valid on ctx->stream
+template <typename GetBatch>
+void mark_changed_impl(slideo_b200_ctx* ctx, int n, int w, int h, bool reset, uint8_t* out_changed, float* out_similarity, GetBatch&& get_batch) {
+    if (ctx->area.sw != w || ctx->area.sh != h) {
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->area.build(w, h);
+        ctx->have_prev_small = false;
+    }
+    if (reset) ctx->have_prev_small = false;
+    const int B = ctx->cfg.max_batch;
+    const size_t small_bytes = (size_t)ctx->area.dw * ctx->area.dh * 3;
+    ctx->d_small.reserve((size_t)(std::min(B, n) + 1) * small_bytes);
+    ctx->d_sumsq.reserve((size_t)B + 1);
+    std::vector<unsigned long long> h_ss((size_t)B + 1);
+    const int p = ctx->area.dw * ctx->area.dh;
+    const float max_error = sqrtf((255.0f * 255.0f * 3.0f) * (float)p);   // image_utils.rs:24-25 (f32)
+    for (int f0 = 0; f0 < n; f0 += B) {
+        const int nb = std::min(B, n - f0);
+        int stride = 0;
+        size_t frame_stride = 0;
+        const uint8_t* d_src = get_batch(f0, nb, &stride, &frame_stride);
+        EventPair t = ctx->begin_timing(0, ctx->stream);
+        area_small_launch(ctx->area, d_src, nb, stride, frame_stride, ctx->d_small.p + small_bytes, ctx->stream);
+        // pairs (slot i, slot i + 1): slot 0 holds the previous batch's last small image
+        small_sumsq_launch(ctx->d_small.p, nb, small_bytes, ctx->d_sumsq.p, ctx->stream);
+        ctx->end_timing(t, ctx->stream);
+        ctx->tm.kernel_launches += 2;
+        SLIDEO_CUDA(cudaMemcpyAsync(h_ss.data(), ctx->d_sumsq.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_small.p, ctx->d_small.p + (size_t)nb * small_bytes, small_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < nb; ++i) {
+            float sim = 0.0f;   // video_capture.rs:92-96: no previous frame -> 0.0
+            if (i > 0 || ctx->have_prev_small) {
+                const double error_l2 = sqrt((double)h_ss[(size_t)i]);            // norm2(a, b, NORM_L2)
+                sim = 1.0f - (float)error_l2 / max_error;                          // image_utils.rs:26
+            }
+            if (out_similarity) out_similarity[f0 + i] = sim;
+            out_changed[f0 + i] = sim < 0.98f ? 1 : 0;                            // video_capture.rs:98
+        }
+        ctx->have_prev_small = true;
+    }
+    ctx->collect_timings();
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t slideo_b200_mark_changed_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h, int32_t stride,
+                                      size_t frame_stride, int32_t reset, uint8_t* out_changed, float* out_similarity) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(n >= 0, "n < 0");
+        if (n == 0) return;
+        arg(frames && out_changed, "frames/out_changed must not be NULL");
+        arg(w >= 16 && h >= 16 && w <= 16384 && h <= 16384, "frame size out of range");
+        arg(stride >= 3 * w, "stride < 3*w");
+        arg(frame_stride >= (size_t)stride * (h - 1) + (size_t)3 * w, "frame_stride too small");
+        const size_t img_bytes = (size_t)3 * w * h;
+        ctx->d_frames[0].reserve((size_t)std::min(ctx->cfg.max_batch, n) * img_bytes);
+        mark_changed_impl(ctx, n, w, h, reset != 0, out_changed, out_similarity, [&](int f0, int nb, int* st, size_t* fst) -> const uint8_t* {
+            EventPair t = ctx->begin_timing(2, ctx->stream);
+            ctx->upload_images(ctx->d_frames[0].p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride, ctx->stream);
+            ctx->end_timing(t, ctx->stream);
+            *st = 3 * w;
+            *fst = img_bytes;
+            return ctx->d_frames[0].p;
+        });
+    });
+}
+
+int32_t slideo_b200_mark_changed_bgr8_device(slideo_b200_ctx* ctx, const void* d_frames, int32_t n, int32_t w, int32_t h, int32_t stride,
+                                             size_t frame_stride, int32_t reset, uint8_t* out_changed, float* out_similarity) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(n >= 0, "n < 0");
+        if (n == 0) return;
+        arg(d_frames && out_changed, "d_frames/out_changed must not be NULL");
+        arg(w >= 16 && h >= 16 && w <= 16384 && h <= 16384, "frame size out of range");
+        arg(stride >= 3 * w, "stride < 3*w");
+        mark_changed_impl(ctx, n, w, h, reset != 0, out_changed, out_similarity, [&](int f0, int, int* st, size_t* fst) -> const uint8_t* {
+            *st = stride;
+            *fst = frame_stride;
+            return (const uint8_t*)d_frames + (size_t)f0 * frame_stride;
+        });
     });
 }
 

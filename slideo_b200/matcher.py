@@ -8,9 +8,11 @@ implemented over the C ABI the way `crates/matching-opencv` implements it over O
     result  = task.process()                                       # VideoMatcherTask -> [Matching]       lib.rs:169-245
 
 What differs, and why (DESIGN.md "Boundary"):
-  * the per-frame decision is the head of the reference's ranking -- (argmax-votes slide, votes), lib.rs:268-295;
-    the RANSAC / warp gates behind it (lib.rs:297-389) are SURVEY.md section 8(f) "next" rows.  `min_votes` stands
-    in for those gates: a frame whose best slide has fewer votes maps to `image=None`.
+  * the per-frame decision: with `geometric_verification=True` (default) the reference's RANSAC gate runs on the GPU
+    (lib.rs:284-333) and the frame maps to the best-rated survivor, or to `image=None` when no slide passes
+    `rating > 50 && rating / best > 0.2`; the warp + similarity gate behind it (lib.rs:335-389) is the next row, so the
+    survivors are ranked by rating instead of by warped-image similarity.  With `geometric_verification=False` the
+    decision is the head of the vote ranking (argmax-votes slide, lib.rs:268-295) and `min_votes` stands in for the gates.
   * frames are matched in batches on the GPU instead of one rayon task per frame (lib.rs:213-214).
   * decoding stays on the host (the reference uses OpenCV's FFmpeg VideoCapture, video_capture.rs:15-57); any
     iterable of (frame_bgr, seconds, frame_idx) can be passed instead of a path.
@@ -72,10 +74,10 @@ def _image_gray(image) -> np.ndarray:
 class B200ImageVideoMatcher:
     """Drop-in for OpenCVImageVideoMatcher (lib.rs:33-75)."""
 
-    def __init__(self, device: int = 0, min_votes: int = 1, **config_overrides):
+    def __init__(self, device: int = 0, min_votes: int = 1, geometric_verification: bool = True, **config_overrides):
         self._device = device
         self._min_votes = min_votes
-        self._overrides = config_overrides
+        self._overrides = dict(config_overrides, geometric_verification=int(geometric_verification))
 
     def create_video_matcher(self, images: Sequence[Any], progress_reporter: Optional[ProgressReporter] = None
                              ) -> "B200VideoMatcher":
@@ -139,8 +141,8 @@ def to_small_image(img: np.ndarray) -> np.ndarray:
     """image_utils.rs:8-19: INTER_AREA resize to ~300x400 area, aspect preserved (host side, prefilter only)."""
     import cv2
     h, w = img.shape[:2]
-    f = math.sqrt(SMALL_IMAGE_AREA / float(w * h))
-    return cv2.resize(img, (int(round(w * f)), int(round(h * f))), interpolation=cv2.INTER_AREA)
+    f = np.sqrt(np.float32(SMALL_IMAGE_AREA) / np.float32(w * h), dtype=np.float32)     # f32 like the reference
+    return cv2.resize(img, (int(np.float32(w) * f), int(np.float32(h) * f)), interpolation=cv2.INTER_AREA)   # `as i32` truncates
 
 
 def compute_similarity(a: np.ndarray, b: np.ndarray) -> float:
@@ -149,8 +151,34 @@ def compute_similarity(a: np.ndarray, b: np.ndarray) -> float:
     return 1.0 - math.sqrt(float((d * d).sum())) / math.sqrt(255.0 * 255.0 * 3.0 * a.shape[0] * a.shape[1])
 
 
+def mark_similar_gpu(ctx: Context, frames: Iterable[Tuple[np.ndarray, float, int]], batch: int = 32
+                     ) -> Iterator[Tuple[bool, np.ndarray, float, int]]:
+    """MarkSimilarIter (video_capture.rs:60-103) through the library (K13, slideo_b200_mark_changed_bgr8)."""
+    buf: List[Tuple[np.ndarray, float, int]] = []
+    first = True
+
+    def flush():
+        nonlocal first
+        if not buf:
+            return
+        changed, _ = ctx.mark_changed_bgr8(np.stack([b[0] for b in buf]), reset=first)
+        first = False
+        for c, (f, t, i) in zip(changed, buf):
+            yield bool(c), f, t, i
+        buf.clear()
+
+    for item in frames:
+        if buf and item[0].shape != buf[0][0].shape:
+            yield from flush()
+            first = True
+        buf.append(item)
+        if len(buf) >= batch:
+            yield from flush()
+    yield from flush()
+
+
 def mark_similar(frames: Iterable[Tuple[np.ndarray, float, int]]) -> Iterator[Tuple[bool, np.ndarray, float, int]]:
-    """MarkSimilarIter (video_capture.rs:60-103): changed iff similarity to the previous sampled frame < 0.98."""
+    """MarkSimilarIter (video_capture.rs:60-103) on the host with cv2 (kept for environments that prefilter before upload)."""
     last = None
     for frame, t, idx in frames:
         small = to_small_image(frame)
@@ -191,7 +219,7 @@ class B200VideoMatcherTask:
         else:
             source = iter(self.video)
             frames_to_process = self.frames_to_process_hint()
-        stream = mark_similar(source) if self.prefilter else ((True, f, t, i) for f, t, i in source)
+        stream = mark_similar_gpu(ctx, source) if self.prefilter else ((True, f, t, i) for f, t, i in source)
 
         done = 0
         batch: List[Tuple[np.ndarray, float, int]] = []
@@ -208,8 +236,13 @@ class B200VideoMatcherTask:
             for shape, idxs in shapes.items():
                 frames = np.stack([batch[j][0] for j in idxs])
                 res = ctx.match_frames_bgr8(frames)
-                for j, (best, votes, _nkp) in zip(idxs, res):
-                    img = images[best] if best >= 0 and votes >= self.vm.min_votes else None
+                ver = ctx.get_verification(0, len(idxs)) if ctx.cfg.geometric_verification else None
+                for n, (j, (best, votes, _nkp)) in enumerate(zip(idxs, res)):
+                    if ver is not None:      # lib.rs:329-333: best-rated survivor of the RANSAC gate
+                        surv = ver[n]["survivors"]
+                        img = images[surv[0][0]] if surv else None
+                    else:
+                        img = images[best] if best >= 0 and votes >= self.vm.min_votes else None
                     results.append(Matching(batch[j][1], batch[j][2], img, int(votes)))
                     done += 1
                     self.reporter.report(done, frames_to_process, f"Processing frames of '{name}'...")

@@ -137,3 +137,30 @@ def make_ransac_golden():
 
 if __name__ == "__main__":
     make_ransac_golden()
+
+
+def make_area_golden():
+    """tests/golden/area.json: cv2.resize(INTER_AREA) to the reference's small size (image_utils.rs:8-19) as CRC32, and
+    compute_similarity (image_utils.rs:21-27) values from cv2.norm, on seeded synthetic frames."""
+    out = {"small_size_1920x1080": [461, 259], "crc": {}, "similarity": {}}
+    smalls = {}
+    for f in (3, 4, 5):
+        fr = synth.make_frame(f, 50)
+        sm = cv2.resize(fr, (461, 259), interpolation=cv2.INTER_AREA)
+        smalls[f] = sm
+        out["crc"][str(f)] = crc(sm)
+    pg = cv2.cvtColor(synth.make_page(2), cv2.COLOR_GRAY2BGR)
+    fac = np.sqrt(np.float32(120000) / np.float32(2001 * 1125), dtype=np.float32)
+    dw, dh = int(np.float32(2001) * fac), int(np.float32(1125) * fac)
+    out["small_size_2001x1125"] = [dw, dh]
+    out["crc"]["page2"] = crc(cv2.resize(pg, (dw, dh), interpolation=cv2.INTER_AREA))
+    for a, b in ((3, 4), (4, 5), (3, 3)):
+        err = cv2.norm(smalls[a], smalls[b], cv2.NORM_L2)
+        sim = np.float32(1.0) - np.float32(err) / np.sqrt(np.float32(255.0 * 255.0 * 3.0) * np.float32(259 * 461), dtype=np.float32)
+        out["similarity"][f"{a}-{b}"] = float(sim)
+    with open(os.path.join(HERE, "area.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+if __name__ == "__main__":
+    make_area_golden()

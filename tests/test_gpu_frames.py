@@ -70,7 +70,7 @@ def test_matcher_mirror_matches_oracle(scene):
     pages, frames, _, expect = scene
     seen = []
     rep = slideo_b200.ProgressReporter(lambda a, b, m: seen.append((a, b, m)))
-    vm = slideo_b200.B200ImageVideoMatcher().create_video_matcher(pages, rep)
+    vm = slideo_b200.B200ImageVideoMatcher(geometric_verification=False).create_video_matcher(pages, rep)
     assert seen[-1][:2] == (NPAGES, NPAGES)
     src = [(frames[i], 5.0 * i, 125 * i) for i in range(NFRAMES)]
     task = vm.match_images_with_video(src, rep)

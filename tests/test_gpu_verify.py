@@ -66,3 +66,23 @@ def test_verification_needs_points():
         with pytest.raises(slideo_b200.SlideoError) as e:
             c.match_frames_bgr8(synth.make_frame(0, 1)[None])
         assert e.value.status == slideo_b200.ffi.E_STATE
+
+
+def test_matcher_mirror_uses_the_gate(scene):
+    """create_video_matcher -> match_images_with_video -> process with the RANSAC gate deciding (lib.rs:329-333)."""
+    import slideo_b200
+    pages, frames, _, expect = scene
+    vm = slideo_b200.B200ImageVideoMatcher().create_video_matcher(pages)
+    task = vm.match_images_with_video([(frames[i], 5.0 * i, 125 * i) for i in range(NFRAMES)])
+    task.prefilter = False
+    out = task.process()
+    want, last = [], "start"
+    for i in range(NFRAMES):
+        img = expect[i]["survivors"][0][0] if expect[i]["survivors"] else None
+        if last != "start" and last == img:
+            continue
+        last = img
+        want.append((125 * i, img))
+    got = [(m.video_frame_idx, None if m.image is None else next(j for j, p in enumerate(pages) if p is m.image)) for m in out]
+    assert got == want
+    vm.ctx.close()
