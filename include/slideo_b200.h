@@ -65,7 +65,8 @@ typedef struct slideo_b200_config {
     int32_t descriptor_kind; /* slideo_b200_descriptor_kind */
     int32_t max_batch;       /* frames processed per internal batch (default 32) */
     int32_t keep_matches;    /* !=0: keep the k-NN rows of the last match call for slideo_b200_get_matches */
-    int32_t geometric_verification; /* !=0: match_frames_* also runs the RANSAC gate (lib.rs:284-333), see slideo_b200_get_verification */
+    int32_t geometric_verification; /* 1: match_frames_* also runs the RANSAC gate (lib.rs:284-333), see slideo_b200_get_verification;
+                                       2: plus the warp + similarity gate (lib.rs:335-389), see slideo_b200_get_decisions */
     int32_t reserved[2];
 } slideo_b200_config;
 
@@ -115,6 +116,17 @@ typedef struct slideo_b200_verify_result {
     int32_t survivor_page[SLIDEO_B200_TOP_RATED];
     int32_t survivor_rating[SLIDEO_B200_TOP_RATED];
 } slideo_b200_verify_result;
+
+/* Final decision for one frame (cfg.geometric_verification == 2): the survivors of the RANSAC gate re-ranked by the similarity
+ * of the warped frame to the slide (lib.rs:335-389: warp_affine(WARP_INVERSE_MAP) with the LM-refined matrix -> to_small_image ->
+ * compute_similarity; sort by similarity; retain > 0.5).  image = rated_page[0] or -1 (Matching.image = None). */
+typedef struct slideo_b200_decision {
+    int32_t image;
+    int32_t n_rated;
+    int32_t rated_page[SLIDEO_B200_TOP_RATED];
+    float rated_similarity[SLIDEO_B200_TOP_RATED];
+    double refined_matrix[SLIDEO_B200_TOP_RATED][4]; /* (a, b, tx, ty) of [a -b tx; b a ty] for the RANSAC-gate survivors, in survivor order */
+} slideo_b200_decision;
 
 typedef struct slideo_b200_ctx slideo_b200_ctx;
 
@@ -178,6 +190,10 @@ int32_t slideo_b200_get_matches(slideo_b200_ctx* ctx, int32_t frame_i, slideo_b2
 /* Verification records of frames [frame0, frame0 + n) of the last match_frames_* call (needs cfg.geometric_verification and
  * pages added through add_page_gray8 / add_page_features). */
 int32_t slideo_b200_get_verification(slideo_b200_ctx* ctx, int32_t frame0, int32_t n, slideo_b200_verify_result* out);
+
+/* Decisions of frames [frame0, frame0 + n) of the last match_frames_* call (needs cfg.geometric_verification == 2 and pages
+ * added through add_page_gray8, all of one size). */
+int32_t slideo_b200_get_decisions(slideo_b200_ctx* ctx, int32_t frame0, int32_t n, slideo_b200_decision* out);
 
 /* ---- changed-frame prefilter  (replaces MarkSimilarIter video_capture.rs:60-103 + image_utils.rs:8-27) -------------- */
 /* For n consecutive SAMPLED frames (HOST, BGR 8UC3): similarity of each frame's small image (resize INTER_AREA to the

@@ -236,6 +236,17 @@ class Context:
                             survivors=[(r.survivor_page[j], r.survivor_rating[j]) for j in range(r.n_survivors)]))
         return out
 
+    def get_decisions(self, frame0: int, n: int):
+        """Warp + similarity gate of frames [frame0, frame0+n) of the last match_frames call (cfg.geometric_verification == 2)."""
+        res = (ffi.Decision * max(n, 1))()
+        self._ck(self._lib.slideo_b200_get_decisions(self._h, frame0, n, res))
+        out = []
+        for i in range(n):
+            r = res[i]
+            out.append(dict(image=r.image, rated=[(r.rated_page[j], np.float32(r.rated_similarity[j])) for j in range(r.n_rated)],
+                            refined=[[r.refined_matrix[j][c] for c in range(4)] for j in range(ffi.TOP_RATED)]))
+        return out
+
     # ---- stage-level entry points ------------------------------------------------------------------------
     def extract_orb(self, img: np.ndarray, cap: int = 16384):
         """ORB::detectAndCompute (feature_extractor.rs:29-46) on one host image (gray [h,w] or BGR [h,w,3]).

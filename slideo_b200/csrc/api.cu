@@ -260,6 +260,19 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_v_corr;
     DevBuf<VerifyRecord> d_v_out;
     std::vector<VerifyRecord> verify_results;   // one per frame of the last match_frames_* call
+    // photometric stage (K14, cfg.geometric_verification == 2)
+    std::vector<slideo_b200_decision> decisions;
+    std::vector<uint8_t> h_page_small;          // gray small image of every page (uniform page geometry)
+    int page_w = 0, page_h = 0;
+    bool page_geom_ok = true;
+    DevBuf<uint8_t> d_page_small, d_all_frames;
+    AreaTables page_area;
+    DevBuf<int32_t> d_v_best_it, d_v_surv_cand;
+    DevBuf<double> d_v_refined;
+    DevBuf<unsigned long long> d_v_sumsq;
+    const uint8_t* photo_frames = nullptr;      // device frames of the current stream (frame i at + i * photo_frame_stride)
+    int photo_w = 0, photo_h = 0, photo_row_stride = 0;
+    size_t photo_frame_stride = 0;
 
     // ---- changed-frame prefilter (K13) --------------------------------------------------------------------
     AreaTables area;
@@ -369,6 +382,13 @@ struct slideo_b200_ctx {
         a.d_frame_pt = d_qs_pt.p; a.d_pool_pt = d_pool_pt.p;
         a.d_cand_page = d_v_cand_page.p; a.d_cand_votes = d_v_cand_votes.p; a.d_n_cand = d_v_n_cand.p; a.d_rating = d_v_rating.p;
         a.d_corr = d_v_corr.p; a.d_out = d_v_out.p;
+        const bool photo = cfg.geometric_verification >= 2;
+        if (photo) {
+            d_v_best_it.reserve(F * VERIFY_TOP_SLIDES);
+            d_v_surv_cand.reserve(F * VERIFY_TOP_RATED);
+        }
+        a.d_best_it = photo ? d_v_best_it.p : nullptr;
+        a.d_survivor_cand = photo ? d_v_surv_cand.p : nullptr;
         EventPair t = begin_timing(5, knn_stream);
         int nl = 0;
         verify_launch(a, knn_stream, &nl);
@@ -377,11 +397,69 @@ struct slideo_b200_ctx {
         const size_t base = verify_results.size();
         verify_results.resize(base + F);
         SLIDEO_CUDA(cudaMemcpyAsync(verify_results.data() + base, d_v_out.p, F * sizeof(VerifyRecord), cudaMemcpyDeviceToHost, knn_stream));
+        if (photo) photometric_stream(a, base);
         SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
+    }
+
+    // K14 on the survivors of the finished stream (lib.rs:335-389); appends one decision per frame
+    void photometric_stream(const VerifyArgs& va, size_t base) {
+        if (!page_geom_ok || h_page_small.empty())
+            throw StateError("the warp + similarity gate needs every page as an image (add_page_gray8) and one page size");
+        if (!photo_frames) throw StateError("frames are not resident for the warp + similarity gate");
+        const size_t F = (size_t)qs_frames;
+        d_v_refined.reserve(F * VERIFY_TOP_RATED * 4);
+        d_v_sumsq.reserve(F * VERIFY_TOP_RATED);
+        PhotoArgs p;
+        p.n_frames = qs_frames; p.k = cfg.knn_k;
+        p.d_records = d_v_out.p; p.d_survivor_cand = d_v_surv_cand.p; p.d_best_it = d_v_best_it.p; p.d_cand_votes = va.d_cand_votes;
+        p.d_corr = va.d_corr; p.d_frame_q0 = va.d_frame_q0; p.d_frame_pt = va.d_frame_pt; p.d_pool_pt = va.d_pool_pt;
+        p.d_frames = photo_frames; p.frame_w = photo_w; p.frame_h = photo_h; p.frame_stride_row = photo_row_stride;
+        p.frame_stride = photo_frame_stride;
+        p.page_w = page_w; p.page_h = page_h; p.small_w = page_area.dw; p.small_h = page_area.dh;
+        p.d_xoff = page_area.d_xoff; p.d_xsi = page_area.d_xsi; p.d_xa = page_area.d_xa;
+        p.d_yoff = page_area.d_yoff; p.d_ysi = page_area.d_ysi; p.d_ya = page_area.d_ya;
+        p.d_page_small = d_page_small.p; p.d_refined = d_v_refined.p; p.d_sumsq = d_v_sumsq.p;
+        EventPair t = begin_timing(5, knn_stream);
+        int nl = 0;
+        photometric_launch(p, knn_stream, &nl);
+        end_timing(t, knn_stream);
+        tm.kernel_launches += nl;
+        std::vector<unsigned long long> ss(F * VERIFY_TOP_RATED);
+        std::vector<double> ref(F * VERIFY_TOP_RATED * 4);
+        SLIDEO_CUDA(cudaMemcpyAsync(ss.data(), d_v_sumsq.p, ss.size() * 8, cudaMemcpyDeviceToHost, knn_stream));
+        SLIDEO_CUDA(cudaMemcpyAsync(ref.data(), d_v_refined.p, ref.size() * 8, cudaMemcpyDeviceToHost, knn_stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
+        const int pcount = page_area.dw * page_area.dh;
+        const float max_error = sqrtf((255.0f * 255.0f * 3.0f) * (float)pcount);   // image_utils.rs:24-25
+        decisions.resize(base + F);
+        for (size_t f = 0; f < F; ++f) {
+            const VerifyRecord& r = verify_results[base + f];
+            slideo_b200_decision& d = decisions[base + f];
+            std::memset(&d, 0, sizeof d);
+            struct Rated { int page; float sim; };
+            std::vector<Rated> rated;
+            for (int j = 0; j < r.n_survivors; ++j) {
+                const double error_l2 = sqrt((double)ss[f * VERIFY_TOP_RATED + j]);
+                const float sim = 1.0f - (float)error_l2 / max_error;               // image_utils.rs:26
+                rated.push_back({r.survivor_page[j], sim});
+                for (int c = 0; c < 4; ++c) d.refined_matrix[j][c] = ref[(f * VERIFY_TOP_RATED + j) * 4 + c];
+            }
+            std::stable_sort(rated.begin(), rated.end(), [](const Rated& a, const Rated& b) { return a.sim > b.sim; });   // lib.rs:370
+            d.image = -1;
+            for (int j = 0; j < VERIFY_TOP_RATED; ++j) { d.rated_page[j] = -1; d.rated_similarity[j] = 0.f; }
+            for (const Rated& x : rated)
+                if (x.sim > 0.5f) {                                                   // lib.rs:381
+                    d.rated_page[d.n_rated] = x.page;
+                    d.rated_similarity[d.n_rated] = x.sim;
+                    ++d.n_rated;
+                }
+            if (d.n_rated) d.image = d.rated_page[0];
+        }
     }
 
     void reset_kept() {
         verify_results.clear();
+        decisions.clear();
         kept_keys.clear();
         kept_l2.clear();
         kept_l2_idx.clear();
@@ -403,6 +481,10 @@ struct slideo_b200_ctx {
         d_page_off.reserve((size_t)n_pages + 1);
         if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_page_of.p, po.data(), (size_t)nt * 2, cudaMemcpyHostToDevice, stream));
         SLIDEO_CUDA(cudaMemcpyAsync(d_page_off.p, page_off.data(), ((size_t)n_pages + 1) * 4, cudaMemcpyHostToDevice, stream));
+        if (cfg.geometric_verification >= 2 && page_geom_ok && !h_page_small.empty()) {
+            d_page_small.reserve(h_page_small.size());
+            SLIDEO_CUDA(cudaMemcpyAsync(d_page_small.p, h_page_small.data(), h_page_small.size(), cudaMemcpyHostToDevice, stream));
+        }
         pool_pts_valid = pool_pts_valid && h_pool_pt.size() == (size_t)nt * 2;
         if (pool_pts_valid && !pts_received) {
             d_pool_pt.reserve((size_t)std::max(nt, 1));
@@ -577,6 +659,25 @@ int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int3
             SLIDEO_CUDA(cudaMemcpyAsync(kpf.data(), ex.d_kp_f(), (size_t)total * 16, cudaMemcpyDeviceToHost, ctx->stream));
         }
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->cfg.geometric_verification >= 2) {   // slide.small_img (lib.rs:105): to_small_image of the gray page replicated to BGR
+            if (ctx->page_w == 0) {
+                ctx->page_w = w;
+                ctx->page_h = h;
+                ctx->page_area.build(w, h);
+            }
+            if (w != ctx->page_w || h != ctx->page_h) {
+                ctx->page_geom_ok = false;
+            } else {
+                const size_t sb = (size_t)ctx->page_area.dw * ctx->page_area.dh;
+                ctx->d_small.reserve(sb);
+                area_small_launch(ctx->page_area, ctx->d_img.p, 1, w, (size_t)w * h, ctx->d_small.p, ctx->stream, 1);
+                const size_t b0 = ctx->h_page_small.size();
+                ctx->h_page_small.resize(b0 + sb);
+                SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_page_small.data() + b0, ctx->d_small.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+                SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+                ctx->tm.kernel_launches += 1;
+            }
+        }
         for (int i = 0; i < total; ++i) {   // KeyPoint.pt of the slide keypoints (lib.rs:299)
             ctx->h_pool_pt.push_back(kpf[(size_t)i * 4]);
             ctx->h_pool_pt.push_back(kpf[(size_t)i * 4 + 1]);
@@ -599,6 +700,7 @@ int32_t slideo_b200_add_page_descriptors(slideo_b200_ctx* ctx, const void* desc,
         if (n) std::memcpy(ctx->h_pool.data() + base, desc, (size_t)n * ctx->desc_bytes);
         ctx->page_off.push_back(ctx->page_off.back() + n);
         if (n) ctx->pool_pts_valid = false;   // no keypoint coordinates for this page: geometric verification unavailable
+        ctx->page_geom_ok = false;
     });
 }
 
@@ -614,6 +716,7 @@ int32_t slideo_b200_add_page_features(slideo_b200_ctx* ctx, const void* desc, co
         ctx->h_pool.resize(base + (size_t)n * 32);
         if (n) std::memcpy(ctx->h_pool.data() + base, desc, (size_t)n * 32);
         ctx->h_pool_pt.insert(ctx->h_pool_pt.end(), pt_xy, pt_xy + (size_t)n * 2);
+        ctx->page_geom_ok = false;   // no page image: the warp + similarity gate is unavailable
         ctx->page_off.push_back(ctx->page_off.back() + n);
     });
 }
@@ -772,11 +875,20 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
             const int ns = std::min(slideo_b200_ctx::SUPER_BATCH, n - s0);
             const int n_batches = cdiv(ns, B);
             ctx->stream_begin(ns, w, h);
+            const bool keep_frames = ctx->cfg.geometric_verification >= 2;   // the warp gate reads the frames again at the end
+            if (keep_frames) {
+                ctx->d_all_frames.reserve((size_t)ns * img_bytes);
+                ctx->photo_frames = ctx->d_all_frames.p;
+                ctx->photo_w = w; ctx->photo_h = h; ctx->photo_row_stride = 3 * w; ctx->photo_frame_stride = img_bytes;
+            }
+            auto batch_dst = [&](int b) -> uint8_t* {
+                return keep_frames ? ctx->d_all_frames.p + (size_t)b * B * img_bytes : ctx->d_frames[b % NBUF].p;
+            };
             auto issue_copy = [&](int b) {
                 const int buf = b % NBUF, f0 = s0 + b * B, nb = std::min(B, s0 + ns - f0);
-                SLIDEO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));  // detection of batch b - NBUF is done
+                if (!keep_frames) SLIDEO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));  // detection of batch b - NBUF is done
                 EventPair t = ctx->begin_timing(2, ctx->copy_stream);
-                ctx->upload_images(ctx->d_frames[buf].p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride,
+                ctx->upload_images(batch_dst(b), frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride,
                                    ctx->copy_stream);
                 ctx->end_timing(t, ctx->copy_stream);
                 SLIDEO_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
@@ -787,7 +899,7 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
             for (int b = 0; b < n_batches; ++b) {
                 const int buf = b % NBUF, f0 = s0 + b * B, nb = std::min(B, s0 + ns - f0);
                 SLIDEO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
-                ctx->stream_detect(ctx->d_frames[buf].p, nb, w, h, 3 * w, img_bytes);
+                ctx->stream_detect(batch_dst(b), nb, w, h, 3 * w, img_bytes);
                 SLIDEO_CUDA(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
                 if (b + NBUF < n_batches) issue_copy(b + NBUF);
                 ctx->stream_match_ready(false);
@@ -824,6 +936,8 @@ int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d
         for (int s0 = 0; s0 < n; s0 += slideo_b200_ctx::SUPER_BATCH) {
             const int ns = std::min(slideo_b200_ctx::SUPER_BATCH, n - s0);
             ctx->stream_begin(ns, w, h);
+            ctx->photo_frames = (const uint8_t*)d_frames + (size_t)s0 * frame_stride;
+            ctx->photo_w = w; ctx->photo_h = h; ctx->photo_row_stride = stride; ctx->photo_frame_stride = frame_stride;
             for (int f0 = s0; f0 < s0 + ns; f0 += B) {
                 const int nb = std::min(B, s0 + ns - f0);
                 ctx->stream_detect((const uint8_t*)d_frames + (size_t)f0 * frame_stride, nb, w, h, stride, frame_stride);
@@ -986,6 +1100,16 @@ int32_t slideo_b200_get_verification(slideo_b200_ctx* ctx, int32_t frame0, int32
         arg(out != nullptr || n == 0, "out must not be NULL");
         static_assert(sizeof(slideo_b200_verify_result) == sizeof(VerifyRecord), "ABI struct and kernel record must agree");
         if (n) std::memcpy(out, ctx->verify_results.data() + frame0, (size_t)n * sizeof(VerifyRecord));
+    });
+}
+
+int32_t slideo_b200_get_decisions(slideo_b200_ctx* ctx, int32_t frame0, int32_t n, slideo_b200_decision* out) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (ctx->cfg.geometric_verification < 2) throw StateError("cfg.geometric_verification is not 2");
+        arg(frame0 >= 0 && n >= 0 && (size_t)frame0 + (size_t)n <= ctx->decisions.size(), "frame range outside the last match call");
+        arg(out != nullptr || n == 0, "out must not be NULL");
+        if (n) std::memcpy(out, ctx->decisions.data() + frame0, (size_t)n * sizeof(slideo_b200_decision));
     });
 }
 

@@ -15,6 +15,7 @@ namespace slideo {
 
 namespace {
 
+template <int CN>
 __global__ void __launch_bounds__(128) area_small_kernel(const uint8_t* __restrict__ frames, int stride, size_t frame_stride, int dw, int dh,
                                                          const int32_t* __restrict__ xoff, const int32_t* __restrict__ xsi,
                                                          const float* __restrict__ xa, const int32_t* __restrict__ yoff,
@@ -24,28 +25,27 @@ __global__ void __launch_bounds__(128) area_small_kernel(const uint8_t* __restri
     if (dx >= dw) return;
     const uint8_t* src = frames + (size_t)img * frame_stride;
     const int x0 = xoff[dx], x1 = xoff[dx + 1], y0 = yoff[dy], y1 = yoff[dy + 1];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float s[CN];
+#pragma unroll
+    for (int c = 0; c < CN; ++c) s[c] = 0.f;
     for (int j = y0; j < y1; ++j) {
         const uint8_t* row = src + (size_t)ysi[j] * stride;
         const float beta = ya[j];
-        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        float b[CN];
+#pragma unroll
+        for (int c = 0; c < CN; ++c) b[c] = 0.f;
         for (int k = x0; k < x1; ++k) {
-            const uint8_t* p = row + 3 * xsi[k];
+            const uint8_t* p = row + CN * xsi[k];
             const float a = xa[k];
-            b0 = __fadd_rn(b0, __fmul_rn((float)p[0], a));
-            b1 = __fadd_rn(b1, __fmul_rn((float)p[1], a));
-            b2 = __fadd_rn(b2, __fmul_rn((float)p[2], a));
+#pragma unroll
+            for (int c = 0; c < CN; ++c) b[c] = __fadd_rn(b[c], __fmul_rn((float)p[c], a));
         }
-        if (j == y0) {
-            s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
-        } else {
-            s0 = __fadd_rn(s0, __fmul_rn(beta, b0)); s1 = __fadd_rn(s1, __fmul_rn(beta, b1)); s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
-        }
+#pragma unroll
+        for (int c = 0; c < CN; ++c) s[c] = j == y0 ? __fmul_rn(beta, b[c]) : __fadd_rn(s[c], __fmul_rn(beta, b[c]));
     }
-    uint8_t* out = small + ((size_t)img * dh + dy) * dw * 3 + (size_t)dx * 3;
-    out[0] = (uint8_t)min(max(__float2int_rn(s0), 0), 255);
-    out[1] = (uint8_t)min(max(__float2int_rn(s1), 0), 255);
-    out[2] = (uint8_t)min(max(__float2int_rn(s2), 0), 255);
+    uint8_t* out = small + ((size_t)img * dh + dy) * dw * CN + (size_t)dx * CN;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) out[c] = (uint8_t)min(max(__float2int_rn(s[c]), 0), 255);
 }
 
 __global__ void __launch_bounds__(256) small_sumsq_kernel(const uint8_t* __restrict__ small, size_t small_bytes, unsigned long long* __restrict__ sumsq) {
@@ -124,10 +124,16 @@ void AreaTables::build(int w, int h) {
     d_yoff = upload(off); d_ysi = upload(si); d_ya = upload(al);
 }
 
-void area_small_launch(const AreaTables& t, const uint8_t* d_frames, int n, int stride, size_t frame_stride, uint8_t* d_small, cudaStream_t stream) {
+void area_small_launch(const AreaTables& t, const uint8_t* d_frames, int n, int stride, size_t frame_stride, uint8_t* d_small, cudaStream_t stream,
+                       int channels) {
     if (n <= 0) return;
-    area_small_kernel<<<dim3(cdiv(t.dw, 128), t.dh, n), 128, 0, stream>>>(d_frames, stride, frame_stride, t.dw, t.dh, t.d_xoff, t.d_xsi, t.d_xa,
-                                                                       t.d_yoff, t.d_ysi, t.d_ya, d_small);
+    const dim3 grid(cdiv(t.dw, 128), t.dh, n);
+    if (channels == 3)
+        area_small_kernel<3><<<grid, 128, 0, stream>>>(d_frames, stride, frame_stride, t.dw, t.dh, t.d_xoff, t.d_xsi, t.d_xa, t.d_yoff, t.d_ysi,
+                                                      t.d_ya, d_small);
+    else
+        area_small_kernel<1><<<grid, 128, 0, stream>>>(d_frames, stride, frame_stride, t.dw, t.dh, t.d_xoff, t.d_xsi, t.d_xa, t.d_yoff, t.d_ysi,
+                                                      t.d_ya, d_small);
     SLIDEO_CUDA(cudaGetLastError());
 }
 

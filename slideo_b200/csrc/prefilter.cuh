@@ -18,8 +18,9 @@ struct AreaTables {
 };
 
 void small_size(int w, int h, int* sw, int* sh);   // image_utils.rs:10-16 (f32, truncating)
-// BGR8 frames (device) -> small images, frame i to d_small + i * (dw*dh*3)
-void area_small_launch(const AreaTables& t, const uint8_t* d_frames, int n, int stride, size_t frame_stride, uint8_t* d_small, cudaStream_t stream);
+// 8-bit images (device, 3 interleaved channels or 1) -> small images, image i to d_small + i * (dw*dh*channels)
+void area_small_launch(const AreaTables& t, const uint8_t* d_frames, int n, int stride, size_t frame_stride, uint8_t* d_small, cudaStream_t stream,
+                       int channels = 3);
 // sumsq[i] = sum over all bytes of (small[i] - small[i+1])^2 for i in [0, n)   (n+1 consecutive small images)
 void small_sumsq_launch(const uint8_t* d_small, int n, size_t small_bytes, unsigned long long* d_sumsq, cudaStream_t stream);
 

@@ -132,14 +132,16 @@ __device__ int update_num_iters(double p, double ep, int max_iters) {
 __global__ void __launch_bounds__(V_THREADS) ransac_kernel(const uint2* __restrict__ corr, const int32_t* __restrict__ frame_q0, int k,
                                                            const int32_t* __restrict__ cand_votes, const int32_t* __restrict__ n_cand,
                                                            const float2* __restrict__ frame_pt, const float2* __restrict__ pool_pt,
-                                                           float thr, int max_iters, double confidence, int32_t* __restrict__ rating) {
+                                                           float thr, int max_iters, double confidence, int32_t* __restrict__ rating,
+                                                           int32_t* __restrict__ best_it_out) {
     extern __shared__ __align__(16) uint8_t v_smem[];
     float4* s_pts = reinterpret_cast<float4*>(v_smem);                                        // [V_SMEM_PTS] (fx, fy, tx, ty)
     uint2* s_pairs = reinterpret_cast<uint2*>(v_smem + (size_t)V_SMEM_PTS * sizeof(float4));  // [max_iters] sample indices
     __shared__ int s_good[V_CHUNK];
-    __shared__ int s_state[3];   // niters, max_good, done
+    __shared__ int s_state[3];   // niters, max_good, iteration of the best model
 
     const int c = blockIdx.x, f = blockIdx.y;
+    if (threadIdx.x == 0 && best_it_out) best_it_out[(size_t)f * VERIFY_TOP_SLIDES + c] = -1;
     if (c >= n_cand[f]) {
         if (threadIdx.x == 0) rating[(size_t)f * VERIFY_TOP_SLIDES + c] = 0;
         return;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(V_THREADS) ransac_kernel(const uint2* __restri
         }
         s_state[0] = max_iters > 1 ? max_iters : 1;
         s_state[1] = 0;
-        s_state[2] = 0;
+        s_state[2] = -1;
     }
     __syncthreads();
 
@@ -223,28 +225,33 @@ __global__ void __launch_bounds__(V_THREADS) ransac_kernel(const uint2* __restri
         __syncthreads();
         if (threadIdx.x == 0) {
             // replay of the sequential loop over this chunk: a hypothesis only counts if the loop would still be running
-            int ni = s_state[0], mg = s_state[1];
+            int ni = s_state[0], mg = s_state[1], bi = s_state[2];
             for (int h = 0; h < V_CHUNK; ++h) {
                 const int it = it0 + h;
                 if (it >= ni) break;
                 const int good = s_good[h];
                 if (good > (mg > 1 ? mg : 1)) {
                     mg = good;
+                    bi = it;
                     ni = update_num_iters(confidence, (double)(n - good) / n, ni);
                 }
             }
             s_state[0] = ni;
             s_state[1] = mg;
+            s_state[2] = bi;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = s_state[1];
+    if (threadIdx.x == 0) {
+        *out = s_state[1];
+        if (best_it_out) best_it_out[(size_t)f * VERIFY_TOP_SLIDES + c] = s_state[2];
+    }
 }
 
 // ---- D: gates (lib.rs:329-333): stable sort by rating, truncate(10), retain(rating > 50 && rating / best > 0.2) -----------
 __global__ void __launch_bounds__(128) gate_kernel(const int32_t* __restrict__ cand_page, const int32_t* __restrict__ cand_votes,
                                                    const int32_t* __restrict__ rating, const int32_t* __restrict__ n_cand, int n_frames,
-                                                   VerifyRecord* __restrict__ out) {
+                                                   VerifyRecord* __restrict__ out, int32_t* __restrict__ survivor_cand) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     VerifyRecord r;
@@ -272,11 +279,233 @@ __global__ void __launch_bounds__(128) gate_kernel(const int32_t* __restrict__ c
         if (v > 50.0 && v / best > 0.2) {
             r.survivor_page[ns] = r.cand_page[order[i]];
             r.survivor_rating[ns] = r.cand_rating[order[i]];
+            if (survivor_cand) survivor_cand[(size_t)f * VERIFY_TOP_RATED + ns] = order[i];
             ++ns;
         }
     }
     r.n_survivors = ns;
     out[f] = r;
+}
+
+
+// ---- K14 a: Levenberg-Marquardt refinement of the survivors' RANSAC models (cv::LMSolver, 10 iterations) ------------------
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    return t;
+}
+__device__ __forceinline__ double block_max(double v, double* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmax(t, s_red[w]);
+    return t;
+}
+// solves the symmetric 4x4 system m x = b by Gaussian elimination with partial pivoting (double)
+__device__ void solve4(const double (&m)[4][4], const double (&b)[4], double (&x)[4]) {
+    double a[4][5];
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) a[i][j] = m[i][j]; a[i][4] = b[i]; }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r) if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+        if (piv != c) for (int j = 0; j < 5; ++j) { const double t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+        for (int r = c + 1; r < 4; ++r) {
+            const double f = a[r][c] / a[c][c];
+            for (int j = c; j < 5; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 3; i >= 0; --i) {
+        double t = a[i][4];
+        for (int j = i + 1; j < 4; ++j) t -= a[i][j] * x[j];
+        x[i] = t / a[i][i];
+    }
+}
+
+__global__ void __launch_bounds__(128) lm_refine_kernel(const PhotoArgs A) {
+    __shared__ double s_red[4];
+    __shared__ double s_h[4];       // parameters every thread evaluates residuals at
+    const int j = blockIdx.x, f = blockIdx.y;
+    const VerifyRecord& rec = A.d_records[f];
+    if (j >= rec.n_survivors) return;
+    const int c = A.d_survivor_cand[(size_t)f * VERIFY_TOP_RATED + j];
+    const int n = A.d_cand_votes[(size_t)f * VERIFY_TOP_SLIDES + c];
+    const int best_it = A.d_best_it[(size_t)f * VERIFY_TOP_SLIDES + c];
+    long long off0 = (long long)A.d_frame_q0[f] * A.k;
+    for (int cc = 0; cc < c; ++cc) off0 += A.d_cand_votes[(size_t)f * VERIFY_TOP_SLIDES + cc];
+    const uint2* list = reinterpret_cast<const uint2*>(A.d_corr) + off0;
+    auto point = [&](int i) -> float4 {
+        const uint2 m = list[i];
+        const float2 to = A.d_frame_pt[m.x], fr = A.d_pool_pt[m.y];
+        return make_float4(fr.x, fr.y, to.x, to.y);
+    };
+    // the winning RANSAC model: replay the sample sequence up to best_it (pure function of n), closed form as in ransac_kernel
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0xFFFFFFFFFFFFFFFFull;
+        uint32_t i0 = 0, i1 = 0;
+        for (int it = 0; it <= best_it; ++it) {
+            i0 = rng_next(s) % (uint32_t)n;
+            do { i1 = rng_next(s) % (uint32_t)n; } while (i1 == i0);
+        }
+        const float4 p0 = point((int)i0), p1 = point((int)i1);
+        const double x1 = p0.x, y1 = p0.y, x2 = p1.x, y2 = p1.y, X1 = p0.z, Y1 = p0.w, X2 = p1.z, Y2 = p1.w;
+        const double d = 1. / ((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+        s_h[0] = d * ((X1 - X2) * (x1 - x2) + (Y1 - Y2) * (y1 - y2));
+        s_h[1] = d * ((Y1 - Y2) * (x1 - x2) - (X1 - X2) * (y1 - y2));
+        s_h[2] = d * ((Y1 - Y2) * (x1 * y2 - x2 * y1) - (X1 * y2 - X2 * y1) * (y1 - y2) - (X1 * x2 - X2 * x1) * (x1 - x2));
+        s_h[3] = d * (-(X1 - X2) * (x1 * y2 - x2 * y1) - (Y1 * x2 - Y2 * x1) * (x1 - x2) - (Y1 * y2 - Y2 * y1) * (y1 - y2));
+    }
+    __syncthreads();
+    // inlier predicate of that model (== the RANSAC best mask): fp32, no contraction
+    const float F0 = (float)s_h[0], F1 = (float)(-s_h[1]), F2 = (float)s_h[2], F3 = (float)s_h[1], F4 = (float)s_h[0], F5 = (float)s_h[3];
+    auto inlier = [&](const float4& p) -> bool {
+        const float a = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F0, p.x), __fmul_rn(F1, p.y)), F2), p.z);
+        const float b = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F3, p.x), __fmul_rn(F4, p.y)), F5), p.w);
+        return __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)) <= 9.0f;
+    };
+    // J^T J depends on the points only: [sxx 0 sx sy; 0 sxx -sy sx; sx -sy n 0; sy sx 0 n]
+    double sxx = 0., sx = 0., sy = 0., cnt = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float4 p = point(i);
+        if (inlier(p)) { sxx += (double)p.x * p.x + (double)p.y * p.y; sx += p.x; sy += p.y; cnt += 1.; }
+    }
+    sxx = block_sum(sxx, s_red); sx = block_sum(sx, s_red); sy = block_sum(sy, s_red); cnt = block_sum(cnt, s_red);
+    // residual sums at parameters h: S = |r|^2, v = J^T r, rmax = |r|_inf
+    auto residuals = [&](const double (&h)[4], double& S, double (&v)[4], double& rmax) {
+        double aS = 0., a0 = 0., a1 = 0., a2 = 0., a3 = 0., am = 0.;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float4 p = point(i);
+            if (inlier(p)) {
+                const double Mx = p.x, My = p.y;
+                const double rx = h[0] * Mx - h[1] * My + h[2] - (double)p.z;
+                const double ry = h[1] * Mx + h[0] * My + h[3] - (double)p.w;
+                aS += rx * rx + ry * ry;
+                a0 += Mx * rx + My * ry;
+                a1 += -My * rx + Mx * ry;
+                a2 += rx;
+                a3 += ry;
+                am = fmax(am, fmax(fabs(rx), fabs(ry)));
+            }
+        }
+        S = block_sum(aS, s_red); v[0] = block_sum(a0, s_red); v[1] = block_sum(a1, s_red); v[2] = block_sum(a2, s_red);
+        v[3] = block_sum(a3, s_red); rmax = block_max(am, s_red);
+    };
+    const double Am[4][4] = {{sxx, 0., sx, sy}, {0., sxx, -sy, sx}, {sx, -sy, cnt, 0.}, {sy, sx, 0., cnt}};
+    double x[4] = {s_h[0], s_h[1], s_h[2], s_h[3]}, v[4], S, rmax;
+    residuals(x, S, v, rmax);
+    double lambda = 1., lc = 0.75;
+    for (int iter = 0; iter < 10;) {
+        // every thread runs the identical scalar control flow on identical (block-reduced) values
+        double Ap[4][4], d[4], xd[4];
+        for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) Ap[a][b] = Am[a][b];
+        for (int a = 0; a < 4; ++a) Ap[a][a] += lambda * Am[a][a];
+        solve4(Ap, v, d);
+        for (int a = 0; a < 4; ++a) xd[a] = x[a] - d[a];
+        double Sd, vd[4], rmaxd;
+        residuals(xd, Sd, vd, rmaxd);
+        double dS = 0.;
+        for (int a = 0; a < 4; ++a) {
+            double t = 2. * v[a];
+            for (int b = 0; b < 4; ++b) t -= Am[a][b] * d[b];
+            dS += d[a] * t;
+        }
+        const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1.);
+        if (R > 0.75) {
+            lambda *= 0.5;
+            if (lambda < lc) lambda = 0.;
+        } else if (R < 0.25) {
+            double t = 0.;
+            for (int a = 0; a < 4; ++a) t += d[a] * v[a];
+            double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1.) + 2.;
+            nu = fmin(fmax(nu, 2.), 10.);
+            if (lambda == 0.) {
+                double maxval = DBL_EPSILON;
+                for (int a = 0; a < 4; ++a) {   // diagonal of inverse(A)
+                    double e[4] = {0., 0., 0., 0.}, col[4];
+                    e[a] = 1.;
+                    solve4(Am, e, col);
+                    maxval = fmax(maxval, fabs(col[a]));
+                }
+                lambda = lc = 1. / maxval;
+                nu *= 0.5;
+            }
+            lambda *= nu;
+        }
+        if (Sd < S) {
+            S = Sd; rmax = rmaxd;
+            for (int a = 0; a < 4; ++a) { x[a] = xd[a]; v[a] = vd[a]; }
+        }
+        ++iter;
+        double dmax = 0.;
+        for (int a = 0; a < 4; ++a) dmax = fmax(dmax, fabs(d[a]));
+        if (!(iter < 10 && dmax >= (double)FLT_EPSILON && rmax >= (double)FLT_EPSILON)) break;
+    }
+    if (threadIdx.x == 0) {
+        double* out = A.d_refined + ((size_t)f * VERIFY_TOP_RATED + j) * 4;
+        out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3];
+    }
+}
+
+// ---- K14 b: warp (nearest, inverse map, AB_BITS = 10) + INTER_AREA small image + squared difference to the slide's small image
+__global__ void __launch_bounds__(128) photometric_kernel(const PhotoArgs A) {
+    __shared__ unsigned long long s_acc[4];
+    const int f = blockIdx.z / VERIFY_TOP_RATED, j = blockIdx.z - f * VERIFY_TOP_RATED;
+    const VerifyRecord& rec = A.d_records[f];
+    if (j >= rec.n_survivors) return;
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+    unsigned long long acc = 0;
+    if (dx < A.small_w) {
+        const double* h = A.d_refined + ((size_t)f * VERIFY_TOP_RATED + j) * 4;
+        const double M0 = h[0], M1 = -h[1], M2 = h[2], M3 = h[1], M4 = h[0], M5 = h[3];
+        const uint8_t* frame = A.d_frames + (size_t)f * A.frame_stride;
+        const int x0 = A.d_xoff[dx], x1 = A.d_xoff[dx + 1], y0 = A.d_yoff[dy], y1 = A.d_yoff[dy + 1];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int jj = y0; jj < y1; ++jj) {
+            const int sy = A.d_ysi[jj];
+            const float beta = A.d_ya[jj];
+            const int X0 = __double2int_rn((M1 * (double)sy + M2) * 1024.) + 512;
+            const int Y0 = __double2int_rn((M4 * (double)sy + M5) * 1024.) + 512;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            for (int kk = x0; kk < x1; ++kk) {
+                const int sx = A.d_xsi[kk];
+                const float al = A.d_xa[kk];
+                const int X = (X0 + __double2int_rn(M0 * (double)sx * 1024.)) >> 10;
+                const int Y = (Y0 + __double2int_rn(M3 * (double)sx * 1024.)) >> 10;
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f;   // BORDER_CONSTANT 0
+                if (X >= 0 && X < A.frame_w && Y >= 0 && Y < A.frame_h) {
+                    const uint8_t* px = frame + (size_t)Y * A.frame_stride_row + 3 * X;
+                    p0 = (float)px[0]; p1 = (float)px[1]; p2 = (float)px[2];
+                }
+                b0 = __fadd_rn(b0, __fmul_rn(p0, al));
+                b1 = __fadd_rn(b1, __fmul_rn(p1, al));
+                b2 = __fadd_rn(b2, __fmul_rn(p2, al));
+            }
+            if (jj == y0) {
+                s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
+            } else {
+                s0 = __fadd_rn(s0, __fmul_rn(beta, b0)); s1 = __fadd_rn(s1, __fmul_rn(beta, b1)); s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
+            }
+        }
+        const int g = A.d_page_small[((size_t)rec.survivor_page[j] * A.small_h + dy) * A.small_w + dx];
+        const int v0 = min(max(__float2int_rn(s0), 0), 255) - g, v1 = min(max(__float2int_rn(s1), 0), 255) - g,
+                  v2 = min(max(__float2int_rn(s2), 0), 255) - g;
+        acc = (unsigned long long)(v0 * v0 + v1 * v1 + v2 * v2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = s_acc[0] + s_acc[1] + s_acc[2] + s_acc[3];
+        if (t) atomicAdd(&A.d_sumsq[(size_t)f * VERIFY_TOP_RATED + j], t);
+    }
 }
 
 }  // namespace
@@ -296,10 +525,23 @@ void verify_launch(const VerifyArgs& a, cudaStream_t stream, int* launches) {
     }
     ransac_kernel<<<dim3(VERIFY_TOP_SLIDES, a.n_frames), V_THREADS, smem, stream>>>((const uint2*)a.d_corr, a.d_frame_q0, a.k, a.d_cand_votes,
                                                                                   a.d_n_cand, a.d_frame_pt, a.d_pool_pt, 3.0f, VERIFY_MAX_ITERS,
-                                                                                  0.99, a.d_rating);
-    gate_kernel<<<cdiv(a.n_frames, 128), 128, 0, stream>>>(a.d_cand_page, a.d_cand_votes, a.d_rating, a.d_n_cand, a.n_frames, a.d_out);
+                                                                                  0.99, a.d_rating, a.d_best_it);
+    gate_kernel<<<cdiv(a.n_frames, 128), 128, 0, stream>>>(a.d_cand_page, a.d_cand_votes, a.d_rating, a.d_n_cand, a.n_frames, a.d_out, a.d_survivor_cand);
     SLIDEO_CUDA(cudaGetLastError());
     if (launches) *launches += 4;
+}
+
+}  // namespace slideo
+
+namespace slideo {
+
+void photometric_launch(const PhotoArgs& a, cudaStream_t stream, int* launches) {
+    if (a.n_frames <= 0) return;
+    SLIDEO_CUDA(cudaMemsetAsync(a.d_sumsq, 0, (size_t)a.n_frames * VERIFY_TOP_RATED * sizeof(unsigned long long), stream));
+    lm_refine_kernel<<<dim3(VERIFY_TOP_RATED, a.n_frames), 128, 0, stream>>>(a);
+    photometric_kernel<<<dim3(cdiv(a.small_w, 128), a.small_h, a.n_frames * VERIFY_TOP_RATED), 128, 0, stream>>>(a);
+    SLIDEO_CUDA(cudaGetLastError());
+    if (launches) *launches += 2;
 }
 
 }  // namespace slideo

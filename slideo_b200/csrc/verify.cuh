@@ -27,7 +27,33 @@ struct VerifyArgs {
     int32_t *d_cand_page, *d_cand_votes, *d_n_cand, *d_rating;   // workspaces: [n_frames][40] x3, [n_frames]
     void* d_corr;                 // verify_corr_bytes(total_q * k)
     VerifyRecord* d_out;          // [n_frames]
+    int32_t* d_best_it;           // [n_frames][40] RANSAC iteration whose model won (photometric stage), may be null
+    int32_t* d_survivor_cand;     // [n_frames][10] candidate slot of each survivor (photometric stage), may be null
 };
+
+// K14: photometric verification of the survivors (lib.rs:335-389): LM-refined matrix -> warpAffine(WARP_INVERSE_MAP, nearest)
+// of the frame into the slide's geometry -> INTER_AREA small image -> sum of squared differences to the slide's small image
+struct PhotoArgs {
+    int n_frames, k;
+    const VerifyRecord* d_records;     // [n_frames]
+    const int32_t* d_survivor_cand;    // [n_frames][10]
+    const int32_t* d_best_it;          // [n_frames][40]
+    const int32_t* d_cand_votes;       // [n_frames][40]
+    const void* d_corr;
+    const int32_t* d_frame_q0;
+    const float2* d_frame_pt;
+    const float2* d_pool_pt;
+    const uint8_t* d_frames;           // BGR8 frames of the group
+    int frame_w, frame_h, frame_stride_row;
+    size_t frame_stride;
+    int page_w, page_h, small_w, small_h;          // uniform page geometry
+    const int32_t *d_xoff, *d_xsi, *d_yoff, *d_ysi; // area tables of (page_w, page_h) -> (small_w, small_h)
+    const float *d_xa, *d_ya;
+    const uint8_t* d_page_small;       // [n_pages][small_h * small_w] gray
+    double* d_refined;                 // [n_frames][10][4]  (a, b, tx, ty)
+    unsigned long long* d_sumsq;       // [n_frames][10]
+};
+void photometric_launch(const PhotoArgs& a, cudaStream_t stream, int* launches);
 
 size_t verify_corr_bytes(long long total_entries);
 void verify_launch(const VerifyArgs& a, cudaStream_t stream, int* launches);

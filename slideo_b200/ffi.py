@@ -49,6 +49,12 @@ class VerifyResult(ctypes.Structure):
                 ("cand_rating", c_i32 * TOP_SLIDES), ("survivor_page", c_i32 * TOP_RATED), ("survivor_rating", c_i32 * TOP_RATED)]
 
 
+class Decision(ctypes.Structure):
+    """slideo_b200_decision: warp + similarity gate of one frame (lib.rs:335-389)."""
+    _fields_ = [("image", c_i32), ("n_rated", c_i32), ("rated_page", c_i32 * TOP_RATED), ("rated_similarity", c_f32 * TOP_RATED),
+                ("refined_matrix", (ctypes.c_double * 4) * TOP_RATED)]
+
+
 class Timings(ctypes.Structure):
     _fields_ = [("ms_detect", c_f32), ("ms_knn", c_f32), ("ms_vote", c_f32), ("ms_h2d", c_f32),
                 ("knn_pairs", ctypes.c_int64), ("knn_launches", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
@@ -79,6 +85,7 @@ SYMBOLS = {
     "slideo_b200_match_descriptors": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp]),
     "slideo_b200_get_matches": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32p]),
     "slideo_b200_get_verification": (c_i32, [c_vp, c_i32, c_i32, c_vp]),
+    "slideo_b200_get_decisions": (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     "slideo_b200_mark_changed_bgr8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_i32, c_vp, c_vp]),
     "slideo_b200_mark_changed_bgr8_device": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_i32, c_vp, c_vp]),
     "slideo_b200_extract_orb": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32p]),

@@ -86,3 +86,45 @@ def test_matcher_mirror_uses_the_gate(scene):
     got = [(m.video_frame_idx, None if m.image is None else next(j for j, p in enumerate(pages) if p is m.image)) for m in out]
     assert got == want
     vm.ctx.close()
+
+
+def test_photometric_gate_equals_oracle(scene):
+    """cfg.geometric_verification == 2: LM-refined matrix -> warpAffine(nearest, inverse) -> INTER_AREA -> similarity gate
+    (lib.rs:335-389) against oracle/photometric.py (pinned against cv2.warpAffine / cv2.estimateAffinePartial2D)."""
+    import slideo_b200
+    from oracle import photometric as ph
+    pages, frames, feats, expect = scene
+    page_desc = [f[2] for f in feats]
+    pool_pts = np.concatenate([f[1][:, :2] for f in feats])
+    offs = np.zeros(NPAGES + 1, np.int32)
+    offs[1:] = np.cumsum([len(d) for d in page_desc])
+    pool = np.concatenate(page_desc)
+    with slideo_b200.Context(slideo_b200.default_config(geometric_verification=2, max_batch=3)) as c:
+        for p in pages:
+            c.add_page_gray8(p)
+        c.finalize_pool()
+        res = c.match_frames_bgr8(frames)
+        ver = c.get_verification(0, NFRAMES)
+        dec = c.get_decisions(0, NFRAMES)
+        import torch
+        d = torch.from_numpy(frames).cuda()
+        res_d = c.match_frames_bgr8_device(d.data_ptr(), NFRAMES, 1920, 1080)
+        dec_d = c.get_decisions(0, NFRAMES)
+    assert np.array_equal(res, res_d)
+    for f in range(NFRAMES):
+        ki, kf, dd = oracle.orb_detect_and_compute(oracle.gray_from_bgr(frames[f]))
+        idx, dist = oracle.bf_knn_hamming(dd, pool, 30)
+        want = ph.decide_frame(idx, dist.astype(np.float32), offs, kf[:, :2], pool_pts, frames[f], pages)
+        assert ver[f]["survivors"] == [tuple(int(v) for v in x) for x in want["survivors"]]
+        assert dec[f]["image"] == want["image"] == dec_d[f]["image"], f"frame {f}"
+        assert [p for p, _ in dec[f]["rated"]] == [p for p, _ in want["rated"]]
+        # similarities: bit-identical whenever the refined matrix lands on the same fixed-point coordinates (it does unless a
+        # coordinate sits within ~1e-9 of a rounding boundary); the matrix itself agrees to 1e-9 (different 4x4 solvers)
+        for (p, s), (_, ws) in zip(dec[f]["rated"], want["rated"]):
+            assert abs(float(s) - float(ws)) <= 1e-6
+        assert [float(s) for _, s in dec[f]["rated"]] == [float(s) for _, s in dec_d[f]["rated"]]
+        for j, (p, _) in enumerate(want["survivors"]):
+            m = want["matrices"][p]
+            assert np.allclose(dec[f]["refined"][j], [m[0, 0], m[1, 0], m[0, 2], m[1, 2]], rtol=0, atol=1e-9)
+        truth = synth.frame_truth(f, NPAGES)
+        assert dec[f]["image"] == (truth if truth >= 0 else -1)
