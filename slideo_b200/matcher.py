@@ -8,11 +8,10 @@ implemented over the C ABI the way `crates/matching-opencv` implements it over O
     result  = task.process()                                       # VideoMatcherTask -> [Matching]       lib.rs:169-245
 
 What differs, and why (DESIGN.md "Boundary"):
-  * the per-frame decision: with `geometric_verification=True` (default) the reference's RANSAC gate runs on the GPU
-    (lib.rs:284-333) and the frame maps to the best-rated survivor, or to `image=None` when no slide passes
-    `rating > 50 && rating / best > 0.2`; the warp + similarity gate behind it (lib.rs:335-389) is the next row, so the
-    survivors are ranked by rating instead of by warped-image similarity.  With `geometric_verification=False` the
-    decision is the head of the vote ranking (argmax-votes slide, lib.rs:268-295) and `min_votes` stands in for the gates.
+  * the per-frame decision: with `geometric_verification=True` (default) the reference's complete tail runs on the GPU --
+    top-40 by votes, RANSAC rating gate (lib.rs:284-333), warp + similarity gate (lib.rs:335-389) -- and the frame maps to the
+    most similar survivor or to `image=None`, exactly like `Matching.image`.  With `geometric_verification=False` the decision
+    is the head of the vote ranking (argmax-votes slide, lib.rs:268-295) and `min_votes` stands in for the gates.
   * frames are matched in batches on the GPU instead of one rayon task per frame (lib.rs:213-214).
   * decoding stays on the host (the reference uses OpenCV's FFmpeg VideoCapture, video_capture.rs:15-57); any
     iterable of (frame_bgr, seconds, frame_idx) can be passed instead of a path.
@@ -77,7 +76,7 @@ class B200ImageVideoMatcher:
     def __init__(self, device: int = 0, min_votes: int = 1, geometric_verification: bool = True, **config_overrides):
         self._device = device
         self._min_votes = min_votes
-        self._overrides = dict(config_overrides, geometric_verification=int(geometric_verification))
+        self._overrides = dict(config_overrides, geometric_verification=2 if geometric_verification else 0)
 
     def create_video_matcher(self, images: Sequence[Any], progress_reporter: Optional[ProgressReporter] = None
                              ) -> "B200VideoMatcher":
@@ -236,9 +235,12 @@ class B200VideoMatcherTask:
             for shape, idxs in shapes.items():
                 frames = np.stack([batch[j][0] for j in idxs])
                 res = ctx.match_frames_bgr8(frames)
-                ver = ctx.get_verification(0, len(idxs)) if ctx.cfg.geometric_verification else None
+                dec = ctx.get_decisions(0, len(idxs)) if ctx.cfg.geometric_verification >= 2 else None
+                ver = ctx.get_verification(0, len(idxs)) if ctx.cfg.geometric_verification == 1 else None
                 for n, (j, (best, votes, _nkp)) in enumerate(zip(idxs, res)):
-                    if ver is not None:      # lib.rs:329-333: best-rated survivor of the RANSAC gate
+                    if dec is not None:      # lib.rs:383-389: the most similar survivor of both gates
+                        img = images[dec[n]["image"]] if dec[n]["image"] >= 0 else None
+                    elif ver is not None:    # lib.rs:329-333 only: best-rated survivor of the RANSAC gate
                         surv = ver[n]["survivors"]
                         img = images[surv[0][0]] if surv else None
                     else:
