@@ -30,7 +30,7 @@ VOTE_RATIO = 1.05     # crates/matching-opencv/src/lib.rs:275
 def build() -> str:
     """Compile liboracle.so (gcc) if missing or stale."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c", "ransac_oracle.c", "area_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c", "ransac_oracle.c", "area_oracle.c", "sift_oracle.c")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -73,6 +73,25 @@ def lib() -> ctypes.CDLL:
         L.area_resize_u8.argtypes = [c_u8p, ci, ci, ci, ci, c_u8p, ci, ci, ci]
         L.area_similarity.argtypes = [c_u8p, c_u8p, ci, ci, ci]
         L.area_similarity.restype = cf
+        c_dp2 = ctypes.POINTER(ctypes.c_double)
+        L.sift_gauss_ksize.argtypes = [ctypes.c_double]
+        L.sift_gauss_ksize.restype = ci
+        L.sift_gauss_taps.argtypes = [ctypes.c_double, ci, c_f32p]
+        L.sift_gauss_blur.argtypes = [c_f32p, ci, ci, c_f32p, ci, c_f32p]
+        L.sift_upsample2.argtypes = [c_u8p, ci, ci, c_f32p]
+        L.sift_exp32f.argtypes = [cf]
+        L.sift_exp32f.restype = cf
+        L.sift_fast_atan2.argtypes = [cf, cf]
+        L.sift_fast_atan2.restype = cf
+        L.sift_magnitude.argtypes = [cf, cf]
+        L.sift_magnitude.restype = cf
+        L.sift_num_octaves.argtypes = [ci, ci]
+        L.sift_num_octaves.restype = ci
+        L.sift_layer_sigmas.argtypes = [c_dp2]
+        L.sift_pyramid_image.argtypes = [c_u8p, ci, ci, ci, ci, ci, c_f32p, c_i32p, c_i32p]
+        L.sift_pyramid_image.restype = ci
+        L.sift_detect_and_compute.argtypes = [c_u8p, ci, ci, c_f32p, c_i32p, c_f32p, ci]
+        L.sift_detect_and_compute.restype = ci
         _LIB = L
     return _LIB
 
@@ -297,3 +316,75 @@ def mark_similar(frames):
         sims.append(s)
         ch.append(bool(s < CHANGED_THRESHOLD))
     return np.array(ch, bool), np.array(sims, np.float32)
+
+
+# ----------------------------------------------------------------------------- SIFT (north_star variant; cv2.SIFT_create() defaults)
+def sift_layer_sigmas():
+    """[sig_diff of the initial image, sig[1..5] of buildGaussianPyramid] (nOctaveLayers 3, sigma 1.6)."""
+    s = np.zeros(6, np.float64)
+    lib().sift_layer_sigmas(_p(s, ctypes.c_double))
+    return s
+
+
+def sift_gauss_taps(sigma: float) -> np.ndarray:
+    n = lib().sift_gauss_ksize(sigma)
+    t = np.zeros(n, np.float32)
+    lib().sift_gauss_taps(sigma, n, _p(t, ctypes.c_float))
+    return t
+
+
+def sift_gauss_blur(img: np.ndarray, sigma: float) -> np.ndarray:
+    """cv2.GaussianBlur(img_f32, (0, 0), sigma) restated."""
+    img = np.ascontiguousarray(img, np.float32)
+    t = sift_gauss_taps(sigma)
+    out = np.empty_like(img)
+    lib().sift_gauss_blur(_p(img, ctypes.c_float), img.shape[1], img.shape[0], _p(t, ctypes.c_float), len(t), _p(out, ctypes.c_float))
+    return out
+
+
+def sift_upsample2(gray: np.ndarray) -> np.ndarray:
+    gray = _u8(gray)
+    out = np.empty((2 * gray.shape[0], 2 * gray.shape[1]), np.float32)
+    lib().sift_upsample2(_p(gray, ctypes.c_uint8), gray.shape[1], gray.shape[0], _p(out, ctypes.c_float))
+    return out
+
+
+def sift_exp(x: np.ndarray) -> np.ndarray:
+    f = lib().sift_exp32f
+    return np.array([f(float(v)) for v in np.asarray(x, np.float32).ravel()], np.float32)
+
+
+def sift_atan2(y: np.ndarray, x: np.ndarray) -> np.ndarray:
+    f = lib().sift_fast_atan2
+    return np.array([f(float(a), float(b)) for a, b in zip(np.asarray(y, np.float32).ravel(), np.asarray(x, np.float32).ravel())], np.float32)
+
+
+def sift_magnitude(x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    f = lib().sift_magnitude
+    return np.array([f(float(a), float(b)) for a, b in zip(np.asarray(x, np.float32).ravel(), np.asarray(y, np.float32).ravel())], np.float32)
+
+
+def sift_pyramid_image(gray: np.ndarray, kind: int, octave: int, layer: int) -> np.ndarray:
+    """kind 0: Gaussian pyramid image, 1: DoG image (octave 0 = the doubled image)."""
+    gray = _u8(gray)
+    w, h = ctypes.c_int32(), ctypes.c_int32()
+    if lib().sift_pyramid_image(_p(gray, ctypes.c_uint8), gray.shape[1], gray.shape[0], kind, octave, layer, None, ctypes.byref(w), ctypes.byref(h)):
+        raise ValueError("octave out of range")
+    out = np.empty((h.value, w.value), np.float32)
+    lib().sift_pyramid_image(_p(gray, ctypes.c_uint8), gray.shape[1], gray.shape[0], kind, octave, layer, _p(out, ctypes.c_float), ctypes.byref(w), ctypes.byref(h))
+    return out
+
+
+def sift_detect_and_compute(gray: np.ndarray, cap: int = 65536):
+    """Restated cv2.SIFT_create().detectAndCompute on an 8-bit gray image, in OpenCV's output order.
+
+    Returns (kp_f [n,5] f32 {pt.x, pt.y, size, angle, response}, octave [n] int32 (packed), desc [n,128] f32)."""
+    gray = _u8(gray)
+    h, w = gray.shape
+    kp_f = np.empty((cap, 5), np.float32)
+    octv = np.empty(cap, np.int32)
+    desc = np.empty((cap, 128), np.float32)
+    n = lib().sift_detect_and_compute(_p(gray, ctypes.c_uint8), w, h, _p(kp_f, ctypes.c_float), _p(octv, ctypes.c_int32), _p(desc, ctypes.c_float), cap)
+    if n > cap:
+        return sift_detect_and_compute(gray, n)
+    return kp_f[:n].copy(), octv[:n].copy(), desc[:n].copy()
