@@ -141,8 +141,8 @@ const char* slideo_b200_last_error(const slideo_b200_ctx* ctx);
 const char* slideo_b200_version(void);
 
 /* ---- page pool  (replaces ProcessedImage::compute lib.rs:93-131 + FlannMatcher::new flann.rs:64-71) ------- */
-/* ORB-extracts one page given as the 8-bit gray that `imread(path, IMREAD_GRAYSCALE)` returns (lib.rs:98) and
- * appends its descriptors to the pool.  Pages get consecutive indices in call order. */
+/* Extracts (ORB256: K1-K7, SIFT128: K11) one page given as the 8-bit gray that `imread(path, IMREAD_GRAYSCALE)` returns
+ * (lib.rs:98) and appends its descriptors to the pool.  Pages get consecutive indices in call order. */
 int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int32_t w, int32_t h, int32_t stride,
                                    int32_t* out_n_keypoints);
 /* Appends a page whose descriptors were computed elsewhere (n x 32 bytes for ORB256, n x 128 floats for SIFT128). */
@@ -171,8 +171,8 @@ int32_t slideo_b200_pool_points_device_view(slideo_b200_ctx* ctx, void** d_pt, s
 
 /* ---- the per-frame hot path  (replaces match_images_with_frame lib.rs:249-295, head of the ranking) ------- */
 /* n BGR 8UC3 frames (what VideoCapture::retrieve yields, video_capture.rs:45-53), HOST memory, frame i at
- * frames + i*frame_stride; rows `stride` bytes apart.  Copies to the device, extracts ORB, k-NN against the pool,
- * votes, writes n results.  Pinned host memory (slideo_b200_host_alloc) makes the copies asynchronous. */
+ * frames + i*frame_stride; rows `stride` bytes apart.  Copies to the device, extracts ORB (or SIFT for a SIFT128 ctx),
+ * k-NN against the pool, votes, writes n results.  Pinned host memory (slideo_b200_host_alloc) makes the copies asynchronous. */
 int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h,
                                       int32_t stride, size_t frame_stride, slideo_b200_frame_result* out);
 /* Same with frames already resident in device memory (HBM-resident throughput measurement). */
@@ -214,6 +214,16 @@ int32_t slideo_b200_mark_changed_bgr8_device(slideo_b200_ctx* ctx, const void* d
 int32_t slideo_b200_extract_orb(slideo_b200_ctx* ctx, const uint8_t* img, int32_t w, int32_t h, int32_t stride,
                                 int32_t channels, int32_t* kp_i, float* kp_f, uint8_t* desc, int32_t cap,
                                 int32_t* out_n);
+/* SIFT::detectAndCompute with cv::SIFT::create()'s defaults (the north_star's SIFT-128 variant; would sit where
+ * feature_extractor.rs:29-46 calls ORB) on one HOST image, channels = 1 (gray) or 3 (BGR).  OpenCV's output order
+ * (KeyPoint_LessThan after removeDuplicated).  kp_f: n x 5 {pt.x, pt.y, size, angle_deg, response}; kp_octave: n packed
+ * cv::KeyPoint::octave; desc: n x 128 floats (integer-valued 0..255).  Any output pointer may be NULL. */
+int32_t slideo_b200_extract_sift(slideo_b200_ctx* ctx, const uint8_t* img, int32_t w, int32_t h, int32_t stride,
+                                 int32_t channels, float* kp_f, int32_t* kp_octave, float* desc, int32_t cap,
+                                 int32_t* out_n);
+/* Gaussian layer (0..5) of octave `octave` of the scale space of the last SIFT extract/match call (image 0), w x h floats. */
+int32_t slideo_b200_debug_fetch_sift(slideo_b200_ctx* ctx, int32_t octave, int32_t layer, float* out, size_t cap_bytes,
+                                     int32_t* out_w, int32_t* out_h, int32_t* out_n_octaves);
 /* Intermediate images of the last extract/match call, image 0 of the batch: what = 0 pyramid level, 1 blurred
  * level, 2 FAST candidates (packed score<<24|y<<12|x, unordered).  Tightly packed into `out`. */
 int32_t slideo_b200_debug_fetch(slideo_b200_ctx* ctx, int32_t what, int32_t level, void* out, size_t cap_bytes,

@@ -278,6 +278,35 @@ class Context:
         self._ck(self._lib.slideo_b200_debug_fetch(self._h, what, level, _ptr(out), out.nbytes, ctypes.byref(w), ctypes.byref(h)))
         return out
 
+    def extract_sift(self, img: np.ndarray, cap: int = 65536):
+        """SIFT::detectAndCompute (cv::SIFT::create() defaults) on one host image (gray [h,w] or BGR [h,w,3]).
+
+        Returns kp_f [n,5] f32 {pt.x, pt.y, size, angle, response}, octave [n] int32 (packed like cv::KeyPoint::octave),
+        desc [n,128] f32 (integer-valued), in OpenCV's output order.
+        """
+        if img.dtype != np.uint8 or img.ndim not in (2, 3):
+            raise TypeError("img must be uint8 [h,w] or [h,w,3]")
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        img = np.ascontiguousarray(img)
+        h, w = img.shape[:2]
+        n = ctypes.c_int32()
+        self._ck(self._lib.slideo_b200_extract_sift(self._h, _ptr(img), w, h, img.strides[0], ch, None, None, None, 0, ctypes.byref(n)))
+        cap = n.value
+        kp_f = np.empty((cap, 5), np.float32)
+        octv = np.empty(cap, np.int32)
+        desc = np.empty((cap, 128), np.float32)
+        self._ck(self._lib.slideo_b200_extract_sift(self._h, _ptr(img), w, h, img.strides[0], ch, _ptr(kp_f), _ptr(octv), _ptr(desc), cap,
+                                                    ctypes.byref(n)))
+        return kp_f[:n.value], octv[:n.value], desc[:n.value]
+
+    def debug_fetch_sift(self, octave: int, layer: int) -> np.ndarray:
+        """Gaussian layer of the scale space of the last SIFT call (image 0)."""
+        w, h, no = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self._lib.slideo_b200_debug_fetch_sift(self._h, octave, layer, None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(no)))
+        out = np.empty((h.value, w.value), np.float32)
+        self._ck(self._lib.slideo_b200_debug_fetch_sift(self._h, octave, layer, _ptr(out), out.nbytes, ctypes.byref(w), ctypes.byref(h), ctypes.byref(no)))
+        return out
+
     def bf_knn_hamming(self, q, t, k: int = 30):
         q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
         t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)

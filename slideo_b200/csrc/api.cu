@@ -19,6 +19,7 @@
 #include "knn_l2.cuh"
 #include "orb.cuh"
 #include "prefilter.cuh"
+#include "sift.cuh"
 #include "verify.cuh"
 
 using namespace slideo;
@@ -86,6 +87,9 @@ struct slideo_b200_ctx {
     // ---- workspaces -------------------------------------------------------------------------------------
     std::map<std::tuple<int, int, int>, std::unique_ptr<OrbExtractor>> extractors;
     OrbExtractor* last_ext = nullptr;
+    std::map<std::tuple<int, int, int>, std::unique_ptr<SiftExtractor>> sift_extractors;   // K11 workspaces (SIFT128 variant)
+    SiftExtractor* last_sift = nullptr;
+    static constexpr int SIFT_BATCH = 8;  // frames per K11 batch (265 MB of fp32 scale space per 1080p frame)
     static constexpr int N_STAGING = 4;  // frame staging buffers (uploads run this many batches ahead)
     DevBuf<uint8_t> d_frames[N_STAGING];
     DevBuf<uint8_t> d_img;               // single-image upload (pages, extract_orb)
@@ -116,6 +120,7 @@ struct slideo_b200_ctx {
         if (copy_stream) cudaStreamSynchronize(copy_stream);
         if (knn_stream) cudaStreamSynchronize(knn_stream);
         extractors.clear();
+        sift_extractors.clear();
         for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto& e : ev_free_list) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (int i = 0; i < N_STAGING; ++i) {
@@ -183,6 +188,95 @@ struct slideo_b200_ctx {
         }
         last_ext = it->second.get();
         return *it->second;
+    }
+
+    SiftExtractor& sift_extractor(int w, int h, int cap) {
+        auto key = std::make_tuple(w, h, cap);
+        auto it = sift_extractors.find(key);
+        if (it == sift_extractors.end()) {
+            if (sift_extractors.size() >= 4) {  // bounded cache of geometries
+                SLIDEO_CUDA(cudaStreamSynchronize(stream));
+                sift_extractors.clear();
+                last_sift = nullptr;
+            }
+            it = sift_extractors.emplace(key, std::make_unique<SiftExtractor>(w, h, cap)).first;
+        }
+        last_sift = it->second.get();
+        return *it->second;
+    }
+
+    // K10 + vote + argmax on nq device-resident fp32 descriptors of nb frames (SIFT128 variant of lib.rs:266-295)
+    void knn_vote_l2(const float* dq, int nq, const int32_t* d_qf, int nb, const int32_t* d_nkp, const std::vector<int32_t>& fo) {
+        d_votes.reserve((size_t)nb * std::max(n_pages, 1));
+        d_results.reserve((size_t)nb * 3);
+        d_idx.reserve((size_t)std::max(nq, 1) * cfg.knn_k);
+        d_dist.reserve((size_t)std::max(nq, 1) * cfg.knn_k);
+        SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)nb * std::max(n_pages, 1) * 4, stream));
+        if (nq > 0) {
+            EventPair tk = begin_timing(1, stream);
+            int nl = 0;
+            l2_knn_launch(l2ws, dq, nq, d_pool.p, d_pool_tail.p, nt, cfg.knn_k, d_idx.p, (float*)d_dist.p, num_sms, stream, &nl);
+            l2_vote_launch(d_idx.p, (const float*)d_dist.p, nq, cfg.knn_k, d_qf, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio, stream);
+            end_timing(tk, stream);
+            tm.knn_launches += nl;
+            tm.kernel_launches += nl + 1;
+            tm.knn_pairs += (int64_t)nq * nt;
+        }
+        vote_argmax_launch(d_votes.p, nb, n_pages, d_nkp, d_results.p, stream);
+        tm.kernel_launches += 1;
+        if (cfg.keep_matches) {
+            const size_t base = kept_l2.size();
+            kept_l2.resize(base + (size_t)nq * cfg.knn_k);
+            kept_l2_idx.resize(base + (size_t)nq * cfg.knn_k);
+            if (nq > 0) {
+                SLIDEO_CUDA(cudaMemcpyAsync(kept_l2.data() + base, d_dist.p, (size_t)nq * cfg.knn_k * 4, cudaMemcpyDeviceToHost, stream));
+                SLIDEO_CUDA(cudaMemcpyAsync(kept_l2_idx.data() + base, d_idx.p, (size_t)nq * cfg.knn_k * 4, cudaMemcpyDeviceToHost, stream));
+            }
+            const int32_t qb = kept_frame_off.back();
+            for (size_t i = 1; i < fo.size(); ++i) kept_frame_off.push_back(qb + fo[i]);
+            SLIDEO_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
+
+    // the per-frame path of the SIFT128 variant: K11 on batches of frames -> K10 against the pool -> vote -> argmax
+    void match_frames_sift(const uint8_t* frames, bool on_device, int n, int w, int h, int stride, size_t frame_stride) {
+        const int B = std::min(cfg.max_batch, SIFT_BATCH);
+        SiftExtractor& ex = sift_extractor(w, h, B);
+        const size_t img_bytes = (size_t)3 * w * h;
+        const int n_batches = cdiv(n, B);
+        if (!on_device)
+            for (int i = 0; i < 2; ++i) d_frames[i].reserve((size_t)std::min(B, n) * img_bytes);
+        auto issue_copy = [&](int b) {
+            const int buf = b & 1, f0 = b * B, nb = std::min(B, n - f0);
+            SLIDEO_CUDA(cudaStreamWaitEvent(copy_stream, ev_free[buf], 0));
+            EventPair t = begin_timing(2, copy_stream);
+            upload_images(d_frames[buf].p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride, copy_stream);
+            end_timing(t, copy_stream);
+            SLIDEO_CUDA(cudaEventRecord(ev_copy[buf], copy_stream));
+        };
+        if (!on_device) issue_copy(0);
+        for (int b = 0; b < n_batches; ++b) {
+            const int f0 = b * B, nb = std::min(B, n - f0);
+            const uint8_t* src = frames + (size_t)f0 * frame_stride;
+            int st = stride;
+            size_t fst = frame_stride;
+            if (!on_device) {
+                if (b + 1 < n_batches) issue_copy(b + 1);
+                SLIDEO_CUDA(cudaStreamWaitEvent(stream, ev_copy[b & 1], 0));
+                src = d_frames[b & 1].p;
+                st = 3 * w;
+                fst = img_bytes;
+            }
+            EventPair t = begin_timing(0, stream);
+            int nl = 0;
+            const int total = ex.run(src, nb, st, fst, 3, stream, &nl);
+            end_timing(t, stream);
+            if (!on_device) SLIDEO_CUDA(cudaEventRecord(ev_free[b & 1], stream));
+            tm.kernel_launches += nl;
+            tm.frames += nb;
+            knn_vote_l2(ex.d_desc(), total, ex.d_q_frame(), nb, ex.d_frame_nkp(), ex.h_frame_off());
+            SLIDEO_CUDA(cudaMemcpyAsync(h_results + (size_t)f0 * 3, d_results.p, (size_t)nb * 3 * 4, cudaMemcpyDeviceToHost, stream));
+        }
     }
 
     void require_orb() const {
@@ -591,6 +685,8 @@ int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_
         arg(cfg->vote_ratio >= 1.0f && cfg->vote_ratio < 16.f, "vote_ratio out of range");
         arg(cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256 || cfg->descriptor_kind == SLIDEO_B200_DESC_SIFT128,
             "unknown descriptor_kind");
+        if (cfg->descriptor_kind == SLIDEO_B200_DESC_SIFT128 && cfg->geometric_verification)
+            throw NotImplError("geometric verification is implemented for the ORB256 path only");
         int n_dev = 0;
         cudaError_t e = cudaGetDeviceCount(&n_dev);
         if (e != cudaSuccess || n_dev == 0)
@@ -640,11 +736,35 @@ int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int3
                                    int32_t* out_n_keypoints) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        ctx->require_orb();
         arg(px != nullptr, "px must not be NULL");
         arg(stride >= w, "stride < w");
         if (ctx->finalized || ctx->reserved) throw StateError("pool already finalized");
         ctx->check_pool_limits((int64_t)ctx->page_off.back(), (int64_t)ctx->page_off.size());
+        if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_SIFT128) {   // K11 on the page; descriptors pooled as n x 128 floats
+            SiftExtractor& sx = ctx->sift_extractor(w, h, 1);
+            ctx->d_img.reserve((size_t)w * h);
+            ctx->upload_images(ctx->d_img.p, px, 1, w, h, stride, (size_t)stride * h, ctx->stream);
+            int nl = 0;
+            const int total = sx.run(ctx->d_img.p, 1, w, (size_t)w * h, 1, ctx->stream, &nl);
+            ctx->tm.kernel_launches += nl;
+            const size_t base = ctx->h_pool.size();
+            ctx->h_pool.resize(base + (size_t)total * 512);
+            std::vector<float> kpf((size_t)total * 5);
+            if (total > 0) {
+                SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_pool.data() + base, sx.d_desc(), (size_t)total * 512, cudaMemcpyDeviceToHost, ctx->stream));
+                SLIDEO_CUDA(cudaMemcpyAsync(kpf.data(), sx.d_kp_f(), (size_t)total * 20, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < total; ++i) {
+                ctx->h_pool_pt.push_back(kpf[(size_t)i * 5]);
+                ctx->h_pool_pt.push_back(kpf[(size_t)i * 5 + 1]);
+            }
+            ctx->page_geom_ok = false;
+            ctx->page_off.push_back(ctx->page_off.back() + total);
+            ctx->check_pool_limits((int64_t)ctx->page_off.back(), (int64_t)ctx->page_off.size() - 1);
+            if (out_n_keypoints) *out_n_keypoints = total;
+            return;
+        }
         OrbExtractor& ex = ctx->extractor(w, h, 1);
         ctx->d_img.reserve((size_t)w * h);
         ctx->upload_images(ctx->d_img.p, px, 1, w, h, stride, (size_t)stride * h, ctx->stream);
@@ -857,7 +977,6 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
                                       int32_t stride, size_t frame_stride, slideo_b200_frame_result* out) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        ctx->require_orb();
         ctx->require_pool();
         arg(n >= 0, "n < 0");
         if (n == 0) return;
@@ -865,6 +984,21 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
         arg(stride >= 3 * w, "stride < 3*w");
         arg(frame_stride >= (size_t)stride * (h - 1) + (size_t)3 * w, "frame_stride too small");
         ctx->reset_kept();
+        if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_SIFT128) {
+            ctx->ensure_host_results((size_t)n);
+            EventPair t_total = ctx->begin_timing(4, ctx->stream);
+            ctx->match_frames_sift(frames, false, n, w, h, stride, frame_stride);
+            ctx->end_timing(t_total, ctx->stream);
+            SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+            SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            ctx->collect_timings();
+            for (int i = 0; i < n; ++i) {
+                out[i].best_slide = ctx->h_results[3 * i];
+                out[i].votes = ctx->h_results[3 * i + 1];
+                out[i].n_keypoints = ctx->h_results[3 * i + 2];
+            }
+            return;
+        }
         EventPair t_total = ctx->begin_timing(4, ctx->stream);
         const int B = ctx->cfg.max_batch;
         const size_t img_bytes = (size_t)3 * w * h;
@@ -923,13 +1057,26 @@ int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d
                                              int32_t stride, size_t frame_stride, slideo_b200_frame_result* out) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        ctx->require_orb();
         ctx->require_pool();
         arg(n >= 0, "n < 0");
         if (n == 0) return;
         arg(d_frames && out, "d_frames/out must not be NULL");
         arg(stride >= 3 * w, "stride < 3*w");
         ctx->reset_kept();
+        if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_SIFT128) {
+            ctx->ensure_host_results((size_t)n);
+            EventPair t_total = ctx->begin_timing(4, ctx->stream);
+            ctx->match_frames_sift((const uint8_t*)d_frames, true, n, w, h, stride, frame_stride);
+            ctx->end_timing(t_total, ctx->stream);
+            SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+            ctx->collect_timings();
+            for (int i = 0; i < n; ++i) {
+                out[i].best_slide = ctx->h_results[3 * i];
+                out[i].votes = ctx->h_results[3 * i + 1];
+                out[i].n_keypoints = ctx->h_results[3 * i + 2];
+            }
+            return;
+        }
         EventPair t_total = ctx->begin_timing(4, ctx->stream);
         const int B = ctx->cfg.max_batch;
         ctx->ensure_host_results((size_t)n);
@@ -1262,6 +1409,53 @@ int32_t slideo_b200_debug_fetch(slideo_b200_ctx* ctx, int32_t what, int32_t leve
         } else {
             throw ArgError("unknown `what`");
         }
+    });
+}
+
+int32_t slideo_b200_extract_sift(slideo_b200_ctx* ctx, const uint8_t* img, int32_t w, int32_t h, int32_t stride, int32_t channels,
+                                 float* kp_f, int32_t* kp_octave, float* desc, int32_t cap, int32_t* out_n) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        arg(img != nullptr, "img must not be NULL");
+        arg(channels == 1 || channels == 3, "channels must be 1 or 3");
+        arg(stride >= w * channels, "stride too small");
+        SiftExtractor& sx = ctx->sift_extractor(w, h, 1);
+        ctx->d_img.reserve((size_t)w * h * channels);
+        ctx->upload_images(ctx->d_img.p, img, 1, w * channels, h, stride, (size_t)stride * h, ctx->stream);
+        int nl = 0;
+        EventPair t = ctx->begin_timing(0, ctx->stream);
+        const int total = sx.run(ctx->d_img.p, 1, w * channels, (size_t)w * h * channels, channels, ctx->stream, &nl);
+        ctx->end_timing(t, ctx->stream);
+        ctx->tm.kernel_launches += nl;
+        if (out_n) *out_n = total;
+        if (total > cap && (kp_f || kp_octave || desc)) throw CapacityError("cap smaller than the number of keypoints");
+        if (total > 0) {
+            if (kp_f) SLIDEO_CUDA(cudaMemcpyAsync(kp_f, sx.d_kp_f(), (size_t)total * 20, cudaMemcpyDeviceToHost, ctx->stream));
+            if (kp_octave) SLIDEO_CUDA(cudaMemcpyAsync(kp_octave, sx.d_kp_octave(), (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            if (desc) SLIDEO_CUDA(cudaMemcpyAsync(desc, sx.d_desc(), (size_t)total * 512, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->collect_timings();
+    });
+}
+
+int32_t slideo_b200_debug_fetch_sift(slideo_b200_ctx* ctx, int32_t octave, int32_t layer, float* out, size_t cap_bytes, int32_t* out_w,
+                                     int32_t* out_h, int32_t* out_n_octaves) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        SiftExtractor* sx = ctx->last_sift;
+        if (!sx) throw StateError("no SIFT extract/match call yet");
+        const SiftGeo& g = sx->geo();
+        if (out_n_octaves) *out_n_octaves = g.n_oct;
+        arg(octave >= 0 && octave < g.n_oct, "octave out of range");
+        arg(layer >= 0 && layer < SIFT_GAUSS, "layer out of range");
+        const SiftOctave& oc = g.oc[octave];
+        if (out_w) *out_w = oc.w;
+        if (out_h) *out_h = oc.h;
+        if (!out) return;
+        arg(cap_bytes >= (size_t)oc.w * oc.h * 4, "cap_bytes too small");
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        SLIDEO_CUDA(cudaMemcpy2D(out, (size_t)oc.w * 4, sx->d_gauss(0, octave, layer), (size_t)oc.pitch * 4, (size_t)oc.w * 4, oc.h, cudaMemcpyDeviceToHost));
     });
 }
 

@@ -1,0 +1,830 @@
+// sift.cu -- K11: batched SIFT (cv::SIFT::create() defaults: nOctaveLayers 3, contrastThreshold 0.04, edgeThreshold 10,
+// sigma 1.6, CV_32F descriptors) for the north_star's SIFT-128 / L2 variant of the path; it sits where
+// crates/matching-opencv/src/feature_extractor.rs:29-46 calls ORB::detectAndCompute.  Every kernel follows the stage of
+// oracle/sift_oracle.c named beside it (S.1 .. S.11), operation for operation: the file is compiled -fmad=false and every
+// fused multiply-add OpenCV's AVX2 build performs is an explicit __fmaf_rn.
+//
+//   sift_gray_kernel      BGR -> gray (cvtColor fixed point)
+//   sift_blur_kernel      S.2/S.3 separable Gaussian on float images, 64x32 tiles staged in shared memory with their halo;
+//                         the 2x INTER_LINEAR upsample of the initial image is evaluated inside the tile load (never stored)
+//   sift_half_kernel      S.5 INTER_NEAREST half of layer 3 -> layer 0 of the next octave
+//   sift_extrema_kernel   S.8 26-neighbour extrema; the DoG images are never materialised (differences of the Gaussian tiles)
+//   sift_refine_kernel    S.6 adjustLocalExtrema + S.7 orientation histogram, one thread per candidate (raster-order sums)
+//   sift_rank_kernel /    S.9 KeyPoint_LessThan order by rank counting, removeDuplicatedSorted, firstOctave = -1 rescale
+//   sift_unique_kernel
+//   sift_descriptor_kernel S.10 4x4x8 histogram, one thread per keypoint with its 360 bins in shared memory
+//
+// The only operations not bit-defined by the oracle's source are libm's cosf / sinf / exp2f (keypoint size, descriptor
+// rotation): the device evaluates them in double and rounds once, which agrees with glibc except for results within ~1e-9
+// relative of a rounding boundary.
+#include "sift.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace slideo {
+
+namespace {
+
+constexpr int TW = 64, TH = 32;      // blur tile
+constexpr int EX_TX = 32, EX_TY = 16;  // extrema tile
+constexpr int ORI_BINS = 36;
+constexpr int DESC_THREADS = 64;
+constexpr int DESC_HIST = 6 * 6 * 10;
+
+__constant__ float c_taps[SIFT_GAUSS][32];
+__constant__ float c_exptab[64];
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+// ---- cvtColor BGR2GRAY 8u ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sift_gray_kernel(const uint8_t* __restrict__ src, int stride, size_t frame_stride,
+                                                        uint8_t* __restrict__ dst, int w, int h) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= w) return;
+    const uint8_t* p = src + (size_t)img * frame_stride + (size_t)y * stride + 3 * x;
+    dst[((size_t)img * h + y) * w + x] = (uint8_t)((p[0] * 3735u + p[1] * 19235u + p[2] * 9798u + 16384u) >> 15);
+}
+
+// ---- S.3: one sample of resize(gray -> 2x, INTER_LINEAR); weights 0.25 / 0.75, every product and sum exact in fp32 -----
+__device__ __forceinline__ float up2_sample(const uint8_t* __restrict__ g, int pitch, int w, int h, int dx, int dy) {
+    int sx = (dx >> 1) - ((dx & 1) ^ 1), sy = (dy >> 1) - ((dy & 1) ^ 1);
+    float fx = (dx & 1) ? 0.25f : 0.75f, fy = (dy & 1) ? 0.25f : 0.75f;
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= w - 1) { fx = 0.f; sx = w - 1; }
+    if (sy < 0) { fy = 0.f; sy = 0; }
+    if (sy >= h - 1) { fy = 0.f; sy = h - 1; }
+    const int sx1 = sx + 1 < w ? sx + 1 : w - 1, sy1 = sy + 1 < h ? sy + 1 : h - 1;
+    const uint8_t* s0 = g + (size_t)sy * pitch;
+    const uint8_t* s1 = g + (size_t)sy1 * pitch;
+    const float a1 = fx, a0 = 1.f - fx, b1 = fy, b0 = 1.f - fy;
+    const float h0 = (float)s0[sx] * a0 + (float)s0[sx1] * a1;
+    const float h1 = (float)s1[sx] * a0 + (float)s1[sx1] * a1;
+    return h0 * b0 + h1 * b1;
+}
+
+// ---- S.2: GaussianBlur on a float image = sepFilter2D, BORDER_REFLECT_101 ------------------------------------------
+//   rows    : s = x0*k0; s = fma(x_i, k_i, s), i ascending            (columns >= W - W%4: mul, then add)
+//   columns : s = c*k_R; s = fma(r[+j] + r[-j], k_{R+j}, s), j ascending (columns >= W - W%8: mul, then add)
+template <int R, bool UP2>
+__global__ void __launch_bounds__(256) sift_blur_kernel(const void* __restrict__ src_, size_t src_img_stride, int src_pitch, int sw, int sh,
+                                                        float* __restrict__ dst, size_t dst_img_stride, int dst_pitch, int W, int H,
+                                                        int tap_set) {
+    constexpr int N = 2 * R + 1, SH = TH + 2 * R, SW = (TW + 2 * R + 3) & ~3, NV = (N + 3 + 3) / 4;
+    __shared__ __align__(16) float s_src[SH * SW];
+    __shared__ __align__(16) float s_row[SH * TW];
+    const int img = blockIdx.z, tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    for (int e = threadIdx.x; e < SH * SW; e += 256) {
+        const int ry = e / SW, rx = e - ry * SW;
+        const int gy = reflect101(ty0 - R + ry, H), gx = reflect101(tx0 - R + rx, W);
+        float v;
+        if (UP2) v = up2_sample(static_cast<const uint8_t*>(src_) + (size_t)img * src_img_stride, src_pitch, sw, sh, gx, gy);
+        else v = static_cast<const float*>(src_)[(size_t)img * src_img_stride + (size_t)gy * src_pitch + gx];
+        s_src[e] = v;
+    }
+    float k[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) k[t] = c_taps[tap_set][t];
+    __syncthreads();
+    const int row_tail = W - (W & 3), col_tail = W - (W & 7);
+    for (int it = threadIdx.x; it < SH * (TW / 4); it += 256) {
+        const int ry = it / (TW / 4), x0 = (it - ry * (TW / 4)) * 4;
+        const float4* p = reinterpret_cast<const float4*>(s_src + ry * SW + x0);
+        float v[NV * 4];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 f = p[q];
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+        float a[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) a[m] = v[m] * k[0];
+        if (tx0 + x0 < row_tail) {
+#pragma unroll
+            for (int t = 1; t < N; ++t)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) a[m] = __fmaf_rn(v[t + m], k[t], a[m]);
+        } else {
+#pragma unroll
+            for (int t = 1; t < N; ++t)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) a[m] = a[m] + v[t + m] * k[t];
+        }
+        *reinterpret_cast<float4*>(s_row + ry * TW + x0) = make_float4(a[0], a[1], a[2], a[3]);
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < TW * (TH / 4); it += 256) {
+        const int x = it % TW, y0 = (it / TW) * 4, gx = tx0 + x;
+        if (gx >= W) continue;
+        float v[2 * R + 4];
+#pragma unroll
+        for (int j = 0; j < 2 * R + 4; ++j) v[j] = s_row[(y0 + j) * TW + x];
+        const bool fused = gx < col_tail;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            float d = v[m + R] * k[R];
+            if (fused) {
+#pragma unroll
+                for (int j = 1; j <= R; ++j) d = __fmaf_rn(v[m + R + j] + v[m + R - j], k[R + j], d);
+            } else {
+#pragma unroll
+                for (int j = 1; j <= R; ++j) d = d + (v[m + R + j] + v[m + R - j]) * k[R + j];
+            }
+            const int gy = ty0 + y0 + m;
+            if (gy < H) dst[(size_t)img * dst_img_stride + (size_t)gy * dst_pitch + gx] = d;
+        }
+    }
+}
+
+// ---- S.5: resize(INTER_NEAREST) of layer nOctaveLayers to (cols/2, rows/2): sx = min(floor(x * ifx), cols - 1) -------------
+__global__ void __launch_bounds__(256) sift_half_kernel(const float* __restrict__ src, size_t img_stride, int spitch, int sw, int sh,
+                                                        float* __restrict__ dst, int dpitch, int W, int H, double ifx, double ify) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= W) return;
+    int sx = (int)floor((double)x * ifx), sy = (int)floor((double)y * ify);
+    sx = sx > sw - 1 ? sw - 1 : sx;
+    sy = sy > sh - 1 ? sh - 1 : sy;
+    dst[(size_t)img * img_stride + (size_t)y * dpitch + x] = src[(size_t)img * img_stride + (size_t)sy * spitch + sx];
+}
+
+// ---- S.8 (first half): 26-neighbour extrema of the DoG stack, |val| > threshold, ties allowed ----------------------------------
+__device__ __forceinline__ int octave_of_tile(const SiftGeo& g, int t) {
+    int o = 0;
+    while (o + 1 < g.n_oct && t >= g.oc[o + 1].tile_base) ++o;
+    return o;
+}
+
+__global__ void __launch_bounds__(256) sift_extrema_kernel(const float* __restrict__ pyr, const __grid_constant__ SiftGeo g,
+                                                           uint32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt, float threshold) {
+    constexpr int PW = EX_TX + 2, PH = EX_TY + 2;
+    __shared__ float s_dog[SIFT_LAYERS + 2][PH * PW];
+    const int img = blockIdx.y;
+    const int o = octave_of_tile(g, blockIdx.x);
+    const SiftOctave& oc = g.oc[o];
+    const int t = blockIdx.x - oc.tile_base;
+    const int x0 = (t % oc.tiles_x) * EX_TX, y0 = (t / oc.tiles_x) * EX_TY;
+    const int W = oc.w, H = oc.h;
+    const float* base = pyr + (size_t)img * g.img_floats + oc.off;
+    for (int e = threadIdx.x; e < PH * PW; e += 256) {
+        const int ly = e / PW, lx = e - ly * PW;
+        int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+        gy = gy < 0 ? 0 : gy > H - 1 ? H - 1 : gy;
+        gx = gx < 0 ? 0 : gx > W - 1 ? W - 1 : gx;
+        const float* p = base + (size_t)gy * oc.pitch + gx;
+        float a = p[0];
+#pragma unroll
+        for (int l = 1; l < SIFT_GAUSS; ++l) {
+            const float b = p[(size_t)l * oc.layer_stride];
+            s_dog[l - 1][e] = b - a;
+            a = b;
+        }
+    }
+    __syncthreads();
+    const int lx = threadIdx.x % EX_TX;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int ly = threadIdx.x / EX_TX + half * (EX_TY / 2);
+        const int r = y0 + ly, c = x0 + lx;
+        if (r < 5 || r >= H - 5 || c < 5 || c >= W - 5) continue;   // SIFT_IMG_BORDER
+        const int ctr = (ly + 1) * PW + lx + 1;
+#pragma unroll
+        for (int i = 1; i <= SIFT_LAYERS; ++i) {
+            const float val = s_dog[i][ctr];
+            if (!(fabsf(val) > threshold)) continue;
+            bool ext = true;
+            if (val > 0) {
+#pragma unroll
+                for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+                    for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+                        for (int dc = -1; dc <= 1; ++dc) ext = ext && (val >= s_dog[i + dl][ctr + dr * PW + dc]);
+            } else {
+#pragma unroll
+                for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+                    for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+                        for (int dc = -1; dc <= 1; ++dc) ext = ext && (val <= s_dog[i + dl][ctr + dr * PW + dc]);
+            }
+            if (!ext) continue;
+            const int slot = atomicAdd(cand_cnt + img, 1);
+            if (slot < g.cand_cap) cand[(size_t)img * g.cand_cap + slot] = ((uint32_t)o << 28) | ((uint32_t)i << 26) | ((uint32_t)r << 13) | (uint32_t)c;
+        }
+    }
+}
+
+// ---- S.4: hal leaf functions as OpenCV's SIMD build evaluates them ---------------------------------------------------------
+__device__ __forceinline__ float sift_exp32f(float x) {   // cv::hal::exp32f: 64-entry table * cubic in the remainder
+    const float prescale = (float)(1.4426950408889634073599246810019 * 64);
+    const float postscale = (float)(1. / 64);
+    const float A0 = (float)(1.000000000000002438532970795181890933776 / .9670371139572337719125840413672004409288e-2);   // A4 of the source
+    const float A3 = (float)(.6931471805521448196800669615864773144641 / .9670371139572337719125840413672004409288e-2);
+    const float A2 = (float)(.2402265109513301490103372422686535526573 / .9670371139572337719125840413672004409288e-2);
+    const float A1 = (float)(.5550339366753125211915322047004666939128e-1 / .9670371139572337719125840413672004409288e-2);
+    const float maxval = (float)(3000. * 64 / (1.4426950408889634073599246810019 * 64)), minval = -maxval;
+    float x0 = fminf(fmaxf(x, minval), maxval);
+    x0 = x0 * prescale;
+    const int xi = __float2int_rn(x0);
+    x0 = (x0 - (float)xi) * postscale;
+    int t = (xi >> 6) + 127;
+    t = t < 0 ? 0 : t > 255 ? 255 : t;
+    const float y = c_exptab[xi & 63] * __int_as_float(t << 23);
+    float z = x0 + A1;
+    z = __fmaf_rn(z, x0, A2);
+    z = __fmaf_rn(z, x0, A3);
+    z = __fmaf_rn(z, x0, A0);
+    return z * y;
+}
+
+__device__ __forceinline__ float sift_fast_atan2(float y, float x) {   // cv::hal::fastAtan2 (v_atan_f32, degrees)
+    const float RAD = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * RAD, p3 = -0.3258083974640975f * RAD, p5 = 0.1555786518463281f * RAD,
+                p7 = -0.04432655554792128f * RAD;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float c = fminf(ax, ay) / (fmaxf(ax, ay) + (float)2.2204460492503131e-16);
+    const float cc = c * c;
+    float a = __fmaf_rn(__fmaf_rn(__fmaf_rn(cc, p7, p5), cc, p3), cc, p1) * c;
+    if (!(ax >= ay)) a = 90.f - a;
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+__device__ __forceinline__ float sift_magnitude(float x, float y) { return sqrtf(__fmaf_rn(x, x, y * y)); }
+
+struct OctView {
+    const float* base;   // Gaussian layer 0
+    size_t ls;
+    int pitch, W, H;
+    __device__ __forceinline__ float G(int l, int r, int c) const { return base[(size_t)l * ls + (size_t)r * pitch + c]; }
+    __device__ __forceinline__ float D(int l, int r, int c) const { return G(l + 1, r, c) - G(l, r, c); }   // DoG layer l
+};
+
+#define SIFT_FMS(p, q, r, s) __fmaf_rn((p), (q), -((r) * (s)))
+#define SIFT_OUT3(p, m1, q, m2, r, m3) __fmaf_rn((r), (m3), __fmaf_rn((p), (m1), -((q) * (m2))))
+
+// ---- S.6 + S.7 + S.8 (second half): one thread per candidate ----------------------------------------------------------------
+__global__ void __launch_bounds__(128) sift_refine_kernel(const float* __restrict__ pyr, const __grid_constant__ SiftGeo g,
+                                                          const uint32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                                                          float* __restrict__ raw, int32_t* __restrict__ raw_cnt) {
+    __shared__ float s_tmp[ORI_BINS][128];
+    __shared__ float s_hist[ORI_BINS][128];
+    const int img = blockIdx.y, tid = threadIdx.x;
+    const int n = min(cand_cnt[img], g.cand_cap);
+    const int ci = blockIdx.x * 128 + tid;
+    if (ci >= n) return;
+    const uint32_t packed = cand[(size_t)img * g.cand_cap + ci];
+    const int octv = packed >> 28;
+    int l = (packed >> 26) & 3, r = (packed >> 13) & 8191, c = packed & 8191;
+    const SiftOctave& oc = g.oc[octv];
+    OctView V{pyr + (size_t)img * g.img_floats + oc.off, oc.layer_stride, oc.pitch, oc.w, oc.h};
+    const int W = oc.w, H = oc.h;
+
+    // ---- adjustLocalExtrema: <= 5 Newton steps on the 3-D quadratic, then the contrast and edge tests
+    const float img_scale = 1.f / 255, deriv_scale = img_scale * 0.5f, second_deriv_scale = img_scale, cross_deriv_scale = img_scale * 0.25f;
+    float xi = 0, xr = 0, xc = 0;
+    int it = 0;
+    for (; it < 5; ++it) {
+        const float v = V.D(l, r, c);
+        const float cxp = V.D(l, r, c + 1), cxm = V.D(l, r, c - 1), cyp = V.D(l, r + 1, c), cym = V.D(l, r - 1, c);
+        const float nx = V.D(l + 1, r, c), pv = V.D(l - 1, r, c);
+        const float dD0 = (cxp - cxm) * deriv_scale, dD1 = (cyp - cym) * deriv_scale, dD2 = (nx - pv) * deriv_scale;
+        const float v2 = v * 2;
+        const float dxx = (cxp + cxm - v2) * second_deriv_scale, dyy = (cyp + cym - v2) * second_deriv_scale, dss = (nx + pv - v2) * second_deriv_scale;
+        const float dxy = (V.D(l, r + 1, c + 1) - V.D(l, r + 1, c - 1) - V.D(l, r - 1, c + 1) + V.D(l, r - 1, c - 1)) * cross_deriv_scale;
+        const float dxs = (V.D(l + 1, r, c + 1) - V.D(l + 1, r, c - 1) - V.D(l - 1, r, c + 1) + V.D(l - 1, r, c - 1)) * cross_deriv_scale;
+        const float dys = (V.D(l + 1, r + 1, c) - V.D(l + 1, r - 1, c) - V.D(l - 1, r + 1, c) + V.D(l - 1, r - 1, c)) * cross_deriv_scale;
+        // Matx33f H(dxx, dxy, dxs, dxy, dyy, dys, dxs, dys, dss); X = H.solve(dD, DECOMP_LU) = Cramer's rule in float, contracted
+        const float a00 = dxx, a01 = dxy, a02 = dxs, a10 = dxy, a11 = dyy, a12 = dys, a20 = dxs, a21 = dys, a22 = dss;
+        const float det = SIFT_OUT3(a00, SIFT_FMS(a11, a22, a21, a12), a01, SIFT_FMS(a10, a22, a20, a12), a02, SIFT_FMS(a10, a21, a20, a11));
+        float X0 = 0, X1 = 0, X2 = 0;
+        if (det != 0) {
+            const float d = 1 / det;
+            X0 = d * SIFT_OUT3(dD0, SIFT_FMS(a11, a22, a12, a21), a01, SIFT_FMS(dD1, a22, a12, dD2), a02, SIFT_FMS(dD1, a21, a11, dD2));
+            X1 = d * SIFT_OUT3(a00, SIFT_FMS(dD1, a22, a12, dD2), dD0, SIFT_FMS(a10, a22, a12, a20), a02, SIFT_FMS(a10, dD2, dD1, a20));
+            X2 = d * SIFT_OUT3(a00, SIFT_FMS(a11, dD2, dD1, a21), a01, SIFT_FMS(a10, dD2, dD1, a20), dD0, SIFT_FMS(a10, a21, a11, a20));
+        }
+        xi = -X2;
+        xr = -X1;
+        xc = -X0;
+        if (fabsf(xi) < 0.5f && fabsf(xr) < 0.5f && fabsf(xc) < 0.5f) break;
+        const float big = (float)(2147483647 / 3);
+        if (fabsf(xi) > big || fabsf(xr) > big || fabsf(xc) > big) return;
+        c += __float2int_rn(xc);
+        r += __float2int_rn(xr);
+        l += __float2int_rn(xi);
+        if (l < 1 || l > SIFT_LAYERS || c < 5 || c >= W - 5 || r < 5 || r >= H - 5) return;
+    }
+    if (it >= 5) return;
+    float contr;
+    {
+        const float v = V.D(l, r, c);
+        const float cxp = V.D(l, r, c + 1), cxm = V.D(l, r, c - 1), cyp = V.D(l, r + 1, c), cym = V.D(l, r - 1, c);
+        const float dD0 = (cxp - cxm) * deriv_scale, dD1 = (cyp - cym) * deriv_scale, dD2 = (V.D(l + 1, r, c) - V.D(l - 1, r, c)) * deriv_scale;
+        const float t = __fmaf_rn(dD2, xi, __fmaf_rn(dD1, xr, dD0 * xc));
+        contr = __fmaf_rn(v, img_scale, t * 0.5f);
+        if (fabsf(contr) * SIFT_LAYERS < (float)0.04) return;
+        const float v2 = v * 2.f;
+        const float dxx = (cxp + cxm - v2) * second_deriv_scale, dyy = (cyp + cym - v2) * second_deriv_scale;
+        const float dxy = (V.D(l, r + 1, c + 1) - V.D(l, r + 1, c - 1) - V.D(l, r - 1, c + 1) + V.D(l, r - 1, c - 1)) * cross_deriv_scale;
+        const float tr = dxx + dyy;
+        const float det = SIFT_FMS(dxx, dyy, dxy, dxy);
+        const float e = 10.f;
+        if (det <= 0 || tr * tr * e >= (e + 1) * (e + 1) * det) return;
+    }
+    const float kx = ((float)c + xc) * (float)(1 << octv);
+    const float ky = ((float)r + xr) * (float)(1 << octv);
+    const int koct = octv + (l << 8) + (__double2int_rn(((double)xi + 0.5) * 255) << 16);
+    const float ksize = (float)1.6 * (float)exp2((double)(((float)l + xi) / SIFT_LAYERS)) * (float)(1 << octv) * 2;
+    const float kresp = fabsf(contr);
+
+    // ---- calcOrientationHist on Gaussian layer l
+    const float scl_octv = ksize * 0.5f / (float)(1 << octv);
+    const int radius = __float2int_rn(4.5f * scl_octv);
+    const float sigma = 1.5f * scl_octv;
+    const float expf_scale = -1.f / (2.f * sigma * sigma);
+#pragma unroll
+    for (int b = 0; b < ORI_BINS; ++b) s_tmp[b][tid] = 0.f;
+    for (int i = -radius; i <= radius; ++i) {
+        const int y = r + i;
+        if (y <= 0 || y >= H - 1) continue;
+        for (int j = -radius; j <= radius; ++j) {
+            const int x = c + j;
+            if (x <= 0 || x >= W - 1) continue;
+            const float dx = V.G(l, y, x + 1) - V.G(l, y, x - 1);
+            const float dy = V.G(l, y - 1, x) - V.G(l, y + 1, x);
+            const float wgt = sift_exp32f((float)(i * i + j * j) * expf_scale);
+            const float ori = sift_fast_atan2(dy, dx);
+            const float mag = sift_magnitude(dx, dy);
+            int bin = __float2int_rn((ORI_BINS / 360.f) * ori);
+            if (bin >= ORI_BINS) bin -= ORI_BINS;
+            if (bin < 0) bin += ORI_BINS;
+            s_tmp[bin][tid] += wgt * mag;
+        }
+    }
+    float maxval = 0.f;
+    for (int b = 0; b < ORI_BINS; ++b) {   // smoothing [1 4 6 4 1]/16: bins 0..31 in the SIMD loop (nested fma), 32..35 in its scalar tail
+        const int m2 = b - 2 < 0 ? b - 2 + ORI_BINS : b - 2, m1 = b - 1 < 0 ? b - 1 + ORI_BINS : b - 1;
+        const int p1 = b + 1 >= ORI_BINS ? b + 1 - ORI_BINS : b + 1, p2 = b + 2 >= ORI_BINS ? b + 2 - ORI_BINS : b + 2;
+        const float sa = s_tmp[m2][tid] + s_tmp[p2][tid], sb = s_tmp[m1][tid] + s_tmp[p1][tid], sc = s_tmp[b][tid];
+        float hv;
+        if (b < 32) hv = __fmaf_rn(sa, 1.f / 16.f, __fmaf_rn(sb, 4.f / 16.f, sc * (6.f / 16.f)));
+        else hv = __fmaf_rn(sc, 6.f / 16.f, sa * (1.f / 16.f) + sb * (4.f / 16.f));
+        s_hist[b][tid] = hv;
+        maxval = b == 0 ? hv : (maxval > hv ? maxval : hv);
+    }
+    const float mag_thr = maxval * 0.8f;
+    for (int j = 0; j < ORI_BINS; ++j) {
+        const int lft = j > 0 ? j - 1 : ORI_BINS - 1, rgt = j < ORI_BINS - 1 ? j + 1 : 0;
+        const float hj = s_hist[j][tid], hl = s_hist[lft][tid], hr = s_hist[rgt][tid];
+        if (hj > hl && hj > hr && hj >= mag_thr) {
+            float bin = (float)j + 0.5f * (hl - hr) / (hl - 2 * hj + hr);
+            bin = bin < 0 ? ORI_BINS + bin : bin >= ORI_BINS ? bin - ORI_BINS : bin;
+            float angle = __fmaf_rn(-(360.f / ORI_BINS), bin, 360.f);
+            if (fabsf(angle - 360.f) < 1.1920928955078125e-7f) angle = 0.f;
+            const int slot = atomicAdd(raw_cnt + img, 1);
+            if (slot < g.kp_cap) {
+                float* o = raw + ((size_t)img * g.kp_cap + slot) * 6;
+                o[0] = kx; o[1] = ky; o[2] = ksize; o[3] = angle; o[4] = kresp; o[5] = __int_as_float(koct);
+            }
+        }
+    }
+}
+
+// ---- S.9: KeyPoint_LessThan rank of every keypoint (rank counting: one thread per keypoint, the list streamed through smem) ----
+struct KpRec { float x, y, size, angle, resp; int oct; };
+__device__ __forceinline__ bool kp_less(const KpRec& a, const KpRec& b) {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    if (a.size != b.size) return a.size > b.size;
+    if (a.angle != b.angle) return a.angle < b.angle;
+    if (a.resp != b.resp) return a.resp > b.resp;
+    if (a.oct != b.oct) return a.oct > b.oct;
+    return false;
+}
+
+__global__ void __launch_bounds__(256) sift_rank_kernel(const float* __restrict__ raw, const int32_t* __restrict__ raw_cnt, int kp_cap,
+                                                        int32_t* __restrict__ order) {
+    __shared__ float s_kp[256 * 6];
+    const int img = blockIdx.y;
+    const int n = min(raw_cnt[img], kp_cap);
+    if (blockIdx.x * 256 >= n) return;
+    const float* list = raw + (size_t)img * kp_cap * 6;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    KpRec me{};
+    if (i < n) me = KpRec{list[i * 6], list[i * 6 + 1], list[i * 6 + 2], list[i * 6 + 3], list[i * 6 + 4], __float_as_int(list[i * 6 + 5])};
+    int rank = 0;
+    for (int t0 = 0; t0 < n; t0 += 256) {
+        const int tn = min(256, n - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < tn * 6; e += 256) s_kp[e] = list[(size_t)t0 * 6 + e];
+        __syncthreads();
+        if (i < n) {
+            for (int j = 0; j < tn; ++j) {
+                const float ox = s_kp[j * 6];
+                if (ox < me.x) { ++rank; continue; }
+                if (ox > me.x) continue;
+                const KpRec other{ox, s_kp[j * 6 + 1], s_kp[j * 6 + 2], s_kp[j * 6 + 3], s_kp[j * 6 + 4], __float_as_int(s_kp[j * 6 + 5])};
+                if (kp_less(other, me) || (!kp_less(me, other) && t0 + j < i)) ++rank;
+            }
+        }
+    }
+    if (i < n) order[(size_t)img * kp_cap + rank] = i;
+}
+
+// removeDuplicatedSorted (unique on pt, size, angle) + the firstOctave = -1 rescale; one CTA per image
+__global__ void __launch_bounds__(1024) sift_unique_kernel(const float* __restrict__ raw, const int32_t* __restrict__ raw_cnt, int kp_cap,
+                                                           const int32_t* __restrict__ order, float* __restrict__ uniq, int32_t* __restrict__ uniq_cnt) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = min(raw_cnt[img], kp_cap);
+    const float* list = raw + (size_t)img * kp_cap * 6;
+    const int32_t* ord = order + (size_t)img * kp_cap;
+    float* out = uniq + (size_t)img * kp_cap * 6;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < n; p0 += 1024) {
+        const int p = p0 + tid;
+        int keep = 0;
+        const float* a = nullptr;
+        if (p < n) {
+            a = list + (size_t)ord[p] * 6;
+            keep = 1;
+            if (p > 0) {
+                const float* b = list + (size_t)ord[p - 1] * 6;
+                keep = (a[0] != b[0] || a[1] != b[1] || a[2] != b[2] || a[3] != b[3]) ? 1 : 0;
+            }
+        }
+        int incl = keep;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if (lane >= d) w += v;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int base = s_base + (wid > 0 ? s_warp[wid - 1] : 0);
+        if (keep) {
+            float* o = out + (size_t)(base + incl - 1) * 6;
+            const int oct = __float_as_int(a[5]);
+            o[0] = a[0] * 0.5f; o[1] = a[1] * 0.5f; o[2] = a[2] * 0.5f; o[3] = a[3]; o[4] = a[4];
+            o[5] = __int_as_float((oct & ~255) | ((oct - 1) & 255));
+        }
+        __syncthreads();
+        if (tid == 1023) s_base = base + incl;
+        __syncthreads();
+    }
+    if (tid == 0) uniq_cnt[img] = s_base;
+}
+
+// ---- S.10 + S.11: calcSIFTDescriptor, one thread per keypoint; the 6x6x10 histogram of thread t lives in s_h[bin * 64 + t] ------
+__global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const float* __restrict__ pyr, const __grid_constant__ SiftGeo g,
+                                                                       const float* __restrict__ uniq, const int32_t* __restrict__ frame_off, int n_img,
+                                                                       int total, float* __restrict__ kp_f, int32_t* __restrict__ kp_oct,
+                                                                       int32_t* __restrict__ q_frame, float* __restrict__ desc) {
+    extern __shared__ float s_h[];
+    const int tid = threadIdx.x;
+    const int gi = blockIdx.x * DESC_THREADS + tid;
+    const bool active = gi < total;
+    if (active) {
+        int lo = 0, hi = n_img;   // image of this keypoint: frame_off[lo] <= gi < frame_off[lo + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (frame_off[mid] <= gi) lo = mid; else hi = mid;
+        }
+        const int img = lo;
+        const float* kp = uniq + ((size_t)img * g.kp_cap + (gi - frame_off[img])) * 6;
+        const float kx = kp[0], ky = kp[1], ksize = kp[2], kangle = kp[3], kresp = kp[4];
+        const int koct = __float_as_int(kp[5]);
+        kp_f[(size_t)gi * 5] = kx; kp_f[(size_t)gi * 5 + 1] = ky; kp_f[(size_t)gi * 5 + 2] = ksize; kp_f[(size_t)gi * 5 + 3] = kangle;
+        kp_f[(size_t)gi * 5 + 4] = kresp;
+        kp_oct[gi] = koct;
+        q_frame[gi] = img;
+        // unpackOctave; the image of (octave - firstOctave, layer)
+        int octave = koct & 255;
+        const int layer = (koct >> 8) & 255;
+        octave = octave < 128 ? octave : (-128 | octave);
+        const float scale = octave >= 0 ? 1.f / (float)(1 << octave) : (float)(1 << -octave);
+        const float size = ksize * scale;
+        const int o = octave + 1;
+        float ori = 360.f - kangle;
+        if (fabsf(ori - 360.f) < 1.1920928955078125e-7f) ori = 0.f;
+        const SiftOctave& oc = g.oc[o];
+        const int W = oc.w, H = oc.h;
+        const float* im = pyr + (size_t)img * g.img_floats + oc.off + (size_t)layer * oc.layer_stride;
+        const int pitch = oc.pitch;
+        const float ptx = kx * scale, pty = ky * scale, scl = size * 0.5f;
+        const int d = 4, n = 8;
+        const int px = __float2int_rn(ptx), py = __float2int_rn(pty);
+        const float ang = ori * (float)(3.14159265358979323846 / 180);
+        float cos_t = (float)cos((double)ang), sin_t = (float)sin((double)ang);
+        const float bins_per_rad = n / 360.f;
+        const float exp_scale = -1.f / (d * d * 0.5f);
+        const float hist_width = 3.f * scl;
+        int radius = __float2int_rn(hist_width * 1.4142135623730951f * (d + 1) * 0.5f);
+        radius = radius > oc.diag ? oc.diag : radius;
+        cos_t = cos_t / hist_width;
+        sin_t = sin_t / hist_width;
+        for (int b = 0; b < DESC_HIST; ++b) s_h[b * DESC_THREADS + tid] = 0.f;
+        for (int i = -radius; i <= radius; ++i) {
+            const int r = py + i;
+            const float is = (float)i * sin_t, ic = (float)i * cos_t;
+            for (int j = -radius; j <= radius; ++j) {
+                const float c_rot = (float)j * cos_t - is;
+                const float r_rot = (float)j * sin_t + ic;
+                float rbin = r_rot + (float)(d / 2) - 0.5f;
+                float cbin = c_rot + (float)(d / 2) - 0.5f;
+                const int c = px + j;
+                if (rbin > -1 && rbin < d && cbin > -1 && cbin < d && r > 0 && r < H - 1 && c > 0 && c < W - 1) {
+                    const float* p = im + (size_t)r * pitch + c;
+                    const float dx = p[1] - p[-1];
+                    const float dy = p[-pitch] - p[pitch];
+                    const float wgt = sift_exp32f((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                    const float og = sift_fast_atan2(dy, dx);
+                    const float mag = sift_magnitude(dx, dy) * wgt;
+                    float obin = (og - ori) * bins_per_rad;
+                    const int r0 = __float2int_rd(rbin), c0 = __float2int_rd(cbin);
+                    int o0 = __float2int_rd(obin);
+                    rbin -= (float)r0;
+                    cbin -= (float)c0;
+                    obin -= (float)o0;
+                    if (o0 < 0) o0 += n;
+                    if (o0 >= n) o0 -= n;
+                    const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                    const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
+                    const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                    const float v_rco111 = v_rc11 * obin, v_rco110 = v_rc11 - v_rco111;
+                    const float v_rco101 = v_rc10 * obin, v_rco100 = v_rc10 - v_rco101;
+                    const float v_rco011 = v_rc01 * obin, v_rco010 = v_rc01 - v_rco011;
+                    const float v_rco001 = v_rc00 * obin, v_rco000 = v_rc00 - v_rco001;
+                    float* hp = s_h + (((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0) * DESC_THREADS + tid;
+                    hp[0] += v_rco000;
+                    hp[1 * DESC_THREADS] += v_rco001;
+                    hp[(n + 2) * DESC_THREADS] += v_rco010;
+                    hp[(n + 3) * DESC_THREADS] += v_rco011;
+                    hp[(d + 2) * (n + 2) * DESC_THREADS] += v_rco100;
+                    hp[((d + 2) * (n + 2) + 1) * DESC_THREADS] += v_rco101;
+                    hp[(d + 3) * (n + 2) * DESC_THREADS] += v_rco110;
+                    hp[((d + 3) * (n + 2) + 1) * DESC_THREADS] += v_rco111;
+                }
+            }
+        }
+        // circular orientation bins, then the descriptor is normalised in place (bins k < 8 of the 16 inner cells)
+        float nrm2 = 0;
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+                float* hp = s_h + (((i + 1) * (d + 2) + (j + 1)) * (n + 2)) * DESC_THREADS + tid;
+                hp[0] += hp[n * DESC_THREADS];
+                hp[DESC_THREADS] += hp[(n + 1) * DESC_THREADS];
+                for (int k = 0; k < n; ++k) nrm2 = __fmaf_rn(hp[k * DESC_THREADS], hp[k * DESC_THREADS], nrm2);
+            }
+        const float thr = sqrtf(nrm2) * 0.2f;
+        nrm2 = 0;
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+                float* hp = s_h + (((i + 1) * (d + 2) + (j + 1)) * (n + 2)) * DESC_THREADS + tid;
+                for (int k = 0; k < n; ++k) {
+                    const float raw = hp[k * DESC_THREADS];
+                    const float val = raw < thr ? raw : thr;
+                    hp[k * DESC_THREADS] = val;
+                    nrm2 = __fmaf_rn(val, val, nrm2);
+                }
+            }
+        const float s = sqrtf(nrm2);
+        const float f = 512.f / (s > 1.1920928955078125e-7f ? s : 1.1920928955078125e-7f);
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+                float* hp = s_h + (((i + 1) * (d + 2) + (j + 1)) * (n + 2)) * DESC_THREADS + tid;
+                for (int k = 0; k < n; ++k) {
+                    int v = __float2int_rn(hp[k * DESC_THREADS] * f);
+                    v = v < 0 ? 0 : v > 255 ? 255 : v;
+                    hp[k * DESC_THREADS] = (float)v;
+                }
+            }
+    }
+    __syncthreads();
+    // coalesced write: row t of the CTA = 128 floats
+    const int rows = min(DESC_THREADS, total - blockIdx.x * DESC_THREADS);
+    for (int e = tid; e < rows * 128; e += DESC_THREADS) {
+        const int t = e >> 7, k = e & 127;
+        const int cell = k >> 3, kk = k & 7, i = cell >> 2, j = cell & 3;
+        desc[((size_t)blockIdx.x * DESC_THREADS + t) * 128 + k] = s_h[((((i + 1) * 6 + (j + 1)) * 10) + kk) * DESC_THREADS + t];
+    }
+}
+
+int cv_round_d(double v) { return (int)lrint(v); }
+
+// S.1 getGaussianKernel(n, sigma, CV_32F) -> getGaussianKernelBitExact (IEEE double arithmetic; exp() is the only libm call)
+void gauss_taps(double sigma, int n, float* taps) {
+    std::vector<double> v((size_t)n), r((size_t)n);
+    const double scale2x = -0.125 / (sigma * sigma);
+    const int n2 = (n - 1) / 2;
+    double sum = 0;
+    for (int i = 0, x = 1 - n; i < n2; ++i, x += 2) {
+        v[i] = exp((double)(x * x) * scale2x);
+        sum += v[i];
+    }
+    sum *= 2;
+    sum += 1;
+    const double mul1 = 1.0 / sum;
+    double sum2 = 0;
+    for (int i = 0; i < n2; ++i) {
+        const double t = v[i] * mul1;
+        r[i] = t;
+        r[n - 1 - i] = t;
+        sum2 += t;
+    }
+    sum2 *= 2;
+    r[n2] = 1.0 * mul1;
+    sum2 += r[n2];
+    r[n2] += 1.0 - sum2;
+    for (int i = 0; i < n; ++i) taps[i] = (float)r[i];
+}
+
+constexpr int kRadius[SIFT_GAUSS] = {5, 5, 6, 8, 10, 13};   // ksize = cvRound(sigma * 8 + 1) | 1 for the six layer sigmas at sigma 1.6
+
+template <bool UP2>
+void launch_blur(int layer, dim3 grid, cudaStream_t st, const void* src, size_t sis, int sp, int sw, int sh, float* dst, size_t dis, int dp, int W,
+                 int H) {
+    switch (kRadius[layer]) {
+        case 5: sift_blur_kernel<5, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
+        case 6: sift_blur_kernel<6, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
+        case 8: sift_blur_kernel<8, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
+        case 10: sift_blur_kernel<10, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
+        default: sift_blur_kernel<13, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+SiftExtractor::SiftExtractor(int w, int h, int batch_cap, int kp_cap_per_image) : w_(w), h_(h), batch_cap_(batch_cap) {
+    if (w < 8 || h < 8 || 2 * w > SIFT_MAX_DIM || 2 * h > SIFT_MAX_DIM) throw ArgError("image size out of range for SIFT (8..4095)");
+    if (batch_cap < 1 || batch_cap > 256) throw ArgError("batch out of range (1..256)");
+    // layer sigmas (S.5) and their taps (S.1)
+    {
+        double sig[SIFT_GAUSS];
+        const float s = (float)1.6;
+        const float dd = s * s - 0.5f * 0.5f * 4;
+        sig[0] = (double)sqrtf(dd > 0.01f ? dd : 0.01f);
+        const double k = pow(2., 1. / SIFT_LAYERS);
+        for (int i = 1; i < SIFT_GAUSS; ++i) {
+            const double sig_prev = pow(k, (double)(i - 1)) * 1.6, sig_total = sig_prev * k;
+            sig[i] = sqrt(sig_total * sig_total - sig_prev * sig_prev);
+        }
+        float taps[SIFT_GAUSS][32];
+        memset(taps, 0, sizeof taps);
+        for (int i = 0; i < SIFT_GAUSS; ++i) {
+            const int n = cv_round_d(sig[i] * 4 * 2 + 1) | 1;
+            if (n != 2 * kRadius[i] + 1) throw NotImplError("unexpected Gaussian kernel size");
+            gauss_taps(sig[i], n, taps[i]);
+        }
+        SLIDEO_CUDA(cudaMemcpyToSymbol(c_taps, taps, sizeof taps));
+        float tab[64];
+        for (int j = 0; j < 64; ++j) tab[j] = (float)(exp2((double)j / 64) * .9670371139572337719125840413672004409288e-2);
+        SLIDEO_CUDA(cudaMemcpyToSymbol(c_exptab, tab, sizeof tab));
+    }
+    SiftGeo& g = geo_;
+    memset(&g, 0, sizeof g);
+    const int m = 2 * (w < h ? w : h);
+    g.n_oct = cv_round_d(log((double)m) / log(2.) - 2) + 1;
+    if (g.n_oct < 1 || g.n_oct > SIFT_MAX_OCT) throw ArgError("unsupported octave count");
+    int W = 2 * w, H = 2 * h, tile_base = 0;
+    size_t off = 0;
+    for (int o = 0; o < g.n_oct; ++o) {
+        SiftOctave& oc = g.oc[o];
+        if (W < 1 || H < 1) { g.n_oct = o; break; }
+        oc.w = W; oc.h = H;
+        oc.pitch = (int)align_up((size_t)W, 4);
+        oc.diag = (int)sqrt((double)W * W + (double)H * H);
+        oc.tiles_x = cdiv(W, EX_TX); oc.tiles_y = cdiv(H, EX_TY);
+        oc.tile_base = tile_base;
+        tile_base += oc.tiles_x * oc.tiles_y;
+        oc.layer_stride = align_up((size_t)oc.pitch * H, 64);
+        oc.off = off;
+        off += oc.layer_stride * SIFT_GAUSS;
+        if (o > 0) {
+            oc.ifx = 1. / ((double)W / g.oc[o - 1].w);
+            oc.ify = 1. / ((double)H / g.oc[o - 1].h);
+        }
+        W /= 2; H /= 2;
+    }
+    g.total_tiles = tile_base;
+    g.img_floats = off;
+    const long long px = (long long)w * h;
+    g.kp_cap = kp_cap_per_image > 0 ? kp_cap_per_image : (px >= 1000000 ? 32768 : px >= 200000 ? 16384 : 8192);
+    g.cand_cap = g.kp_cap * 8;
+    total_cap_ = (size_t)batch_cap * g.kp_cap;
+
+    const size_t B = (size_t)batch_cap;
+    SLIDEO_CUDA(cudaMalloc(&d_pyr_, B * g.img_floats * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_gray_, B * (size_t)w * h));
+    SLIDEO_CUDA(cudaMalloc(&d_cand_, B * g.cand_cap * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_cnt_, 3 * B * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_raw_, B * g.kp_cap * 6 * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_order_, B * g.kp_cap * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_uniq_, B * g.kp_cap * 6 * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_kp_f_, total_cap_ * 5 * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_kp_oct_, total_cap_ * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_q_frame_, total_cap_ * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_desc_, total_cap_ * 128 * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_frame_off_, (B + 1) * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_frame_nkp_, B * 4));
+    SLIDEO_CUDA(cudaMallocHost(&h_pinned_, (3 * B + 4) * 4));
+    SLIDEO_CUDA(cudaFuncSetAttribute(sift_descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_HIST * DESC_THREADS * 4));
+}
+
+SiftExtractor::~SiftExtractor() {
+    cudaFree(d_pyr_); cudaFree(d_gray_); cudaFree(d_cand_); cudaFree(d_cnt_); cudaFree(d_raw_); cudaFree(d_order_); cudaFree(d_uniq_);
+    cudaFree(d_kp_f_); cudaFree(d_kp_oct_); cudaFree(d_q_frame_); cudaFree(d_desc_); cudaFree(d_frame_off_); cudaFree(d_frame_nkp_);
+    cudaFreeHost(h_pinned_);
+}
+
+int SiftExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream, int* launches) {
+    if (n < 1 || n > batch_cap_) throw ArgError("batch size out of range");
+    if (channels != 1 && channels != 3) throw ArgError("channels must be 1 or 3");
+    const SiftGeo& g = geo_;
+    const size_t B = (size_t)batch_cap_;
+    int nl = 0;
+    int32_t *d_cand_cnt = d_cnt_, *d_raw_cnt = d_cnt_ + B, *d_uniq_cnt = d_cnt_ + 2 * B;
+    SLIDEO_CUDA(cudaMemsetAsync(d_cnt_, 0, 3 * B * 4, stream));
+
+    const uint8_t* gray = d_src;
+    int gpitch = stride;
+    size_t gstride = frame_stride;
+    if (channels == 3) {
+        sift_gray_kernel<<<dim3(cdiv(w_, 256), h_, n), 256, 0, stream>>>(d_src, stride, frame_stride, d_gray_, w_, h_);
+        ++nl;
+        gray = d_gray_;
+        gpitch = w_;
+        gstride = (size_t)w_ * h_;
+    }
+    // S.5 buildGaussianPyramid
+    for (int o = 0; o < g.n_oct; ++o) {
+        const SiftOctave& oc = g.oc[o];
+        float* L0 = d_pyr_ + oc.off;
+        const dim3 grid(cdiv(oc.w, TW), cdiv(oc.h, TH), n);
+        if (o == 0) {
+            launch_blur<true>(0, grid, stream, gray, gstride, gpitch, w_, h_, L0, g.img_floats, oc.pitch, oc.w, oc.h);
+        } else {
+            const SiftOctave& po = g.oc[o - 1];
+            sift_half_kernel<<<dim3(cdiv(oc.w, 256), oc.h, n), 256, 0, stream>>>(d_pyr_ + po.off + SIFT_LAYERS * po.layer_stride, g.img_floats, po.pitch,
+                                                                                 po.w, po.h, L0, oc.pitch, oc.w, oc.h, oc.ifx, oc.ify);
+        }
+        ++nl;
+        for (int i = 1; i < SIFT_GAUSS; ++i) {
+            launch_blur<false>(i, grid, stream, L0 + (size_t)(i - 1) * oc.layer_stride, g.img_floats, oc.pitch, oc.w, oc.h,
+                               L0 + (size_t)i * oc.layer_stride, g.img_floats, oc.pitch, oc.w, oc.h);
+            ++nl;
+        }
+    }
+    const float threshold = (float)(int)floor(0.5 * 0.04 / SIFT_LAYERS * 255);
+    sift_extrema_kernel<<<dim3(g.total_tiles, n), 256, 0, stream>>>(d_pyr_, g, d_cand_, d_cand_cnt, threshold);
+    ++nl;
+    sift_refine_kernel<<<dim3(cdiv(g.cand_cap, 128), n), 128, 0, stream>>>(d_pyr_, g, d_cand_, d_cand_cnt, d_raw_, d_raw_cnt);
+    ++nl;
+    sift_rank_kernel<<<dim3(cdiv(g.kp_cap, 256), n), 256, 0, stream>>>(d_raw_, d_raw_cnt, g.kp_cap, d_order_);
+    ++nl;
+    sift_unique_kernel<<<n, 1024, 0, stream>>>(d_raw_, d_raw_cnt, g.kp_cap, d_order_, d_uniq_, d_uniq_cnt);
+    ++nl;
+    SLIDEO_CUDA(cudaGetLastError());
+    SLIDEO_CUDA(cudaMemcpyAsync(h_pinned_, d_cnt_, 3 * B * 4, cudaMemcpyDeviceToHost, stream));
+    SLIDEO_CUDA(cudaStreamSynchronize(stream));   // keypoint counts size the descriptor launch
+    h_frame_off_.assign(1, 0);
+    last_cand_ = 0;
+    for (int i = 0; i < n; ++i) {
+        if (h_pinned_[i] > g.cand_cap) throw CapacityError("SIFT extrema candidate capacity exceeded on at least one image");
+        if (h_pinned_[B + i] > g.kp_cap) throw CapacityError("SIFT keypoint capacity exceeded on at least one image");
+        last_cand_ += h_pinned_[i];
+        h_frame_off_.push_back(h_frame_off_.back() + h_pinned_[2 * B + i]);
+    }
+    const int total = h_frame_off_.back();
+    SLIDEO_CUDA(cudaMemcpyAsync(d_frame_off_, h_frame_off_.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, stream));
+    SLIDEO_CUDA(cudaMemcpyAsync(d_frame_nkp_, d_uniq_cnt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+    if (total > 0) {
+        sift_descriptor_kernel<<<cdiv(total, DESC_THREADS), DESC_THREADS, DESC_HIST * DESC_THREADS * 4, stream>>>(
+            d_pyr_, g, d_uniq_, d_frame_off_, n, total, d_kp_f_, d_kp_oct_, d_q_frame_, d_desc_);
+        ++nl;
+        SLIDEO_CUDA(cudaGetLastError());
+    }
+    if (launches) *launches += nl;
+    return total;
+}
+
+}  // namespace slideo

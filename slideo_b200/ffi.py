@@ -90,6 +90,8 @@ SYMBOLS = {
     "slideo_b200_mark_changed_bgr8_device": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_i32, c_vp, c_vp]),
     "slideo_b200_extract_orb": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32p]),
     "slideo_b200_debug_fetch": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_sz, c_i32p, c_i32p]),
+    "slideo_b200_extract_sift": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32p]),
+    "slideo_b200_debug_fetch_sift": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_sz, c_i32p, c_i32p, c_i32p]),
     "slideo_b200_bf_knn_hamming": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "slideo_b200_bf_knn_hamming_device": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "slideo_b200_bf_knn_l2": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
