@@ -124,7 +124,9 @@ def test_sift_frame_path_equals_oracle_pipeline():
 def test_sift_batched_equals_single(ctx):
     """Batch composition must not change the result: frames through the batched path vs one by one (bitwise)."""
     pages = [textured(20 + p, 300, 400) for p in range(3)]
-    frames = np.stack([np.stack([pages[p]] * 3, axis=2) for p in (1, 2, 0, 1, 0)])
+    rng = np.random.default_rng(3)   # noise: an exact copy has best distance 0 and, by the reference's rule (lib.rs:275), casts no vote
+    noisy = [np.clip(pages[p].astype(np.int16) + rng.integers(-3, 4, pages[p].shape), 0, 255).astype(np.uint8) for p in (1, 2, 0, 1, 0)]
+    frames = np.stack([np.stack([g] * 3, axis=2) for g in noisy])
     out = []
     for mb in (1, 4):
         with slideo_b200.Context(slideo_b200.default_config(descriptor_kind=slideo_b200.ffi.DESC_SIFT128, max_batch=mb)) as c:
