@@ -380,6 +380,37 @@ def main():
         except Exception as ex:  # the extra must never break the contract line
             verify_detail = {"error": str(ex)}
 
+    # ---- extra (rank 0, N=1): the SIFT-128 / L2 variant of the same path (north_star; BASELINE configs[3] geometry at this run's
+    #      page count): K11 SIFT on the GPU for pages and frames -> K10 tcgen05 L2 k-NN -> vote, on a bounded sample of the frames ----
+    sift_detail = None
+    if rank == 0 and world == 1:
+        try:
+            ns = min(args.frames, 64)
+            sctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=8, descriptor_kind=slideo_b200.ffi.DESC_SIFT128))
+            t0 = time.perf_counter()
+            for p in range(args.pages):
+                sctx.add_page_gray8(pages[p])
+            sctx.finalize_pool()
+            t_spool = time.perf_counter() - t0
+            s_n, _ = sctx.pool_info()
+            sctx.match_frames_bgr8_device(dev.data_ptr(), min(ns, 8), FRAME_W, FRAME_H)
+            sctx.timings(reset=True)
+            t0 = time.perf_counter()
+            rs = sctx.match_frames_bgr8_device(dev.data_ptr(), ns, FRAME_W, FRAME_H)
+            dts = time.perf_counter() - t0
+            tms = sctx.timings(reset=True)
+            bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1368.2)))
+            k10_tflops = 2.0 * 144.0 * float(tms["knn_pairs"]) / max(tms["ms_knn"], 1e-9) / 1e9
+            sift_detail = {"frames": ns, "frames_per_s": ns / dts, "pool_descriptors": s_n, "pool_build_s": t_spool,
+                           "keypoints_per_frame": float(np.mean(rs[:, 2])), "ms_k11_per_frame": tms["ms_detect"] / ns,
+                           "ms_k10_per_frame": tms["ms_knn"] / ns,
+                           "k10_roofline": {"bound": "tensor", "achieved": k10_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
+                                            "frac": k10_tflops / bf16_peak, "flops": "2*(128+16)*Nq*Nt per launch"},
+                           "frames_with_truth_match": int(sum(1 for i in range(ns) if _truth_ok(rs, f_lo + i, i, args.pages)))}
+            sctx.close()
+        except Exception as ex:  # the extra must never break the contract line
+            sift_detail = {"error": str(ex)}
+
     if rank == 0:
         parity = None
         if cpu_results is not None:
@@ -401,7 +432,7 @@ def main():
                        "pool_build_s": t_pool, "keypoints_per_frame": float(np.mean(res_dev[:, 2])),
                        "frames_with_truth_match": int(sum(1 for i in range(args.frames) if _truth_ok(res_dev, f_lo + i, i, args.pages))),
                        "cpu_sample_matches_gpu": parity, "descriptor_pairs_per_s": pairs * world / t_dev,
-                       "with_geometric_verification": verify_detail},
+                       "with_geometric_verification": verify_detail, "sift128_variant": sift_detail},
         }
         print(json.dumps(line), flush=True)
     pin.close()

@@ -159,7 +159,9 @@ int32_t slideo_b200_pool_export(const slideo_b200_ctx* ctx, void* desc, int32_t*
 int32_t slideo_b200_pool_import(slideo_b200_ctx* ctx, const void* desc, int32_t n_desc, const int32_t* page_offsets,
                                 int32_t n_pages);
 /* Device variant for an NCCL broadcast done by the host process (torch.distributed / ncclBroadcast): reserve a
- * pool of the given geometry, expose its device buffers, then call slideo_b200_pool_commit once they are filled. */
+ * pool of the given geometry, expose its device buffers, then call slideo_b200_pool_commit once they are filled.
+ * The descriptor buffer holds n_desc x 32 bytes (ORB256) or n_desc x 128 floats (SIFT128; the bf16 tensor-core
+ * operands are derived from it at commit). */
 int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n_pages);
 int32_t slideo_b200_pool_device_view(slideo_b200_ctx* ctx, void** d_desc, size_t* desc_bytes, void** d_page_offsets,
                                      size_t* offsets_bytes);

@@ -79,6 +79,7 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_pool48;            // ORB: the 48 B expanded rows K8 streams (knn_pool_expand_launch)
     DevBuf<uint8_t> d_t48;               // expanded copy of a caller-provided pool (stage-level k-NN)
     DevBuf<uint8_t> d_pool_tail;         // SIFT: bf16 norm tails of the pool (knn_l2.cu)
+    DevBuf<uint8_t> d_pool_f32;          // SIFT: the pooled descriptors as fp32 (what the NCCL broadcast moves; bf16 operands are derived)
     DevBuf<uint16_t> d_page_of;          // nt
     DevBuf<int32_t> d_page_off;          // n_pages + 1
     int nt = 0, n_pages = 0;
@@ -847,12 +848,12 @@ static void finalize_from_host(slideo_b200_ctx* ctx) {
     if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) {
         ctx->upload_pool_orb(ctx->h_pool.data());
     } else {
-        ctx->d_t.reserve((size_t)std::max(ctx->nt, 1) * 512);
+        ctx->d_pool_f32.reserve((size_t)std::max(ctx->nt, 1) * 512);
         if (ctx->nt > 0)
-            SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_t.p, ctx->h_pool.data(), (size_t)ctx->nt * 512, cudaMemcpyHostToDevice, ctx->stream));
+            SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_pool_f32.p, ctx->h_pool.data(), (size_t)ctx->nt * 512, cudaMemcpyHostToDevice, ctx->stream));
         ctx->d_pool.reserve(l2_main_bytes(ctx->nt));
         ctx->d_pool_tail.reserve(l2_tail_bytes(ctx->nt));
-        l2_prepare_launch((const float*)ctx->d_t.p, ctx->nt, false, ctx->d_pool.p, ctx->d_pool_tail.p, ctx->stream);
+        l2_prepare_launch((const float*)ctx->d_pool_f32.p, ctx->nt, false, ctx->d_pool.p, ctx->d_pool_tail.p, ctx->stream);
         ctx->tm.kernel_launches += 1;
         ctx->build_page_of();
     }
@@ -909,7 +910,6 @@ int32_t slideo_b200_pool_import(slideo_b200_ctx* ctx, const void* desc, int32_t 
 int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n_pages) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        ctx->require_orb();
         arg(n_desc >= 0 && n_pages >= 0, "negative size");
         ctx->check_pool_limits(n_desc, n_pages);
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -922,7 +922,8 @@ int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n
         ctx->pool_pts_valid = n_desc == 0;
         ctx->pts_received = false;
         ctx->page_off.assign((size_t)n_pages + 1, 0);
-        ctx->d_pool.reserve((size_t)std::max(n_desc, 1) * 32 + 64);
+        if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) ctx->d_pool.reserve((size_t)std::max(n_desc, 1) * 32 + 64);
+        else ctx->d_pool_f32.reserve((size_t)std::max(n_desc, 1) * 512);
         ctx->d_page_off.reserve((size_t)n_pages + 1);
     });
 }
@@ -931,10 +932,10 @@ int32_t slideo_b200_pool_device_view(slideo_b200_ctx* ctx, void** d_desc, size_t
                                      size_t* offsets_bytes) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        ctx->require_orb();
         if (!ctx->finalized && !ctx->reserved) throw StateError("no device pool yet (finalize_pool or pool_reserve first)");
-        if (d_desc) *d_desc = ctx->d_pool.p;
-        if (desc_bytes) *desc_bytes = (size_t)ctx->nt * 32;
+        const bool orb = ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256;
+        if (d_desc) *d_desc = orb ? (void*)ctx->d_pool.p : (void*)ctx->d_pool_f32.p;
+        if (desc_bytes) *desc_bytes = (size_t)ctx->nt * ctx->desc_bytes;
         if (d_page_offsets) *d_page_offsets = ctx->d_page_off.p;
         if (offsets_bytes) *offsets_bytes = ((size_t)ctx->n_pages + 1) * 4;
     });
@@ -943,7 +944,6 @@ int32_t slideo_b200_pool_device_view(slideo_b200_ctx* ctx, void** d_desc, size_t
 int32_t slideo_b200_pool_points_device_view(slideo_b200_ctx* ctx, void** d_pt, size_t* bytes, int32_t* has_points, int32_t received) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        ctx->require_orb();
         if (!ctx->finalized && !ctx->reserved) throw StateError("no device pool yet (finalize_pool or pool_reserve first)");
         if (ctx->reserved) {
             ctx->d_pool_pt.reserve((size_t)std::max(ctx->nt, 1));
@@ -965,6 +965,12 @@ int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx) {
         for (int p = 0; p < ctx->n_pages; ++p)
             if (ctx->page_off[p] > ctx->page_off[p + 1]) throw ArgError("received page offsets are not monotone");
         const bool got_pts = ctx->pts_received;
+        if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_SIFT128) {   // the broadcast moved fp32 rows; derive the K10 operands
+            ctx->d_pool.reserve(l2_main_bytes(ctx->nt));
+            ctx->d_pool_tail.reserve(l2_tail_bytes(ctx->nt));
+            l2_prepare_launch((const float*)ctx->d_pool_f32.p, ctx->nt, false, ctx->d_pool.p, ctx->d_pool_tail.p, ctx->stream);
+            ctx->tm.kernel_launches += 1;
+        }
         ctx->build_page_of();              // (no host copy of the coordinates on this rank: the device copy filled by the caller stays)
         if (got_pts) ctx->pool_pts_valid = true;
         ctx->reserved = false;

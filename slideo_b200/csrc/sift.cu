@@ -5,13 +5,15 @@
 // fused multiply-add OpenCV's AVX2 build performs is an explicit __fmaf_rn.
 //
 //   sift_gray_kernel      BGR -> gray (cvtColor fixed point)
-//   sift_blur_kernel      S.2/S.3 separable Gaussian on float images, 64x32 tiles staged in shared memory with their halo;
+//   sift_blur_kernel      S.2/S.3 separable Gaussian on float images, 64x64 tiles staged in shared memory with their halo;
 //                         the 2x INTER_LINEAR upsample of the initial image is evaluated inside the tile load (never stored)
 //   sift_half_kernel      S.5 INTER_NEAREST half of layer 3 -> layer 0 of the next octave
 //   sift_extrema_kernel   S.8 26-neighbour extrema; the DoG images are never materialised (differences of the Gaussian tiles)
-//   sift_refine_kernel    S.6 adjustLocalExtrema + S.7 orientation histogram, one thread per candidate (raster-order sums)
+//   sift_refine_kernel    S.6 adjustLocalExtrema, one thread per candidate, survivors compacted
+//   sift_orient_kernel    S.7 orientation histogram (raster-order sums) + peaks, one thread per refined candidate
 //   sift_rank_kernel /    S.9 KeyPoint_LessThan order by rank counting, removeDuplicatedSorted, firstOctave = -1 rescale
 //   sift_unique_kernel
+//   sift_bucket_*         descriptor threads are scheduled by window radius (counting sort), so warps run equal-length loops
 //   sift_descriptor_kernel S.10 4x4x8 histogram, one thread per keypoint with its 360 bins in shared memory
 //
 // The only operations not bit-defined by the oracle's source are libm's cosf / sinf / exp2f (keypoint size, descriptor
@@ -26,7 +28,7 @@ namespace slideo {
 
 namespace {
 
-constexpr int TW = 64, TH = 32;      // blur tile
+constexpr int TW = 64, TH = 64;      // blur tile
 constexpr int EX_TX = 32, EX_TY = 16;  // extrema tile
 constexpr int ORI_BINS = 36;
 constexpr int DESC_THREADS = 64;
@@ -70,21 +72,39 @@ __device__ __forceinline__ float up2_sample(const uint8_t* __restrict__ g, int p
 // ---- S.2: GaussianBlur on a float image = sepFilter2D, BORDER_REFLECT_101 ------------------------------------------
 //   rows    : s = x0*k0; s = fma(x_i, k_i, s), i ascending            (columns >= W - W%4: mul, then add)
 //   columns : s = c*k_R; s = fma(r[+j] + r[-j], k_{R+j}, s), j ascending (columns >= W - W%8: mul, then add)
+// Tile = 64 x 64 outputs.  The source tile is staged with a 16-column halo on both sides (so that its rows start 16-byte
+// aligned and interior tiles are moved with 128-bit loads and stores) and R rows above and below.
+constexpr int BLUR_SW = TW + 32;
+template <int R>
+constexpr int blur_smem_bytes() { return ((TH + 2 * R) * BLUR_SW + (TH + 2 * R) * TW) * 4; }
+
 template <int R, bool UP2>
 __global__ void __launch_bounds__(256) sift_blur_kernel(const void* __restrict__ src_, size_t src_img_stride, int src_pitch, int sw, int sh,
                                                         float* __restrict__ dst, size_t dst_img_stride, int dst_pitch, int W, int H,
                                                         int tap_set) {
-    constexpr int N = 2 * R + 1, SH = TH + 2 * R, SW = (TW + 2 * R + 3) & ~3, NV = (N + 3 + 3) / 4;
-    __shared__ __align__(16) float s_src[SH * SW];
-    __shared__ __align__(16) float s_row[SH * TW];
+    constexpr int N = 2 * R + 1, SH = TH + 2 * R, SW = BLUR_SW;
+    constexpr int BASE = (16 - R) & ~3, OFS = (16 - R) & 3, NV = (OFS + N + 3 + 3) / 4;   // row-pass window inside the staged row
+    static_assert(R <= 16, "halo");
+    extern __shared__ __align__(16) float s_blur[];
+    float* s_src = s_blur;
+    float* s_row = s_blur + SH * SW;
     const int img = blockIdx.z, tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    for (int e = threadIdx.x; e < SH * SW; e += 256) {
-        const int ry = e / SW, rx = e - ry * SW;
-        const int gy = reflect101(ty0 - R + ry, H), gx = reflect101(tx0 - R + rx, W);
-        float v;
-        if (UP2) v = up2_sample(static_cast<const uint8_t*>(src_) + (size_t)img * src_img_stride, src_pitch, sw, sh, gx, gy);
-        else v = static_cast<const float*>(src_)[(size_t)img * src_img_stride + (size_t)gy * src_pitch + gx];
-        s_src[e] = v;
+    const bool interior = !UP2 && tx0 >= 16 && tx0 + TW + 16 <= W && ty0 >= R && ty0 + TH + R <= H;
+    if (interior) {
+        const float* base = static_cast<const float*>(src_) + (size_t)img * src_img_stride + (size_t)(ty0 - R) * src_pitch + (tx0 - 16);
+        for (int e = threadIdx.x; e < SH * (SW / 4); e += 256) {
+            const int ry = e / (SW / 4), q = e - ry * (SW / 4);
+            reinterpret_cast<float4*>(s_src + ry * SW)[q] = __ldg(reinterpret_cast<const float4*>(base + (size_t)ry * src_pitch) + q);
+        }
+    } else {
+        for (int e = threadIdx.x; e < SH * SW; e += 256) {
+            const int ry = e / SW, rx = e - ry * SW;
+            const int gy = reflect101(ty0 - R + ry, H), gx = reflect101(tx0 - 16 + rx, W);
+            float v;
+            if (UP2) v = up2_sample(static_cast<const uint8_t*>(src_) + (size_t)img * src_img_stride, src_pitch, sw, sh, gx, gy);
+            else v = static_cast<const float*>(src_)[(size_t)img * src_img_stride + (size_t)gy * src_pitch + gx];
+            s_src[e] = v;
+        }
     }
     float k[N];
 #pragma unroll
@@ -93,7 +113,7 @@ __global__ void __launch_bounds__(256) sift_blur_kernel(const void* __restrict__
     const int row_tail = W - (W & 3), col_tail = W - (W & 7);
     for (int it = threadIdx.x; it < SH * (TW / 4); it += 256) {
         const int ry = it / (TW / 4), x0 = (it - ry * (TW / 4)) * 4;
-        const float4* p = reinterpret_cast<const float4*>(s_src + ry * SW + x0);
+        const float4* p = reinterpret_cast<const float4*>(s_src + ry * SW + x0 + BASE);
         float v[NV * 4];
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
@@ -102,17 +122,17 @@ __global__ void __launch_bounds__(256) sift_blur_kernel(const void* __restrict__
         }
         float a[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) a[m] = v[m] * k[0];
+        for (int m = 0; m < 4; ++m) a[m] = v[OFS + m] * k[0];
         if (tx0 + x0 < row_tail) {
 #pragma unroll
             for (int t = 1; t < N; ++t)
 #pragma unroll
-                for (int m = 0; m < 4; ++m) a[m] = __fmaf_rn(v[t + m], k[t], a[m]);
+                for (int m = 0; m < 4; ++m) a[m] = __fmaf_rn(v[OFS + t + m], k[t], a[m]);
         } else {
 #pragma unroll
             for (int t = 1; t < N; ++t)
 #pragma unroll
-                for (int m = 0; m < 4; ++m) a[m] = a[m] + v[t + m] * k[t];
+                for (int m = 0; m < 4; ++m) a[m] = a[m] + v[OFS + t + m] * k[t];
         }
         *reinterpret_cast<float4*>(s_row + ry * TW + x0) = make_float4(a[0], a[1], a[2], a[3]);
     }
@@ -268,12 +288,16 @@ struct OctView {
 #define SIFT_FMS(p, q, r, s) __fmaf_rn((p), (q), -((r) * (s)))
 #define SIFT_OUT3(p, m1, q, m2, r, m3) __fmaf_rn((r), (m3), __fmaf_rn((p), (m1), -((q) * (m2))))
 
-// ---- S.6 + S.7 + S.8 (second half): one thread per candidate ----------------------------------------------------------------
+// ---- S.6: adjustLocalExtrema, one thread per candidate; survivors go to a compact list so that the (long) orientation loops
+//      of the next kernel run on full warps -----------------------------------------------------------------------------------
+struct RefinedCand {
+    float kx, ky, ksize, kresp;
+    int koct, packed;   // packed = octave << 28 | layer << 26 | r << 13 | c  (refined integer position)
+};
+
 __global__ void __launch_bounds__(128) sift_refine_kernel(const float* __restrict__ pyr, const __grid_constant__ SiftGeo g,
                                                           const uint32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
-                                                          float* __restrict__ raw, int32_t* __restrict__ raw_cnt) {
-    __shared__ float s_tmp[ORI_BINS][128];
-    __shared__ float s_hist[ORI_BINS][128];
+                                                          RefinedCand* __restrict__ refined, int32_t* __restrict__ refined_cnt) {
     const int img = blockIdx.y, tid = threadIdx.x;
     const int n = min(cand_cnt[img], g.cand_cap);
     const int ci = blockIdx.x * 128 + tid;
@@ -285,7 +309,7 @@ __global__ void __launch_bounds__(128) sift_refine_kernel(const float* __restric
     OctView V{pyr + (size_t)img * g.img_floats + oc.off, oc.layer_stride, oc.pitch, oc.w, oc.h};
     const int W = oc.w, H = oc.h;
 
-    // ---- adjustLocalExtrema: <= 5 Newton steps on the 3-D quadratic, then the contrast and edge tests
+    // <= 5 Newton steps on the 3-D quadratic, then the contrast and edge tests
     const float img_scale = 1.f / 255, deriv_scale = img_scale * 0.5f, second_deriv_scale = img_scale, cross_deriv_scale = img_scale * 0.25f;
     float xi = 0, xr = 0, xc = 0;
     int it = 0;
@@ -337,34 +361,62 @@ __global__ void __launch_bounds__(128) sift_refine_kernel(const float* __restric
         const float e = 10.f;
         if (det <= 0 || tr * tr * e >= (e + 1) * (e + 1) * det) return;
     }
-    const float kx = ((float)c + xc) * (float)(1 << octv);
-    const float ky = ((float)r + xr) * (float)(1 << octv);
-    const int koct = octv + (l << 8) + (__double2int_rn(((double)xi + 0.5) * 255) << 16);
-    const float ksize = (float)1.6 * (float)exp2((double)(((float)l + xi) / SIFT_LAYERS)) * (float)(1 << octv) * 2;
-    const float kresp = fabsf(contr);
+    RefinedCand rc;
+    rc.kx = ((float)c + xc) * (float)(1 << octv);
+    rc.ky = ((float)r + xr) * (float)(1 << octv);
+    rc.koct = octv + (l << 8) + (__double2int_rn(((double)xi + 0.5) * 255) << 16);
+    rc.ksize = (float)1.6 * (float)exp2((double)(((float)l + xi) / SIFT_LAYERS)) * (float)(1 << octv) * 2;
+    rc.kresp = fabsf(contr);
+    rc.packed = (int)(((uint32_t)octv << 28) | ((uint32_t)l << 26) | ((uint32_t)r << 13) | (uint32_t)c);
+    const int slot = atomicAdd(refined_cnt + img, 1);
+    if (slot < g.kp_cap) refined[(size_t)img * g.kp_cap + slot] = rc;
+}
 
-    // ---- calcOrientationHist on Gaussian layer l
-    const float scl_octv = ksize * 0.5f / (float)(1 << octv);
+// ---- S.7 + S.8 (second half): calcOrientationHist on Gaussian layer l (sums in raster order) and the orientation peaks;
+//      one thread per refined candidate, its 36 bins in shared memory; two window samples are evaluated per iteration (ILP) ----
+__global__ void __launch_bounds__(128) sift_orient_kernel(const float* __restrict__ pyr, const __grid_constant__ SiftGeo g,
+                                                          const RefinedCand* __restrict__ refined, const int32_t* __restrict__ refined_cnt,
+                                                          float* __restrict__ raw, int32_t* __restrict__ raw_cnt) {
+    __shared__ float s_tmp[ORI_BINS][128];
+    __shared__ float s_hist[ORI_BINS][128];
+    const int img = blockIdx.y, tid = threadIdx.x;
+    const int n = min(refined_cnt[img], g.kp_cap);
+    const int ci = blockIdx.x * 128 + tid;
+    if (ci >= n) return;
+    const RefinedCand rc = refined[(size_t)img * g.kp_cap + ci];
+    const uint32_t packed = (uint32_t)rc.packed;
+    const int octv = packed >> 28, l = (packed >> 26) & 3, r = (packed >> 13) & 8191, c = packed & 8191;
+    const SiftOctave& oc = g.oc[octv];
+    const int W = oc.w, H = oc.h, pitch = oc.pitch;
+    const float* im = pyr + (size_t)img * g.img_floats + oc.off + (size_t)l * oc.layer_stride;
+    const float scl_octv = rc.ksize * 0.5f / (float)(1 << octv);
     const int radius = __float2int_rn(4.5f * scl_octv);
     const float sigma = 1.5f * scl_octv;
     const float expf_scale = -1.f / (2.f * sigma * sigma);
 #pragma unroll
     for (int b = 0; b < ORI_BINS; ++b) s_tmp[b][tid] = 0.f;
+    const int j_lo = max(-radius, 1 - c), j_hi = min(radius, W - 2 - c);   // 0 < x < W - 1
     for (int i = -radius; i <= radius; ++i) {
         const int y = r + i;
         if (y <= 0 || y >= H - 1) continue;
-        for (int j = -radius; j <= radius; ++j) {
-            const int x = c + j;
-            if (x <= 0 || x >= W - 1) continue;
-            const float dx = V.G(l, y, x + 1) - V.G(l, y, x - 1);
-            const float dy = V.G(l, y - 1, x) - V.G(l, y + 1, x);
-            const float wgt = sift_exp32f((float)(i * i + j * j) * expf_scale);
-            const float ori = sift_fast_atan2(dy, dx);
-            const float mag = sift_magnitude(dx, dy);
-            int bin = __float2int_rn((ORI_BINS / 360.f) * ori);
-            if (bin >= ORI_BINS) bin -= ORI_BINS;
-            if (bin < 0) bin += ORI_BINS;
-            s_tmp[bin][tid] += wgt * mag;
+        const float* row = im + (size_t)y * pitch + c;
+        for (int j = j_lo; j <= j_hi; j += 2) {
+            const bool two = j + 1 <= j_hi;
+            const float* p0 = row + j;
+            const float* p1 = row + (two ? j + 1 : j);
+            const float dx0 = p0[1] - p0[-1], dy0 = p0[-pitch] - p0[pitch];
+            const float dx1 = p1[1] - p1[-1], dy1 = p1[-pitch] - p1[pitch];
+            const float w0 = sift_exp32f((float)(i * i + j * j) * expf_scale);
+            const float w1 = sift_exp32f((float)(i * i + (j + 1) * (j + 1)) * expf_scale);
+            const float o0 = sift_fast_atan2(dy0, dx0), o1 = sift_fast_atan2(dy1, dx1);
+            const float m0 = sift_magnitude(dx0, dy0), m1 = sift_magnitude(dx1, dy1);
+            int b0 = __float2int_rn((ORI_BINS / 360.f) * o0), b1 = __float2int_rn((ORI_BINS / 360.f) * o1);
+            if (b0 >= ORI_BINS) b0 -= ORI_BINS;
+            if (b0 < 0) b0 += ORI_BINS;
+            if (b1 >= ORI_BINS) b1 -= ORI_BINS;
+            if (b1 < 0) b1 += ORI_BINS;
+            s_tmp[b0][tid] += w0 * m0;
+            if (two) s_tmp[b1][tid] += w1 * m1;
         }
     }
     float maxval = 0.f;
@@ -390,7 +442,7 @@ __global__ void __launch_bounds__(128) sift_refine_kernel(const float* __restric
             const int slot = atomicAdd(raw_cnt + img, 1);
             if (slot < g.kp_cap) {
                 float* o = raw + ((size_t)img * g.kp_cap + slot) * 6;
-                o[0] = kx; o[1] = ky; o[2] = ksize; o[3] = angle; o[4] = kresp; o[5] = __int_as_float(koct);
+                o[0] = rc.kx; o[1] = rc.ky; o[2] = rc.ksize; o[3] = angle; o[4] = rc.kresp; o[5] = __int_as_float(rc.koct);
             }
         }
     }
@@ -410,7 +462,8 @@ __device__ __forceinline__ bool kp_less(const KpRec& a, const KpRec& b) {
 
 __global__ void __launch_bounds__(256) sift_rank_kernel(const float* __restrict__ raw, const int32_t* __restrict__ raw_cnt, int kp_cap,
                                                         int32_t* __restrict__ order) {
-    __shared__ float s_kp[256 * 6];
+    constexpr int TILE = 1024;
+    __shared__ __align__(16) float s_x[TILE];   // pt.x of the tile: the comparison that decides almost every pair
     const int img = blockIdx.y;
     const int n = min(raw_cnt[img], kp_cap);
     if (blockIdx.x * 256 >= n) return;
@@ -419,25 +472,51 @@ __global__ void __launch_bounds__(256) sift_rank_kernel(const float* __restrict_
     KpRec me{};
     if (i < n) me = KpRec{list[i * 6], list[i * 6 + 1], list[i * 6 + 2], list[i * 6 + 3], list[i * 6 + 4], __float_as_int(list[i * 6 + 5])};
     int rank = 0;
-    for (int t0 = 0; t0 < n; t0 += 256) {
-        const int tn = min(256, n - t0);
+    for (int t0 = 0; t0 < n; t0 += TILE) {
+        const int tn = min(TILE, n - t0);
         __syncthreads();
-        for (int e = threadIdx.x; e < tn * 6; e += 256) s_kp[e] = list[(size_t)t0 * 6 + e];
+        for (int e = threadIdx.x; e < TILE; e += 256) s_x[e] = e < tn ? list[(size_t)(t0 + e) * 6] : __int_as_float(0x7f800000);   // +inf: never less, never equal
         __syncthreads();
         if (i < n) {
-            for (int j = 0; j < tn; ++j) {
-                const float ox = s_kp[j * 6];
-                if (ox < me.x) { ++rank; continue; }
-                if (ox > me.x) continue;
-                const KpRec other{ox, s_kp[j * 6 + 1], s_kp[j * 6 + 2], s_kp[j * 6 + 3], s_kp[j * 6 + 4], __float_as_int(s_kp[j * 6 + 5])};
-                if (kp_less(other, me) || (!kp_less(me, other) && t0 + j < i)) ++rank;
+            const float4* x4 = reinterpret_cast<const float4*>(s_x);
+            for (int j4 = 0; j4 < (tn + 3) / 4; ++j4) {
+                const float4 o = x4[j4];
+                rank += (o.x < me.x) + (o.y < me.x) + (o.z < me.x) + (o.w < me.x);
+                if (o.x == me.x || o.y == me.x || o.z == me.x || o.w == me.x) {   // rare: same pt.x -> the full KeyPoint_LessThan order
+                    const float ox[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = t0 + j4 * 4 + q;
+                        if (ox[q] != me.x || j >= n) continue;
+                        const float* r = list + (size_t)j * 6;
+                        const KpRec other{r[0], r[1], r[2], r[3], r[4], __float_as_int(r[5])};
+                        if (kp_less(other, me) || (!kp_less(me, other) && j < i)) ++rank;
+                    }
+                }
             }
         }
     }
     if (i < n) order[(size_t)img * kp_cap + rank] = i;
 }
 
-// removeDuplicatedSorted (unique on pt, size, angle) + the firstOctave = -1 rescale; one CTA per image
+// descriptor window radius of a keypoint (S.10 / S.11), shared by the bucket kernels and the descriptor kernel
+__device__ __forceinline__ int desc_radius(float ksize, int koct, const SiftGeo& g, int* o_out, int* layer_out, float* scale_out) {
+    int octave = koct & 255;
+    *layer_out = (koct >> 8) & 255;
+    octave = octave < 128 ? octave : (-128 | octave);
+    const float scale = octave >= 0 ? 1.f / (float)(1 << octave) : (float)(1 << -octave);
+    const float size = ksize * scale;
+    const float scl = size * 0.5f;
+    const float hist_width = 3.f * scl;
+    int radius = __float2int_rn(hist_width * 1.4142135623730951f * 5 * 0.5f);
+    const int o = octave + 1;
+    radius = radius > g.oc[o].diag ? g.oc[o].diag : radius;
+    *o_out = o;
+    *scale_out = scale;
+    return radius;
+}
+__device__ __forceinline__ int radius_bucket(int radius) { return 63 - (radius > 63 ? 63 : radius); }
+
 __global__ void __launch_bounds__(1024) sift_unique_kernel(const float* __restrict__ raw, const int32_t* __restrict__ raw_cnt, int kp_cap,
                                                            const int32_t* __restrict__ order, float* __restrict__ uniq, int32_t* __restrict__ uniq_cnt) {
     __shared__ int s_warp[32];
@@ -493,23 +572,73 @@ __global__ void __launch_bounds__(1024) sift_unique_kernel(const float* __restri
     if (tid == 0) uniq_cnt[img] = s_base;
 }
 
-// ---- S.10 + S.11: calcSIFTDescriptor, one thread per keypoint; the 6x6x10 histogram of thread t lives in s_h[bin * 64 + t] ------
-__global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const float* __restrict__ pyr, const __grid_constant__ SiftGeo g,
-                                                                       const float* __restrict__ uniq, const int32_t* __restrict__ frame_off, int n_img,
-                                                                       int total, float* __restrict__ kp_f, int32_t* __restrict__ kp_oct,
-                                                                       int32_t* __restrict__ q_frame, float* __restrict__ desc) {
-    extern __shared__ float s_h[];
-    const int tid = threadIdx.x;
-    const int gi = blockIdx.x * DESC_THREADS + tid;
-    const bool active = gi < total;
-    if (active) {
-        int lo = 0, hi = n_img;   // image of this keypoint: frame_off[lo] <= gi < frame_off[lo + 1]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (frame_off[mid] <= gi) lo = mid; else hi = mid;
+// ---- scheduling order of the descriptor threads: keypoints bucketed by window radius, largest first, so that the threads of
+//      a warp run loops of (nearly) equal length.  perm entry = image << 16 | index within the image. ----------------------------
+__global__ void __launch_bounds__(256) sift_bucket_count_kernel(const float* __restrict__ uniq, const int32_t* __restrict__ uniq_cnt,
+                                                                const __grid_constant__ SiftGeo g, int32_t* __restrict__ bucket_cnt) {
+    __shared__ int s_cnt[64];
+    const int img = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.x * 256 >= uniq_cnt[img]) return;
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (j < uniq_cnt[img]) {
+        const float* kp = uniq + ((size_t)img * g.kp_cap + j) * 6;
+        int o, layer;
+        float scale;
+        atomicAdd(&s_cnt[radius_bucket(desc_radius(kp[2], __float_as_int(kp[5]), g, &o, &layer, &scale))], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && s_cnt[threadIdx.x]) atomicAdd(bucket_cnt + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+__global__ void sift_bucket_scan_kernel(const int32_t* __restrict__ bucket_cnt, int32_t* __restrict__ bucket_cursor) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < 64; ++b) {
+            bucket_cursor[b] = acc;
+            acc += bucket_cnt[b];
         }
-        const int img = lo;
-        const float* kp = uniq + ((size_t)img * g.kp_cap + (gi - frame_off[img])) * 6;
+    }
+}
+
+__global__ void __launch_bounds__(256) sift_bucket_scatter_kernel(const float* __restrict__ uniq, const int32_t* __restrict__ uniq_cnt,
+                                                                  const __grid_constant__ SiftGeo g, int32_t* __restrict__ bucket_cursor,
+                                                                  uint32_t* __restrict__ perm) {
+    const int img = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= uniq_cnt[img]) return;
+    const float* kp = uniq + ((size_t)img * g.kp_cap + j) * 6;
+    int o, layer;
+    float scale;
+    const int b = radius_bucket(desc_radius(kp[2], __float_as_int(kp[5]), g, &o, &layer, &scale));
+    perm[atomicAdd(bucket_cursor + b, 1)] = ((uint32_t)img << 16) | (uint32_t)j;
+}
+
+// ---- S.10 + S.11: calcSIFTDescriptor, one thread per keypoint; the 6x6x10 histogram of thread t lives in s_h[bin * 64 + t].
+//      Per window row only the columns that can pass the rotated-window test are visited (a conservative interval, the exact
+//      float test decides inside it), two samples per iteration for ILP; histogram updates stay in raster order. ----------------
+struct DescSample {
+    bool ok;
+    int idx;
+    float mag, rb, cb, ob;
+};
+
+__global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const float* __restrict__ pyr, const __grid_constant__ SiftGeo g,
+                                                                       const float* __restrict__ uniq, const int32_t* __restrict__ frame_off,
+                                                                       const uint32_t* __restrict__ perm, int total, float* __restrict__ kp_f,
+                                                                       int32_t* __restrict__ kp_oct, int32_t* __restrict__ q_frame,
+                                                                       float* __restrict__ desc) {
+    extern __shared__ float s_h[];
+    __shared__ int s_row[DESC_THREADS];
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.x * DESC_THREADS + tid;
+    const bool active = slot < total;
+    s_row[tid] = -1;
+    if (active) {
+        const uint32_t pe = perm[slot];
+        const int img = pe >> 16, jj = pe & 0xFFFF;
+        const int gi = frame_off[img] + jj;
+        s_row[tid] = gi;
+        const float* kp = uniq + ((size_t)img * g.kp_cap + jj) * 6;
         const float kx = kp[0], ky = kp[1], ksize = kp[2], kangle = kp[3], kresp = kp[4];
         const int koct = __float_as_int(kp[5]);
         kp_f[(size_t)gi * 5] = kx; kp_f[(size_t)gi * 5 + 1] = ky; kp_f[(size_t)gi * 5 + 2] = ksize; kp_f[(size_t)gi * 5 + 3] = kangle;
@@ -517,12 +646,10 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
         kp_oct[gi] = koct;
         q_frame[gi] = img;
         // unpackOctave; the image of (octave - firstOctave, layer)
-        int octave = koct & 255;
-        const int layer = (koct >> 8) & 255;
-        octave = octave < 128 ? octave : (-128 | octave);
-        const float scale = octave >= 0 ? 1.f / (float)(1 << octave) : (float)(1 << -octave);
+        int o, layer;
+        float scale;
+        const int radius = desc_radius(ksize, koct, g, &o, &layer, &scale);
         const float size = ksize * scale;
-        const int o = octave + 1;
         float ori = 360.f - kangle;
         if (fabsf(ori - 360.f) < 1.1920928955078125e-7f) ori = 0.f;
         const SiftOctave& oc = g.oc[o];
@@ -537,52 +664,78 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
         const float bins_per_rad = n / 360.f;
         const float exp_scale = -1.f / (d * d * 0.5f);
         const float hist_width = 3.f * scl;
-        int radius = __float2int_rn(hist_width * 1.4142135623730951f * (d + 1) * 0.5f);
-        radius = radius > oc.diag ? oc.diag : radius;
         cos_t = cos_t / hist_width;
         sin_t = sin_t / hist_width;
         for (int b = 0; b < DESC_HIST; ++b) s_h[b * DESC_THREADS + tid] = 0.f;
+        // conservative column interval of a window row: |j*sin + i*cos| and |j*cos - i*sin| must stay below ~2.5; a constraint
+        // whose slope is tiny is skipped (the exact test then decides), otherwise one column of slack covers the float rounding
+        const bool use_s = fabsf(sin_t) >= 1e-3f, use_c = fabsf(cos_t) >= 1e-3f;
+        const float inv_s = use_s ? 1.f / sin_t : 0.f, inv_c = use_c ? 1.f / cos_t : 0.f;
+        const int c_lo = max(-radius, 1 - px), c_hi = min(radius, W - 2 - px);   // 0 < c < W - 1
         for (int i = -radius; i <= radius; ++i) {
             const int r = py + i;
+            if (r <= 0 || r >= H - 1) continue;
             const float is = (float)i * sin_t, ic = (float)i * cos_t;
-            for (int j = -radius; j <= radius; ++j) {
+            int jlo = c_lo, jhi = c_hi;
+            if (use_s) {   // -2.6 < j*sin_t + ic < 2.6
+                const float a = (-2.6f - ic) * inv_s, b = (2.6f - ic) * inv_s;
+                jlo = max(jlo, __float2int_rd(fminf(a, b)) - 1);
+                jhi = min(jhi, __float2int_ru(fmaxf(a, b)) + 1);
+            }
+            if (use_c) {   // -2.6 < j*cos_t - is < 2.6
+                const float a = (-2.6f + is) * inv_c, b = (2.6f + is) * inv_c;
+                jlo = max(jlo, __float2int_rd(fminf(a, b)) - 1);
+                jhi = min(jhi, __float2int_ru(fmaxf(a, b)) + 1);
+            }
+            const float* row = im + (size_t)r * pitch + px;
+            auto eval = [&](int j, bool in_range) -> DescSample {
+                DescSample sm;
                 const float c_rot = (float)j * cos_t - is;
                 const float r_rot = (float)j * sin_t + ic;
                 float rbin = r_rot + (float)(d / 2) - 0.5f;
                 float cbin = c_rot + (float)(d / 2) - 0.5f;
-                const int c = px + j;
-                if (rbin > -1 && rbin < d && cbin > -1 && cbin < d && r > 0 && r < H - 1 && c > 0 && c < W - 1) {
-                    const float* p = im + (size_t)r * pitch + c;
-                    const float dx = p[1] - p[-1];
-                    const float dy = p[-pitch] - p[pitch];
-                    const float wgt = sift_exp32f((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                    const float og = sift_fast_atan2(dy, dx);
-                    const float mag = sift_magnitude(dx, dy) * wgt;
-                    float obin = (og - ori) * bins_per_rad;
-                    const int r0 = __float2int_rd(rbin), c0 = __float2int_rd(cbin);
-                    int o0 = __float2int_rd(obin);
-                    rbin -= (float)r0;
-                    cbin -= (float)c0;
-                    obin -= (float)o0;
-                    if (o0 < 0) o0 += n;
-                    if (o0 >= n) o0 -= n;
-                    const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
-                    const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
-                    const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
-                    const float v_rco111 = v_rc11 * obin, v_rco110 = v_rc11 - v_rco111;
-                    const float v_rco101 = v_rc10 * obin, v_rco100 = v_rc10 - v_rco101;
-                    const float v_rco011 = v_rc01 * obin, v_rco010 = v_rc01 - v_rco011;
-                    const float v_rco001 = v_rc00 * obin, v_rco000 = v_rc00 - v_rco001;
-                    float* hp = s_h + (((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0) * DESC_THREADS + tid;
-                    hp[0] += v_rco000;
-                    hp[1 * DESC_THREADS] += v_rco001;
-                    hp[(n + 2) * DESC_THREADS] += v_rco010;
-                    hp[(n + 3) * DESC_THREADS] += v_rco011;
-                    hp[(d + 2) * (n + 2) * DESC_THREADS] += v_rco100;
-                    hp[((d + 2) * (n + 2) + 1) * DESC_THREADS] += v_rco101;
-                    hp[(d + 3) * (n + 2) * DESC_THREADS] += v_rco110;
-                    hp[((d + 3) * (n + 2) + 1) * DESC_THREADS] += v_rco111;
-                }
+                sm.ok = in_range && rbin > -1 && rbin < d && cbin > -1 && cbin < d;
+                const float* p = row + (sm.ok ? j : 0);
+                const float dx = p[1] - p[-1];
+                const float dy = p[-pitch] - p[pitch];
+                const float wgt = sift_exp32f((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                const float og = sift_fast_atan2(dy, dx);
+                sm.mag = sift_magnitude(dx, dy) * wgt;
+                float obin = (og - ori) * bins_per_rad;
+                const int r0 = __float2int_rd(rbin), c0 = __float2int_rd(cbin);
+                int o0 = __float2int_rd(obin);
+                sm.rb = rbin - (float)r0;
+                sm.cb = cbin - (float)c0;
+                sm.ob = obin - (float)o0;
+                if (o0 < 0) o0 += n;
+                if (o0 >= n) o0 -= n;
+                sm.idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
+                return sm;
+            };
+            auto apply = [&](const DescSample& sm) {
+                if (!sm.ok) return;
+                const float v_r1 = sm.mag * sm.rb, v_r0 = sm.mag - v_r1;
+                const float v_rc11 = v_r1 * sm.cb, v_rc10 = v_r1 - v_rc11;
+                const float v_rc01 = v_r0 * sm.cb, v_rc00 = v_r0 - v_rc01;
+                const float v_rco111 = v_rc11 * sm.ob, v_rco110 = v_rc11 - v_rco111;
+                const float v_rco101 = v_rc10 * sm.ob, v_rco100 = v_rc10 - v_rco101;
+                const float v_rco011 = v_rc01 * sm.ob, v_rco010 = v_rc01 - v_rco011;
+                const float v_rco001 = v_rc00 * sm.ob, v_rco000 = v_rc00 - v_rco001;
+                float* hp = s_h + sm.idx * DESC_THREADS + tid;
+                hp[0] += v_rco000;
+                hp[1 * DESC_THREADS] += v_rco001;
+                hp[(n + 2) * DESC_THREADS] += v_rco010;
+                hp[(n + 3) * DESC_THREADS] += v_rco011;
+                hp[(d + 2) * (n + 2) * DESC_THREADS] += v_rco100;
+                hp[((d + 2) * (n + 2) + 1) * DESC_THREADS] += v_rco101;
+                hp[(d + 3) * (n + 2) * DESC_THREADS] += v_rco110;
+                hp[((d + 3) * (n + 2) + 1) * DESC_THREADS] += v_rco111;
+            };
+            for (int j = jlo; j <= jhi; j += 2) {
+                const DescSample a = eval(j, true);
+                const DescSample b = eval(j + 1, j + 1 <= jhi);
+                apply(a);
+                apply(b);
             }
         }
         // circular orientation bins, then the descriptor is normalised in place (bins k < 8 of the 16 inner cells)
@@ -619,12 +772,13 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
             }
     }
     __syncthreads();
-    // coalesced write: row t of the CTA = 128 floats
-    const int rows = min(DESC_THREADS, total - blockIdx.x * DESC_THREADS);
-    for (int e = tid; e < rows * 128; e += DESC_THREADS) {
+    // coalesced write: thread-row t of the CTA = the 128 floats of keypoint s_row[t]
+    for (int e = tid; e < DESC_THREADS * 128; e += DESC_THREADS) {
         const int t = e >> 7, k = e & 127;
+        const int gi = s_row[t];
+        if (gi < 0) continue;
         const int cell = k >> 3, kk = k & 7, i = cell >> 2, j = cell & 3;
-        desc[((size_t)blockIdx.x * DESC_THREADS + t) * 128 + k] = s_h[((((i + 1) * 6 + (j + 1)) * 10) + kk) * DESC_THREADS + t];
+        desc[(size_t)gi * 128 + k] = s_h[((((i + 1) * 6 + (j + 1)) * 10) + kk) * DESC_THREADS + t];
     }
 }
 
@@ -659,15 +813,27 @@ void gauss_taps(double sigma, int n, float* taps) {
 
 constexpr int kRadius[SIFT_GAUSS] = {5, 5, 6, 8, 10, 13};   // ksize = cvRound(sigma * 8 + 1) | 1 for the six layer sigmas at sigma 1.6
 
+template <int R, bool UP2>
+void launch_blur_r(int layer, dim3 grid, cudaStream_t st, const void* src, size_t sis, int sp, int sw, int sh, float* dst, size_t dis, int dp, int W,
+                   int H) {
+    sift_blur_kernel<R, UP2><<<grid, 256, blur_smem_bytes<R>(), st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer);
+}
+
+template <int R>
+void configure_blur() {   // > 48 KB of dynamic shared memory needs the opt-in (per device: called from every extractor's constructor)
+    SLIDEO_CUDA(cudaFuncSetAttribute(sift_blur_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes<R>()));
+    SLIDEO_CUDA(cudaFuncSetAttribute(sift_blur_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes<R>()));
+}
+
 template <bool UP2>
 void launch_blur(int layer, dim3 grid, cudaStream_t st, const void* src, size_t sis, int sp, int sw, int sh, float* dst, size_t dis, int dp, int W,
                  int H) {
     switch (kRadius[layer]) {
-        case 5: sift_blur_kernel<5, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
-        case 6: sift_blur_kernel<6, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
-        case 8: sift_blur_kernel<8, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
-        case 10: sift_blur_kernel<10, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
-        default: sift_blur_kernel<13, UP2><<<grid, 256, 0, st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer); break;
+        case 5: launch_blur_r<5, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
+        case 6: launch_blur_r<6, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
+        case 8: launch_blur_r<8, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
+        case 10: launch_blur_r<10, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
+        default: launch_blur_r<13, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
     }
 }
 
@@ -736,7 +902,10 @@ SiftExtractor::SiftExtractor(int w, int h, int batch_cap, int kp_cap_per_image) 
     SLIDEO_CUDA(cudaMalloc(&d_pyr_, B * g.img_floats * 4));
     SLIDEO_CUDA(cudaMalloc(&d_gray_, B * (size_t)w * h));
     SLIDEO_CUDA(cudaMalloc(&d_cand_, B * g.cand_cap * 4));
-    SLIDEO_CUDA(cudaMalloc(&d_cnt_, 3 * B * 4));
+    if (batch_cap * (long long)g.kp_cap >= (1ll << 31) || g.kp_cap > 65536) throw ArgError("SIFT keypoint capacity out of range");
+    SLIDEO_CUDA(cudaMalloc(&d_cnt_, (4 * B + 128) * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_refined_, B * g.kp_cap * 6 * 4));
+    SLIDEO_CUDA(cudaMalloc(&d_perm_, total_cap_ * 4));
     SLIDEO_CUDA(cudaMalloc(&d_raw_, B * g.kp_cap * 6 * 4));
     SLIDEO_CUDA(cudaMalloc(&d_order_, B * g.kp_cap * 4));
     SLIDEO_CUDA(cudaMalloc(&d_uniq_, B * g.kp_cap * 6 * 4));
@@ -746,12 +915,14 @@ SiftExtractor::SiftExtractor(int w, int h, int batch_cap, int kp_cap_per_image) 
     SLIDEO_CUDA(cudaMalloc(&d_desc_, total_cap_ * 128 * 4));
     SLIDEO_CUDA(cudaMalloc(&d_frame_off_, (B + 1) * 4));
     SLIDEO_CUDA(cudaMalloc(&d_frame_nkp_, B * 4));
-    SLIDEO_CUDA(cudaMallocHost(&h_pinned_, (3 * B + 4) * 4));
+    SLIDEO_CUDA(cudaMallocHost(&h_pinned_, (4 * B + 4) * 4));
     SLIDEO_CUDA(cudaFuncSetAttribute(sift_descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_HIST * DESC_THREADS * 4));
+    configure_blur<5>(); configure_blur<6>(); configure_blur<8>(); configure_blur<10>(); configure_blur<13>();
 }
 
 SiftExtractor::~SiftExtractor() {
     cudaFree(d_pyr_); cudaFree(d_gray_); cudaFree(d_cand_); cudaFree(d_cnt_); cudaFree(d_raw_); cudaFree(d_order_); cudaFree(d_uniq_);
+    cudaFree(d_refined_); cudaFree(d_perm_);
     cudaFree(d_kp_f_); cudaFree(d_kp_oct_); cudaFree(d_q_frame_); cudaFree(d_desc_); cudaFree(d_frame_off_); cudaFree(d_frame_nkp_);
     cudaFreeHost(h_pinned_);
 }
@@ -762,8 +933,9 @@ int SiftExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_str
     const SiftGeo& g = geo_;
     const size_t B = (size_t)batch_cap_;
     int nl = 0;
-    int32_t *d_cand_cnt = d_cnt_, *d_raw_cnt = d_cnt_ + B, *d_uniq_cnt = d_cnt_ + 2 * B;
-    SLIDEO_CUDA(cudaMemsetAsync(d_cnt_, 0, 3 * B * 4, stream));
+    int32_t *d_cand_cnt = d_cnt_, *d_raw_cnt = d_cnt_ + B, *d_uniq_cnt = d_cnt_ + 2 * B, *d_ref_cnt = d_cnt_ + 3 * B;
+    int32_t *d_bucket_cnt = d_cnt_ + 4 * B, *d_bucket_cursor = d_cnt_ + 4 * B + 64;
+    SLIDEO_CUDA(cudaMemsetAsync(d_cnt_, 0, (4 * B + 128) * 4, stream));
 
     const uint8_t* gray = d_src;
     int gpitch = stride;
@@ -797,20 +969,26 @@ int SiftExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_str
     const float threshold = (float)(int)floor(0.5 * 0.04 / SIFT_LAYERS * 255);
     sift_extrema_kernel<<<dim3(g.total_tiles, n), 256, 0, stream>>>(d_pyr_, g, d_cand_, d_cand_cnt, threshold);
     ++nl;
-    sift_refine_kernel<<<dim3(cdiv(g.cand_cap, 128), n), 128, 0, stream>>>(d_pyr_, g, d_cand_, d_cand_cnt, d_raw_, d_raw_cnt);
+    sift_refine_kernel<<<dim3(cdiv(g.cand_cap, 128), n), 128, 0, stream>>>(d_pyr_, g, d_cand_, d_cand_cnt, static_cast<RefinedCand*>(d_refined_), d_ref_cnt);
+    ++nl;
+    sift_orient_kernel<<<dim3(cdiv(g.kp_cap, 128), n), 128, 0, stream>>>(d_pyr_, g, static_cast<const RefinedCand*>(d_refined_), d_ref_cnt, d_raw_, d_raw_cnt);
     ++nl;
     sift_rank_kernel<<<dim3(cdiv(g.kp_cap, 256), n), 256, 0, stream>>>(d_raw_, d_raw_cnt, g.kp_cap, d_order_);
     ++nl;
     sift_unique_kernel<<<n, 1024, 0, stream>>>(d_raw_, d_raw_cnt, g.kp_cap, d_order_, d_uniq_, d_uniq_cnt);
     ++nl;
+    sift_bucket_count_kernel<<<dim3(cdiv(g.kp_cap, 256), n), 256, 0, stream>>>(d_uniq_, d_uniq_cnt, g, d_bucket_cnt);
+    sift_bucket_scan_kernel<<<1, 32, 0, stream>>>(d_bucket_cnt, d_bucket_cursor);
+    sift_bucket_scatter_kernel<<<dim3(cdiv(g.kp_cap, 256), n), 256, 0, stream>>>(d_uniq_, d_uniq_cnt, g, d_bucket_cursor, d_perm_);
+    nl += 3;
     SLIDEO_CUDA(cudaGetLastError());
-    SLIDEO_CUDA(cudaMemcpyAsync(h_pinned_, d_cnt_, 3 * B * 4, cudaMemcpyDeviceToHost, stream));
+    SLIDEO_CUDA(cudaMemcpyAsync(h_pinned_, d_cnt_, 4 * B * 4, cudaMemcpyDeviceToHost, stream));
     SLIDEO_CUDA(cudaStreamSynchronize(stream));   // keypoint counts size the descriptor launch
     h_frame_off_.assign(1, 0);
     last_cand_ = 0;
     for (int i = 0; i < n; ++i) {
         if (h_pinned_[i] > g.cand_cap) throw CapacityError("SIFT extrema candidate capacity exceeded on at least one image");
-        if (h_pinned_[B + i] > g.kp_cap) throw CapacityError("SIFT keypoint capacity exceeded on at least one image");
+        if (h_pinned_[B + i] > g.kp_cap || h_pinned_[3 * B + i] > g.kp_cap) throw CapacityError("SIFT keypoint capacity exceeded on at least one image");
         last_cand_ += h_pinned_[i];
         h_frame_off_.push_back(h_frame_off_.back() + h_pinned_[2 * B + i]);
     }
@@ -819,7 +997,7 @@ int SiftExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_str
     SLIDEO_CUDA(cudaMemcpyAsync(d_frame_nkp_, d_uniq_cnt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
     if (total > 0) {
         sift_descriptor_kernel<<<cdiv(total, DESC_THREADS), DESC_THREADS, DESC_HIST * DESC_THREADS * 4, stream>>>(
-            d_pyr_, g, d_uniq_, d_frame_off_, n, total, d_kp_f_, d_kp_oct_, d_q_frame_, d_desc_);
+            d_pyr_, g, d_uniq_, d_frame_off_, d_perm_, total, d_kp_f_, d_kp_oct_, d_q_frame_, d_desc_);
         ++nl;
         SLIDEO_CUDA(cudaGetLastError());
     }

@@ -70,7 +70,9 @@ private:
     float* d_pyr_ = nullptr;
     uint8_t* d_gray_ = nullptr;
     uint32_t* d_cand_ = nullptr;
-    int32_t *d_cnt_ = nullptr;        // [3][batch]: candidates, raw keypoints, unique keypoints; then flags
+    int32_t* d_cnt_ = nullptr;        // [4][batch]: candidates, raw keypoints, unique keypoints, refined candidates; radius buckets
+    void* d_refined_ = nullptr;       // [batch][kp_cap] candidates that survived adjustLocalExtrema
+    uint32_t* d_perm_ = nullptr;      // descriptor scheduling order (image << 16 | index), by window radius
     float* d_raw_ = nullptr;          // [batch][kp_cap][6] unsorted keypoints (x, y, size, angle, response, octave bits)
     int32_t* d_order_ = nullptr;      // [batch][kp_cap]
     float* d_uniq_ = nullptr;         // [batch][kp_cap][6] sorted + unique

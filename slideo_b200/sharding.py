@@ -53,7 +53,7 @@ def broadcast_pool_host(desc: Optional[np.ndarray], page_offsets: Optional[np.nd
 
 
 def broadcast_pool_device(ctx, src: int = 0) -> None:
-    """ORB256 pools: ONE NCCL broadcast of the pooled descriptors straight between the library's device buffers
+    """ONE NCCL broadcast of the pooled descriptors (ORB256: n x 32 B, SIFT128: n x 128 fp32) straight between the library's device buffers
     (plus the tiny page-offset table and a two-word header).  On return every rank's ctx holds the finalized pool."""
     import torch
     import torch.distributed as dist

@@ -28,4 +28,22 @@ if rank == 0:
     same = all(torch.equal(outs[0], o) for o in outs)
     print("ranks agree:", same, "| frame results:", res[:, :2].tolist(), "| survivors:", [v["survivors"] for v in ver])
     assert same
+# SIFT128 variant: pool built by K11 on rank 0, fp32 rows broadcast, every rank derives its own bf16 operands
+ctx2 = slideo_b200.Context(slideo_b200.default_config(device=local, descriptor_kind=slideo_b200.ffi.DESC_SIFT128, max_batch=4))
+small = [np.ascontiguousarray(p[60:700, 100:1060]) for p in pages[:3]]
+if rank == 0:
+    for p in small:
+        ctx2.add_page_gray8(p)
+    ctx2.finalize_pool()
+sharding.broadcast_pool_device(ctx2, src=0)
+rng = np.random.default_rng(5)
+fr = np.stack([np.stack([np.clip(small[p].astype(np.int16) + rng.integers(-3, 4, small[p].shape), 0, 255).astype(np.uint8)] * 3, axis=2) for p in (2, 0, 1, 2)])
+res2 = ctx2.match_frames_bgr8(fr)
+t2 = torch.from_numpy(res2.astype(np.int32)).cuda()
+outs2 = [torch.empty_like(t2) for _ in range(world)]
+dist.all_gather(outs2, t2)
+if rank == 0:
+    same2 = all(torch.equal(outs2[0], o) for o in outs2)
+    print("SIFT ranks agree:", same2, "| frame results:", res2.tolist())
+    assert same2 and res2[:, 0].tolist() == [2, 0, 1, 2]
 dist.destroy_process_group()
