@@ -17,7 +17,8 @@
 //     warps 2-5   epilogue group 0  tcgen05.ld.32x32b.x32: thread = query row, 32 pooled columns per load; the epilogue of
 //     warps 6-9   epilogue group 1  a pair is ONE fp32 compare against the row's running k-th distance; survivors are
 //                                   appended as 64-bit keys (d2 bits << 32 | index) to a 128-slot per-(group,row) buffer in
-//                                   L2 scratch, compacted by a warp-cooperative 128-key bitonic sort when it fills up
+//                                   L2 scratch, cut back to its k best by a warp-cooperative streaming bitonic top-32 AFTER the
+//                                   accumulator has been released (the tensor pipe never waits for a sort)
 // The two groups drain alternate pool tiles (TMEM buffer = tile parity) so the tensor pipe never waits for one epilogue;
 // at the end of a work item both lists are merged and the row is emitted in oracle order.
 #include <cuda.h>
@@ -40,7 +41,8 @@ constexpr int L2_BM = 128;              // queries per tile (TMEM lanes)
 constexpr int L2_BN = 256;              // pooled descriptors per tile (TMEM columns)
 constexpr int L2_STAGES = 2;            // B stages in shared memory
 constexpr int L2_THREADS = 320;
-constexpr int L2_SLOTS = 128;           // candidate keys per (group, row)
+constexpr int L2_TRIGGER = 128;         // upper bound of L2Params::trigger: a (group, row) list longer than the trigger is cut back to its k best after the tile
+constexpr int L2_SLOTS = L2_TRIGGER + L2_BN;   // candidate keys per (group, row): a whole tile can be appended without a check
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint64_t KEY64_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 
@@ -51,7 +53,7 @@ constexpr uint32_t B_TAIL_BYTES = L2_BN * 32;
 constexpr uint32_t A_BYTES = 2 * A_MAIN_BYTES + A_TAIL_BYTES;   // 36 KB
 constexpr uint32_t B_BYTES = 2 * B_MAIN_BYTES + B_TAIL_BYTES;   // 72 KB
 constexpr uint32_t SMEM_OPERANDS = A_BYTES + L2_STAGES * B_BYTES;   // 180 KB
-constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 128 + 2 * L2_BM * 4 + 1024;   // + barriers/tmem ptr + tau exchange + alignment slack
+constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 128 + 4 * L2_BM * 4 + 1024;   // + barriers/tmem ptr + tau / half-rank exchange + alignment slack
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,43 +121,36 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes
 // N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L2_BN >> 3) << 17) | ((uint32_t)(L2_BM >> 4) << 24);
 
-// 128-key ascending bitonic sort of 64-bit keys across a warp: position p = r * 32 + lane, r = 0..3
-__device__ __forceinline__ void warp_sort128(uint64_t (&k)[4], int lane) {
+// 32 keys, one per lane.  warp_sort32_desc: full bitonic sort, descending in lane order.  warp_merge32_asc: the last 5
+// stages only -- sorts a BITONIC sequence ascending.  Together they give a streaming "32 smallest": with `top` ascending and a
+// fresh chunk x descending, min(top, x) lane by lane holds the 32 smallest of both as a bitonic sequence.
+__device__ __forceinline__ uint64_t warp_cmpx(uint64_t v, int stride, bool take_min) {
+    const uint64_t o = __shfl_xor_sync(FULL, v, stride);
+    const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
+    return take_min ? mn : mx;
+}
+__device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t v, int lane) {
 #pragma unroll
-    for (int size = 2; size <= 128; size <<= 1) {
+    for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 32) {
-                const int rs = stride >> 5;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if ((r & rs) == 0) {
-                        const int p = r * 32;   // lane bits do not matter for size >= 64
-                        const bool up = size == 128 ? true : ((p & size) == 0);
-                        const uint64_t a = k[r], b = k[r | rs];
-                        const bool sw = up ? (a > b) : (a < b);
-                        k[r] = sw ? b : a;
-                        k[r | rs] = sw ? a : b;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int p = r * 32 + lane;
-                    const uint64_t o = __shfl_xor_sync(FULL, k[r], stride);
-                    const bool lower = (lane & stride) == 0;
-                    const bool up = size == 128 ? true : ((p & size) == 0);
-                    const uint64_t mn = k[r] < o ? k[r] : o, mx = k[r] < o ? o : k[r];
-                    k[r] = (lower == up) ? mn : mx;
-                }
-            }
+            const bool lower = (lane & stride) == 0;
+            const bool desc = size == 32 ? true : ((lane & size) == 0);   // final direction descending
+            v = warp_cmpx(v, stride, lower != desc);
         }
     }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_merge32_asc(uint64_t v, int lane) {
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) v = warp_cmpx(v, stride, (lane & stride) == 0);
+    return v;
 }
 
 struct L2Params {
     int nq, nt, k;
     int n_mtiles, n_ntiles, n_splits;
+    int trigger;           // list length that schedules a cut-back (k < trigger <= L2_TRIGGER)
     int dbg;               // developer switch (SLIDEO_L2_DEBUG): 1 = epilogue skips the TMEM drain, 2 = drains but never selects
     uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
     uint64_t* partial;     // [nq][n_splits][k]   (n_splits > 1)
@@ -188,6 +183,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     uint64_t* acc_empty = bars + 8;              // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
     volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 12);   // [2][L2_BM]: running k-th distance of each (group, row) list
+    volatile float* s_half = s_tau + 2 * L2_BM;                             // [2][L2_BM]: its ceil(k/2)-th distance
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -198,7 +194,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * L2_BM; i += L2_THREADS) s_tau[i] = __int_as_float(0x7F800000);
+    for (int i = tid; i < 4 * L2_BM; i += L2_THREADS) s_tau[i] = __int_as_float(0x7F800000);   // s_tau and s_half
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -281,26 +277,31 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
             int cnt = 0;
 
             auto compact = [&](bool force) {
-                // warp-cooperative: lanes whose buffer is nearly full (all lanes at the end of an item) get it sorted and
-                // cut to the k best; at the end of an item the list length is published in slot 32 (k <= 32) for the merge
-                unsigned need = force ? FULL : __ballot_sync(FULL, cnt > L2_SLOTS - 32);
+                // warp-cooperative: lanes whose list passed the trigger (all lanes at the end of an item) get it cut to the k
+                // best, sorted; at the end of an item the list length is published in slot 32 (k <= 32) for the merge
+                unsigned need = force ? FULL : __ballot_sync(FULL, cnt > P.trigger);
                 while (need) {
                     const int L = __ffs(need) - 1;
                     need &= need - 1;
                     uint64_t* buf = my_buf + ((ptrdiff_t)L - lane) * L2_SLOTS;
                     const int n = __shfl_sync(FULL, cnt, L);
-                    uint64_t kk[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) kk[r] = r * 32 + lane < n ? __ldcg(buf + r * 32 + lane) : KEY64_EMPTY;
-                    warp_sort128(kk, lane);
-                    if (lane < P.k) buf[lane] = kk[0];
+                    uint64_t top = KEY64_EMPTY;
+                    for (int c0 = 0; c0 < n; c0 += 32) {
+                        uint64_t x = c0 + lane < n ? __ldcg(buf + c0 + lane) : KEY64_EMPTY;
+                        x = warp_sort32_desc(x, lane);
+                        top = warp_merge32_asc(top < x ? top : x, lane);
+                    }
+                    __syncwarp();
+                    if (lane < P.k) buf[lane] = top;
                     if (force && lane == 0) buf[32] = (uint64_t)min(n, P.k);
-                    const uint64_t kth = __shfl_sync(FULL, kk[0], P.k - 1);
+                    const uint64_t kth = __shfl_sync(FULL, top, P.k - 1);
+                    const uint64_t hth = __shfl_sync(FULL, top, (P.k + 1) / 2 - 1);
                     if (lane == L) {
                         if (kth != KEY64_EMPTY) {
                             tau = __uint_as_float((uint32_t)(kth >> 32));
                             s_tau[g * L2_BM + row] = tau;   // the other group may prune against it (non-strictly)
                         }
+                        if (hth != KEY64_EMPTY) s_half[g * L2_BM + row] = __uint_as_float((uint32_t)(hth >> 32));
                         cnt = min(n, P.k);
                     }
                 }
@@ -316,8 +317,13 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 // with a smaller index could still displace its k-th entry), whichever is tighter
                 float thr = tau;
                 {
+                    const float inf = __int_as_float(0x7F800000);
                     const float other = s_tau[(g ^ 1) * L2_BM + row];
-                    if (other < thr) thr = fminf(thr, nextafterf(other, __int_as_float(0x7F800000)));
+                    if (other < thr) thr = fminf(thr, nextafterf(other, inf));
+                    // both lists hold >= ceil(k/2) entries at or below the larger of their ceil(k/2)-th distances, so k entries of
+                    // the union do: anything above it cannot reach the final k (ties may, hence non-strict)
+                    const float hx = fmaxf(s_half[row], s_half[L2_BM + row]);
+                    if (hx < thr) thr = fminf(thr, nextafterf(hx, inf));
                 }
                 const int n_chunks = P.dbg == 1 ? 0 : L2_BN / 32;
                 uint32_t va[32], vb[32];
@@ -334,42 +340,43 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                             tc_ld_wait();
                             if (c + 2 < n_chunks) tc_ld32(taddr_base + (uint32_t)(c + 2) * 32, va);
                         }
-                        // fast path: one compare per pair, four group predicates
-                        bool h0 = false, h1 = false, h2 = false, h3 = false;
+                        // fast path: a 3-input-min tree per 4 columns, one compare per group
+                        bool hit[8];
+                        bool any = false;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            h0 |= __uint_as_float(v[i]) < thr;
-                            h1 |= __uint_as_float(v[8 + i]) < thr;
-                            h2 |= __uint_as_float(v[16 + i]) < thr;
-                            h3 |= __uint_as_float(v[24 + i]) < thr;
+                        for (int q = 0; q < 8; ++q) {
+                            const float m = fminf(fminf(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                                  fminf(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+                            hit[q] = m < thr;
+                            any |= hit[q];
                         }
-                        if (P.dbg == 2) { h0 = h0 && v[0] == 0x12345678u; h1 = h2 = h3 = false; }
-                        if (h0 | h1 | h2 | h3) {
+                        if (P.dbg == 2) any = any && v[0] == 0x12345678u;
+                        if (any) {
                             const uint32_t cbase = (uint32_t)(col0 + (c + half) * 32);
-                            auto append8 = [&](int o) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    if (__uint_as_float(v[o + i]) < thr) {
-                                        my_buf[cnt] = ((uint64_t)v[o + i] << 32) | (cbase + (uint32_t)(o + i));
-                                        ++cnt;
-                                    }
+                            for (int q = 0; q < 8; ++q) {
+                                if (!hit[q]) continue;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {   // straight-line, predicated stores: a sparse hit must not cost a branch per element
+                                    const float val = __uint_as_float(v[4 * q + i]);
+                                    asm volatile(
+                                        "{\n\t.reg .pred p;\n\t"
+                                        "setp.lt.f32 p, %0, %1;\n\t"
+                                        "@p st.global.v2.u32 [%2], {%3, %4};\n\t}"
+                                        ::"f"(val), "f"(thr), "l"(my_buf + cnt), "r"(cbase + (uint32_t)(4 * q + i)), "r"(v[4 * q + i])
+                                        : "memory");
+                                    cnt += val < thr ? 1 : 0;
                                 }
-                            };
-                            if (h0) append8(0);
-                            if (h1) append8(8);
-                            if (h2) append8(16);
-                            if (h3) append8(24);
-                        }
-                        if (__any_sync(FULL, cnt > L2_SLOTS - 32)) {
-                            __syncwarp();
-                            compact(false);
-                            thr = fminf(thr, tau);
+                            }
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[g]);
+                // lists are cut back only now, after the accumulator has been handed back: the tensor pipe refills this TMEM
+                // buffer while the warp sorts (a list can take a whole tile of appends past the trigger: L2_SLOTS)
+                if (__any_sync(FULL, cnt > P.trigger)) compact(false);
             }
 
             // end of item: every list sorted and cut to k, then group 0 merges both lists of a row and emits it
@@ -377,6 +384,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
             compact(true);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             s_tau[g * L2_BM + row] = __int_as_float(0x7F800000);   // next item starts unpruned (nobody reads it until the 2nd barrier)
+            s_half[g * L2_BM + row] = __int_as_float(0x7F800000);
             if (g == 0) {
                 const uint64_t* base0 = P.scratch + (((size_t)blockIdx.x * 2 + 0) * L2_BM + quarter * 32) * L2_SLOTS;
                 const uint64_t* base1 = P.scratch + (((size_t)blockIdx.x * 2 + 1) * L2_BM + quarter * 32) * L2_SLOTS;
@@ -386,14 +394,12 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                     if (qq >= P.nq) break;   // warp-uniform
                     const int n0 = (int)__ldcg(base0 + (size_t)L * L2_SLOTS + 32);
                     const int n1 = (int)__ldcg(base1 + (size_t)L * L2_SLOTS + 32);
-                    uint64_t kk[4];
-                    kk[0] = lane < n0 ? __ldcg(base0 + (size_t)L * L2_SLOTS + lane) : KEY64_EMPTY;
-                    kk[1] = lane < n1 ? __ldcg(base1 + (size_t)L * L2_SLOTS + lane) : KEY64_EMPTY;
-                    kk[2] = KEY64_EMPTY;
-                    kk[3] = KEY64_EMPTY;
-                    warp_sort128(kk, lane);
-                    if (P.n_splits == 1) emit_l2_row(kk[0], lane, qq, P.k, P.idx_out, P.dist_out);
-                    else if (lane < P.k) P.partial[((size_t)qq * P.n_splits + sp) * P.k + lane] = kk[0];
+                    // list 0 ascending, list 1 read back to front (descending): lane-wise min = the 32 smallest, bitonic
+                    const uint64_t a = lane < n0 ? __ldcg(base0 + (size_t)L * L2_SLOTS + lane) : KEY64_EMPTY;
+                    const uint64_t b = 31 - lane < n1 ? __ldcg(base1 + (size_t)L * L2_SLOTS + (31 - lane)) : KEY64_EMPTY;
+                    const uint64_t m = warp_merge32_asc(a < b ? a : b, lane);
+                    if (P.n_splits == 1) emit_l2_row(m, lane, qq, P.k, P.idx_out, P.dist_out);
+                    else if (lane < P.k) P.partial[((size_t)qq * P.n_splits + sp) * P.k + lane] = m;
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -414,14 +420,12 @@ __global__ void __launch_bounds__(128) l2_merge_kernel(const uint64_t* __restric
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
-    uint64_t kk[4] = {KEY64_EMPTY, KEY64_EMPTY, KEY64_EMPTY, KEY64_EMPTY};
+    uint64_t top = KEY64_EMPTY;   // ascending; every partial row is ascending too, so it is read back to front
     for (int s = 0; s < n_splits; ++s) {
-        kk[1] = lane < k ? partial[((size_t)q * n_splits + s) * k + lane] : KEY64_EMPTY;
-        kk[2] = KEY64_EMPTY;
-        kk[3] = KEY64_EMPTY;
-        warp_sort128(kk, lane);
+        const uint64_t x = 31 - lane < k ? partial[((size_t)q * n_splits + s) * k + (31 - lane)] : KEY64_EMPTY;
+        top = warp_merge32_asc(top < x ? top : x, lane);
     }
-    emit_l2_row(kk[0], lane, q, k, idx_out, dist_out);
+    emit_l2_row(top, lane, q, k, idx_out, dist_out);
 }
 
 // fp32 rows -> bf16 GEMM operands.  One warp per row, 4 elements per lane.
@@ -566,6 +570,7 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.partial = (uint64_t*)ws.d_part;
     P.idx_out = d_idx;
     P.dist_out = d_dist;
+    P.trigger = getenv("SLIDEO_L2_TRIGGER") ? std::min(L2_TRIGGER, std::max(k + 1, atoi(getenv("SLIDEO_L2_TRIGGER")))) : 64;
     P.dbg = getenv("SLIDEO_L2_DEBUG") ? atoi(getenv("SLIDEO_L2_DEBUG")) : 0;
 
     const int q_pad = l2_rows_padded(nq), t_pad = l2_rows_padded(nt);

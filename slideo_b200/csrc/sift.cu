@@ -6,7 +6,7 @@
 //
 //   sift_gray_kernel      BGR -> gray (cvtColor fixed point)
 //   sift_blur_kernel      S.2/S.3 separable Gaussian on float images, 64x64 tiles staged in shared memory with their halo;
-//                         the 2x INTER_LINEAR upsample of the initial image is evaluated inside the tile load (never stored)
+//                         (interior tiles by 16-byte cp.async); sift_up2_kernel writes the 2x INTER_LINEAR initial image
 //   sift_half_kernel      S.5 INTER_NEAREST half of layer 3 -> layer 0 of the next octave
 //   sift_extrema_kernel   S.8 26-neighbour extrema; the DoG images are never materialised (differences of the Gaussian tiles)
 //   sift_refine_kernel    S.6 adjustLocalExtrema, one thread per candidate, survivors compacted
@@ -69,6 +69,22 @@ __device__ __forceinline__ float up2_sample(const uint8_t* __restrict__ g, int p
     return h0 * b0 + h1 * b1;
 }
 
+// the whole 2x image (S.3), one thread per 2x2 output block; written once, read once by the first blur
+__global__ void __launch_bounds__(256) sift_up2_kernel(const uint8_t* __restrict__ gray, size_t gray_img_stride, int gpitch, int w, int h,
+                                                       float* __restrict__ dst, size_t dst_img_stride, int dpitch) {
+    const int sx = blockIdx.x * 256 + threadIdx.x, sy = blockIdx.y, img = blockIdx.z;
+    if (sx >= w) return;
+    const uint8_t* g = gray + (size_t)img * gray_img_stride;
+    float* d = dst + (size_t)img * dst_img_stride;
+    float2 r0, r1;
+    r0.x = up2_sample(g, gpitch, w, h, 2 * sx, 2 * sy);
+    r0.y = up2_sample(g, gpitch, w, h, 2 * sx + 1, 2 * sy);
+    r1.x = up2_sample(g, gpitch, w, h, 2 * sx, 2 * sy + 1);
+    r1.y = up2_sample(g, gpitch, w, h, 2 * sx + 1, 2 * sy + 1);
+    *reinterpret_cast<float2*>(d + (size_t)(2 * sy) * dpitch + 2 * sx) = r0;
+    *reinterpret_cast<float2*>(d + (size_t)(2 * sy + 1) * dpitch + 2 * sx) = r1;
+}
+
 // ---- S.2: GaussianBlur on a float image = sepFilter2D, BORDER_REFLECT_101 ------------------------------------------
 //   rows    : s = x0*k0; s = fma(x_i, k_i, s), i ascending            (columns >= W - W%4: mul, then add)
 //   columns : s = c*k_R; s = fma(r[+j] + r[-j], k_{R+j}, s), j ascending (columns >= W - W%8: mul, then add)
@@ -78,8 +94,8 @@ constexpr int BLUR_SW = TW + 32;
 template <int R>
 constexpr int blur_smem_bytes() { return ((TH + 2 * R) * BLUR_SW + (TH + 2 * R) * TW) * 4; }
 
-template <int R, bool UP2>
-__global__ void __launch_bounds__(256) sift_blur_kernel(const void* __restrict__ src_, size_t src_img_stride, int src_pitch, int sw, int sh,
+template <int R>
+__global__ void __launch_bounds__(256) sift_blur_kernel(const float* __restrict__ src, size_t src_img_stride, int src_pitch,
                                                         float* __restrict__ dst, size_t dst_img_stride, int dst_pitch, int W, int H,
                                                         int tap_set) {
     constexpr int N = 2 * R + 1, SH = TH + 2 * R, SW = BLUR_SW;
@@ -89,21 +105,22 @@ __global__ void __launch_bounds__(256) sift_blur_kernel(const void* __restrict__
     float* s_src = s_blur;
     float* s_row = s_blur + SH * SW;
     const int img = blockIdx.z, tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const bool interior = !UP2 && tx0 >= 16 && tx0 + TW + 16 <= W && ty0 >= R && ty0 + TH + R <= H;
+    const bool interior = tx0 >= 16 && tx0 + TW + 16 <= W && ty0 >= R && ty0 + TH + R <= H;
     if (interior) {
-        const float* base = static_cast<const float*>(src_) + (size_t)img * src_img_stride + (size_t)(ty0 - R) * src_pitch + (tx0 - 16);
+        const float* base = src + (size_t)img * src_img_stride + (size_t)(ty0 - R) * src_pitch + (tx0 - 16);
+        // 16-byte asynchronous copies straight into shared memory: every copy of the tile is in flight at once
         for (int e = threadIdx.x; e < SH * (SW / 4); e += 256) {
             const int ry = e / (SW / 4), q = e - ry * (SW / 4);
-            reinterpret_cast<float4*>(s_src + ry * SW)[q] = __ldg(reinterpret_cast<const float4*>(base + (size_t)ry * src_pitch) + q);
+            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(s_src + ry * SW + 4 * q);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(base + (size_t)ry * src_pitch + 4 * q) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
         for (int e = threadIdx.x; e < SH * SW; e += 256) {
             const int ry = e / SW, rx = e - ry * SW;
             const int gy = reflect101(ty0 - R + ry, H), gx = reflect101(tx0 - 16 + rx, W);
-            float v;
-            if (UP2) v = up2_sample(static_cast<const uint8_t*>(src_) + (size_t)img * src_img_stride, src_pitch, sw, sh, gx, gy);
-            else v = static_cast<const float*>(src_)[(size_t)img * src_img_stride + (size_t)gy * src_pitch + gx];
-            s_src[e] = v;
+            s_src[e] = src[(size_t)img * src_img_stride + (size_t)gy * src_pitch + gx];
         }
     }
     float k[N];
@@ -731,11 +748,15 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
                 hp[(d + 3) * (n + 2) * DESC_THREADS] += v_rco110;
                 hp[((d + 3) * (n + 2) + 1) * DESC_THREADS] += v_rco111;
             };
-            for (int j = jlo; j <= jhi; j += 2) {
+            for (int j = jlo; j <= jhi; j += 4) {
                 const DescSample a = eval(j, true);
                 const DescSample b = eval(j + 1, j + 1 <= jhi);
+                const DescSample c = eval(j + 2, j + 2 <= jhi);
+                const DescSample e = eval(j + 3, j + 3 <= jhi);
                 apply(a);
                 apply(b);
+                apply(c);
+                apply(e);
             }
         }
         // circular orientation bins, then the descriptor is normalised in place (bins k < 8 of the 16 inner cells)
@@ -813,27 +834,23 @@ void gauss_taps(double sigma, int n, float* taps) {
 
 constexpr int kRadius[SIFT_GAUSS] = {5, 5, 6, 8, 10, 13};   // ksize = cvRound(sigma * 8 + 1) | 1 for the six layer sigmas at sigma 1.6
 
-template <int R, bool UP2>
-void launch_blur_r(int layer, dim3 grid, cudaStream_t st, const void* src, size_t sis, int sp, int sw, int sh, float* dst, size_t dis, int dp, int W,
-                   int H) {
-    sift_blur_kernel<R, UP2><<<grid, 256, blur_smem_bytes<R>(), st>>>(src, sis, sp, sw, sh, dst, dis, dp, W, H, layer);
+template <int R>
+void configure_blur() {   // > 48 KB of dynamic shared memory needs the opt-in (per device: called from every extractor's constructor)
+    SLIDEO_CUDA(cudaFuncSetAttribute(sift_blur_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes<R>()));
 }
 
 template <int R>
-void configure_blur() {   // > 48 KB of dynamic shared memory needs the opt-in (per device: called from every extractor's constructor)
-    SLIDEO_CUDA(cudaFuncSetAttribute(sift_blur_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes<R>()));
-    SLIDEO_CUDA(cudaFuncSetAttribute(sift_blur_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes<R>()));
+void launch_blur_r(int layer, dim3 grid, cudaStream_t st, const float* src, size_t sis, int sp, float* dst, size_t dis, int dp, int W, int H) {
+    sift_blur_kernel<R><<<grid, 256, blur_smem_bytes<R>(), st>>>(src, sis, sp, dst, dis, dp, W, H, layer);
 }
 
-template <bool UP2>
-void launch_blur(int layer, dim3 grid, cudaStream_t st, const void* src, size_t sis, int sp, int sw, int sh, float* dst, size_t dis, int dp, int W,
-                 int H) {
+void launch_blur(int layer, dim3 grid, cudaStream_t st, const float* src, size_t sis, int sp, float* dst, size_t dis, int dp, int W, int H) {
     switch (kRadius[layer]) {
-        case 5: launch_blur_r<5, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
-        case 6: launch_blur_r<6, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
-        case 8: launch_blur_r<8, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
-        case 10: launch_blur_r<10, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
-        default: launch_blur_r<13, UP2>(layer, grid, st, src, sis, sp, sw, sh, dst, dis, dp, W, H); break;
+        case 5: launch_blur_r<5>(layer, grid, st, src, sis, sp, dst, dis, dp, W, H); break;
+        case 6: launch_blur_r<6>(layer, grid, st, src, sis, sp, dst, dis, dp, W, H); break;
+        case 8: launch_blur_r<8>(layer, grid, st, src, sis, sp, dst, dis, dp, W, H); break;
+        case 10: launch_blur_r<10>(layer, grid, st, src, sis, sp, dst, dis, dp, W, H); break;
+        default: launch_blur_r<13>(layer, grid, st, src, sis, sp, dst, dis, dp, W, H); break;
     }
 }
 
@@ -952,8 +969,11 @@ int SiftExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_str
         const SiftOctave& oc = g.oc[o];
         float* L0 = d_pyr_ + oc.off;
         const dim3 grid(cdiv(oc.w, TW), cdiv(oc.h, TH), n);
-        if (o == 0) {
-            launch_blur<true>(0, grid, stream, gray, gstride, gpitch, w_, h_, L0, g.img_floats, oc.pitch, oc.w, oc.h);
+        if (o == 0) {   // the 2x image is parked in the slot of layer 5 (written for real only after layers 0..4 exist)
+            float* up = L0 + (size_t)(SIFT_GAUSS - 1) * oc.layer_stride;
+            sift_up2_kernel<<<dim3(cdiv(w_, 256), h_, n), 256, 0, stream>>>(gray, gstride, gpitch, w_, h_, up, g.img_floats, oc.pitch);
+            ++nl;
+            launch_blur(0, grid, stream, up, g.img_floats, oc.pitch, L0, g.img_floats, oc.pitch, oc.w, oc.h);
         } else {
             const SiftOctave& po = g.oc[o - 1];
             sift_half_kernel<<<dim3(cdiv(oc.w, 256), oc.h, n), 256, 0, stream>>>(d_pyr_ + po.off + SIFT_LAYERS * po.layer_stride, g.img_floats, po.pitch,
@@ -961,8 +981,8 @@ int SiftExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_str
         }
         ++nl;
         for (int i = 1; i < SIFT_GAUSS; ++i) {
-            launch_blur<false>(i, grid, stream, L0 + (size_t)(i - 1) * oc.layer_stride, g.img_floats, oc.pitch, oc.w, oc.h,
-                               L0 + (size_t)i * oc.layer_stride, g.img_floats, oc.pitch, oc.w, oc.h);
+            launch_blur(i, grid, stream, L0 + (size_t)(i - 1) * oc.layer_stride, g.img_floats, oc.pitch, L0 + (size_t)i * oc.layer_stride, g.img_floats,
+                        oc.pitch, oc.w, oc.h);
             ++nl;
         }
     }
