@@ -15,15 +15,16 @@
 //     warp 1      MMA issuer        tcgen05.mma.cta_group::1.kind::f16, M = 128 queries x N = 256 pooled rows, 9 K-steps,
 //                                   fp32 accumulators in TMEM (2 x 256 columns = all 512), tcgen05.commit -> mbarriers
 //     warps 2-5   epilogue group 0  tcgen05.ld.32x32b.x32: thread = query row, 32 pooled columns per load; the epilogue of
-//     warps 6-9   epilogue group 1  a pair is ONE fp32 compare against the row's running k-th distance; survivors are
+//     warps 6-9   epilogue group 1  a pair is a 3-input-min tree + ONE fp32 compare per 4 columns against the row's running k-th distance; survivors are
 //                                   appended as 64-bit keys (d2 bits << 32 | index) to a 128-slot per-(group,row) buffer in
 //                                   L2 scratch, cut back to its k best by a warp-cooperative streaming bitonic top-32 AFTER the
 //                                   accumulator has been released (the tensor pipe never waits for a sort)
-// The two groups drain alternate pool tiles (TMEM buffer = tile parity) so the tensor pipe never waits for one epilogue;
-// at the end of a work item both lists are merged and the row is emitted in oracle order.
+// Both groups drain every tile, half of its columns each (TMEM buffer = tile parity), so an accumulator is back with the tensor
+// pipe after half a drain; at the end of a work item both lists are merged and the row is emitted in oracle order.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -41,8 +42,11 @@ constexpr int L2_BM = 128;              // queries per tile (TMEM lanes)
 constexpr int L2_BN = 256;              // pooled descriptors per tile (TMEM columns)
 constexpr int L2_STAGES = 2;            // B stages in shared memory
 constexpr int L2_THREADS = 320;
-constexpr int L2_TRIGGER = 128;         // upper bound of L2Params::trigger: a (group, row) list longer than the trigger is cut back to its k best after the tile
-constexpr int L2_SLOTS = L2_TRIGGER + L2_BN;   // candidate keys per (group, row): a whole tile can be appended without a check
+constexpr int L2_BNH = L2_BN / 2;       // pooled columns of a tile drained by one epilogue group
+constexpr int L2_TRIGGER = 64;          // upper bound of L2Params::trigger (new candidates of a list that schedule a cut-back)
+// candidate keys per (group, row): slots [0, 32) hold the sorted k best of the last cut-back, new candidates are appended from
+// slot 32 on; a whole half tile can be appended past the trigger without a check
+constexpr int L2_SLOTS = 32 + L2_TRIGGER + L2_BNH;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint64_t KEY64_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 
@@ -119,6 +123,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
+// (N = 128 MMAs with four 128-column TMEM buffers were measured: the tensor ceiling drops from 1354 to 1131 TFLOP/s -- the A operand
+//  is re-read from shared memory twice as often -- so the tile stays at N = 256 with two buffers)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L2_BN >> 3) << 17) | ((uint32_t)(L2_BM >> 4) << 24);
 
 // 32 keys, one per lane.  warp_sort32_desc: full bitonic sort, descending in lane order.  warp_merge32_asc: the last 5
@@ -150,7 +156,8 @@ __device__ __forceinline__ uint64_t warp_merge32_asc(uint64_t v, int lane) {
 struct L2Params {
     int nq, nt, k;
     int n_mtiles, n_ntiles, n_splits;
-    int trigger;           // list length that schedules a cut-back (k < trigger <= L2_TRIGGER)
+    int trigger;           // new candidates of a list that schedule its cut-back (1..L2_TRIGGER)
+    unsigned long long* prof;  // developer instrument (SLIDEO_L2_PROF): cycles of epilogue warps in {acc wait, drain, cut-back, item tail}, MMA warp in {acc_empty wait, b_full wait}
     int dbg;               // developer switch (SLIDEO_L2_DEBUG): 1 = epilogue skips the TMEM drain, 2 = drains but never selects
     uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
     uint64_t* partial;     // [nq][n_splits][k]   (n_splits > 1)
@@ -179,10 +186,10 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;                 // [L2_STAGES]
     uint64_t* b_empty = bars + 4;                // [L2_STAGES]
-    uint64_t* acc_full = bars + 6;               // [2]
-    uint64_t* acc_empty = bars + 8;              // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
-    volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 12);   // [2][L2_BM]: running k-th distance of each (group, row) list
+    uint64_t* acc_full = bars + 6;               // [2]: TMEM buffer = tile parity, 256 columns each
+    uint64_t* acc_empty = bars + 10;             // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 16);   // [2][L2_BM]: running k-th distance of each (group, row) list
     volatile float* s_half = s_tau + 2 * L2_BM;                             // [2][L2_BM]: its ceil(k/2)-th distance
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -191,7 +198,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int s = 0; s < L2_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 4 * L2_BM; i += L2_THREADS) s_tau[i] = __int_as_float(0x7F800000);   // s_tau and s_half
@@ -233,6 +240,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t it = 0, bcount = 0, acc_use[2] = {0, 0};
+            long long mw_acc = 0, mw_b = 0;
             const uint32_t a0 = smem_u32(sA), a1 = a0 + A_MAIN_BYTES, at = a0 + 2 * A_MAIN_BYTES;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
@@ -241,9 +249,12 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 for (int j = j0; j < j1; ++j, ++bcount) {
                     const int b = (j - j0) & 1;
                     const int s = bcount % L2_STAGES;
-                    mbar_wait(&acc_empty[b], (acc_use[b] & 1) ^ 1);   // epilogue drained this TMEM buffer
+                    const long long m0 = P.prof ? clock64() : 0;
+                    mbar_wait(&acc_empty[b], (acc_use[b] & 1) ^ 1);   // both epilogue groups drained this TMEM buffer
                     ++acc_use[b];
+                    const long long m1 = P.prof ? clock64() : 0;
                     mbar_wait(&b_full[s], (bcount / L2_STAGES) & 1);
+                    if (P.prof) { mw_acc += m1 - m0; mw_b += clock64() - m1; }
                     tc_fence_after();
                     const uint32_t b0 = smem_u32(sB + (size_t)s * B_BYTES), b1 = b0 + B_MAIN_BYTES, bt = b0 + 2 * B_MAIN_BYTES;
                     const uint32_t d = tmem_base + (uint32_t)b * L2_BN;
@@ -259,41 +270,49 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 }
                 tc_commit(a_empty);
             }
+            if (P.prof) { atomicAdd(P.prof + 4, (unsigned long long)mw_acc); atomicAdd(P.prof + 5, (unsigned long long)mw_b); }
         }
     } else {
         // ===================== epilogue groups =====================
-        const int g = (warp - 2) >> 2;               // 0: even tiles, 1: odd tiles
+        const int g = (warp - 2) >> 2;               // 0: columns 0..127 of every tile, 1: columns 128..255
         const int quarter = warp & 3;                // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;         // query row within the tile
         uint64_t* my_buf = P.scratch + (((size_t)blockIdx.x * 2 + g) * L2_BM + row) * L2_SLOTS;
-        const uint32_t taddr_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * L2_BN;
-        uint32_t acc_seen = 0;
+        const uint32_t taddr_group = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * L2_BNH;
+        uint32_t acc_seen[2] = {0, 0};
+        long long pw = 0, pd = 0, pc = 0, pt = 0;
 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
             const int j0 = (int)((long long)P.n_ntiles * sp / P.n_splits), j1 = (int)((long long)P.n_ntiles * (sp + 1) / P.n_splits);
             const int q = mt * L2_BM + row;
             float tau = q < P.nq ? __int_as_float(0x7F800000) : -1.f;   // +inf / never
-            int cnt = 0;
+            int cnt = 32;              // next free slot of this row's list
+            bool have_base = false;    // slots 0..31 hold a sorted cut-back of this item
 
             auto compact = [&](bool force) {
-                // warp-cooperative: lanes whose list passed the trigger (all lanes at the end of an item) get it cut to the k
-                // best, sorted; at the end of an item the list length is published in slot 32 (k <= 32) for the merge
-                unsigned need = force ? FULL : __ballot_sync(FULL, cnt > P.trigger);
+                // warp-cooperative cut-back of the lists that passed the trigger (all lists at the end of an item): the sorted k
+                // best of the last cut-back (slots 0..31) are merged with the new candidates (slot 32 on), 32 at a time:
+                // chunk sorted descending, lane-wise min with the ascending best = the 32 smallest as a bitonic sequence
+                unsigned need = force ? FULL : __ballot_sync(FULL, cnt > 32 + P.trigger);
                 while (need) {
                     const int L = __ffs(need) - 1;
                     need &= need - 1;
                     uint64_t* buf = my_buf + ((ptrdiff_t)L - lane) * L2_SLOTS;
                     const int n = __shfl_sync(FULL, cnt, L);
-                    uint64_t top = KEY64_EMPTY;
-                    for (int c0 = 0; c0 < n; c0 += 32) {
-                        uint64_t x = c0 + lane < n ? __ldcg(buf + c0 + lane) : KEY64_EMPTY;
-                        x = warp_sort32_desc(x, lane);
-                        top = warp_merge32_asc(top < x ? top : x, lane);
+                    const bool hb = __shfl_sync(FULL, (int)have_base, L) != 0;
+                    uint64_t top = hb ? __ldcg(buf + lane) : KEY64_EMPTY;                   // all three loads in flight together
+                    uint64_t x0 = 32 + lane < n ? __ldcg(buf + 32 + lane) : KEY64_EMPTY;
+                    uint64_t x1 = 64 + lane < n ? __ldcg(buf + 64 + lane) : KEY64_EMPTY;
+                    if (n > 32) top = warp_merge32_asc(min(top, warp_sort32_desc(x0, lane)), lane);
+                    if (n > 64) top = warp_merge32_asc(min(top, warp_sort32_desc(x1, lane)), lane);
+                    for (int c0 = 96; c0 < n; c0 += 32) {
+                        const uint64_t x = c0 + lane < n ? __ldcg(buf + c0 + lane) : KEY64_EMPTY;
+                        top = warp_merge32_asc(min(top, warp_sort32_desc(x, lane)), lane);
                     }
+                    if (lane >= P.k) top = KEY64_EMPTY;
                     __syncwarp();
-                    if (lane < P.k) buf[lane] = top;
-                    if (force && lane == 0) buf[32] = (uint64_t)min(n, P.k);
+                    buf[lane] = top;
                     const uint64_t kth = __shfl_sync(FULL, top, P.k - 1);
                     const uint64_t hth = __shfl_sync(FULL, top, (P.k + 1) / 2 - 1);
                     if (lane == L) {
@@ -302,17 +321,24 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                             s_tau[g * L2_BM + row] = tau;   // the other group may prune against it (non-strictly)
                         }
                         if (hth != KEY64_EMPTY) s_half[g * L2_BM + row] = __uint_as_float((uint32_t)(hth >> 32));
-                        cnt = min(n, P.k);
+                        cnt = 32;
+                        have_base = true;
                     }
                 }
                 __syncwarp();
             };
 
-            for (int j = j0 + g; j < j1; j += 2) {
-                mbar_wait(&acc_full[g], acc_seen & 1);
-                ++acc_seen;
+            for (int j = j0; j < j1; ++j) {
+                // both groups drain EVERY tile, half of its columns each: the accumulator goes back to the tensor pipe after
+                // half a drain, and the MMA of tile j + 2 never queues behind a whole-tile epilogue
+                const int b = (j - j0) & 1;
+                const long long t0 = P.prof ? clock64() : 0;
+                mbar_wait(&acc_full[b], acc_seen[b] & 1);
+                ++acc_seen[b];
                 tc_fence_after();
-                const int col0 = j * L2_BN;
+                const long long t1 = P.prof ? clock64() : 0;
+                const int col0 = j * L2_BN + g * L2_BNH;
+                const uint32_t taddr_base = taddr_group + (uint32_t)b * L2_BN;
                 // effective threshold: own k-th distance (strict) or the other group's (non-strict: an equal distance
                 // with a smaller index could still displace its k-th entry), whichever is tighter
                 float thr = tau;
@@ -325,7 +351,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                     const float hx = fmaxf(s_half[row], s_half[L2_BM + row]);
                     if (hx < thr) thr = fminf(thr, nextafterf(hx, inf));
                 }
-                const int n_chunks = P.dbg == 1 ? 0 : L2_BN / 32;
+                const int n_chunks = P.dbg == 1 ? 0 : L2_BNH / 32;
                 uint32_t va[32], vb[32];
                 if (n_chunks) tc_ld32(taddr_base, va);
 #pragma unroll 1
@@ -373,13 +399,19 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[g]);
+                if (lane == 0) mbar_arrive(&acc_empty[b]);
+                const long long t2 = P.prof ? clock64() : 0;
                 // lists are cut back only now, after the accumulator has been handed back: the tensor pipe refills this TMEM
                 // buffer while the warp sorts (a list can take a whole tile of appends past the trigger: L2_SLOTS)
-                if (__any_sync(FULL, cnt > P.trigger)) compact(false);
+                if (__any_sync(FULL, cnt > 32 + P.trigger)) compact(false);
+                if (P.prof && lane == 0) {
+                    const long long t3 = clock64();
+                    pw += t1 - t0; pd += t2 - t1; pc += t3 - t2;
+                }
             }
 
             // end of item: every list sorted and cut to k, then group 0 merges both lists of a row and emits it
+            const long long t4 = P.prof ? clock64() : 0;
             __syncwarp();
             compact(true);
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -388,21 +420,24 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
             if (g == 0) {
                 const uint64_t* base0 = P.scratch + (((size_t)blockIdx.x * 2 + 0) * L2_BM + quarter * 32) * L2_SLOTS;
                 const uint64_t* base1 = P.scratch + (((size_t)blockIdx.x * 2 + 1) * L2_BM + quarter * 32) * L2_SLOTS;
-                // every list holds its min(cnt, k) best keys, sorted, with the length published in slot 32 by compact(true)
+                // every list holds its k best keys in slots 0..31, sorted, padded with empty keys
                 for (int L = 0; L < 32; ++L) {
                     const int qq = mt * L2_BM + quarter * 32 + L;
                     if (qq >= P.nq) break;   // warp-uniform
-                    const int n0 = (int)__ldcg(base0 + (size_t)L * L2_SLOTS + 32);
-                    const int n1 = (int)__ldcg(base1 + (size_t)L * L2_SLOTS + 32);
                     // list 0 ascending, list 1 read back to front (descending): lane-wise min = the 32 smallest, bitonic
-                    const uint64_t a = lane < n0 ? __ldcg(base0 + (size_t)L * L2_SLOTS + lane) : KEY64_EMPTY;
-                    const uint64_t b = 31 - lane < n1 ? __ldcg(base1 + (size_t)L * L2_SLOTS + (31 - lane)) : KEY64_EMPTY;
+                    const uint64_t a = __ldcg(base0 + (size_t)L * L2_SLOTS + lane);
+                    const uint64_t b = __ldcg(base1 + (size_t)L * L2_SLOTS + (31 - lane));
                     const uint64_t m = warp_merge32_asc(a < b ? a : b, lane);
                     if (P.n_splits == 1) emit_l2_row(m, lane, qq, P.k, P.idx_out, P.dist_out);
                     else if (lane < P.k) P.partial[((size_t)qq * P.n_splits + sp) * P.k + lane] = m;
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (P.prof && lane == 0) pt += clock64() - t4;
+        }
+        if (P.prof && lane == 0) {
+            atomicAdd(P.prof + 0, (unsigned long long)pw); atomicAdd(P.prof + 1, (unsigned long long)pd);
+            atomicAdd(P.prof + 2, (unsigned long long)pc); atomicAdd(P.prof + 3, (unsigned long long)pt);
         }
     }
 
@@ -570,7 +605,8 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.partial = (uint64_t*)ws.d_part;
     P.idx_out = d_idx;
     P.dist_out = d_dist;
-    P.trigger = getenv("SLIDEO_L2_TRIGGER") ? std::min(L2_TRIGGER, std::max(k + 1, atoi(getenv("SLIDEO_L2_TRIGGER")))) : 64;
+    P.trigger = getenv("SLIDEO_L2_TRIGGER") ? std::min(L2_TRIGGER, std::max(1, atoi(getenv("SLIDEO_L2_TRIGGER")))) : 26;
+    P.prof = nullptr;
     P.dbg = getenv("SLIDEO_L2_DEBUG") ? atoi(getenv("SLIDEO_L2_DEBUG")) : 0;
 
     const int q_pad = l2_rows_padded(nq), t_pad = l2_rows_padded(nt);
@@ -584,8 +620,22 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
         SLIDEO_CUDA(cudaFuncSetAttribute(knn_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
         configured = true;
     }
+    static unsigned long long* d_prof = nullptr;
+    if (getenv("SLIDEO_L2_PROF")) {
+        if (!d_prof) SLIDEO_CUDA(cudaMalloc(&d_prof, 8 * sizeof(unsigned long long)));
+        SLIDEO_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), stream));
+        P.prof = d_prof;
+    }
     knn_l2_kernel<<<grid, L2_THREADS, SMEM_TOTAL, stream>>>(tq_main, tq_tail, tt_main, tt_tail, P);
     SLIDEO_CUDA(cudaGetLastError());
+    if (P.prof) {
+        unsigned long long h[8];
+        SLIDEO_CUDA(cudaStreamSynchronize(stream));
+        SLIDEO_CUDA(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
+        const double ew = 8.0 * grid, mw = 1.0 * grid;   // epilogue warps, MMA warps
+        fprintf(stderr, "[l2 prof] per epilogue warp (Mcycles): acc wait %.2f drain %.2f cut-back %.2f tail %.2f | per MMA warp: acc_empty wait %.2f b_full wait %.2f\n",
+                h[0] / ew / 1e6, h[1] / ew / 1e6, h[2] / ew / 1e6, h[3] / ew / 1e6, h[4] / mw / 1e6, h[5] / mw / 1e6);
+    }
     if (launches) ++*launches;
     if (ns > 1) {
         l2_merge_kernel<<<cdiv(nq, 4), 128, 0, stream>>>((const uint64_t*)ws.d_part, nq, ns, k, d_idx, d_dist);
