@@ -4,9 +4,11 @@
 // lib.rs:249-295 (per-frame path) and flann.rs:64-89 (matcher); all arithmetic runs in the CUDA kernels of
 // orb.cu / knn_hamming.cu / knn_l2.cu.  There is no CPU fallback: without a device every entry point fails.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -268,6 +270,9 @@ struct slideo_b200_ctx {
                 st = 3 * w;
                 fst = img_bytes;
             }
+            const bool trace = getenv("SLIDEO_TRACE") != nullptr;
+            auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            const double h0 = trace ? now() : 0;
             EventPair t = begin_timing(0, stream);
             int nl = 0;
             const int total = ex.run(src, nb, st, fst, 3, stream, &nl);
@@ -275,8 +280,11 @@ struct slideo_b200_ctx {
             if (!on_device) SLIDEO_CUDA(cudaEventRecord(ev_free[b & 1], stream));
             tm.kernel_launches += nl;
             tm.frames += nb;
+            const double h1 = trace ? now() : 0;
             knn_vote_l2(ex.d_desc(), total, ex.d_q_frame(), nb, ex.d_frame_nkp(), ex.h_frame_off());
+            const double h2 = trace ? now() : 0;
             SLIDEO_CUDA(cudaMemcpyAsync(h_results + (size_t)f0 * 3, d_results.p, (size_t)nb * 3 * 4, cudaMemcpyDeviceToHost, stream));
+            if (trace) fprintf(stderr, "[trace] batch %d: K11 run (host) %.2f ms, knn_vote_l2 enqueue (host) %.2f ms, d2h enqueue %.2f ms, nq %d\n", b, h1 - h0, h2 - h1, now() - h2, total);
         }
     }
 
