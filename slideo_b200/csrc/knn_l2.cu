@@ -123,6 +123,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
+// Measured alternatives of the epilogue (65 k x 1 M, this file's version 923 TFLOP/s): four groups of 4 warps on 64-column
+// slices with x16 loads 907; the same with one x64 load per slice 731 (96 registers, spills) -- a drain without any selection
+// takes ~945 cycles per 128 x 256 fp32 tile however many warps share it, i.e. TMEM reads deliver ~139 B/clk per SM: that, not
+// the warp count, is the floor under the epilogue.
 // (N = 128 MMAs with four 128-column TMEM buffers were measured: the tensor ceiling drops from 1354 to 1131 TFLOP/s -- the A operand
 //  is re-read from shared memory twice as often -- so the tile stays at N = 256 with two buffers)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L2_BN >> 3) << 17) | ((uint32_t)(L2_BM >> 4) << 24);
