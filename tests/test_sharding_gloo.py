@@ -77,3 +77,63 @@ def test_two_rank_run_equals_single_process(tmp_path, n_frames):
         best, votes, _ = oracle.match_frame(q, pages)
         want.append((best, votes, len(q)))
     assert np.array_equal(got, np.array(want, np.int32))
+
+
+def _sift_rows(n, seed):
+    """Integer-valued 0..255 rows with norm ~512, like cv2 SIFT descriptors."""
+    rng = np.random.default_rng(seed)
+    x = rng.gamma(0.6, 1.0, (n, 128)).astype(np.float32)
+    x = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-6) * 512.0
+    return np.minimum(np.rint(x), 255).astype(np.float32)
+
+
+def _sift_frame(pool, offs, f):
+    rng = np.random.default_rng(900 + f)
+    page = (0, 1, 3)[f % 3]                     # page 2 is empty on purpose
+    src = rng.integers(offs[page], offs[page + 1], 25)
+    q = np.clip(pool[src] + rng.integers(-2, 3, (25, 128)), 0, 255).astype(np.float32)
+    return np.concatenate([q, _sift_rows(10, 950 + f)])
+
+
+def _sift_match(q, pool, offs):
+    import oracle
+    idx, dist = oracle.bf_knn_l2(q, pool, 30)
+    best, votes, _ = oracle.vote(idx, dist, offs)
+    return best, votes, len(q)
+
+
+def _sift_worker(rank, world, port, n_frames, out_path):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        desc = offs = None
+        if rank == 0:
+            pages = [_sift_rows(n, 600 + i) for i, n in enumerate((150, 80, 0, 120))]
+            desc = np.concatenate(pages)
+            offs = np.zeros(len(pages) + 1, np.int32)
+            offs[1:] = np.cumsum([len(p) for p in pages])
+        # SIFT128 pools travel as fp32 rows (n x 128), like slideo_b200_pool_device_view on a SIFT128 ctx
+        desc, offs = sharding.broadcast_pool_host(desc, offs, src=0, desc_width=128, dtype=np.float32)
+        lo, hi = sharding.shard_range(n_frames, rank, world)
+        local = np.array([_sift_match(_sift_frame(desc, offs, f), desc, offs) for f in range(lo, hi)], np.int32).reshape(-1, 3)
+        allr = sharding.gather_results(local, n_frames)
+        if rank == 0:
+            np.save(out_path, allr)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sift_pool_equals_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "gathered_sift.npy")
+    n_frames = 5
+    mp.spawn(_sift_worker, args=(2, _free_port(), n_frames, out), nprocs=2, join=True)
+    got = np.load(out)
+    pages = [_sift_rows(n, 600 + i) for i, n in enumerate((150, 80, 0, 120))]
+    desc = np.concatenate(pages)
+    offs = np.zeros(len(pages) + 1, np.int32)
+    offs[1:] = np.cumsum([len(p) for p in pages])
+    want = np.array([_sift_match(_sift_frame(desc, offs, f), desc, offs) for f in range(n_frames)], np.int32)
+    assert np.array_equal(got, want)
+    assert list(want[:, 0]) == [0, 1, 3, 0, 1]
