@@ -416,24 +416,35 @@ __global__ void __launch_bounds__(128) sift_orient_kernel(const float* __restric
     for (int i = -radius; i <= radius; ++i) {
         const int y = r + i;
         if (y <= 0 || y >= H - 1) continue;
-        const float* row = im + (size_t)y * pitch + c;
-        for (int j = j_lo; j <= j_hi; j += 2) {
-            const bool two = j + 1 <= j_hi;
-            const float* p0 = row + j;
-            const float* p1 = row + (two ? j + 1 : j);
-            const float dx0 = p0[1] - p0[-1], dy0 = p0[-pitch] - p0[pitch];
-            const float dx1 = p1[1] - p1[-1], dy1 = p1[-pitch] - p1[pitch];
-            const float w0 = sift_exp32f((float)(i * i + j * j) * expf_scale);
-            const float w1 = sift_exp32f((float)(i * i + (j + 1) * (j + 1)) * expf_scale);
-            const float o0 = sift_fast_atan2(dy0, dx0), o1 = sift_fast_atan2(dy1, dx1);
-            const float m0 = sift_magnitude(dx0, dy0), m1 = sift_magnitude(dx1, dy1);
-            int b0 = __float2int_rn((ORI_BINS / 360.f) * o0), b1 = __float2int_rn((ORI_BINS / 360.f) * o1);
-            if (b0 >= ORI_BINS) b0 -= ORI_BINS;
-            if (b0 < 0) b0 += ORI_BINS;
-            if (b1 >= ORI_BINS) b1 -= ORI_BINS;
-            if (b1 < 0) b1 += ORI_BINS;
-            s_tmp[b0][tid] += w0 * m0;
-            if (two) s_tmp[b1][tid] += w1 * m1;
+        // four window samples per iteration from 16-byte aligned loads of the three rows (a quarter of the L1 lookups that
+        // per-sample scalar loads cost, and 4-way ILP); samples outside [j_lo, j_hi] are computed and dropped
+        const float* rowm = im + (size_t)y * pitch;
+        for (int c4 = (c + j_lo) & ~3; c4 <= c + j_hi; c4 += 4) {
+            const float4 up = __ldg(reinterpret_cast<const float4*>(rowm - pitch + c4));
+            const float4 mid = __ldg(reinterpret_cast<const float4*>(rowm + c4));
+            const float4 dn = __ldg(reinterpret_cast<const float4*>(rowm + pitch + c4));
+            const float left = c4 > 0 ? __ldg(rowm + c4 - 1) : 0.f;
+            const float right = c4 + 4 < pitch ? __ldg(rowm + c4 + 4) : 0.f;
+            const float dxs[4] = {mid.y - left, mid.z - mid.x, mid.w - mid.y, right - mid.z};
+            const float dys[4] = {up.x - dn.x, up.y - dn.y, up.z - dn.z, up.w - dn.w};
+            float wm[4];
+            int bn[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = c4 + m - c;
+                const float w = sift_exp32f((float)(i * i + j * j) * expf_scale);
+                const float o = sift_fast_atan2(dys[m], dxs[m]);
+                const float mg = sift_magnitude(dxs[m], dys[m]);
+                int bb = __float2int_rn((ORI_BINS / 360.f) * o);
+                if (bb >= ORI_BINS) bb -= ORI_BINS;
+                if (bb < 0) bb += ORI_BINS;
+                const bool ok = j >= j_lo && j <= j_hi;
+                bn[m] = ok ? bb : -1;
+                wm[m] = w * mg;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                if (bn[m] >= 0) s_tmp[bn[m]][tid] += wm[m];
         }
     }
     float maxval = 0.f;
@@ -704,17 +715,14 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
                 jlo = max(jlo, __float2int_rd(fminf(a, b)) - 1);
                 jhi = min(jhi, __float2int_ru(fmaxf(a, b)) + 1);
             }
-            const float* row = im + (size_t)r * pitch + px;
-            auto eval = [&](int j, bool in_range) -> DescSample {
+            const float* rowm = im + (size_t)r * pitch;
+            auto eval = [&](int j, bool in_range, float dx, float dy) -> DescSample {
                 DescSample sm;
                 const float c_rot = (float)j * cos_t - is;
                 const float r_rot = (float)j * sin_t + ic;
                 float rbin = r_rot + (float)(d / 2) - 0.5f;
                 float cbin = c_rot + (float)(d / 2) - 0.5f;
                 sm.ok = in_range && rbin > -1 && rbin < d && cbin > -1 && cbin < d;
-                const float* p = row + (sm.ok ? j : 0);
-                const float dx = p[1] - p[-1];
-                const float dy = p[-pitch] - p[pitch];
                 const float wgt = sift_exp32f((c_rot * c_rot + r_rot * r_rot) * exp_scale);
                 const float og = sift_fast_atan2(dy, dx);
                 sm.mag = sift_magnitude(dx, dy) * wgt;
@@ -748,11 +756,18 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
                 hp[(d + 3) * (n + 2) * DESC_THREADS] += v_rco110;
                 hp[((d + 3) * (n + 2) + 1) * DESC_THREADS] += v_rco111;
             };
-            for (int j = jlo; j <= jhi; j += 4) {
-                const DescSample a = eval(j, true);
-                const DescSample b = eval(j + 1, j + 1 <= jhi);
-                const DescSample c = eval(j + 2, j + 2 <= jhi);
-                const DescSample e = eval(j + 3, j + 3 <= jhi);
+            // four samples per iteration from 16-byte aligned loads of the three image rows (see sift_orient_kernel)
+            for (int c4 = (px + jlo) & ~3; c4 <= px + jhi; c4 += 4) {
+                const float4 up = __ldg(reinterpret_cast<const float4*>(rowm - pitch + c4));
+                const float4 mid = __ldg(reinterpret_cast<const float4*>(rowm + c4));
+                const float4 dn = __ldg(reinterpret_cast<const float4*>(rowm + pitch + c4));
+                const float left = c4 > 0 ? __ldg(rowm + c4 - 1) : 0.f;
+                const float right = c4 + 4 < pitch ? __ldg(rowm + c4 + 4) : 0.f;
+                const int j = c4 - px;
+                const DescSample a = eval(j, j >= jlo && j <= jhi, mid.y - left, up.x - dn.x);
+                const DescSample b = eval(j + 1, j + 1 >= jlo && j + 1 <= jhi, mid.z - mid.x, up.y - dn.y);
+                const DescSample c = eval(j + 2, j + 2 >= jlo && j + 2 <= jhi, mid.w - mid.y, up.z - dn.z);
+                const DescSample e = eval(j + 3, j + 3 >= jlo && j + 3 <= jhi, right - mid.z, up.w - dn.w);
                 apply(a);
                 apply(b);
                 apply(c);
@@ -911,7 +926,7 @@ SiftExtractor::SiftExtractor(int w, int h, int batch_cap, int kp_cap_per_image) 
     g.total_tiles = tile_base;
     g.img_floats = off;
     const long long px = (long long)w * h;
-    g.kp_cap = kp_cap_per_image > 0 ? kp_cap_per_image : (px >= 1000000 ? 32768 : px >= 200000 ? 16384 : 8192);
+    g.kp_cap = kp_cap_per_image > 0 ? kp_cap_per_image : (px >= 1000000 ? 65536 : px >= 200000 ? 32768 : 16384);
     g.cand_cap = g.kp_cap * 8;
     total_cap_ = (size_t)batch_cap * g.kp_cap;
 
