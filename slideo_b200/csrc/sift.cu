@@ -278,12 +278,14 @@ __device__ __forceinline__ float sift_exp32f(float x) {   // cv::hal::exp32f: 64
     return z * y;
 }
 
-__device__ __forceinline__ float sift_fast_atan2(float y, float x) {   // cv::hal::fastAtan2 (v_atan_f32, degrees)
+// cv::hal::fastAtan2 (v_atan_f32, degrees) and cv::hal::magnitude32f = sqrtf(fma(x, x, y * y)) are evaluated in stages, see below
+// fastAtan2 in two halves around its division, so that the IEEE divisions (and square roots) of several window samples can be
+// issued back to back: each carries a rarely-taken slow-path branch that stops the compiler from interleaving whole samples
+__device__ __forceinline__ float sift_atan2_post(float c, float y, float x) {
     const float RAD = (float)(180.0 / 3.14159265358979323846);
     const float p1 = 0.9997878412794807f * RAD, p3 = -0.3258083974640975f * RAD, p5 = 0.1555786518463281f * RAD,
                 p7 = -0.04432655554792128f * RAD;
     const float ax = fabsf(x), ay = fabsf(y);
-    const float c = fminf(ax, ay) / (fmaxf(ax, ay) + (float)2.2204460492503131e-16);
     const float cc = c * c;
     float a = __fmaf_rn(__fmaf_rn(__fmaf_rn(cc, p7, p5), cc, p3), cc, p1) * c;
     if (!(ax >= ay)) a = 90.f - a;
@@ -291,8 +293,6 @@ __device__ __forceinline__ float sift_fast_atan2(float y, float x) {   // cv::ha
     if (y < 0) a = 360.f - a;
     return a;
 }
-
-__device__ __forceinline__ float sift_magnitude(float x, float y) { return sqrtf(__fmaf_rn(x, x, y * y)); }
 
 struct OctView {
     const float* base;   // Gaussian layer 0
@@ -427,20 +427,31 @@ __global__ void __launch_bounds__(128) sift_orient_kernel(const float* __restric
             const float right = c4 + 4 < pitch ? __ldg(rowm + c4 + 4) : 0.f;
             const float dxs[4] = {mid.y - left, mid.z - mid.x, mid.w - mid.y, right - mid.z};
             const float dys[4] = {up.x - dn.x, up.y - dn.y, up.z - dn.z, up.w - dn.w};
-            float wm[4];
+            float wm[4], num[4], den[4], q[4], sq[4];
             int bn[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < 4; ++m) {   // stage 1: weights and the operands of the division / square root
                 const int j = c4 + m - c;
-                const float w = sift_exp32f((float)(i * i + j * j) * expf_scale);
-                const float o = sift_fast_atan2(dys[m], dxs[m]);
-                const float mg = sift_magnitude(dxs[m], dys[m]);
+                wm[m] = sift_exp32f((float)(i * i + j * j) * expf_scale);
+                const float ax = fabsf(dxs[m]), ay = fabsf(dys[m]);
+                num[m] = fminf(ax, ay);
+                den[m] = fmaxf(ax, ay) + (float)2.2204460492503131e-16;
+                sq[m] = __fmaf_rn(dxs[m], dxs[m], dys[m] * dys[m]);
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) q[m] = num[m] / den[m];          // stage 2: the four divisions
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sq[m] = sqrtf(sq[m]);            // stage 3: the four square roots (magnitude32f)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {   // stage 4: angle polynomial, bin, weight
+                const int j = c4 + m - c;
+                const float o = sift_atan2_post(q[m], dys[m], dxs[m]);
                 int bb = __float2int_rn((ORI_BINS / 360.f) * o);
                 if (bb >= ORI_BINS) bb -= ORI_BINS;
                 if (bb < 0) bb += ORI_BINS;
                 const bool ok = j >= j_lo && j <= j_hi;
                 bn[m] = ok ? bb : -1;
-                wm[m] = w * mg;
+                wm[m] = wm[m] * sq[m];
             }
 #pragma unroll
             for (int m = 0; m < 4; ++m)
@@ -716,27 +727,6 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
                 jhi = min(jhi, __float2int_ru(fmaxf(a, b)) + 1);
             }
             const float* rowm = im + (size_t)r * pitch;
-            auto eval = [&](int j, bool in_range, float dx, float dy) -> DescSample {
-                DescSample sm;
-                const float c_rot = (float)j * cos_t - is;
-                const float r_rot = (float)j * sin_t + ic;
-                float rbin = r_rot + (float)(d / 2) - 0.5f;
-                float cbin = c_rot + (float)(d / 2) - 0.5f;
-                sm.ok = in_range && rbin > -1 && rbin < d && cbin > -1 && cbin < d;
-                const float wgt = sift_exp32f((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                const float og = sift_fast_atan2(dy, dx);
-                sm.mag = sift_magnitude(dx, dy) * wgt;
-                float obin = (og - ori) * bins_per_rad;
-                const int r0 = __float2int_rd(rbin), c0 = __float2int_rd(cbin);
-                int o0 = __float2int_rd(obin);
-                sm.rb = rbin - (float)r0;
-                sm.cb = cbin - (float)c0;
-                sm.ob = obin - (float)o0;
-                if (o0 < 0) o0 += n;
-                if (o0 >= n) o0 -= n;
-                sm.idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
-                return sm;
-            };
             auto apply = [&](const DescSample& sm) {
                 if (!sm.ok) return;
                 const float v_r1 = sm.mag * sm.rb, v_r0 = sm.mag - v_r1;
@@ -763,15 +753,45 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
                 const float4 dn = __ldg(reinterpret_cast<const float4*>(rowm + pitch + c4));
                 const float left = c4 > 0 ? __ldg(rowm + c4 - 1) : 0.f;
                 const float right = c4 + 4 < pitch ? __ldg(rowm + c4 + 4) : 0.f;
-                const int j = c4 - px;
-                const DescSample a = eval(j, j >= jlo && j <= jhi, mid.y - left, up.x - dn.x);
-                const DescSample b = eval(j + 1, j + 1 >= jlo && j + 1 <= jhi, mid.z - mid.x, up.y - dn.y);
-                const DescSample c = eval(j + 2, j + 2 >= jlo && j + 2 <= jhi, mid.w - mid.y, up.z - dn.z);
-                const DescSample e = eval(j + 3, j + 3 >= jlo && j + 3 <= jhi, right - mid.z, up.w - dn.w);
-                apply(a);
-                apply(b);
-                apply(c);
-                apply(e);
+                const int j0 = c4 - px;
+                const float dxs[4] = {mid.y - left, mid.z - mid.x, mid.w - mid.y, right - mid.z};
+                const float dys[4] = {up.x - dn.x, up.y - dn.y, up.z - dn.z, up.w - dn.w};
+                DescSample sm[4];
+                float wgt[4], num[4], den[4], q[4], sq[4], rbin[4], cbin[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {   // stage 1: rotated coordinates, window test, weight, operands of the division / square root
+                    const int j = j0 + m;
+                    const float c_rot = (float)j * cos_t - is;
+                    const float r_rot = (float)j * sin_t + ic;
+                    rbin[m] = r_rot + (float)(d / 2) - 0.5f;
+                    cbin[m] = c_rot + (float)(d / 2) - 0.5f;
+                    sm[m].ok = j >= jlo && j <= jhi && rbin[m] > -1 && rbin[m] < d && cbin[m] > -1 && cbin[m] < d;
+                    wgt[m] = sift_exp32f((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                    const float ax = fabsf(dxs[m]), ay = fabsf(dys[m]);
+                    num[m] = fminf(ax, ay);
+                    den[m] = fmaxf(ax, ay) + (float)2.2204460492503131e-16;
+                    sq[m] = __fmaf_rn(dxs[m], dxs[m], dys[m] * dys[m]);
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m) q[m] = num[m] / den[m];      // stage 2: the four divisions of fastAtan2
+#pragma unroll
+                for (int m = 0; m < 4; ++m) sq[m] = sqrtf(sq[m]);        // stage 3: the four square roots of magnitude32f
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {   // stage 4: angle, bins, interpolation weights
+                    const float og = sift_atan2_post(q[m], dys[m], dxs[m]);
+                    sm[m].mag = sq[m] * wgt[m];
+                    float obin = (og - ori) * bins_per_rad;
+                    const int r0 = __float2int_rd(rbin[m]), c0 = __float2int_rd(cbin[m]);
+                    int o0 = __float2int_rd(obin);
+                    sm[m].rb = rbin[m] - (float)r0;
+                    sm[m].cb = cbin[m] - (float)c0;
+                    sm[m].ob = obin - (float)o0;
+                    if (o0 < 0) o0 += n;
+                    if (o0 >= n) o0 -= n;
+                    sm[m].idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m) apply(sm[m]);                // stage 5: histogram updates, in raster order
             }
         }
         // circular orientation bins, then the descriptor is normalised in place (bins k < 8 of the 16 inner cells)
