@@ -137,3 +137,30 @@ def test_sift_batched_equals_single(ctx):
     assert np.array_equal(out[0][0], out[1][0])
     assert np.array_equal(out[0][1], out[1][1])
     assert list(out[0][1][:, 0]) == [1, 2, 0, 1, 0]
+
+
+def test_sift_edge_cases_flat_frames_and_empty_pages():
+    """A flat page adds no descriptors (empty page in the pool), a flat frame has no keypoints (best_slide -1, 0 votes), and a
+    batch may mix both with ordinary frames; k = 7 exercises k < 30 on the SIFT path."""
+    pages = [textured(40, 200, 260), np.full((200, 260), 255, np.uint8), textured(41, 200, 260)]
+    rng = np.random.default_rng(9)
+    noisy = lambda p: np.clip(pages[p].astype(np.int16) + rng.integers(-3, 4, pages[p].shape), 0, 255).astype(np.uint8)
+    grays = [noisy(2), np.full((200, 260), 17, np.uint8), noisy(0), np.full((200, 260), 200, np.uint8), noisy(2)]
+    frames = np.stack([np.stack([g] * 3, axis=2) for g in grays])
+    with slideo_b200.Context(slideo_b200.default_config(descriptor_kind=slideo_b200.ffi.DESC_SIFT128, max_batch=3, knn_k=7)) as c:
+        counts = [c.add_page_gray8(p) for p in pages]
+        c.finalize_pool()
+        pool, offs = c.pool_export()
+        res = c.match_frames_bgr8(frames)
+        assert c.match_frames_bgr8(frames[:0]).shape == (0, 3)
+    assert counts[1] == 0 and offs[1] == offs[2]
+    ref_pool = np.concatenate([oracle.sift_detect_and_compute(p)[2] for p in pages])
+    for i, g in enumerate(grays):
+        de = oracle.sift_detect_and_compute(g)[2]
+        if len(de) == 0:
+            assert tuple(res[i]) == (-1, 0, 0)
+            continue
+        idx, dist = oracle.bf_knn_l2(de, ref_pool, 7)
+        best, votes, _ = oracle.vote(idx, dist, offs)
+        assert res[i, 0] == best == (2, -1, 0, -1, 2)[i] and res[i, 2] == len(de)
+        assert abs(int(res[i, 1]) - votes) <= max(2, votes // 100)
