@@ -11,6 +11,7 @@
 //   K6 blur_kernel      7x7 sigma-2 Gaussian, separable fp32 with OpenCV's exact fma order, all levels in one launch
 //   K5+K7 describe_kernel  intensity-centroid angle (fastAtan2) + 256-bit steered descriptor, one warp per keypoint
 #include "orb.cuh"
+#include "tma.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -140,13 +141,16 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k127) {
     return (((x & 0x7F7F7F7Fu) + k127) | x) & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ pyr, const Geo* __restrict__ gp,
+struct FastMaps { CUtensorMap lv[ORB_MAX_LEVELS]; };   // one rank-3 u8 tensor {x, y, image} per pyramid level
+
+__global__ void __launch_bounds__(256) fast_kernel(const FastMaps* __restrict__ maps, const Geo* __restrict__ gp,
                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
     // pixel tile: 40 rows x 20 words = columns tx0-8 .. tx0+71; score tile: 34 rows x 72 columns = tx0-4 .. tx0+67, i.e. the
     // 64 x 32 pixels of the tile plus the halo the 3x3 NMS needs, rounded to whole words so every thread handles 4 pixels
-    constexpr int PH = TILE_H + 8, PWW = (TILE_W + 16) / 4, PWB = PWW * 4;
+    constexpr int PH = TILE_H + 8, PWW = (TILE_W + 32) / 4, PWB = PWW * 4, PX0 = 2;   // the staged rows start 16 B-aligned at tx0 - 16 (TMA): PX0 words before tx0 - 8
     constexpr int SH = TILE_H + 2, SWW = (TILE_W + 8) / 4, SWB = SWW * 4;
-    __shared__ __align__(16) uint32_t s_px[PH][PWW];
+    __shared__ __align__(128) uint32_t s_px[PH][PWW];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint8_t s_sc[SH][SWB + 8];
     __shared__ uint16_t s_list[SH * SWB];              // (row << 7 | col) of the positions that pass the cheap necessary test
     __shared__ int s_n;
@@ -158,20 +162,19 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ p
     const int t = blockIdx.x - L.tile_base;
     const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
     const int img = blockIdx.y;
-    const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
 
-    if (threadIdx.x == 0) s_n = 0;
-    // tile load, one 32-bit word (4 pixels) per thread and step: tx0 and the level pitch are multiples of 4 and the level
-    // rows are padded to 16 B inside the allocation, so whole words inside [0, pitch) are always readable
-    for (int i = threadIdx.x; i < PH * PWW; i += blockDim.x) {
-        const int py = i / PWW, pw = i - py * PWW;
-        const int gx = tx0 - 8 + pw * 4, gy = ty0 - 4 + py;
-        uint32_t w = 0;
-        if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch) w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gy * L.pitch + gx));
-        s_px[py][pw] = w;
+    // tile load by TMA: one 96 x 40 byte box of the level's {x, y, image} tensor (columns tx0-16 .., rows ty0-4 ..) lands in s_px
+    // while the threads clear the score tile; elements outside the level (negative coordinates included) arrive as zero,
+    // which is what FAST needs there (it is only evaluated 3 pixels inside the level)
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        tma_mbar_init(&s_bar, 1);
+        tma_mbar_expect_tx(&s_bar, PH * PWB);
+        tma_load_3d(&s_px[0][0], &maps->lv[l], tx0 - 16, ty0 - 4, img, &s_bar);
     }
     for (int i = threadIdx.x; i < SH * (SWB + 8) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(&s_sc[0][0])[i] = 0;
     __syncthreads();
+    tma_mbar_wait(&s_bar, 0);
 
     // pass 1, 4 pixels per thread: a corner needs two ADJACENT compass points (N,E,S,W at distance 3) on the same side of the
     // centre by more than thr (any 9-arc contains two adjacent compass points); the test below drops the "same side"
@@ -182,7 +185,8 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ p
     const bool interior = tx0 - 4 >= 3 && tx0 + TILE_W + 4 <= L.w - 3 && ty0 - 1 >= 3 && ty0 + TILE_H + 1 <= L.h - 3;
     for (int i = threadIdx.x; i < SH * SWW; i += blockDim.x) {
         const int r = i / SWW, wq = i - r * SWW + 1;      // score row r <-> pixel row r + 3; score word wq - 1 <-> pixel word wq
-        const uint32_t C = s_px[r + 3][wq], Wm = s_px[r + 3][wq - 1], Wp = s_px[r + 3][wq + 1], U = s_px[r][wq], D = s_px[r + 6][wq];
+        const int pw = wq + PX0;
+        const uint32_t C = s_px[r + 3][pw], Wm = s_px[r + 3][pw - 1], Wp = s_px[r + 3][pw + 1], U = s_px[r][pw], D = s_px[r + 6][pw];
         const uint32_t Lw = __byte_perm(Wm, C, 0x4321), Rw = __byte_perm(C, Wp, 0x6543);
         uint32_t f = (bytes_gt(__vabsdiffu4(U, C), k127) | bytes_gt(__vabsdiffu4(D, C), k127)) &
                      (bytes_gt(__vabsdiffu4(Lw, C), k127) | bytes_gt(__vabsdiffu4(Rw, C), k127));
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ p
     const int n_list = s_n;
     for (int j = threadIdx.x; j < n_list; j += blockDim.x) {
         const int code = s_list[j], r = code >> 7, c = code & 127;
-        const uint8_t* sp = reinterpret_cast<const uint8_t*>(&s_px[r + 3][0]) + (c + 4);
+        const uint8_t* sp = reinterpret_cast<const uint8_t*>(&s_px[r + 3][0]) + (c + 4 + 4 * PX0);
         const int sc = fast_score(sp, PWB);
         if (sc > thr) s_sc[r][c] = (uint8_t)(sc - 1);
     }
@@ -656,6 +660,15 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
             ++v0;
         }
     }
+    {   // tensor maps of the pyramid levels for the FAST tile loads (width = the padded row, so the box never depends on W % 4)
+        FastMaps fm;
+        memset(&fm, 0, sizeof fm);
+        for (int l = 0; l < L; ++l)
+            fm.lv[l] = tma_map_3d(CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, d_pyr_ + lv_[l].img_off, (uint64_t)lv_[l].pitch, (uint64_t)lv_[l].h, (uint64_t)batch_cap,
+                                  (uint64_t)lv_[l].pitch, (uint64_t)pyr_img_bytes_, TILE_W + 32, TILE_H + 8);
+        SLIDEO_CUDA(cudaMalloc(&fast_maps_, sizeof fm));   // the maps live in global memory (64-byte aligned by cudaMalloc)
+        SLIDEO_CUDA(cudaMemcpy(fast_maps_, &fm, sizeof fm, cudaMemcpyHostToDevice));
+    }
     {
         Geo g;
         memset(&g, 0, sizeof g);
@@ -674,6 +687,7 @@ OrbExtractor::~OrbExtractor() {
     cudaFree(d_kp_off_); cudaFree(d_frame_off_); cudaFree(d_frame_nkp_); cudaFree(d_flags_); cudaFree(d_kp_src_);
     cudaFree(d_q_frame_); cudaFree(d_kp_i_); cudaFree(d_kp_f_); cudaFree(d_desc_); cudaFree(d_tables_);
     cudaFree(d_pattern_); cudaFree(d_geom_);
+    cudaFree(fast_maps_);
     cudaFreeHost(h_pinned_);
 }
 
@@ -699,7 +713,7 @@ int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stri
                                                 d.pitch, d_tables_ + d.tab_off);
         ++nl;
     }
-    fast_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, g, d_cand_, d_cand_cnt_);
+    fast_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(static_cast<const FastMaps*>(fast_maps_), g, d_cand_, d_cand_cnt_);
     ++nl;
     {
         int max_sel = 0;

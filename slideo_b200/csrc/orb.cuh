@@ -90,6 +90,7 @@ private:
             *d_frame_nkp_ = nullptr, *d_q_frame_ = nullptr, *d_kp_i_ = nullptr, *d_tables_ = nullptr, *d_flags_ = nullptr;
     float* d_kp_f_ = nullptr;
     void* d_geom_ = nullptr;     // OrbLevelGeom[nlevels] on the device
+    void* fast_maps_ = nullptr;  // per-level TMA tensor maps of the pyramid (device memory)
     int8_t* d_pattern_ = nullptr;  // 512 x 2 int8
     int32_t* h_pinned_ = nullptr;  // [0] total, [1] flags, [2..] frame offsets
     std::vector<int32_t> h_frame_off_;
