@@ -371,11 +371,15 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp
 // (row: acc = k0*p0; acc = fma(k_i, p_i, acc) left to right; column: acc = k3*r3; acc = fma(k_{3+j}, r_{3+j} + r_{3-j},
 // acc); round-half-even, saturate) -- SURVEY A.7.
 __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
-                                                   const Geo* __restrict__ gp) {
+                                                   const Geo* __restrict__ gp, const FastMaps* __restrict__ maps) {
     constexpr int PH = TILE_H + 6;            // 3-px halo above and below
     constexpr int PWW = (TILE_W + 8) / 4;     // 18 words per row: columns tx0-4 .. tx0+67 (the filter needs tx0-3 .. tx0+66)
-    __shared__ uint32_t s_px[PH][PWW];
+    // staged as the same 96 x 40 byte box FAST loads (columns tx0-16 .., rows ty0-4 ..), so interior tiles arrive by TMA through
+    // the level's tensor map; the filter's rows / words sit at offset (OY, OX) inside the box
+    constexpr int BH = TILE_H + 8, BWW = (TILE_W + 32) / 4, OY = 1, OX = 3;
+    __shared__ __align__(128) uint32_t s_px[BH][BWW];
     __shared__ float4 s_row[PH][TILE_W / 4];
+    __shared__ __align__(8) uint64_t s_bar;
 
     const Geo& g = *gp;
     int l = 0;
@@ -387,28 +391,39 @@ __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ p
     const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
     uint8_t* dst = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
 
-    // tile load, 4 pixels per thread and step: whole words where they lie inside the image, reflected bytes at the borders
-    for (int i = threadIdx.x; i < PH * PWW; i += blockDim.x) {
-        const int py = i / PWW, pw = i - py * PWW;
-        const int gx = tx0 - 4 + 4 * pw, gy = reflect101(ty0 + py - 3, L.h);
-        const uint8_t* row = src + (size_t)gy * L.pitch;
-        uint32_t w;
-        if (gx >= 0 && gx + 3 < L.w) {
-            w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-        } else {
-            w = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
-                ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
+    const bool interior = tx0 >= 16 && tx0 + TILE_W + 16 <= L.w && ty0 >= 4 && ty0 + TILE_H + 4 <= L.h;   // box inside the level: no reflection
+    if (interior) {
+        if (threadIdx.x == 0) {
+            tma_mbar_init(&s_bar, 1);
+            tma_mbar_expect_tx(&s_bar, BH * BWW * 4);
+            tma_load_3d(&s_px[0][0], &maps->lv[l], tx0 - 16, ty0 - 4, img, &s_bar);
         }
-        s_px[py][pw] = w;
+        __syncthreads();
+        tma_mbar_wait(&s_bar, 0);
+    } else {
+        // border tiles, 4 pixels per thread and step: whole words where they lie inside the image, reflected bytes at the borders
+        for (int i = threadIdx.x; i < PH * PWW; i += blockDim.x) {
+            const int py = i / PWW, pw = i - py * PWW;
+            const int gx = tx0 - 4 + 4 * pw, gy = reflect101(ty0 + py - 3, L.h);
+            const uint8_t* row = src + (size_t)gy * L.pitch;
+            uint32_t w;
+            if (gx >= 0 && gx + 3 < L.w) {
+                w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+            } else {
+                w = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
+                    ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
+            }
+            s_px[py + OY][pw + OX] = w;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // getGaussianKernel(7, 2, CV_32F) as exact bit patterns
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
     // row pass: 4 outputs per thread from 3 words (12 pixels: outputs x..x+3 use smem columns x+1 .. x+10)
     for (int i = threadIdx.x; i < PH * (TILE_W / 4); i += blockDim.x) {
         const int py = i / (TILE_W / 4), x4 = i - py * (TILE_W / 4);
-        const uint32_t w0 = s_px[py][x4], w1 = s_px[py][x4 + 1], w2 = s_px[py][x4 + 2];
+        const uint32_t w0 = s_px[py + OY][x4 + OX], w1 = s_px[py + OY][x4 + OX + 1], w2 = s_px[py + OY][x4 + OX + 2];
         float p[12];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -728,7 +743,7 @@ int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stri
     scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_,
                                                    sink ? sink->q_frame : nullptr, sink ? sink->frame_base : 0, sink ? sink->cap : 0);
     ++nl;
-    blur_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, d_blur_, g);
+    blur_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, d_blur_, g, static_cast<const FastMaps*>(fast_maps_));
     ++nl;
     SLIDEO_CUDA(cudaGetLastError());
     SLIDEO_CUDA(cudaStreamSynchronize(stream));   // total keypoints of the batch sizes the remaining launches
