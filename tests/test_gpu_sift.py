@@ -164,3 +164,30 @@ def test_sift_edge_cases_flat_frames_and_empty_pages():
         best, votes, _ = oracle.vote(idx, dist, offs)
         assert res[i, 0] == best == (2, -1, 0, -1, 2)[i] and res[i, 2] == len(de)
         assert abs(int(res[i, 1]) - votes) <= max(2, votes // 100)
+
+
+def test_gpu_sift_equals_cv2_directly(ctx):
+    """The GPU against the real OpenCV (cv2.SIFT_create().detectAndCompute, IPP off, one thread -- OpenCV's own deterministic code
+    path), at the tolerance cv2 shows against itself (tests/test_oracle_sift.py): identical keypoint count, coordinates and packed
+    octaves; size / angle / response bit-identical on >= 95 % and within 1e-5 relative; descriptors +-1 on < 0.1 % of the elements."""
+    cv2 = pytest.importorskip("cv2")
+    ipp, thr = cv2.ipp.useIPP(), cv2.getNumThreads()
+    cv2.ipp.setUseIPP(False)
+    cv2.setNumThreads(1)
+    try:
+        for img in (textured(51, 203, 271), np.ascontiguousarray(synth.make_page(5)[100:500, 40:680])):
+            kp, d = cv2.SIFT_create().detectAndCompute(img, None)
+            gkf = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in kp], np.float32).reshape(-1, 5)
+            goc = np.array([k.octave for k in kp], np.int32)
+            kf, oc, de = ctx.extract_sift(img)
+            assert len(kf) == len(gkf) > 100
+            assert np.array_equal(oc, goc)
+            assert np.array_equal(kf[:, :2], gkf[:, :2])
+            for col in (2, 3, 4):
+                assert np.mean(kf[:, col] == gkf[:, col]) >= 0.95
+                assert np.allclose(kf[:, col], gkf[:, col], rtol=1e-5, atol=1e-4 if col == 3 else 0)
+            diff = np.abs(de.astype(np.int32) - d.astype(np.int32))
+            assert diff.max() <= 1 and np.mean(diff == 0) >= 0.999
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+        cv2.setNumThreads(thr)
