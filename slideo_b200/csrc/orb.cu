@@ -109,31 +109,30 @@ __global__ void __launch_bounds__(128) resize_kernel(uint8_t* __restrict__ pyr, 
 // pixels of max(min(c - p), min(p - c)); corner iff score > t; response = score - 1; NMS strict > over 8 neighbours
 // (SURVEY A.4).  Then KeyPointsFilter::runByImageBorder(edgeThreshold) (A.5).
 __device__ __forceinline__ int fast_score(const uint8_t* sp, int pitch) {
-    // sp points at the centre pixel inside the shared tile
+    // sp points at the centre pixel inside the shared tile.  Both polarities run in one pass on packed 16-bit lanes
+    // (VIMNMX3.S16x2): lane 0 holds c - p ("darker" margin), lane 1 holds p - c ("brighter" margin); the min over a 9-arc is
+    // min3 of three min3's over 3 consecutive circle pixels, the score is the max over the 16 arcs and both lanes, floored at 0.
     const int c = sp[0];
-    int d[16];
-    d[0] = c - sp[3 * pitch];      d[1] = c - sp[3 * pitch + 1];  d[2] = c - sp[2 * pitch + 2];  d[3] = c - sp[pitch + 3];
-    d[4] = c - sp[3];              d[5] = c - sp[-pitch + 3];     d[6] = c - sp[-2 * pitch + 2]; d[7] = c - sp[-3 * pitch + 1];
-    d[8] = c - sp[-3 * pitch];     d[9] = c - sp[-3 * pitch - 1]; d[10] = c - sp[-2 * pitch - 2]; d[11] = c - sp[-pitch - 3];
-    d[12] = c - sp[-3];            d[13] = c - sp[pitch - 3];     d[14] = c - sp[2 * pitch - 2]; d[15] = c - sp[3 * pitch - 1];
-    // "all nine brighter" is evaluated as a min-tree over e = -d rather than as -max(d): on sm_100a (CUDA 12.9) the
-    // max/negate form was observed to miscompile (scores too high next to strong edges); min-only trees are exact.
-    int e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = -d[k];
-    int a2[16], b2[16], a4[16], b4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { a2[k] = min(d[k], d[(k + 1) & 15]); b2[k] = min(e[k], e[(k + 1) & 15]); }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { a4[k] = min(a2[k], a2[(k + 2) & 15]); b4[k] = min(b2[k], b2[(k + 2) & 15]); }
-    int best = 0;
+    const int off[16] = {3 * pitch,      3 * pitch + 1,  2 * pitch + 2,  pitch + 3,  3,  -pitch + 3,  -2 * pitch + 2, -3 * pitch + 1,
+                         -3 * pitch,     -3 * pitch - 1, -2 * pitch - 2, -pitch - 3, -3, pitch - 3,   2 * pitch - 2,  3 * pitch - 1};
+    uint32_t de[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const int a9 = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);   // min over d[k..k+8]: all nine darker
-        const int b9 = min(min(b4[k], b4[(k + 4) & 15]), e[(k + 8) & 15]);   // min over -d[k..k+8]: all nine brighter
-        best = max(best, max(a9, b9));
+        const int p = sp[off[k]];
+        de[k] = __byte_perm((uint32_t)(c - p), (uint32_t)(p - c), 0x5410);
     }
-    return best;
+    uint32_t a3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a3[k] = __vimin3_s16x2(de[k], de[(k + 1) & 15], de[(k + 2) & 15]);
+    uint32_t best = 0;   // (0, 0): scores are floored at 0 like the scalar max(best = 0, ...)
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a9 = __vimin3_s16x2(a3[k], a3[(k + 3) & 15], a3[(k + 6) & 15]);
+        const uint32_t b9 = __vimin3_s16x2(a3[k + 1], a3[(k + 4) & 15], a3[(k + 7) & 15]);
+        best = __vimax3_s16x2(best, a9, b9);
+    }
+    const int lo = (int)(short)(best & 0xFFFFu), hi = (int)best >> 16;
+    return max(lo, hi);
 }
 
 // byte flags (0x80 per byte) of the bytes of x that are > thr, for thr < 127:  k127 = (127 - thr) * 0x01010101
@@ -162,6 +161,10 @@ __global__ void __launch_bounds__(256) fast_kernel(const FastMaps* __restrict__ 
     const int t = blockIdx.x - L.tile_base;
     const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
     const int img = blockIdx.y;
+    // keypoints survive only edge pixels inside the level (runByImageBorder): tiles that lie entirely in that band do nothing,
+    // and inside a tile scores are only needed for rows / columns [edge - 1, size - edge] (the 3x3 NMS looks one pixel out)
+    const int eb = g.edge;
+    if (tx0 + TILE_W <= eb || tx0 >= L.w - eb || ty0 + TILE_H <= eb || ty0 >= L.h - eb) return;
 
     // tile load by TMA: one 96 x 40 byte box of the level's {x, y, image} tensor (columns tx0-16 .., rows ty0-4 ..) lands in s_px
     // while the threads clear the score tile; elements outside the level (negative coordinates included) arrive as zero,
@@ -185,6 +188,10 @@ __global__ void __launch_bounds__(256) fast_kernel(const FastMaps* __restrict__ 
     const bool interior = tx0 - 4 >= 3 && tx0 + TILE_W + 4 <= L.w - 3 && ty0 - 1 >= 3 && ty0 + TILE_H + 1 <= L.h - 3;
     for (int i = threadIdx.x; i < SH * SWW; i += blockDim.x) {
         const int r = i / SWW, wq = i - r * SWW + 1;      // score row r <-> pixel row r + 3; score word wq - 1 <-> pixel word wq
+        {
+            const int gy = ty0 - 1 + r, gx0 = tx0 - 8 + wq * 4;
+            if (gy < eb - 1 || gy > L.h - eb || gx0 + 3 < eb - 1 || gx0 > L.w - eb) continue;   // outside the band that can matter
+        }
         const int pw = wq + PX0;
         const uint32_t C = s_px[r + 3][pw], Wm = s_px[r + 3][pw - 1], Wp = s_px[r + 3][pw + 1], U = s_px[r][pw], D = s_px[r + 6][pw];
         const uint32_t Lw = __byte_perm(Wm, C, 0x4321), Rw = __byte_perm(C, Wp, 0x6543);
