@@ -21,8 +21,14 @@ pub struct slideo_b200_config {
     pub descriptor_kind: i32,
     pub max_batch: i32,
     pub keep_matches: i32,
-    pub reserved: [i32; 3],
+    /// 1: also the RANSAC gate (lib.rs:284-333); 2: plus the warp + similarity gate (lib.rs:335-389)
+    pub geometric_verification: i32,
+    pub reserved: [i32; 2],
 }
+
+/// `descriptor_kind`: the reference's ORB / Hamming path, or the SIFT-128 / L2 variant (K11 + K10)
+pub const SLIDEO_B200_DESC_ORB256: i32 = 0;
+pub const SLIDEO_B200_DESC_SIFT128: i32 = 1;
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
@@ -57,6 +63,11 @@ extern "C" {
         out: *mut slideo_b200_frame_result,
     ) -> i32;
     pub fn slideo_b200_get_matches(ctx: *mut slideo_b200_ctx, frame_i: i32, out: *mut slideo_b200_match, cap_rows: i32, out_rows: *mut i32) -> i32;
+    /// SIFT::detectAndCompute (cv::SIFT::create() defaults): kp_f n x 5, kp_octave n, desc n x 128 floats; any pointer may be null
+    pub fn slideo_b200_extract_sift(
+        ctx: *mut slideo_b200_ctx, img: *const u8, w: i32, h: i32, stride: i32, channels: i32, kp_f: *mut f32, kp_octave: *mut i32,
+        desc: *mut f32, cap: i32, out_n: *mut i32,
+    ) -> i32;
     pub fn slideo_b200_host_alloc(out: *mut *mut c_void, bytes: size_t) -> i32;
     pub fn slideo_b200_host_free(p: *mut c_void) -> i32;
 }
