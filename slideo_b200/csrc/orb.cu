@@ -431,12 +431,14 @@ __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ p
     for (int i = threadIdx.x; i < PH * (TILE_W / 4); i += blockDim.x) {
         const int py = i / (TILE_W / 4), x4 = i - py * (TILE_W / 4);
         const uint32_t w0 = s_px[py + OY][x4 + OX], w1 = s_px[py + OY][x4 + OX + 1], w2 = s_px[py + OY][x4 + OX + 2];
+        // u8 -> fp32 without the conversion pipe: byte b | 0x4B000000 is the float 2^23 + b, exactly; subtract 2^23
+        // (one PRMT on the ALU pipe + one FADD instead of shift, mask and I2F on the quarter-rate XU pipe)
         float p[12];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            p[b] = (float)((w0 >> (8 * b)) & 255u);
-            p[4 + b] = (float)((w1 >> (8 * b)) & 255u);
-            p[8 + b] = (float)((w2 >> (8 * b)) & 255u);
+            p[b] = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7540 + b)) - 8388608.f;
+            p[4 + b] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7540 + b)) - 8388608.f;
+            p[8 + b] = __uint_as_float(__byte_perm(w2, 0x4B000000u, 0x7540 + b)) - 8388608.f;
         }
         float o[4];
 #pragma unroll
@@ -470,7 +472,8 @@ __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ p
             acc = __fmaf_rn(k2, __fadd_rn(c4[b], c2[b]), acc);
             acc = __fmaf_rn(k1, __fadd_rn(c5[b], c1[b]), acc);
             acc = __fmaf_rn(k0, __fadd_rn(c6[b], c0[b]), acc);
-            const int v = __float2int_rn(acc);
+            // round-half-even without F2I: acc + 1.5 * 2^23 has the rounded integer in its low mantissa bits (0 <= acc < 2^22)
+            const int v = __float_as_int(__fadd_rn(acc, 12582912.f)) - 0x4B400000;
             out |= (uint32_t)min(max(v, 0), 255) << (8 * b);
         }
         *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
@@ -551,13 +554,16 @@ __global__ void __launch_bounds__(256) describe_kernel(const uint8_t* __restrict
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         // word j holds the two points of bit j: (x0, y0, x1, y1) as int8
-        const uint32_t wv = words[j];
+        // conversions without the quarter-rate XU pipe: int8 -> fp32 as (byte ^ 0x80) | 0x4B000000 = 2^23 + 128 + value, exactly;
+        // cvRound as the low mantissa bits of v + 1.5 * 2^23 (round-half-even, |v| < 2^22)
+        const uint32_t wv = words[j] ^ 0x80808080u;
         int val[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-            const float px = (float)(int)(int8_t)((wv >> (16 * t)) & 255), py = (float)(int)(int8_t)((wv >> (16 * t + 8)) & 255);
-            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const float px = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7540 + 2 * t)), 8388736.f);
+            const float py = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7541 + 2 * t)), 8388736.f);
+            const int ix = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.f)) - 0x4B400000;
+            const int iy = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.f)) - 0x4B400000;
             val[t] = bl[(size_t)reflect101(cy + iy, L.h) * L.pitch + reflect101(cx + ix, L.w)];
         }
         byte |= (uint32_t)(val[0] < val[1]) << j;
