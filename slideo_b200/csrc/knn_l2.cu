@@ -159,15 +159,37 @@ __device__ __forceinline__ uint64_t warp_merge32_asc(uint64_t v, int lane) {
 
 struct L2Params {
     int nq, nt, k;
-    int n_mtiles, n_ntiles, n_splits;
+    int n_mtiles, n_ntiles;
+    int mt_a, ns_a, ns_b;  // query tiles [0, mt_a) are split ns_a ways over the pool, tiles [mt_a, n_mtiles) ns_b ways; partial rows have ns_max slots
+    int ns_max;
     int trigger;           // new candidates of a list that schedule its cut-back (1..L2_TRIGGER)
     unsigned long long* prof;  // developer instrument (SLIDEO_L2_PROF): cycles of epilogue warps in {acc wait, drain, cut-back, item tail}, MMA warp in {acc_empty wait, b_full wait}
     int dbg;               // developer switch (SLIDEO_L2_DEBUG): 1 = epilogue skips the TMEM drain, 2 = drains but never selects
     uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
-    uint64_t* partial;     // [nq][n_splits][k]   (n_splits > 1)
+    uint64_t* partial;     // [nq][ns_max][k]   (only rows of split tiles are used)
     int32_t* idx_out;      // [nq][k]
     float* dist_out;       // [nq][k]
 };
+
+// work item -> (query tile, pool split, splits of that tile, pool tile range)
+struct L2Item { int mt, sp, ns, j0, j1; };
+__device__ __forceinline__ L2Item l2_item(const L2Params& P, int item) {
+    L2Item w;
+    const int items_a = P.mt_a * P.ns_a;
+    if (item < items_a) {
+        w.ns = P.ns_a;
+        w.mt = item / P.ns_a;
+        w.sp = item - w.mt * P.ns_a;
+    } else {
+        const int j = item - items_a;
+        w.ns = P.ns_b;
+        w.mt = P.mt_a + j / P.ns_b;
+        w.sp = j - (j / P.ns_b) * P.ns_b;
+    }
+    w.j0 = (int)((long long)P.n_ntiles * w.sp / w.ns);
+    w.j1 = (int)((long long)P.n_ntiles * (w.sp + 1) / w.ns);
+    return w;
+}
 
 __device__ __forceinline__ void emit_l2_row(uint64_t key, int lane, int q, int k, int32_t* idx_out, float* dist_out) {
     if (lane < k) {
@@ -215,15 +237,15 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int n_items = P.n_mtiles * P.n_splits;
+    const int n_items = P.mt_a * P.ns_a + (P.n_mtiles - P.mt_a) * P.ns_b;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0, bcount = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
-                const int j0 = (int)((long long)P.n_ntiles * sp / P.n_splits), j1 = (int)((long long)P.n_ntiles * (sp + 1) / P.n_splits);
+                const L2Item w = l2_item(P, item);
+                const int mt = w.mt, j0 = w.j0, j1 = w.j1;
                 mbar_wait(a_empty, (it & 1) ^ 1);      // MMAs of the previous item no longer read A
                 mbar_expect_tx(a_full, A_BYTES);
                 tma_load_2d(sA, &tm_q_main, 0, mt * L2_BM, a_full);
@@ -247,8 +269,8 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
             long long mw_acc = 0, mw_b = 0;
             const uint32_t a0 = smem_u32(sA), a1 = a0 + A_MAIN_BYTES, at = a0 + 2 * A_MAIN_BYTES;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
-                const int j0 = (int)((long long)P.n_ntiles * sp / P.n_splits), j1 = (int)((long long)P.n_ntiles * (sp + 1) / P.n_splits);
+                const L2Item w = l2_item(P, item);
+                const int j0 = w.j0, j1 = w.j1;
                 mbar_wait(a_full, it & 1);
                 for (int j = j0; j < j1; ++j, ++bcount) {
                     const int b = (j - j0) & 1;
@@ -287,8 +309,8 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         long long pw = 0, pd = 0, pc = 0, pt = 0;
 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int mt = item / P.n_splits, sp = item - mt * P.n_splits;
-            const int j0 = (int)((long long)P.n_ntiles * sp / P.n_splits), j1 = (int)((long long)P.n_ntiles * (sp + 1) / P.n_splits);
+            const L2Item w = l2_item(P, item);
+            const int mt = w.mt, sp = w.sp, j0 = w.j0, j1 = w.j1;
             const int q = mt * L2_BM + row;
             float tau = q < P.nq ? __int_as_float(0x7F800000) : -1.f;   // +inf / never
             int cnt = 32;              // next free slot of this row's list
@@ -432,8 +454,8 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                     const uint64_t a = __ldcg(base0 + (size_t)L * L2_SLOTS + lane);
                     const uint64_t b = __ldcg(base1 + (size_t)L * L2_SLOTS + (31 - lane));
                     const uint64_t m = warp_merge32_asc(a < b ? a : b, lane);
-                    if (P.n_splits == 1) emit_l2_row(m, lane, qq, P.k, P.idx_out, P.dist_out);
-                    else if (lane < P.k) P.partial[((size_t)qq * P.n_splits + sp) * P.k + lane] = m;
+                    if (w.ns == 1) emit_l2_row(m, lane, qq, P.k, P.idx_out, P.dist_out);
+                    else if (lane < P.k) P.partial[((size_t)qq * P.ns_max + sp) * P.k + lane] = m;
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -454,14 +476,14 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
 }
 
 // merge of per-split partial rows: one warp per query
-__global__ void __launch_bounds__(128) l2_merge_kernel(const uint64_t* __restrict__ partial, int nq, int n_splits, int k, int32_t* idx_out,
-                                                       float* dist_out) {
+__global__ void __launch_bounds__(128) l2_merge_kernel(const uint64_t* __restrict__ partial, int q_begin, int q_end, int n_splits, int ns_max,
+                                                       int k, int32_t* idx_out, float* dist_out) {
     const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= nq) return;
+    const int q = q_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= q_end) return;
     uint64_t top = KEY64_EMPTY;   // ascending; every partial row is ascending too, so it is read back to front
     for (int s = 0; s < n_splits; ++s) {
-        const uint64_t x = 31 - lane < k ? partial[((size_t)q * n_splits + s) * k + (31 - lane)] : KEY64_EMPTY;
+        const uint64_t x = 31 - lane < k ? partial[((size_t)q * ns_max + s) * k + (31 - lane)] : KEY64_EMPTY;
         top = warp_merge32_asc(top < x ? top : x, lane);
     }
     emit_l2_row(top, lane, q, k, idx_out, dist_out);
@@ -598,13 +620,23 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.nq = nq; P.nt = nt; P.k = k;
     P.n_mtiles = cdiv(nq, L2_BM);
     P.n_ntiles = l2_rows_padded(nt) / L2_BN;
-    // pool splits only when there are too few query tiles to fill the machine
-    int ns = 1;
-    if (P.n_mtiles < num_sms) ns = std::min(P.n_ntiles, std::max(1, num_sms / P.n_mtiles));
-    P.n_splits = ns;
-    const int grid = std::min(P.n_mtiles * ns, num_sms);
+    // work items = query tiles (x pool splits) on a persistent grid of one CTA per SM.  Splitting a tile's pool restarts its
+    // selection per part (measured: 921 -> 855 TFLOP/s when every tile is split in two), so tiles are split only
+    //  * when there are too few of them to fill the machine (all tiles, ns_a ways), or
+    //  * in the LAST wave: the n_mtiles % SMs tiles that would leave most SMs idle are split so that their parts fill one wave.
+    P.mt_a = P.n_mtiles; P.ns_a = 1; P.ns_b = 1;
+    if (P.n_mtiles < num_sms) {
+        P.ns_a = std::min(P.n_ntiles, std::max(1, num_sms / P.n_mtiles));
+    } else if (!getenv("SLIDEO_L2_NO_SPLIT")) {
+        const int r = P.n_mtiles % num_sms;
+        const int c = r > 0 ? std::min(std::min(4, P.n_ntiles), num_sms / r) : 1;
+        if (c >= 2) { P.mt_a = P.n_mtiles - r; P.ns_b = c; }
+    }
+    P.ns_max = std::max(P.ns_a, P.ns_b);
+    const int n_items = P.mt_a * P.ns_a + (P.n_mtiles - P.mt_a) * P.ns_b;
+    const int grid = std::min(n_items, num_sms);
     grow(&ws.d_scratch, &ws.scratch_cap, (size_t)grid * 2 * L2_BM * L2_SLOTS * 8);
-    if (ns > 1) grow(&ws.d_part, &ws.part_cap, (size_t)nq * ns * k * 8);
+    if (P.ns_max > 1) grow(&ws.d_part, &ws.part_cap, (size_t)nq * P.ns_max * k * 8);
     P.scratch = (uint64_t*)ws.d_scratch;
     P.partial = (uint64_t*)ws.d_part;
     P.idx_out = d_idx;
@@ -641,8 +673,16 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
                 h[0] / ew / 1e6, h[1] / ew / 1e6, h[2] / ew / 1e6, h[3] / ew / 1e6, h[4] / mw / 1e6, h[5] / mw / 1e6);
     }
     if (launches) ++*launches;
-    if (ns > 1) {
-        l2_merge_kernel<<<cdiv(nq, 4), 128, 0, stream>>>((const uint64_t*)ws.d_part, nq, ns, k, d_idx, d_dist);
+    // merge of the partial rows of the split tiles (one warp per query)
+    if (P.ns_a > 1) {
+        const int q1 = std::min(nq, P.mt_a * L2_BM);
+        l2_merge_kernel<<<cdiv(q1, 4), 128, 0, stream>>>((const uint64_t*)ws.d_part, 0, q1, P.ns_a, P.ns_max, k, d_idx, d_dist);
+        SLIDEO_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    if (P.ns_b > 1 && P.mt_a * L2_BM < nq) {
+        const int q0 = P.mt_a * L2_BM;
+        l2_merge_kernel<<<cdiv(nq - q0, 4), 128, 0, stream>>>((const uint64_t*)ws.d_part, q0, nq, P.ns_b, P.ns_max, k, d_idx, d_dist);
         SLIDEO_CUDA(cudaGetLastError());
         if (launches) ++*launches;
     }
