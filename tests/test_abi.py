@@ -94,3 +94,14 @@ def test_product_never_imports_the_oracle():
                 assert "liboracle" not in txt and "orb_oracle" not in txt.replace("oracle/orb_oracle.c", ""), f
     code = "import sys; sys.path.insert(0, %r); import slideo_b200; assert 'oracle' not in sys.modules and 'cv2' not in sys.modules" % ROOT
     subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_tools_and_bench_compile():
+    """bench.py, __graft_entry__.py and every developer tool under tools/ at least parse (they only run on the GPU box)."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(root, "tools", "*.py")))
+    assert len(files) > 5
+    for f in files:
+        py_compile.compile(f, doraise=True)
