@@ -386,7 +386,7 @@ def main():
     if rank == 0 and world == 1:
         try:
             ns = min(args.frames, 64)
-            sctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=8, descriptor_kind=slideo_b200.ffi.DESC_SIFT128))
+            sctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=16, descriptor_kind=slideo_b200.ffi.DESC_SIFT128))
             t0 = time.perf_counter()
             for p in range(args.pages):
                 sctx.add_page_gray8(pages[p])

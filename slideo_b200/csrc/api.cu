@@ -92,7 +92,7 @@ struct slideo_b200_ctx {
     OrbExtractor* last_ext = nullptr;
     std::map<std::tuple<int, int, int>, std::unique_ptr<SiftExtractor>> sift_extractors;   // K11 workspaces (SIFT128 variant)
     SiftExtractor* last_sift = nullptr;
-    static constexpr int SIFT_BATCH = 8;  // frames per K11 batch (265 MB of fp32 scale space per 1080p frame)
+    static constexpr int SIFT_BATCH = 16; // upper bound of the frames per K11 batch (265 MB of fp32 scale space per 1080p frame)
     static constexpr int N_STAGING = 4;  // frame staging buffers (uploads run this many batches ahead)
     DevBuf<uint8_t> d_frames[N_STAGING];
     DevBuf<uint8_t> d_img;               // single-image upload (pages, extract_orb)

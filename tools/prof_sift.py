@@ -16,14 +16,14 @@ nf = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 npg = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 pages = [synth.make_page(p) for p in range(npg)]
 frames = np.stack([synth.make_frame(f, npg, pages) for f in range(nf)])
-ctx = slideo_b200.Context(slideo_b200.default_config(descriptor_kind=slideo_b200.ffi.DESC_SIFT128, max_batch=8))
+ctx = slideo_b200.Context(slideo_b200.default_config(descriptor_kind=slideo_b200.ffi.DESC_SIFT128, max_batch=int(os.environ.get("SIFT_MAX_BATCH", "8"))))
 t0 = time.time()
 nk = [ctx.add_page_gray8(p) for p in pages]
 ctx.finalize_pool()
 t_pages = time.time() - t0
 d = torch.from_numpy(frames).cuda()
 h, w = frames.shape[1:3]
-ctx.match_frames_bgr8_device(d.data_ptr(), min(nf, 8), w, h)   # warm-up (workspace allocation)
+ctx.match_frames_bgr8_device(d.data_ptr(), nf, w, h)   # warm-up (workspaces grow to the sizes of this run)
 ctx.timings(reset=True)
 res = ctx.match_frames_bgr8_device(d.data_ptr(), nf, w, h)
 tm = ctx.timings(reset=True)
