@@ -34,6 +34,8 @@ def check_sift(kf, oc, de, gkf, goc, gde):
     assert len(kf) == len(gkf), (len(kf), len(gkf))
     assert np.array_equal(oc, goc)
     assert np.array_equal(kf[:, :2], gkf[:, :2]), "keypoint coordinates differ"
+    if len(kf) == 0:
+        return
     for col, name in ((2, "size"), (3, "angle"), (4, "response")):
         same = np.mean(kf[:, col] == gkf[:, col])
         assert same >= 0.95, (name, same)
@@ -121,3 +123,16 @@ def test_sift_on_reference_fixture():
     kf, oc, de = oracle.sift_detect_and_compute(g)
     assert len(kf) == 2120          # SURVEY.md D5 probe: cv2 SIFT on 1-frame.png
     check_sift(kf, oc, de, *mg.cv2_sift(g))
+
+
+@pytest.mark.parametrize("shape", [(9, 8), (16, 33), (64, 64)])
+def test_sift_edge_sizes_equal_cv2(shape):
+    """Tiny and small images (few octaves, blur kernels wider than the image: multiple reflect-101 wraps) and a flat image."""
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    img = cv2.resize(rng.integers(0, 256, (max(2, shape[0] // 4), max(2, shape[1] // 4)), dtype=np.uint8), (shape[1], shape[0]),
+                     interpolation=cv2.INTER_CUBIC)
+    kf, oc, de = oracle.sift_detect_and_compute(img)
+    check_sift(kf, oc, de, *mg.cv2_sift(img))
+    flat = np.full(shape, 123, np.uint8)
+    kf, oc, de = oracle.sift_detect_and_compute(flat)
+    assert len(kf) == 0 and len(mg.cv2_sift(flat)[0]) == 0
