@@ -191,3 +191,13 @@ def test_gpu_sift_equals_cv2_directly(ctx):
     finally:
         cv2.ipp.setUseIPP(ipp)
         cv2.setNumThreads(thr)
+
+
+@pytest.mark.parametrize("shape", [(9, 8), (16, 33), (33, 47)])
+def test_tiny_images_equal_oracle(ctx, shape):
+    """Images smaller than the blur kernels (every tile is a border tile, reflect-101 wraps several times) and with 2-3 octaves only."""
+    g = textured(60 + shape[0], shape[0], shape[1], cell=4)
+    check_against_oracle(ctx.extract_sift(g), oracle.sift_detect_and_compute(g))
+    n_oct = oracle.lib().sift_num_octaves(shape[1], shape[0])
+    mine, ref = ctx.debug_fetch_sift(n_oct - 1, 5), oracle.sift_pyramid_image(g, 0, n_oct - 1, 5)
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
