@@ -67,7 +67,9 @@ typedef struct slideo_b200_config {
     int32_t keep_matches;    /* !=0: keep the k-NN rows of the last match call for slideo_b200_get_matches */
     int32_t geometric_verification; /* 1: match_frames_* also runs the RANSAC gate (lib.rs:284-333), see slideo_b200_get_verification;
                                        2: plus the warp + similarity gate (lib.rs:335-389), see slideo_b200_get_decisions */
-    int32_t reserved[2];
+    int32_t knn_impl;        /* 0 (= 5): bit-sliced K8 v5 everywhere; 4: the XOR/POPC K8 v4 in the stage-level k-NN entry points (kept as an
+                                independent implementation for cross-checks; the frame path always runs v5) */
+    int32_t reserved[1];
 } slideo_b200_config;
 
 /* Hot-path output per frame: the head of the reference's ranking, lib.rs:268-295.
@@ -181,6 +183,20 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
 int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d_frames, int32_t n, int32_t w,
                                              int32_t h, int32_t stride, size_t frame_stride,
                                              slideo_b200_frame_result* out);
+/* The same path, asynchronous (the reference's streaming loop spawns one job per changed frame while decoding goes on,
+ * lib.rs:196-220).  submit enqueues the uploads, the extraction and the k-NN launches of n frames and returns at once with a
+ * ticket; nothing on the host waits for the GPU.  collect blocks until the results of that ticket are complete and writes
+ * n results.  Several tickets may be in flight (at most 65536 uncollected frames); the query stream is continuous across
+ * submits, so the upload + extraction of one call overlap the k-NN of the previous one.  The host frame buffer of a submit
+ * must stay valid (and should be pinned) until its ticket is collected.  ORB256 ctxs without geometric_verification /
+ * keep_matches (those need match_frames_*, which is submit + collect + the verification tail).
+ * match_frames_bgr8 == submit_frames_bgr8 + collect, result for result. */
+int32_t slideo_b200_submit_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h, int32_t stride,
+                                       size_t frame_stride, int64_t* out_ticket);
+int32_t slideo_b200_submit_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d_frames, int32_t n, int32_t w, int32_t h,
+                                              int32_t stride, size_t frame_stride, int64_t* out_ticket);
+/* out may be NULL (drop the results); cap = capacity of out in frames; *out_n = frames of the ticket. */
+int32_t slideo_b200_collect(slideo_b200_ctx* ctx, int64_t ticket, slideo_b200_frame_result* out, int32_t cap, int32_t* out_n);
 /* Match pre-extracted descriptors of n frames (frame i owns rows [frame_offsets[i], frame_offsets[i+1])). */
 int32_t slideo_b200_match_descriptors(slideo_b200_ctx* ctx, const void* desc, const int32_t* frame_offsets, int32_t n,
                                       slideo_b200_frame_result* out);

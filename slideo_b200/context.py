@@ -189,6 +189,38 @@ class Context:
                                                                 frame_stride, res))
         return self._results(res, n)
 
+    # asynchronous variant: submit returns a ticket at once, collect blocks until that ticket's results are complete
+    def submit_frames_bgr8_ptr(self, host_ptr: int, n: int, w: int, h: int, stride: Optional[int] = None,
+                               frame_stride: Optional[int] = None) -> int:
+        """HOST frames (pinned memory makes the uploads asynchronous; the buffer must stay valid until `collect`)."""
+        stride = stride or 3 * w
+        frame_stride = frame_stride or stride * h
+        t = ctypes.c_int64()
+        self._ck(self._lib.slideo_b200_submit_frames_bgr8(self._h, ctypes.c_void_p(host_ptr), n, w, h, stride, frame_stride, ctypes.byref(t)))
+        return t.value
+
+    def submit_frames_bgr8(self, frames: np.ndarray) -> int:
+        if frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8 or not frames.flags["C_CONTIGUOUS"]:
+            raise TypeError("frames must be a C-contiguous [n, h, w, 3] uint8 array (kept alive by the caller until collect)")
+        n, h, w, _ = frames.shape
+        return self.submit_frames_bgr8_ptr(frames.ctypes.data, n, w, h)
+
+    def submit_frames_bgr8_device(self, dev_ptr: int, n: int, w: int, h: int, stride: Optional[int] = None,
+                                  frame_stride: Optional[int] = None) -> int:
+        stride = stride or 3 * w
+        frame_stride = frame_stride or stride * h
+        t = ctypes.c_int64()
+        self._ck(self._lib.slideo_b200_submit_frames_bgr8_device(self._h, ctypes.c_void_p(dev_ptr), n, w, h, stride, frame_stride,
+                                                                 ctypes.byref(t)))
+        return t.value
+
+    def collect(self, ticket: int, n: int) -> np.ndarray:
+        """Results of one ticket: int32 [n, 3] = (best_slide, votes, n_keypoints)."""
+        res = (ffi.FrameResult * max(n, 1))()
+        got = ctypes.c_int32()
+        self._ck(self._lib.slideo_b200_collect(self._h, ticket, res, n, ctypes.byref(got)))
+        return self._results(res, got.value)
+
     def match_descriptors(self, desc, frame_offsets) -> np.ndarray:
         a = self._desc_array(desc)
         fo = np.ascontiguousarray(frame_offsets, np.int32)

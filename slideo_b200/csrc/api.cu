@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" boundary of libslideo_b200.so (include/slideo_b200.h) and the per-ctx host logic:
-// device-resident page pool, frame batching with double-buffered uploads, K1-K7 -> K8/K9 -> per-frame result.
+// device-resident page pool, the streaming frame path (uploads -> K1-K7 -> K8/K9 -> per-frame result, no host synchronisation
+// between submit and collect: keypoint counts, K8 ranges and finished frames are all tracked on the device).
 // Host-side counterpart of the reference's orchestration in crates/matching-opencv/src/lib.rs:37-64 (page pool),
 // lib.rs:249-295 (per-frame path) and flann.rs:64-89 (matcher); all arithmetic runs in the CUDA kernels of
 // orb.cu / knn_hamming.cu / knn_l2.cu.  There is no CPU fallback: without a device every entry point fails.
@@ -10,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -78,8 +80,10 @@ struct slideo_b200_ctx {
     DevBuf<float2> d_pool_pt;
     bool finalized = false;
     DevBuf<uint8_t> d_pool;              // nt x 32 (ORB) / nt x 128 bf16 (SIFT)
-    DevBuf<uint8_t> d_pool48;            // ORB: the 48 B expanded rows K8 streams (knn_pool_expand_launch)
-    DevBuf<uint8_t> d_t48;               // expanded copy of a caller-provided pool (stage-level k-NN)
+    DevBuf<uint8_t> d_pool5;             // ORB: the pool as bit-sliced slabs, what K8 v5 streams (knn5_pool_prepare_launch)
+    DevBuf<uint8_t> d_t5;                // bit-sliced copy of a caller-provided pool (stage-level k-NN)
+    DevBuf<uint8_t> d_t48;               // 48 B expanded copy of a caller-provided pool (stage-level k-NN, cfg.knn_impl == 4)
+    DevBuf<uint32_t> d_partial5;         // K8 v5 partial rows (split tiles)
     DevBuf<uint8_t> d_pool_tail;         // SIFT: bf16 norm tails of the pool (knn_l2.cu)
     DevBuf<uint8_t> d_pool_f32;          // SIFT: the pooled descriptors as fp32 (what the NCCL broadcast moves; bf16 operands are derived)
     DevBuf<uint16_t> d_page_of;          // nt
@@ -124,6 +128,7 @@ struct slideo_b200_ctx {
         if (knn_stream) cudaStreamSynchronize(knn_stream);
         extractors.clear();
         sift_extractors.clear();
+        engine_destroy();
         for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto& e : ev_free_list) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (int i = 0; i < N_STAGING; ++i) {
@@ -317,16 +322,15 @@ struct slideo_b200_ctx {
         d_results.reserve((size_t)n_frames * 3);
         SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)n_frames * std::max(n_pages, 1) * 4, stream));
         if (nq > 0) {
-            KnnPlan plan = knn_hamming_plan(nq, nt, cfg.knn_k, num_sms);
-            d_scratch.reserve(plan.scratch_bytes / 4);
-            if (plan.partial_bytes) d_partial.reserve(plan.partial_bytes / 4);
+            Knn5Plan plan = knn5_plan(nq, nt, cfg.knn_k, num_sms);
+            if (plan.partial_bytes) d_partial5.reserve(plan.partial_bytes / 4);
             if (want_keys) d_keys.reserve((size_t)nq * cfg.knn_k);
             VoteArgs va{d_qf, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio};
             EventPair t = begin_timing(1, stream);
             int nl = 0;
-            knn_hamming_launch(plan, dq, d_pool48.p, want_keys ? d_keys.p : nullptr, d_scratch.p, d_partial.p, &va, stream, &nl);
+            knn5_launch(plan, dq, d_pool5.p, want_keys ? d_keys.p : nullptr, d_partial5.p, &va, stream, &nl);
             end_timing(t, stream);
-            tm.knn_launches += nl;
+            tm.knn_launches += 1;
             tm.kernel_launches += nl;
             tm.knn_pairs += (int64_t)nq * nt;
         }
@@ -353,13 +357,49 @@ struct slideo_b200_ctx {
         SLIDEO_CUDA(cudaStreamSynchronize(st));
     }
 
-    // ---- the per-frame hot path, decoupled: detection appends descriptors of many batches to one query stream, K8 then
-    //      runs over that stream in chunks of exactly (resident CTAs x tile) queries, whatever the frame boundaries ----
-    DevBuf<uint8_t> d_qs_desc;           // query stream: descriptors
-    DevBuf<int32_t> d_qs_frame;          // frame (within the super-batch) of each query
-    DevBuf<int32_t> d_qs_nkp;            // keypoints per frame
-    DevBuf<float2> d_qs_pt;              // KeyPoint.pt of each query (geometric verification)
-    DevBuf<int32_t> d_v_cand_page, d_v_cand_votes, d_v_n_cand, d_v_rating, d_v_q0;
+    // ---- the per-frame hot path as a device-driven stream ------------------------------------------------------------------
+    // Detection (K1-K7, `stream`) appends the descriptors of every batch to a query stream; the keypoint counts stay on the device
+    // (KnnStream).  After each batch a one-thread plan kernel cuts the next K8 range (whole waves of 148 x 128 queries; the
+    // remainder rides with the next launch), K8 v5 + the finalize kernels run on `knn_stream` and write finished frames straight
+    // into a host-mapped result ring plus a progress word.  Nothing on the host ever waits for a count: submit() only enqueues,
+    // collect() waits for launch events until the progress word covers the ticket.  The stream is continuous across submit
+    // calls, so the upload + detection of call i+1 overlap K8 of call i (the reference's streaming loop, lib.rs:196-220).
+    // Query-stream buffers come in two sets ("epochs" of EPOCH_FRAMES frames) that alternate.
+    static constexpr int EPOCH_FRAMES = 2048;
+    static constexpr int RING = 1 << 16;          // frames of the host result ring
+    static constexpr int DYN_SLOTS = 256;         // K8 launch descriptors in flight
+    struct Epoch {
+        DevBuf<uint8_t> desc;                     // [q_cap x 32]
+        DevBuf<int32_t> q_frame, frame_q0, frame_nkp, votes;
+        DevBuf<float2> pt;                        // KeyPoint.pt of each query (geometric verification)
+        DevBuf<uint32_t> keys;                    // k-NN rows (keep_matches / geometric verification)
+        KnnStream* d_state = nullptr;
+        cudaEvent_t ev_done = nullptr;            // K8 side of the epoch finished
+        long long seq_base = 0;                   // global number of the epoch's frame 0
+        int frames = 0, q_cap = 0;
+        bool used = false;
+    };
+    Epoch ep[2];
+    int cur_ep = 0;
+    bool ep_open = false;
+    int ep_w = 0, ep_h = 0;
+    long long seq_submitted = 0;
+    KnnDyn* d_dyn = nullptr;
+    cudaEvent_t ev_plan[DYN_SLOTS] = {}, ev_knn[DYN_SLOTS] = {};
+    long long launch_seq = 0, launch_synced = 0;  // K8 launch groups enqueued / known to be complete
+    long long batch_seq = 0;                      // staging-ring position (uploads)
+    unsigned long long pairs_seen = 0;            // device pair counters already folded into tm.knn_pairs
+    int32_t* h_ring = nullptr;                    // pinned + mapped: RING x 3 results, then the progress word and the flags word
+    volatile long long* h_progress = nullptr;
+    volatile int* h_flags = nullptr;
+    struct Ticket { long long id, seq0, seq1; };
+    std::deque<Ticket> tickets;
+    long long next_ticket = 1;
+    bool span_open = false, span_closed = false;  // ms_total: first submit after a timings reset .. last collect
+    cudaEvent_t ev_span0 = nullptr, ev_span1 = nullptr;
+
+    // verification state of the last match call
+    DevBuf<int32_t> d_v_cand_page, d_v_cand_votes, d_v_n_cand, d_v_rating;
     DevBuf<uint8_t> d_v_corr;
     DevBuf<VerifyRecord> d_v_out;
     std::vector<VerifyRecord> verify_results;   // one per frame of the last match_frames_* call
@@ -368,121 +408,324 @@ struct slideo_b200_ctx {
     std::vector<uint8_t> h_page_small;          // gray small image of every page (uniform page geometry)
     int page_w = 0, page_h = 0;
     bool page_geom_ok = true;
+    bool page_small_ready = false;              // d_page_small holds the small image of every page (built here or replicated)
     DevBuf<uint8_t> d_page_small, d_all_frames;
     AreaTables page_area;
     DevBuf<int32_t> d_v_best_it, d_v_surv_cand;
     DevBuf<double> d_v_refined;
     DevBuf<unsigned long long> d_v_sumsq;
-    const uint8_t* photo_frames = nullptr;      // device frames of the current stream (frame i at + i * photo_frame_stride)
+    const uint8_t* photo_frames = nullptr;      // device frames of the current group (frame i at + i * photo_frame_stride)
     int photo_w = 0, photo_h = 0, photo_row_stride = 0;
     size_t photo_frame_stride = 0;
 
     // ---- changed-frame prefilter (K13) --------------------------------------------------------------------
     AreaTables area;
-    DevBuf<uint8_t> d_small;                    // [batch + 1] small images: slot 0 = last frame of the previous batch
+    DevBuf<uint8_t> d_small;                    // [max_batch + 1] small images: slot 0 = last frame of the previous batch / call
+    DevBuf<uint8_t> d_page_small_tmp;           // small image of the page being added
     DevBuf<unsigned long long> d_sumsq;
     bool have_prev_small = false;
-    int qs_total = 0, qs_frames = 0;
-    size_t qs_cap = 0;
-    static constexpr int SUPER_BATCH = 2048;   // frames per query stream (bounds the stream buffers)
 
+    bool want_keys() const { return cfg.keep_matches != 0 || cfg.geometric_verification != 0; }
     size_t kp_per_frame_cap(int w, int h) { return extractor(w, h, cfg.max_batch).kp_cap() / (size_t)cfg.max_batch; }
 
-    void stream_begin(int n_frames, int w, int h) {
-        SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));   // K8 of a previous stream no longer reads the buffers reused below
-        qs_cap = (size_t)n_frames * kp_per_frame_cap(w, h);
-        d_qs_desc.reserve(qs_cap * 32 + 64);
-        d_qs_frame.reserve(qs_cap + 64);
-        d_qs_nkp.reserve((size_t)n_frames + 64);
-        if (cfg.geometric_verification) d_qs_pt.reserve(qs_cap + 64);
-        qs_total = 0;
-        qs_frames = 0;
-        qs_matched = 0;
-        const int np = std::max(n_pages, 1);
-        d_votes.reserve((size_t)n_frames * np);
-        d_results.reserve((size_t)n_frames * 3);
-        if (cfg.keep_matches || cfg.geometric_verification) d_keys.reserve(qs_cap * cfg.knn_k);
-        SLIDEO_CUDA(cudaMemsetAsync(d_votes.p, 0, (size_t)n_frames * np * 4, knn_stream));
-    }
-    // K1-K7 on nb device-resident frames, appended to the query stream
-    void stream_detect(const uint8_t* d_src, int nb, int w, int h, int stride, size_t frame_stride) {
-        OrbExtractor& ex = extractor(w, h, cfg.max_batch);
-        OrbExtractor::Sink sink{d_qs_desc.p + (size_t)qs_total * 32, d_qs_frame.p + qs_total, d_qs_nkp.p + qs_frames,
-                                cfg.geometric_verification ? d_qs_pt.p + qs_total : nullptr, qs_frames, qs_cap - (size_t)qs_total};
-        EventPair t = begin_timing(0, stream);
-        int nl = 0;
-        const int total = ex.run(d_src, nb, stride, frame_stride, 3, stream, &nl, &sink);
-        end_timing(t, stream);
-        SLIDEO_CUDA(cudaEventRecord(ev_detect, stream));
-        tm.kernel_launches += nl;
-        qs_total += total;
-        qs_frames += nb;
-        tm.frames += nb;
-    }
-    // K8 + K9 over the part of the stream that is ready: whole chunks of (resident CTAs x tile) queries while detection is
-    // still appending (flush = false), everything that is left at the end (flush = true)
-    int qs_matched = 0;
-    int FRAME_PATH_CTAS = getenv("SLIDEO_FRAME_CTAS") ? atoi(getenv("SLIDEO_FRAME_CTAS")) : 4;   // K8 CTAs per SM in the frame path (measured: 4 beats 3 + more K1-K7 overlap, profiles/r1_frame_ctas.txt)
-    void stream_match_ready(bool flush) {
-        const bool want_keys = cfg.keep_matches != 0 || cfg.geometric_verification != 0;
-        const int chunk = num_sms * FRAME_PATH_CTAS * KNN_TILE_QUERIES;   // one full wave of K8 tiles: every CTA owns one tile
-        VoteArgs va{nullptr, d_page_of.p, d_votes.p, n_pages, cfg.vote_ratio};
-        bool waited = false;
-        while (qs_total - qs_matched >= chunk || (flush && qs_total > qs_matched)) {
-            if (!waited) {
-                SLIDEO_CUDA(cudaStreamWaitEvent(knn_stream, ev_detect, 0));   // the queries of this chunk have been written
-                waited = true;
-            }
-            const int q0 = qs_matched, nq = std::min(chunk, qs_total - q0);
-            KnnPlan plan = knn_hamming_plan(nq, nt, cfg.knn_k, num_sms, FRAME_PATH_CTAS);
-            d_scratch.reserve(plan.scratch_bytes / 4);
-            if (plan.partial_bytes) d_partial.reserve(plan.partial_bytes / 4);
-            va.q_frame = d_qs_frame.p + q0;
-            EventPair t = begin_timing(1, knn_stream);
-            int nl = 0;
-            knn_hamming_launch(plan, d_qs_desc.p + (size_t)q0 * 32, d_pool48.p, want_keys ? d_keys.p + (size_t)q0 * cfg.knn_k : nullptr,
-                               d_scratch.p, d_partial.p, &va, knn_stream, &nl);
-            end_timing(t, knn_stream);
-            tm.knn_launches += 1;
-            tm.kernel_launches += nl;
-            tm.knn_pairs += (int64_t)nq * nt;
-            qs_matched += nq;
+    void engine_init() {
+        SLIDEO_CUDA(cudaMalloc(&d_dyn, sizeof(KnnDyn) * DYN_SLOTS));
+        SLIDEO_CUDA(cudaMemset(d_dyn, 0, sizeof(KnnDyn) * DYN_SLOTS));
+        for (int i = 0; i < DYN_SLOTS; ++i) {
+            SLIDEO_CUDA(cudaEventCreateWithFlags(&ev_plan[i], cudaEventDisableTiming));
+            SLIDEO_CUDA(cudaEventCreateWithFlags(&ev_knn[i], cudaEventDisableTiming));
         }
-    }
-    // per-frame argmax + results of the finished stream into h_out
-    void stream_finish(int32_t* h_out) {
-        stream_match_ready(true);
-        SLIDEO_CUDA(cudaStreamWaitEvent(knn_stream, ev_detect, 0));   // frame_nkp of the last batch (and the empty-stream case)
-        vote_argmax_launch(d_votes.p, qs_frames, n_pages, d_qs_nkp.p, d_results.p, knn_stream);
-        tm.kernel_launches += 1;
-        SLIDEO_CUDA(cudaMemcpyAsync(h_out, d_results.p, (size_t)qs_frames * 3 * 4, cudaMemcpyDeviceToHost, knn_stream));
-        std::vector<int32_t> fo(1, 0);
-        if (cfg.keep_matches || cfg.geometric_verification) {
-            std::vector<int32_t> nkp((size_t)qs_frames);
-            SLIDEO_CUDA(cudaMemcpyAsync(nkp.data(), d_qs_nkp.p, (size_t)qs_frames * 4, cudaMemcpyDeviceToHost, knn_stream));
-            SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
-            for (int f = 0; f < qs_frames; ++f) fo.push_back(fo.back() + nkp[f]);
+        void* hp = nullptr;
+        SLIDEO_CUDA(cudaHostAlloc(&hp, (size_t)RING * 12 + 64, cudaHostAllocMapped));
+        std::memset(hp, 0, (size_t)RING * 12 + 64);
+        h_ring = (int32_t*)hp;
+        h_progress = (volatile long long*)((uint8_t*)hp + (size_t)RING * 12);
+        h_flags = (volatile int*)((uint8_t*)hp + (size_t)RING * 12 + 16);
+        for (int i = 0; i < 2; ++i) {
+            SLIDEO_CUDA(cudaMalloc(&ep[i].d_state, sizeof(KnnStream)));
+            SLIDEO_CUDA(cudaMemset(ep[i].d_state, 0, sizeof(KnnStream)));
+            SLIDEO_CUDA(cudaEventCreateWithFlags(&ep[i].ev_done, cudaEventDisableTiming));
         }
-        if (cfg.geometric_verification) verify_stream(fo);
-        if (cfg.keep_matches) keep_batch_keys(qs_total, fo, knn_stream);
+        SLIDEO_CUDA(cudaEventCreate(&ev_span0));
+        SLIDEO_CUDA(cudaEventCreate(&ev_span1));
+        d_partial5.reserve(knn5_dyn_partial_bytes(num_sms, KNN_MAX_K) / 4);
+    }
+    void engine_destroy() {
+        if (d_dyn) cudaFree(d_dyn);
+        for (int i = 0; i < DYN_SLOTS; ++i) {
+            if (ev_plan[i]) cudaEventDestroy(ev_plan[i]);
+            if (ev_knn[i]) cudaEventDestroy(ev_knn[i]);
+        }
+        if (h_ring) cudaFreeHost(h_ring);
+        for (int i = 0; i < 2; ++i) {
+            if (ep[i].d_state) cudaFree(ep[i].d_state);
+            if (ep[i].ev_done) cudaEventDestroy(ep[i].ev_done);
+        }
+        if (ev_span0) cudaEventDestroy(ev_span0);
+        if (ev_span1) cudaEventDestroy(ev_span1);
     }
 
-    // K12 on the frames of the finished stream (lib.rs:284-333); appends one record per frame to verify_results
-    void verify_stream(const std::vector<int32_t>& frame_q0) {
+    // one K8 launch group over whatever part of the current epoch's stream is ready (flush: all of it)
+    void launch_group(bool flush) {
+        const int slot = (int)(launch_seq % DYN_SLOTS);
+        if (launch_seq >= DYN_SLOTS) {   // the descriptor slot is reused: its previous launch must be complete
+            SLIDEO_CUDA(cudaEventSynchronize(ev_knn[slot]));
+            launch_synced = std::max(launch_synced, launch_seq - DYN_SLOTS + 1);
+        }
+        Epoch& e = ep[cur_ep];
+        knn5_plan_launch(e.d_state, d_dyn + slot, nt, num_sms, flush ? 1 : 0, stream);
+        SLIDEO_CUDA(cudaEventRecord(ev_plan[slot], stream));
+        SLIDEO_CUDA(cudaStreamWaitEvent(knn_stream, ev_plan[slot], 0));
+        VoteArgs va{e.q_frame.p, d_page_of.p, e.votes.p, n_pages, cfg.vote_ratio};
+        EventPair t = begin_timing(1, knn_stream);
+        int nl = 0;
+        knn5_launch_dyn(d_dyn + slot, e.q_cap, nt, cfg.knn_k, num_sms, e.desc.p, d_pool5.p, want_keys() ? e.keys.p : nullptr, d_partial5.p,
+                        &va, knn_stream, &nl);
+        end_timing(t, knn_stream);
+        stream_finalize_launch(e.d_state, d_dyn + slot, e.frame_q0.p, e.votes.p, n_pages, e.frame_nkp.p, h_ring, RING - 1, e.seq_base,
+                               nullptr, h_progress, h_flags, knn_stream);
+        SLIDEO_CUDA(cudaEventRecord(ev_knn[slot], knn_stream));
+        ++launch_seq;
+        tm.knn_launches += 1;
+        tm.kernel_launches += nl + 3;
+    }
+
+    void close_epoch() {
+        if (!ep_open) return;
+        launch_group(true);
+        SLIDEO_CUDA(cudaEventRecord(ep[cur_ep].ev_done, knn_stream));
+        ep_open = false;
+    }
+
+    void open_epoch(int w, int h) {
+        if (ep[cur_ep].used) cur_ep ^= 1;
+        Epoch& e = ep[cur_ep];
+        const size_t per_frame = kp_per_frame_cap(w, h);
+        const size_t q_cap = (size_t)EPOCH_FRAMES * per_frame;
+        const int np = std::max(n_pages, 1);
+        const bool grow = q_cap * 32 + 64 > e.desc.cap || (size_t)EPOCH_FRAMES * np > e.votes.cap ||
+                          (want_keys() && q_cap * cfg.knn_k > e.keys.cap) || (cfg.geometric_verification && q_cap + 64 > e.pt.cap);
+        if (e.used) {
+            if (grow) SLIDEO_CUDA(cudaEventSynchronize(e.ev_done));                  // the buffers are about to be reallocated
+            else SLIDEO_CUDA(cudaStreamWaitEvent(stream, e.ev_done, 0));             // K8 of two epochs ago is done with this set
+        }
+        e.desc.reserve(q_cap * 32 + 64);
+        e.q_frame.reserve(q_cap + 64);
+        e.frame_q0.reserve((size_t)EPOCH_FRAMES + 2);
+        e.frame_nkp.reserve((size_t)EPOCH_FRAMES + 1);
+        e.votes.reserve((size_t)EPOCH_FRAMES * np);
+        if (cfg.geometric_verification) e.pt.reserve(q_cap + 64);
+        if (want_keys()) e.keys.reserve(q_cap * cfg.knn_k);
+        SLIDEO_CUDA(cudaMemsetAsync(e.d_state, 0, 24, stream));                      // counters + flags; `pairs` keeps accumulating
+        SLIDEO_CUDA(cudaMemsetAsync(e.frame_q0.p, 0, 4, stream));
+        SLIDEO_CUDA(cudaMemsetAsync(e.votes.p, 0, (size_t)EPOCH_FRAMES * np * 4, stream));
+        e.seq_base = seq_submitted;
+        e.frames = 0;
+        e.q_cap = (int)std::min<size_t>(q_cap, 0x7FFFFFFF);
+        e.used = true;
+        ep_open = true;
+        ep_w = w;
+        ep_h = h;
+    }
+
+    // enqueues uploads (host frames), detection and K8 launches of n frames; returns at once.  keep_dst != nullptr: the frames are
+    // uploaded into that device buffer (and stay there) instead of the staging ring.
+    void enqueue_frames(const uint8_t* frames, bool on_device, int n, int w, int h, int stride, size_t frame_stride, uint8_t* keep_dst) {
+        const int B = cfg.max_batch;
+        const size_t img_bytes = (size_t)3 * w * h;
+        OrbExtractor& ex = extractor(w, h, B);
+        if (!on_device && !keep_dst)
+            for (int i = 0; i < N_STAGING; ++i) {
+                if ((size_t)std::min(B, n) * img_bytes > d_frames[i].cap) {   // growing a staging buffer: nothing may still use it
+                    SLIDEO_CUDA(cudaStreamSynchronize(copy_stream));
+                    SLIDEO_CUDA(cudaStreamSynchronize(stream));
+                    d_frames[i].reserve((size_t)B * img_bytes);
+                }
+            }
+        if (!span_open) {
+            SLIDEO_CUDA(cudaEventRecord(ev_span0, stream));
+            span_open = true;
+        }
+        const int n_batches = cdiv(n, B);
+        const long long b0 = batch_seq;
+        auto issue_copy = [&](int b) {
+            const long long bs = b0 + b;
+            const int buf = (int)(bs % N_STAGING), f0 = b * B, nb = std::min(B, n - f0);
+            uint8_t* dst = keep_dst ? keep_dst + (size_t)f0 * img_bytes : d_frames[buf].p;
+            if (!keep_dst && bs >= N_STAGING) SLIDEO_CUDA(cudaStreamWaitEvent(copy_stream, ev_free[buf], 0));   // detection of batch bs - N_STAGING is done
+            EventPair t = begin_timing(2, copy_stream);
+            upload_images(dst, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride, copy_stream);
+            end_timing(t, copy_stream);
+            SLIDEO_CUDA(cudaEventRecord(ev_copy[buf], copy_stream));
+        };
+        // uploads run N_STAGING batches ahead on the copy stream
+        if (!on_device)
+            for (int b = 0; b < std::min(N_STAGING - 1, n_batches); ++b) issue_copy(b);
+        for (int b = 0; b < n_batches; ++b) {
+            const int f0 = b * B, nb = std::min(B, n - f0);
+            if (!ep_open || ep_w != w || ep_h != h || ep[cur_ep].frames + nb > EPOCH_FRAMES) {
+                close_epoch();
+                open_epoch(w, h);
+            }
+            Epoch& e = ep[cur_ep];
+            const uint8_t* src = frames + (size_t)f0 * frame_stride;
+            int st = stride;
+            size_t fst = frame_stride;
+            const int buf = (int)((b0 + b) % N_STAGING);
+            if (!on_device) {
+                if (b + N_STAGING - 1 < n_batches) issue_copy(b + N_STAGING - 1);
+                SLIDEO_CUDA(cudaStreamWaitEvent(stream, ev_copy[buf], 0));
+                src = keep_dst ? keep_dst + (size_t)f0 * img_bytes : d_frames[buf].p;
+                st = 3 * w;
+                fst = img_bytes;
+            }
+            OrbExtractor::StreamSink sink{e.desc.p, e.q_frame.p, cfg.geometric_verification ? e.pt.p : nullptr, e.frame_q0.p, e.frame_nkp.p,
+                                          e.d_state, e.q_cap, EPOCH_FRAMES};
+            EventPair t = begin_timing(0, stream);
+            int nl = 0;
+            ex.run_stream(src, nb, st, fst, 3, stream, &nl, sink, num_sms);
+            end_timing(t, stream);
+            if (!on_device && !keep_dst) SLIDEO_CUDA(cudaEventRecord(ev_free[buf], stream));
+            tm.kernel_launches += nl;
+            tm.frames += nb;
+            e.frames += nb;
+            seq_submitted += nb;
+            launch_group(false);
+        }
+        if (!on_device) batch_seq += n_batches;
+    }
+
+    // waits until the results of frames [.., seq_end) are in the host ring; flushes the stream when its tail sits in a partial wave
+    void wait_progress(long long seq_end, bool check_flags) {
+        bool flushed = false;
+        while (*h_progress < seq_end) {
+            if (launch_synced < launch_seq) {
+                SLIDEO_CUDA(cudaEventSynchronize(ev_knn[launch_synced % DYN_SLOTS]));
+                ++launch_synced;
+                continue;
+            }
+            if (!ep_open || flushed) {   // everything has run and the frames are still missing: a capacity bit dropped them
+                if (*h_flags) break;
+                throw std::runtime_error("frame stream lost results (progress word behind the submitted frames)");
+            }
+            launch_group(true);
+            flushed = true;
+        }
+        if (!check_flags) return;
+        const int fl = *h_flags;
+        if (fl) {
+            *h_flags = 0;
+            if (fl & 1) throw CapacityError("FAST candidate capacity exceeded on at least one frame");
+            if (fl & 2) throw CapacityError("selected-keypoint capacity exceeded on at least one frame");
+            throw CapacityError("query stream capacity exceeded");
+        }
+    }
+
+    long long submit(const uint8_t* frames, bool on_device, int n, int w, int h, int stride, size_t frame_stride) {
+        if (seq_submitted + n - (tickets.empty() ? seq_submitted : tickets.front().seq0) > RING)
+            throw StateError("too many frames in flight: collect earlier tickets first");
+        Ticket t{next_ticket++, seq_submitted, 0};
+        enqueue_frames(frames, on_device, n, w, h, stride, frame_stride, nullptr);
+        t.seq1 = seq_submitted;
+        tickets.push_back(t);
+        return t.id;
+    }
+
+    int collect(long long id, slideo_b200_frame_result* out, int cap) {
+        size_t i = 0;
+        while (i < tickets.size() && tickets[i].id != id) ++i;
+        if (i == tickets.size()) throw ArgError("unknown or already collected ticket");
+        const Ticket t = tickets[i];
+        const int n = (int)(t.seq1 - t.seq0);
+        if (out && cap < n) throw ArgError("cap smaller than the number of frames of the ticket");
+        wait_progress(t.seq1, true);
+        if (out)
+            for (int f = 0; f < n; ++f) {
+                const int32_t* r = h_ring + (size_t)((t.seq0 + f) & (RING - 1)) * 3;
+                out[f].best_slide = r[0];
+                out[f].votes = r[1];
+                out[f].n_keypoints = r[2];
+            }
+        tickets.erase(tickets.begin() + (long)i);
+        SLIDEO_CUDA(cudaEventRecord(ev_span1, knn_stream));
+        span_closed = true;
+        return n;
+    }
+
+    // drains the frame stream: every ticket stays collectable, all device work of the path is complete afterwards
+    void drain() {
+        if (ep_open && seq_submitted > 0) wait_progress(seq_submitted, false);
+        SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(copy_stream));
+        launch_synced = launch_seq;
+    }
+
+    // the synchronous variant with the reference's decision tail (cfg.geometric_verification) and / or kept k-NN rows: groups of
+    // at most EPOCH_FRAMES frames, each one an epoch of its own that is verified before the next starts
+    void match_verified(const uint8_t* frames, bool on_device, int n, int w, int h, int stride, size_t frame_stride,
+                        slideo_b200_frame_result* out) {
+        const size_t img_bytes = (size_t)3 * w * h;
+        const bool keep_frames = cfg.geometric_verification >= 2 && !on_device;   // the warp gate reads the frames again at the end
+        for (int s0 = 0; s0 < n; s0 += EPOCH_FRAMES) {
+            const int ns = std::min(EPOCH_FRAMES, n - s0);
+            close_epoch();
+            if (keep_frames) {
+                if ((size_t)ns * img_bytes > d_all_frames.cap) drain();
+                d_all_frames.reserve((size_t)ns * img_bytes);
+            }
+            const long long seq0 = seq_submitted;
+            enqueue_frames(frames + (size_t)s0 * frame_stride, on_device, ns, w, h, stride, frame_stride, keep_frames ? d_all_frames.p : nullptr);
+            const int set = cur_ep;
+            close_epoch();
+            wait_progress(seq_submitted, true);
+            SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
+            for (int f = 0; f < ns; ++f) {
+                const int32_t* r = h_ring + (size_t)((seq0 + f) & (RING - 1)) * 3;
+                out[s0 + f].best_slide = r[0];
+                out[s0 + f].votes = r[1];
+                out[s0 + f].n_keypoints = r[2];
+            }
+            Epoch& e = ep[set];
+            std::vector<int32_t> fo((size_t)ns + 1);
+            SLIDEO_CUDA(cudaMemcpy(fo.data(), e.frame_q0.p, ((size_t)ns + 1) * 4, cudaMemcpyDeviceToHost));
+            if (cfg.geometric_verification) {
+                if (keep_frames) {
+                    photo_frames = d_all_frames.p;
+                    photo_w = w; photo_h = h; photo_row_stride = 3 * w; photo_frame_stride = img_bytes;
+                } else {
+                    photo_frames = on_device ? frames + (size_t)s0 * frame_stride : nullptr;
+                    photo_w = w; photo_h = h; photo_row_stride = stride; photo_frame_stride = frame_stride;
+                }
+                verify_epoch(e, ns, fo.back());
+            }
+            if (cfg.keep_matches) {
+                const size_t base = kept_keys.size();
+                kept_keys.resize(base + (size_t)fo.back() * cfg.knn_k);
+                if (fo.back() > 0)
+                    SLIDEO_CUDA(cudaMemcpy(kept_keys.data() + base, e.keys.p, (size_t)fo.back() * cfg.knn_k * 4, cudaMemcpyDeviceToHost));
+                const int32_t q0 = kept_frame_off.back();
+                for (size_t i = 1; i < fo.size(); ++i) kept_frame_off.push_back(q0 + fo[i]);
+            }
+        }
+        SLIDEO_CUDA(cudaEventRecord(ev_span1, knn_stream));
+        span_closed = true;
+    }
+
+    // K12 on the frames of a finished epoch (lib.rs:284-333); appends one record per frame to verify_results
+    void verify_epoch(Epoch& e, int n_frames, int total_q) {
         if (!pool_pts_valid) throw StateError("geometric verification needs the keypoint coordinates of every page (add_page_gray8 / add_page_features)");
-        const size_t F = (size_t)qs_frames;
+        const size_t F = (size_t)n_frames;
         d_v_cand_page.reserve(F * VERIFY_TOP_SLIDES);
         d_v_cand_votes.reserve(F * VERIFY_TOP_SLIDES);
         d_v_rating.reserve(F * VERIFY_TOP_SLIDES);
         d_v_n_cand.reserve(F + 1);
-        d_v_q0.reserve(F + 1);
         d_v_out.reserve(F + 1);
-        d_v_corr.reserve(verify_corr_bytes((long long)qs_total * cfg.knn_k));
-        SLIDEO_CUDA(cudaMemcpyAsync(d_v_q0.p, frame_q0.data(), (F + 1) * 4, cudaMemcpyHostToDevice, knn_stream));
+        d_v_corr.reserve(verify_corr_bytes((long long)total_q * cfg.knn_k));
         VerifyArgs a;
-        a.n_frames = qs_frames; a.n_pages = n_pages; a.k = cfg.knn_k; a.ratio = cfg.vote_ratio;
-        a.d_votes = d_votes.p; a.d_keys = d_keys.p; a.d_frame_q0 = d_v_q0.p; a.d_page_of = d_page_of.p;
-        a.d_frame_pt = d_qs_pt.p; a.d_pool_pt = d_pool_pt.p;
+        a.n_frames = n_frames; a.n_pages = n_pages; a.k = cfg.knn_k; a.ratio = cfg.vote_ratio;
+        a.d_votes = e.votes.p; a.d_keys = e.keys.p; a.d_frame_q0 = e.frame_q0.p; a.d_page_of = d_page_of.p;
+        a.d_frame_pt = e.pt.p; a.d_pool_pt = d_pool_pt.p;
         a.d_cand_page = d_v_cand_page.p; a.d_cand_votes = d_v_cand_votes.p; a.d_n_cand = d_v_n_cand.p; a.d_rating = d_v_rating.p;
         a.d_corr = d_v_corr.p; a.d_out = d_v_out.p;
         const bool photo = cfg.geometric_verification >= 2;
@@ -500,20 +743,20 @@ struct slideo_b200_ctx {
         const size_t base = verify_results.size();
         verify_results.resize(base + F);
         SLIDEO_CUDA(cudaMemcpyAsync(verify_results.data() + base, d_v_out.p, F * sizeof(VerifyRecord), cudaMemcpyDeviceToHost, knn_stream));
-        if (photo) photometric_stream(a, base);
+        if (photo) photometric_epoch(a, n_frames, base);
         SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
     }
 
-    // K14 on the survivors of the finished stream (lib.rs:335-389); appends one decision per frame
-    void photometric_stream(const VerifyArgs& va, size_t base) {
-        if (!page_geom_ok || h_page_small.empty())
+    // K14 on the survivors of a finished epoch (lib.rs:335-389); appends one decision per frame
+    void photometric_epoch(const VerifyArgs& va, int n_frames, size_t base) {
+        if (!page_geom_ok || !page_small_ready)
             throw StateError("the warp + similarity gate needs every page as an image (add_page_gray8) and one page size");
         if (!photo_frames) throw StateError("frames are not resident for the warp + similarity gate");
-        const size_t F = (size_t)qs_frames;
+        const size_t F = (size_t)n_frames;
         d_v_refined.reserve(F * VERIFY_TOP_RATED * 4);
         d_v_sumsq.reserve(F * VERIFY_TOP_RATED);
         PhotoArgs p;
-        p.n_frames = qs_frames; p.k = cfg.knn_k;
+        p.n_frames = n_frames; p.k = cfg.knn_k;
         p.d_records = d_v_out.p; p.d_survivor_cand = d_v_surv_cand.p; p.d_best_it = d_v_best_it.p; p.d_cand_votes = va.d_cand_votes;
         p.d_corr = va.d_corr; p.d_frame_q0 = va.d_frame_q0; p.d_frame_pt = va.d_frame_pt; p.d_pool_pt = va.d_pool_pt;
         p.d_frames = photo_frames; p.frame_w = photo_w; p.frame_h = photo_h; p.frame_stride_row = photo_row_stride;
@@ -587,6 +830,7 @@ struct slideo_b200_ctx {
         if (cfg.geometric_verification >= 2 && page_geom_ok && !h_page_small.empty()) {
             d_page_small.reserve(h_page_small.size());
             SLIDEO_CUDA(cudaMemcpyAsync(d_page_small.p, h_page_small.data(), h_page_small.size(), cudaMemcpyHostToDevice, stream));
+            page_small_ready = true;
         }
         pool_pts_valid = pool_pts_valid && h_pool_pt.size() == (size_t)nt * 2;
         if (pool_pts_valid && !pts_received) {
@@ -594,9 +838,9 @@ struct slideo_b200_ctx {
             if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_pool_pt.p, h_pool_pt.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, stream));
         }
         if (cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) {
-            d_pool48.reserve(knn_pool_expanded_bytes(nt) + 64);
-            knn_pool_expand_launch(d_pool.p, nt, d_pool48.p, stream);
-            tm.kernel_launches += nt > 0 ? 1 : 0;
+            d_pool5.reserve(knn5_pool_bytes(std::max(nt, 1)) + 64);
+            knn5_pool_prepare_launch(d_pool.p, nt, d_pool5.p, stream);
+            tm.kernel_launches += 1;
         }
         SLIDEO_CUDA(cudaStreamSynchronize(stream));
     }
@@ -694,6 +938,7 @@ int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_
         arg(cfg->vote_ratio >= 1.0f && cfg->vote_ratio < 16.f, "vote_ratio out of range");
         arg(cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256 || cfg->descriptor_kind == SLIDEO_B200_DESC_SIFT128,
             "unknown descriptor_kind");
+        arg(cfg->knn_impl == 0 || cfg->knn_impl == 4 || cfg->knn_impl == 5, "knn_impl must be 0, 4 or 5");
         if (cfg->descriptor_kind == SLIDEO_B200_DESC_SIFT128 && cfg->geometric_verification)
             throw NotImplError("geometric verification is implemented for the ORB256 path only");
         int n_dev = 0;
@@ -722,6 +967,7 @@ int32_t slideo_b200_create(const slideo_b200_config* cfg, slideo_b200_ctx** out_
             SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
             SLIDEO_CUDA(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
         }
+        if (cfg->descriptor_kind == SLIDEO_B200_DESC_ORB256) c->engine_init();
         *out_ctx = c.release();
     });
 }
@@ -798,11 +1044,11 @@ int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int3
                 ctx->page_geom_ok = false;
             } else {
                 const size_t sb = (size_t)ctx->page_area.dw * ctx->page_area.dh;
-                ctx->d_small.reserve(sb);
-                area_small_launch(ctx->page_area, ctx->d_img.p, 1, w, (size_t)w * h, ctx->d_small.p, ctx->stream, 1);
+                ctx->d_page_small_tmp.reserve(sb);
+                area_small_launch(ctx->page_area, ctx->d_img.p, 1, w, (size_t)w * h, ctx->d_page_small_tmp.p, ctx->stream, 1);
                 const size_t b0 = ctx->h_page_small.size();
                 ctx->h_page_small.resize(b0 + sb);
-                SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_page_small.data() + b0, ctx->d_small.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+                SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_page_small.data() + b0, ctx->d_page_small_tmp.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
                 SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
                 ctx->tm.kernel_launches += 1;
             }
@@ -987,6 +1233,41 @@ int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx) {
 }
 
 // ---- the per-frame hot path -----------------------------------------------------------------------------------
+namespace {
+
+// shared body of the synchronous frame entry points: submit + collect on the device-driven stream (ORB256), or the K11 -> K10
+// loop (SIFT128)
+void match_frames_common(slideo_b200_ctx* ctx, const uint8_t* frames, bool on_device, int n, int w, int h, int stride, size_t frame_stride,
+                         slideo_b200_frame_result* out) {
+    ctx->reset_kept();
+    if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_SIFT128) {
+        ctx->ensure_host_results((size_t)n);
+        EventPair t_total = ctx->begin_timing(4, ctx->stream);
+        ctx->match_frames_sift(frames, on_device, n, w, h, stride, frame_stride);
+        ctx->end_timing(t_total, ctx->stream);
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->collect_timings();
+        for (int i = 0; i < n; ++i) {
+            out[i].best_slide = ctx->h_results[3 * i];
+            out[i].votes = ctx->h_results[3 * i + 1];
+            out[i].n_keypoints = ctx->h_results[3 * i + 2];
+        }
+        return;
+    }
+    if (ctx->cfg.geometric_verification || ctx->cfg.keep_matches) {
+        ctx->match_verified(frames, on_device, n, w, h, stride, frame_stride, out);
+        return;
+    }
+    for (int f0 = 0; f0 < n; f0 += slideo_b200_ctx::RING / 2) {   // (the host result ring bounds one ticket)
+        const int nn = std::min(slideo_b200_ctx::RING / 2, n - f0);
+        const long long id = ctx->submit(frames + (size_t)f0 * frame_stride, on_device, nn, w, h, stride, frame_stride);
+        ctx->collect(id, out + f0, nn);
+    }
+}
+
+}  // namespace
+
 int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h,
                                       int32_t stride, size_t frame_stride, slideo_b200_frame_result* out) {
     REQUIRE_CTX(ctx);
@@ -997,73 +1278,7 @@ int32_t slideo_b200_match_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
         arg(frames && out, "frames/out must not be NULL");
         arg(stride >= 3 * w, "stride < 3*w");
         arg(frame_stride >= (size_t)stride * (h - 1) + (size_t)3 * w, "frame_stride too small");
-        ctx->reset_kept();
-        if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_SIFT128) {
-            ctx->ensure_host_results((size_t)n);
-            EventPair t_total = ctx->begin_timing(4, ctx->stream);
-            ctx->match_frames_sift(frames, false, n, w, h, stride, frame_stride);
-            ctx->end_timing(t_total, ctx->stream);
-            SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
-            SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-            ctx->collect_timings();
-            for (int i = 0; i < n; ++i) {
-                out[i].best_slide = ctx->h_results[3 * i];
-                out[i].votes = ctx->h_results[3 * i + 1];
-                out[i].n_keypoints = ctx->h_results[3 * i + 2];
-            }
-            return;
-        }
-        EventPair t_total = ctx->begin_timing(4, ctx->stream);
-        const int B = ctx->cfg.max_batch;
-        const size_t img_bytes = (size_t)3 * w * h;
-        constexpr int NBUF = slideo_b200_ctx::N_STAGING;
-        for (int i = 0; i < NBUF; ++i) ctx->d_frames[i].reserve((size_t)std::min(B, n) * img_bytes);
-        ctx->ensure_host_results((size_t)n);
-        for (int s0 = 0; s0 < n; s0 += slideo_b200_ctx::SUPER_BATCH) {
-            const int ns = std::min(slideo_b200_ctx::SUPER_BATCH, n - s0);
-            const int n_batches = cdiv(ns, B);
-            ctx->stream_begin(ns, w, h);
-            const bool keep_frames = ctx->cfg.geometric_verification >= 2;   // the warp gate reads the frames again at the end
-            if (keep_frames) {
-                ctx->d_all_frames.reserve((size_t)ns * img_bytes);
-                ctx->photo_frames = ctx->d_all_frames.p;
-                ctx->photo_w = w; ctx->photo_h = h; ctx->photo_row_stride = 3 * w; ctx->photo_frame_stride = img_bytes;
-            }
-            auto batch_dst = [&](int b) -> uint8_t* {
-                return keep_frames ? ctx->d_all_frames.p + (size_t)b * B * img_bytes : ctx->d_frames[b % NBUF].p;
-            };
-            auto issue_copy = [&](int b) {
-                const int buf = b % NBUF, f0 = s0 + b * B, nb = std::min(B, s0 + ns - f0);
-                if (!keep_frames) SLIDEO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));  // detection of batch b - NBUF is done
-                EventPair t = ctx->begin_timing(2, ctx->copy_stream);
-                ctx->upload_images(batch_dst(b), frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride,
-                                   ctx->copy_stream);
-                ctx->end_timing(t, ctx->copy_stream);
-                SLIDEO_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
-            };
-            // uploads run NBUF batches ahead on the copy stream; K8 chunks are interleaved with detection on the compute
-            // stream, so the DMA engine keeps filling staging buffers while K8 owns the SMs
-            for (int b = 0; b < std::min(NBUF, n_batches); ++b) issue_copy(b);
-            for (int b = 0; b < n_batches; ++b) {
-                const int buf = b % NBUF, f0 = s0 + b * B, nb = std::min(B, s0 + ns - f0);
-                SLIDEO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
-                ctx->stream_detect(batch_dst(b), nb, w, h, 3 * w, img_bytes);
-                SLIDEO_CUDA(cudaEventRecord(ctx->ev_free[buf], ctx->stream));
-                if (b + NBUF < n_batches) issue_copy(b + NBUF);
-                ctx->stream_match_ready(false);
-            }
-            ctx->stream_finish(ctx->h_results + (size_t)s0 * 3);
-        }
-        ctx->end_timing(t_total, ctx->knn_stream);
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->knn_stream));
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-        ctx->collect_timings();
-        for (int i = 0; i < n; ++i) {
-            out[i].best_slide = ctx->h_results[3 * i];
-            out[i].votes = ctx->h_results[3 * i + 1];
-            out[i].n_keypoints = ctx->h_results[3 * i + 2];
-        }
+        match_frames_common(ctx, frames, false, n, w, h, stride, frame_stride, out);
     });
 }
 
@@ -1076,45 +1291,48 @@ int32_t slideo_b200_match_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d
         if (n == 0) return;
         arg(d_frames && out, "d_frames/out must not be NULL");
         arg(stride >= 3 * w, "stride < 3*w");
-        ctx->reset_kept();
-        if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_SIFT128) {
-            ctx->ensure_host_results((size_t)n);
-            EventPair t_total = ctx->begin_timing(4, ctx->stream);
-            ctx->match_frames_sift((const uint8_t*)d_frames, true, n, w, h, stride, frame_stride);
-            ctx->end_timing(t_total, ctx->stream);
-            SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
-            ctx->collect_timings();
-            for (int i = 0; i < n; ++i) {
-                out[i].best_slide = ctx->h_results[3 * i];
-                out[i].votes = ctx->h_results[3 * i + 1];
-                out[i].n_keypoints = ctx->h_results[3 * i + 2];
-            }
-            return;
-        }
-        EventPair t_total = ctx->begin_timing(4, ctx->stream);
-        const int B = ctx->cfg.max_batch;
-        ctx->ensure_host_results((size_t)n);
-        for (int s0 = 0; s0 < n; s0 += slideo_b200_ctx::SUPER_BATCH) {
-            const int ns = std::min(slideo_b200_ctx::SUPER_BATCH, n - s0);
-            ctx->stream_begin(ns, w, h);
-            ctx->photo_frames = (const uint8_t*)d_frames + (size_t)s0 * frame_stride;
-            ctx->photo_w = w; ctx->photo_h = h; ctx->photo_row_stride = stride; ctx->photo_frame_stride = frame_stride;
-            for (int f0 = s0; f0 < s0 + ns; f0 += B) {
-                const int nb = std::min(B, s0 + ns - f0);
-                ctx->stream_detect((const uint8_t*)d_frames + (size_t)f0 * frame_stride, nb, w, h, stride, frame_stride);
-                ctx->stream_match_ready(false);
-            }
-            ctx->stream_finish(ctx->h_results + (size_t)s0 * 3);
-        }
-        ctx->end_timing(t_total, ctx->knn_stream);
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->knn_stream));
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->collect_timings();
-        for (int i = 0; i < n; ++i) {
-            out[i].best_slide = ctx->h_results[3 * i];
-            out[i].votes = ctx->h_results[3 * i + 1];
-            out[i].n_keypoints = ctx->h_results[3 * i + 2];
-        }
+        match_frames_common(ctx, (const uint8_t*)d_frames, true, n, w, h, stride, frame_stride, out);
+    });
+}
+
+// ---- the same path, asynchronous: submit returns as soon as everything is enqueued, collect waits for one ticket ---------
+int32_t slideo_b200_submit_frames_bgr8(slideo_b200_ctx* ctx, const uint8_t* frames, int32_t n, int32_t w, int32_t h, int32_t stride,
+                                       size_t frame_stride, int64_t* out_ticket) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_pool();
+        ctx->require_orb();
+        arg(n >= 1 && n <= slideo_b200_ctx::RING / 2, "n must be in 1..32768");
+        arg(frames && out_ticket, "frames/out_ticket must not be NULL");
+        arg(stride >= 3 * w, "stride < 3*w");
+        arg(frame_stride >= (size_t)stride * (h - 1) + (size_t)3 * w, "frame_stride too small");
+        if (ctx->cfg.geometric_verification || ctx->cfg.keep_matches)
+            throw NotImplError("submit/collect carries the vote results only: use match_frames_* for the verification tail / kept matches");
+        *out_ticket = ctx->submit(frames, false, n, w, h, stride, frame_stride);
+    });
+}
+
+int32_t slideo_b200_submit_frames_bgr8_device(slideo_b200_ctx* ctx, const void* d_frames, int32_t n, int32_t w, int32_t h, int32_t stride,
+                                              size_t frame_stride, int64_t* out_ticket) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_pool();
+        ctx->require_orb();
+        arg(n >= 1 && n <= slideo_b200_ctx::RING / 2, "n must be in 1..32768");
+        arg(d_frames && out_ticket, "d_frames/out_ticket must not be NULL");
+        arg(stride >= 3 * w, "stride < 3*w");
+        if (ctx->cfg.geometric_verification || ctx->cfg.keep_matches)
+            throw NotImplError("submit/collect carries the vote results only: use match_frames_* for the verification tail / kept matches");
+        *out_ticket = ctx->submit((const uint8_t*)d_frames, true, n, w, h, stride, frame_stride);
+    });
+}
+
+int32_t slideo_b200_collect(slideo_b200_ctx* ctx, int64_t ticket, slideo_b200_frame_result* out, int32_t cap, int32_t* out_n) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->require_orb();
+        const int n = ctx->collect(ticket, out, cap);
+        if (out_n) *out_n = n;
     });
 }
 
@@ -1290,7 +1508,7 @@ void mark_changed_impl(slideo_b200_ctx* ctx, int n, int w, int h, bool reset, ui
     if (reset) ctx->have_prev_small = false;
     const int B = ctx->cfg.max_batch;
     const size_t small_bytes = (size_t)ctx->area.dw * ctx->area.dh * 3;
-    ctx->d_small.reserve((size_t)(std::min(B, n) + 1) * small_bytes);
+    ctx->d_small.reserve((size_t)(B + 1) * small_bytes);   // fixed per geometry: slot 0 (the chain state) must survive from call to call
     ctx->d_sumsq.reserve((size_t)B + 1);
     std::vector<unsigned long long> h_ss((size_t)B + 1);
     const int p = ctx->area.dw * ctx->area.dh;
@@ -1483,15 +1701,25 @@ int32_t slideo_b200_bf_knn_hamming_device(slideo_b200_ctx* ctx, const void* d_q,
         if (nq == 0) return;
         arg(d_q && d_keys_out && (d_t || nt == 0), "NULL buffer");
         arg(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0, "device buffers must be 16-byte aligned");
-        KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
-        ctx->d_scratch.reserve(plan.scratch_bytes / 4);
-        if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
-        ctx->d_t48.reserve(plan.pool_bytes + 64);
-        knn_pool_expand_launch(d_t, nt, ctx->d_t48.p, ctx->stream);   // once per pool in the frame path; per call here
-        EventPair t = ctx->begin_timing(1, ctx->stream);
         int nl = 0;
-        knn_hamming_launch(plan, d_q, ctx->d_t48.p, (uint32_t*)d_keys_out, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
-        ctx->end_timing(t, ctx->stream);
+        if (ctx->cfg.knn_impl == 4) {   // the XOR / POPC kernel of round 1, kept as an independent implementation
+            KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
+            ctx->d_scratch.reserve(plan.scratch_bytes / 4);
+            if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
+            ctx->d_t48.reserve(plan.pool_bytes + 64);
+            knn_pool_expand_launch(d_t, nt, ctx->d_t48.p, ctx->stream);
+            EventPair t = ctx->begin_timing(1, ctx->stream);
+            knn_hamming_launch(plan, d_q, ctx->d_t48.p, (uint32_t*)d_keys_out, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
+            ctx->end_timing(t, ctx->stream);
+        } else {
+            Knn5Plan plan = knn5_plan(nq, nt, k, ctx->num_sms);
+            if (plan.partial_bytes) ctx->d_partial5.reserve(plan.partial_bytes / 4);
+            ctx->d_t5.reserve(knn5_pool_bytes(std::max(nt, 1)) + 64);
+            knn5_pool_prepare_launch(d_t, nt, ctx->d_t5.p, ctx->stream);   // once per pool in the frame path; per call here
+            EventPair t = ctx->begin_timing(1, ctx->stream);
+            knn5_launch(plan, d_q, ctx->d_t5.p, (uint32_t*)d_keys_out, ctx->d_partial5.p, nullptr, ctx->stream, &nl);
+            ctx->end_timing(t, ctx->stream);
+        }
         ctx->tm.knn_launches += nl;
         ctx->tm.kernel_launches += nl;
         ctx->tm.knn_pairs += (int64_t)nq * nt;
@@ -1514,15 +1742,25 @@ int32_t slideo_b200_bf_knn_hamming(slideo_b200_ctx* ctx, const uint8_t* q, int32
         ctx->d_dist.reserve((size_t)nq * k);
         SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
         if (nt) SLIDEO_CUDA(cudaMemcpyAsync(ctx->d_t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, ctx->stream));
-        KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
-        ctx->d_scratch.reserve(plan.scratch_bytes / 4);
-        if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
-        ctx->d_t48.reserve(plan.pool_bytes + 64);
-        knn_pool_expand_launch(ctx->d_t.p, nt, ctx->d_t48.p, ctx->stream);
-        EventPair tk = ctx->begin_timing(1, ctx->stream);
         int nl = 0;
-        knn_hamming_launch(plan, ctx->d_q.p, ctx->d_t48.p, ctx->d_keys.p, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
-        ctx->end_timing(tk, ctx->stream);
+        if (ctx->cfg.knn_impl == 4) {
+            KnnPlan plan = knn_hamming_plan(nq, nt, k, ctx->num_sms);
+            ctx->d_scratch.reserve(plan.scratch_bytes / 4);
+            if (plan.partial_bytes) ctx->d_partial.reserve(plan.partial_bytes / 4);
+            ctx->d_t48.reserve(plan.pool_bytes + 64);
+            knn_pool_expand_launch(ctx->d_t.p, nt, ctx->d_t48.p, ctx->stream);
+            EventPair tk = ctx->begin_timing(1, ctx->stream);
+            knn_hamming_launch(plan, ctx->d_q.p, ctx->d_t48.p, ctx->d_keys.p, ctx->d_scratch.p, ctx->d_partial.p, nullptr, ctx->stream, &nl);
+            ctx->end_timing(tk, ctx->stream);
+        } else {
+            Knn5Plan plan = knn5_plan(nq, nt, k, ctx->num_sms);
+            if (plan.partial_bytes) ctx->d_partial5.reserve(plan.partial_bytes / 4);
+            ctx->d_t5.reserve(knn5_pool_bytes(std::max(nt, 1)) + 64);
+            knn5_pool_prepare_launch(ctx->d_t.p, nt, ctx->d_t5.p, ctx->stream);
+            EventPair tk = ctx->begin_timing(1, ctx->stream);
+            knn5_launch(plan, ctx->d_q.p, ctx->d_t5.p, ctx->d_keys.p, ctx->d_partial5.p, nullptr, ctx->stream, &nl);
+            ctx->end_timing(tk, ctx->stream);
+        }
         keys_to_idx_dist_launch(ctx->d_keys.p, (size_t)nq * k, ctx->d_idx.p, ctx->d_dist.p, ctx->stream);
         ctx->tm.knn_launches += nl;
         ctx->tm.kernel_launches += nl + 1;
@@ -1615,10 +1853,24 @@ int32_t slideo_b200_host_free(void* p) {
 int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, int32_t reset) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->knn_stream));
+        ctx->drain();
         ctx->collect_timings();
+        if (ctx->d_dyn) {   // pairs handed to K8 by the plan kernels live on the device
+            unsigned long long pairs = 0;
+            for (int i = 0; i < 2; ++i) {
+                KnnStream st;
+                SLIDEO_CUDA(cudaMemcpy(&st, ctx->ep[i].d_state, sizeof st, cudaMemcpyDeviceToHost));
+                pairs += st.pairs;
+            }
+            ctx->tm.knn_pairs += (int64_t)(pairs - ctx->pairs_seen);
+            ctx->pairs_seen = pairs;
+            if (ctx->span_open && ctx->span_closed) {
+                float ms = 0.f;
+                SLIDEO_CUDA(cudaEventElapsedTime(&ms, ctx->ev_span0, ctx->ev_span1));
+                ctx->tm.ms_total += ms;
+            }
+            ctx->span_open = ctx->span_closed = false;
+        }
         if (out) *out = ctx->tm;
         if (reset) ctx->tm = slideo_b200_timings{};
     });
@@ -1636,8 +1888,7 @@ int32_t slideo_b200_microbench(slideo_b200_ctx* ctx, int32_t which, double* out_
 int32_t slideo_b200_synchronize(slideo_b200_ctx* ctx) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->drain();
         ctx->collect_timings();
     });
 }

@@ -75,4 +75,49 @@ void vote_argmax_launch(const int32_t* d_votes, int n_frames, int n_pages, const
 void keys_to_idx_dist_launch(const uint32_t* d_keys, size_t n, int32_t* d_idx, int32_t* d_dist, cudaStream_t stream);
 double microbench_run(int which, int num_sms, cudaStream_t stream);
 
+// ---- K8 v5: bit-sliced Hamming k-NN (knn_hamming5.cu) ---------------------------------------------------------------
+// The pool lives as "slabs" of 4096 rows: 256 bit rows + 9 planes of (256 - popcount) + a valid mask, 512 B each.
+constexpr int KNN5_TILE = 128;            // queries per work item (one CTA of 16 warps, 8 queries per warp)
+constexpr int KNN5_SLAB_ROWS = 4096;
+constexpr int KNN5_SLAB_BYTES = 266 * 512;
+inline int knn5_slabs(int nt) { return (nt + KNN5_SLAB_ROWS - 1) / KNN5_SLAB_ROWS; }
+
+// Device-side state of a query stream (the frame path): detection appends, plan kernels hand ranges to K8, finalize kernels
+// turn finished frames into results.  All counters are per epoch (see api.cu).
+struct KnnStream {
+    int q_write;               // queries appended by detection so far
+    int q_matched;             // queries handed to K8 so far
+    int f_write;               // frames appended so far
+    int f_done;                // frames whose results have been written
+    int flags;                 // sticky capacity bits: 1 FAST candidates, 2 selected keypoints, 4 query stream, 8 frame table
+    int pad;
+    unsigned long long pairs;  // descriptor pairs handed to K8 (accounting)
+};
+// One K8 launch over a range of the stream, written by knn5_plan_kernel, read by K8 / merge / finalize.
+struct KnnDyn {
+    int q0, nq, n_tiles, splits;
+    int f_limit;               // frames appended when the range was cut
+    int pad[3];
+};
+
+struct Knn5Plan {
+    int nq = 0, nt = 0, k = 0, n_tiles = 0, n_slabs = 0, splits = 1, grid = 0;
+    size_t partial_bytes = 0;  // per-split partial rows (0 when no tile is split)
+};
+size_t knn5_pool_bytes(int nt);
+void knn5_pool_prepare_launch(const void* d_pool32, int nt, void* d_slabs, cudaStream_t stream);
+Knn5Plan knn5_plan(int nq, int nt, int k, int num_sms);
+void knn5_launch(const Knn5Plan& plan, const void* d_q, const void* d_slabs, uint32_t* d_keys_out, uint32_t* d_partial,
+                 const VoteArgs* vote, cudaStream_t stream, int* launches);
+// Device-driven variant: the range comes from *d_dyn (filled by knn5_plan_launch earlier in stream order); the bases are the
+// bases of the whole stream.  flush == 0: whole waves of tiles only, the remainder rides with the next launch.
+size_t knn5_dyn_partial_bytes(int num_sms, int k);
+void knn5_plan_launch(KnnStream* d_state, KnnDyn* d_dyn, int nt, int num_sms, int flush, cudaStream_t stream);
+void knn5_launch_dyn(const KnnDyn* d_dyn, int nq_max, int nt, int k, int num_sms, const void* d_q_base, const void* d_slabs,
+                     uint32_t* d_keys_base, uint32_t* d_partial, const VoteArgs* vote_base, cudaStream_t stream, int* launches);
+// frames of the stream whose queries are all matched -> (best_slide, votes, n_keypoints) rows in a host-mapped ring + progress word
+void stream_finalize_launch(KnnStream* d_state, const KnnDyn* d_dyn, const int32_t* d_frame_q0, const int32_t* d_votes, int n_pages,
+                            const int32_t* d_frame_nkp, int32_t* h_ring, int ring_mask, long long seq_base, int32_t* d_results,
+                            volatile long long* h_progress, volatile int* h_flags, cudaStream_t stream);
+
 }  // namespace slideo

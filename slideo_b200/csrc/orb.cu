@@ -16,6 +16,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+
 namespace slideo {
 
 namespace {
@@ -318,11 +320,16 @@ __global__ void __launch_bounds__(256) select_kernel(const Geo* __restrict__ gp,
     if (threadIdx.x == 0) sel_cnt[img * g.nlevels + l] = m;
 }
 
-// exclusive scan of sel_cnt over (image, level) -> kp_off[n*nlevels + 1], frame_off[n + 1], frame_nkp[n]
+// exclusive scan of sel_cnt over (image, level) -> kp_off[n*nlevels + 1] (batch-local), frame_off[n + 1], frame_nkp[n], and the
+// batch header info[] = {total keypoints, first query index of the batch in the stream, first frame index, flags}.
+// Stream mode (st != nullptr): the batch is appended to a query stream whose counters live on the device (KnnStream), so the
+// host never needs the counts: frame_q0 / frame_nkp of the stream are extended here and the counters advanced.
 __global__ void __launch_bounds__(256) scan_kernel(const int32_t* __restrict__ sel_cnt, int n_img, int nlevels,
                                                    int32_t* __restrict__ kp_off, int32_t* __restrict__ frame_off,
                                                    int32_t* __restrict__ frame_nkp, const int32_t* __restrict__ flags,
-                                                   int32_t* __restrict__ h_out, int32_t* __restrict__ frame_nkp2) {
+                                                   int32_t* __restrict__ info, int32_t* __restrict__ h_out, KnnStream* st,
+                                                   int32_t* __restrict__ s_frame_q0, int32_t* __restrict__ s_frame_nkp, int q_cap,
+                                                   int f_cap, int kp_cap) {
     __shared__ int s_tot[1024];
     const int tid = threadIdx.x;
     for (int f = tid; f < n_img; f += blockDim.x) {
@@ -330,23 +337,50 @@ __global__ void __launch_bounds__(256) scan_kernel(const int32_t* __restrict__ s
         for (int l = 0; l < nlevels; ++l) t += sel_cnt[f * nlevels + l];
         s_tot[f] = t;
         frame_nkp[f] = t;
-        if (frame_nkp2) frame_nkp2[f] = t;
     }
     __syncthreads();
     if (tid == 0) {
+        const int base_q = st ? st->q_write : 0, base_f = st ? st->f_write : 0;
         int acc = 0;
         for (int f = 0; f < n_img; ++f) {
             frame_off[f] = acc;
-            h_out[2 + f] = acc;
+            if (h_out) h_out[2 + f] = acc;
             int a2 = acc;
             for (int l = 0; l < nlevels; ++l) { kp_off[f * nlevels + l] = a2; a2 += sel_cnt[f * nlevels + l]; }
             acc += s_tot[f];
         }
         frame_off[n_img] = acc;
         kp_off[n_img * nlevels] = acc;
-        h_out[2 + n_img] = acc;
-        h_out[0] = acc;
-        h_out[1] = flags[0];
+        int fl = flags[0];
+        if (acc > kp_cap) fl |= 4;
+        if (st) {
+            if ((long long)base_q + acc > q_cap) fl |= 4;
+            if (base_f + n_img > f_cap) fl |= 8;
+        }
+        if (fl & 12) acc = 0;                          // never read / write past a buffer: the batch is dropped and the flag fails the call
+        if (st) {
+            if (!(fl & 8)) {
+                int a3 = base_q;
+                for (int f = 0; f < n_img; ++f) {
+                    const int t = (fl & 4) ? 0 : s_tot[f];
+                    a3 += t;
+                    s_frame_q0[base_f + f + 1] = a3;
+                    s_frame_nkp[base_f + f] = (fl & 4) ? -1 : t;
+                }
+                st->f_write = base_f + n_img;
+            }
+            st->q_write = base_q + acc;
+            st->flags |= fl;
+        }
+        info[0] = acc;
+        info[1] = base_q;
+        info[2] = base_f;
+        info[3] = fl;
+        if (h_out) {
+            h_out[2 + n_img] = acc;
+            h_out[0] = acc;
+            h_out[1] = fl;
+        }
     }
 }
 
@@ -355,10 +389,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp
                                                       const int32_t* __restrict__ sel_cnt,
                                                       const int32_t* __restrict__ kp_off, uint32_t* __restrict__ kp_src,
                                                       int32_t* __restrict__ q_frame, int32_t* __restrict__ kp_i,
-                                                      size_t kp_cap, int32_t* __restrict__ q_frame2, int frame_base, size_t cap2) {
+                                                      size_t kp_cap, const int32_t* __restrict__ info, int32_t* __restrict__ s_q_frame) {
     const Geo& g = *gp;
     const int l = blockIdx.x, img = blockIdx.y;
     const OrbLevelGeom L = g.lv[l];
+    if (info[0] == 0) return;                          // empty batch, or a batch dropped by a capacity flag
+    const int base_q = info[1], base_f = info[2];
     const int m = sel_cnt[img * g.nlevels + l], off = kp_off[img * g.nlevels + l];
     const uint32_t* s = sel + (size_t)img * g.sel_img_words + L.sel_off;
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
@@ -368,7 +404,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp
         kp_src[2 * o] = v;
         kp_src[2 * o + 1] = ((uint32_t)img << 8) | (uint32_t)l;
         q_frame[o] = img;
-        if (q_frame2 && o < cap2) q_frame2[o] = frame_base + img;
+        if (s_q_frame) s_q_frame[(size_t)base_q + o] = base_f + img;
         reinterpret_cast<int4*>(kp_i)[o] = make_int4((int)(v & 0xFFF), (int)((v >> 12) & 0xFFF), l, (int)(v >> 24));
     }
 }
@@ -502,73 +538,105 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// SAFE: the disc of the moments (radius half, read in whole words: half + 3) and the reach of the steered pattern (<= half*sqrt(2)
+// + 1) stay inside the level for every keypoint runByImageBorder(edge) keeps, so no coordinate is ever reflected.  True for the
+// reference's configuration (edge 62, patch 62).  The moments then run on packed bytes: a row of the disc is 16-17 aligned words,
+// sum(u * I) over a word = u0 * dp4a(w, 0x01010101) + dp4a(w, 0x03020100), the disc boundary is a byte mask on the two end words.
+template <bool SAFE>
 __global__ void __launch_bounds__(256) describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
-                                                       const Geo* __restrict__ gp, const uint32_t* __restrict__ kp_src, int total,
-                                                       const int8_t* __restrict__ pattern, float* __restrict__ kp_f,
-                                                       uint8_t* __restrict__ desc, float2* __restrict__ pt_out) {
+                                                       const Geo* __restrict__ gp, const uint32_t* __restrict__ kp_src,
+                                                       const int32_t* __restrict__ info, const int8_t* __restrict__ pattern,
+                                                       float* __restrict__ kp_f, uint8_t* __restrict__ desc, float2* __restrict__ pt_out,
+                                                       int stream_mode) {
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= total) return;
-    const uint32_t v = kp_src[2 * k], fl = kp_src[2 * k + 1];
-    const int x = v & 0xFFF, y = (v >> 12) & 0xFFF, l = fl & 0xFF, img = fl >> 8;
+    const int total = info[0];
+    const size_t out_base = stream_mode ? (size_t)info[1] : 0;   // descriptors / points go to the stream position of the batch
     const Geo& g = *gp;
-    const OrbLevelGeom L = g.lv[l];
-    const uint8_t* im = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
     const int half = g.half;
-
-    // K5: intensity centroid over the disc of radius `half` on the unblurred level
-    int m10 = 0, m01 = 0;
-    for (int vv = -half; vv <= half; ++vv) {
-        const int du = g.umax[vv < 0 ? -vv : vv];
-        const int yy = reflect101(y + vv, L.h);
-        const uint8_t* row = im + (size_t)yy * L.pitch;
-        for (int u = -half + lane; u <= half; u += 32) {
-            if (u >= -du && u <= du) {
-                const int val = row[reflect101(x + u, L.w)];
-                m10 += u * val;
-                m01 += vv * val;
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(FULL, m10, o);
-        m01 += __shfl_xor_sync(FULL, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-    const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
-    if (lane == 0) {
-        reinterpret_cast<float4*>(kp_f)[k] = make_float4(ptx, pty, __fmul_rn((float)g.patch, L.scale), angle);
-        if (pt_out) pt_out[k] = make_float2(ptx, pty);
-    }
-
-    // K7: steered BRIEF on the blurred level (pattern = cv::RNG(0x34985739) points)
-    const uint8_t* bl = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
-    const int cx = __float2int_rn(__fmul_rn(ptx, L.inv_scale)), cy = __float2int_rn(__fmul_rn(pty, L.inv_scale));
-    const float th = __fmul_rn(angle, __uint_as_float(0x3c8efa35u));  // (float)(CV_PI / 180)
-    const float a = (float)cos((double)th), b = (float)sin((double)th);
     const uint4* pat4 = reinterpret_cast<const uint4*>(pattern) + lane * 2;
     const uint4 w0 = __ldg(pat4), w1 = __ldg(pat4 + 1);
     const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    uint32_t byte = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        // word j holds the two points of bit j: (x0, y0, x1, y1) as int8
-        // conversions without the quarter-rate XU pipe: int8 -> fp32 as (byte ^ 0x80) | 0x4B000000 = 2^23 + 128 + value, exactly;
-        // cvRound as the low mantissa bits of v + 1.5 * 2^23 (round-half-even, |v| < 2^22)
-        const uint32_t wv = words[j] ^ 0x80808080u;
-        int val[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const float px = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7540 + 2 * t)), 8388736.f);
-            const float py = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7541 + 2 * t)), 8388736.f);
-            const int ix = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.f)) - 0x4B400000;
-            const int iy = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.f)) - 0x4B400000;
-            val[t] = bl[(size_t)reflect101(cy + iy, L.h) * L.pitch + reflect101(cx + ix, L.w)];
+    for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < total; k += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t v = kp_src[2 * k], fl = kp_src[2 * k + 1];
+        const int x = v & 0xFFF, y = (v >> 12) & 0xFFF, l = fl & 0xFF, img = fl >> 8;
+        const OrbLevelGeom L = g.lv[l];
+        const uint8_t* im = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
+
+        // K5: intensity centroid over the disc of radius `half` on the unblurred level
+        int m10 = 0, m01 = 0;
+        if (SAFE) {
+            const int a = (x - half) & 3;
+            const uint8_t* col0 = im + (x - half - a);                      // 4-byte aligned (rows are 16-byte aligned)
+            for (int vv = -half + lane; vv <= half; vv += 32) {
+                const int du = g.umax[vv < 0 ? -vv : vv];
+                const int p_lo = a + half - du, p_hi = a + half + du;        // byte positions of the row's first / last disc pixel
+                const int j_lo = p_lo >> 2, j_hi = p_hi >> 2;
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(col0 + (size_t)(y + vv) * L.pitch);
+                int srow = 0, mrow = 0;
+                for (int j = j_lo; j <= j_hi; ++j) {
+                    uint32_t w = __ldg(row + j);
+                    if (j == j_lo) w &= 0xFFFFFFFFu << (8 * (p_lo & 3));
+                    if (j == j_hi) w &= 0xFFFFFFFFu >> (8 * (3 - (p_hi & 3)));
+                    const int S = (int)__dp4a(w, 0x01010101u, 0u), T = (int)__dp4a(w, 0x03020100u, 0u);
+                    mrow += (4 * j - a - half) * S + T;
+                    srow += S;
+                }
+                m10 += mrow;
+                m01 += vv * srow;
+            }
+        } else {
+            for (int vv = -half; vv <= half; ++vv) {
+                const int du = g.umax[vv < 0 ? -vv : vv];
+                const int yy = reflect101(y + vv, L.h);
+                const uint8_t* row = im + (size_t)yy * L.pitch;
+                for (int u = -half + lane; u <= half; u += 32) {
+                    if (u >= -du && u <= du) {
+                        const int val = row[reflect101(x + u, L.w)];
+                        m10 += u * val;
+                        m01 += vv * val;
+                    }
+                }
+            }
         }
-        byte |= (uint32_t)(val[0] < val[1]) << j;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(FULL, m10, o);
+            m01 += __shfl_xor_sync(FULL, m01, o);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
+        if (lane == 0) {
+            reinterpret_cast<float4*>(kp_f)[k] = make_float4(ptx, pty, __fmul_rn((float)g.patch, L.scale), angle);
+            if (pt_out) pt_out[out_base + k] = make_float2(ptx, pty);
+        }
+
+        // K7: steered BRIEF on the blurred level (pattern = cv::RNG(0x34985739) points)
+        const uint8_t* bl = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
+        const int cx = __float2int_rn(__fmul_rn(ptx, L.inv_scale)), cy = __float2int_rn(__fmul_rn(pty, L.inv_scale));
+        const float th = __fmul_rn(angle, __uint_as_float(0x3c8efa35u));  // (float)(CV_PI / 180)
+        const float a = (float)cos((double)th), b = (float)sin((double)th);
+        const uint8_t* ctr = bl + (size_t)cy * L.pitch + cx;
+        uint32_t byte = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            // word j holds the two points of bit j: (x0, y0, x1, y1) as int8
+            // conversions without the quarter-rate XU pipe: int8 -> fp32 as (byte ^ 0x80) | 0x4B000000 = 2^23 + 128 + value, exactly;
+            // cvRound as the low mantissa bits of v + 1.5 * 2^23 (round-half-even, |v| < 2^22)
+            const uint32_t wv = words[j] ^ 0x80808080u;
+            int val[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const float px = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7540 + 2 * t)), 8388736.f);
+                const float py = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7541 + 2 * t)), 8388736.f);
+                const int ix = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.f)) - 0x4B400000;
+                const int iy = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.f)) - 0x4B400000;
+                if (SAFE) val[t] = ctr[iy * L.pitch + ix];
+                else val[t] = bl[(size_t)reflect101(cy + iy, L.h) * L.pitch + reflect101(cx + ix, L.w)];
+            }
+            byte |= (uint32_t)(val[0] < val[1]) << j;
+        }
+        desc[(out_base + k) * 32 + lane] = (uint8_t)byte;
     }
-    desc[(size_t)k * 32 + lane] = (uint8_t)byte;
 }
 
 // host-side restatement of the geometry helpers (same arithmetic as oracle/orb_oracle.c)
@@ -657,6 +725,7 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
     SLIDEO_CUDA(cudaMalloc(&d_frame_off_, (B + 1) * 4));
     SLIDEO_CUDA(cudaMalloc(&d_frame_nkp_, B * 4));
     SLIDEO_CUDA(cudaMalloc(&d_flags_, 4));
+    SLIDEO_CUDA(cudaMalloc(&d_info_, 16));
     SLIDEO_CUDA(cudaMalloc(&d_kp_src_, kp_cap_ * 8));
     SLIDEO_CUDA(cudaMalloc(&d_q_frame_, kp_cap_ * 4));
     SLIDEO_CUDA(cudaMalloc(&d_kp_i_, kp_cap_ * 16));
@@ -688,6 +757,11 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
             ++v0;
         }
     }
+    {   // see describe_kernel<SAFE>
+        const int half = cfg.patch_size / 2;
+        const int reach = (int)ceil(half * sqrt(2.0)) + 1;
+        safe_ = cfg.edge_threshold >= half + 4 && cfg.edge_threshold >= reach + 1;
+    }
     {   // tensor maps of the pyramid levels for the FAST tile loads (width = the padded row, so the box never depends on W % 4)
         FastMaps fm;
         memset(&fm, 0, sizeof fm);
@@ -712,15 +786,15 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
 
 OrbExtractor::~OrbExtractor() {
     cudaFree(d_pyr_); cudaFree(d_blur_); cudaFree(d_cand_); cudaFree(d_sel_); cudaFree(d_cand_cnt_); cudaFree(d_sel_cnt_);
-    cudaFree(d_kp_off_); cudaFree(d_frame_off_); cudaFree(d_frame_nkp_); cudaFree(d_flags_); cudaFree(d_kp_src_);
+    cudaFree(d_kp_off_); cudaFree(d_frame_off_); cudaFree(d_frame_nkp_); cudaFree(d_flags_); cudaFree(d_info_); cudaFree(d_kp_src_);
     cudaFree(d_q_frame_); cudaFree(d_kp_i_); cudaFree(d_kp_f_); cudaFree(d_desc_); cudaFree(d_tables_);
     cudaFree(d_pattern_); cudaFree(d_geom_);
     cudaFree(fast_maps_);
     cudaFreeHost(h_pinned_);
 }
 
-int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
-                      int* launches, const Sink* sink) {
+void OrbExtractor::enqueue(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
+                           int* launches, const StreamSink* sink, int num_sms) {
     if (n < 1 || n > batch_cap_) throw ArgError("batch size out of range");
     if (channels != 1 && channels != 3) throw ArgError("channels must be 1 or 3");
     const int L = cfg_.nlevels;
@@ -750,30 +824,45 @@ int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stri
         ++nl;
     }
     int32_t* d_hout = nullptr;
-    SLIDEO_CUDA(cudaHostGetDevicePointer(&d_hout, h_pinned_, 0));
-    scan_kernel<<<1, 256, 0, stream>>>(d_sel_cnt_, n, L, d_kp_off_, d_frame_off_, d_frame_nkp_, d_flags_, d_hout, sink ? sink->frame_nkp : nullptr);
+    if (!sink) SLIDEO_CUDA(cudaHostGetDevicePointer(&d_hout, h_pinned_, 0));
+    scan_kernel<<<1, 256, 0, stream>>>(d_sel_cnt_, n, L, d_kp_off_, d_frame_off_, d_frame_nkp_, d_flags_, d_info_, d_hout,
+                                       sink ? sink->st : nullptr, sink ? sink->frame_q0 : nullptr, sink ? sink->frame_nkp : nullptr,
+                                       sink ? sink->q_cap : 0, sink ? sink->f_cap : 0, (int)kp_cap_);
     ++nl;
-    scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_,
-                                                   sink ? sink->q_frame : nullptr, sink ? sink->frame_base : 0, sink ? sink->cap : 0);
+    scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_, d_info_,
+                                                   sink ? sink->q_frame : nullptr);
     ++nl;
     blur_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, d_blur_, g, static_cast<const FastMaps*>(fast_maps_));
     ++nl;
+    {
+        // the keypoint total of the batch lives on the device: a fixed grid of warps strides over it
+        const size_t per_img = kp_cap_ / (size_t)batch_cap_;
+        const int grid = (int)std::min<size_t>((size_t)num_sms * 8, (size_t)cdiv((int)std::min<size_t>(per_img * n, 1u << 30), 8));
+        uint8_t* dd = sink ? sink->desc : d_desc_;
+        float2* pp = sink ? sink->pt : nullptr;
+        if (safe_) describe_kernel<true><<<grid, 256, 0, stream>>>(d_pyr_, d_blur_, g, d_kp_src_, d_info_, d_pattern_, d_kp_f_, dd, pp, sink ? 1 : 0);
+        else describe_kernel<false><<<grid, 256, 0, stream>>>(d_pyr_, d_blur_, g, d_kp_src_, d_info_, d_pattern_, d_kp_f_, dd, pp, sink ? 1 : 0);
+        ++nl;
+    }
     SLIDEO_CUDA(cudaGetLastError());
-    SLIDEO_CUDA(cudaStreamSynchronize(stream));   // total keypoints of the batch sizes the remaining launches
+    if (launches) *launches += nl;
+}
+
+int OrbExtractor::run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
+                      int* launches, int num_sms) {
+    enqueue(d_src, n, stride, frame_stride, channels, stream, launches, nullptr, num_sms);
+    SLIDEO_CUDA(cudaStreamSynchronize(stream));   // single images (pages, stage-level extraction): the caller wants the count
     const int total = h_pinned_[0], flags = h_pinned_[1];
     h_frame_off_.assign(h_pinned_ + 2, h_pinned_ + 2 + n + 1);
     if (flags & 1) throw CapacityError("FAST candidate capacity exceeded on at least one image");
     if (flags & 2) throw CapacityError("selected-keypoint capacity exceeded on at least one image");
-    if ((size_t)total > kp_cap_) throw CapacityError("keypoint capacity exceeded");
-    if (sink && (size_t)total > sink->cap) throw CapacityError("descriptor sink capacity exceeded");
-    if (total > 0) {
-        describe_kernel<<<cdiv(total, 8), 256, 0, stream>>>(d_pyr_, d_blur_, g, d_kp_src_, total, d_pattern_, d_kp_f_,
-                                                           sink ? sink->desc : d_desc_, sink ? sink->pt : nullptr);
-        ++nl;
-        SLIDEO_CUDA(cudaGetLastError());
-    }
-    if (launches) *launches += nl;
+    if ((flags & 4) || (size_t)total > kp_cap_) throw CapacityError("keypoint capacity exceeded");
     return total;
+}
+
+void OrbExtractor::run_stream(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
+                              int* launches, const StreamSink& sink, int num_sms) {
+    enqueue(d_src, n, stride, frame_stride, channels, stream, launches, &sink, num_sms);
 }
 
 }  // namespace slideo

@@ -46,21 +46,24 @@ public:
     int nlevels() const { return cfg_.nlevels; }
     const OrbLevelGeom& level(int l) const { return lv_[l]; }
 
-    // Runs the whole extractor on n device images (channels 1 or 3).  Returns the total keypoint count of the
-    // batch (one small D2H + stream sync after the selection stage).  Throws CapacityError on overflow.
-    // `sink` (optional) redirects the per-keypoint outputs a matcher needs into caller-owned arrays, so that several
-    // batches can be appended back to back: descriptors to sink->desc, the frame of each keypoint (+ frame_base) to
-    // sink->q_frame, the per-frame keypoint counts to sink->frame_nkp.
-    struct Sink {
-        uint8_t* desc;       // [.. x 32], this batch starts at element 0
-        int32_t* q_frame;    // [..]
-        int32_t* frame_nkp;  // [n]
-        float2* pt;          // [..] KeyPoint.pt (may be null)
-        int frame_base;
-        size_t cap;          // keypoints the arrays can hold
+    // Runs the whole extractor on n device images (channels 1 or 3) and returns the total keypoint count of the batch (one
+    // stream synchronisation: meant for single images -- pages, stage-level extraction).  Throws CapacityError on overflow.
+    int run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream, int* launches,
+            int num_sms = 148);
+    // The frame path: no host synchronisation at all.  The batch is appended to a query stream whose counters live on the
+    // device (KnnStream, common.cuh): descriptors / frame ids / KeyPoint.pt go to the stream position of the batch, the frame
+    // table of the stream is extended, capacity problems raise sticky bits in st->flags.
+    struct StreamSink {
+        uint8_t* desc;        // [q_cap x 32]
+        int32_t* q_frame;     // [q_cap] frame (within the stream) of each query
+        float2* pt;           // [q_cap] KeyPoint.pt (may be null)
+        int32_t* frame_q0;    // [f_cap + 1] first query of each frame; frame_q0[0] = 0 is set by the owner
+        int32_t* frame_nkp;   // [f_cap]
+        KnnStream* st;
+        int q_cap, f_cap;
     };
-    int run(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream,
-            int* launches, const Sink* sink = nullptr);
+    void run_stream(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream, int* launches,
+                    const StreamSink& sink, int num_sms = 148);
 
     // results of the last run (device pointers; canonical order frame, octave, y, x)
     const uint8_t* d_desc() const { return d_desc_; }          // total x 32
@@ -79,7 +82,10 @@ public:
     const int32_t* d_cand_count() const { return d_cand_cnt_; }  // [batch][nlevels]
 
 private:
+    void enqueue(const uint8_t* d_src, int n, int stride, size_t frame_stride, int channels, cudaStream_t stream, int* launches,
+                 const StreamSink* sink, int num_sms);
     OrbConfig cfg_;
+    bool safe_ = false;          // see describe_kernel<SAFE> (orb.cu)
     int w_, h_, batch_cap_;
     std::vector<OrbLevelGeom> lv_;
     int total_tiles_ = 0;
@@ -87,7 +93,8 @@ private:
     uint8_t *d_pyr_ = nullptr, *d_blur_ = nullptr, *d_desc_ = nullptr;
     uint32_t *d_cand_ = nullptr, *d_sel_ = nullptr, *d_kp_src_ = nullptr;
     int32_t *d_cand_cnt_ = nullptr, *d_sel_cnt_ = nullptr, *d_kp_off_ = nullptr, *d_frame_off_ = nullptr,
-            *d_frame_nkp_ = nullptr, *d_q_frame_ = nullptr, *d_kp_i_ = nullptr, *d_tables_ = nullptr, *d_flags_ = nullptr;
+            *d_frame_nkp_ = nullptr, *d_q_frame_ = nullptr, *d_kp_i_ = nullptr, *d_tables_ = nullptr, *d_flags_ = nullptr,
+            *d_info_ = nullptr;   // batch header {total, stream query base, stream frame base, flags}
     float* d_kp_f_ = nullptr;
     void* d_geom_ = nullptr;     // OrbLevelGeom[nlevels] on the device
     void* fast_maps_ = nullptr;  // per-level TMA tensor maps of the pyramid (device memory)

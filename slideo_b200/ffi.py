@@ -28,7 +28,7 @@ class Config(ctypes.Structure):
     _fields_ = [("abi_version", c_i32), ("device", c_i32), ("nfeatures", c_i32), ("scale_factor", c_f32),
                 ("nlevels", c_i32), ("edge_threshold", c_i32), ("patch_size", c_i32), ("fast_threshold", c_i32),
                 ("knn_k", c_i32), ("vote_ratio", c_f32), ("descriptor_kind", c_i32), ("max_batch", c_i32),
-                ("keep_matches", c_i32), ("geometric_verification", c_i32), ("reserved", c_i32 * 2)]
+                ("keep_matches", c_i32), ("geometric_verification", c_i32), ("knn_impl", c_i32), ("reserved", c_i32 * 1)]
 
 
 class FrameResult(ctypes.Structure):
@@ -82,6 +82,9 @@ SYMBOLS = {
     "slideo_b200_pool_points_device_view": (c_i32, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_sz), c_i32p, c_i32]),
     "slideo_b200_match_frames_bgr8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_vp]),
     "slideo_b200_match_frames_bgr8_device": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_vp]),
+    "slideo_b200_submit_frames_bgr8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, ctypes.POINTER(ctypes.c_int64)]),
+    "slideo_b200_submit_frames_bgr8_device": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, ctypes.POINTER(ctypes.c_int64)]),
+    "slideo_b200_collect": (c_i32, [c_vp, ctypes.c_int64, c_vp, c_i32, c_i32p]),
     "slideo_b200_match_descriptors": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp]),
     "slideo_b200_get_matches": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32p]),
     "slideo_b200_get_verification": (c_i32, [c_vp, c_i32, c_i32, c_vp]),
