@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--max-batch", type=int, default=64,
                     help="frames per detection batch (K8 runs on chunks of the pooled query stream, independent of this)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the detail blocks (decision tail, SIFT variant, configs[2])")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -282,20 +283,28 @@ def main():
 
     sampler = ClockSampler(local_rank)
 
-    def timed(fn):
-        for _ in range(args.warmup):
-            res = fn()
+    def timed(submit):
+        """K steps, software-pipelined through the library's asynchronous entry points: step s+1 is submitted (uploads, K1-K7
+        and K8 launches enqueued) before the results of step s are collected, so the GPU never drains between steps.  Every
+        step's work, its H2D copies and the D2H of its results lie inside the bracket."""
+        def run(k):
+            res, prev = None, submit()
+            for _ in range(k - 1):
+                nxt = submit()
+                res = ctx.collect(prev, args.frames)
+                prev = nxt
+            return ctx.collect(prev, args.frames)
+        res = run(args.warmup)
         ctx.timings(reset=True)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = fn()
+        res = run(args.steps)
         ctx.synchronize()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tm = ctx.timings(reset=True)
         barrier()
-        # device time of the K steps (CUDA events on the library's stream) and the host bracket; take the larger
+        # device time of the K steps (CUDA events on the library's streams) and the host bracket; take the larger
         dev_s = tm["ms_total"] * 1e-3
         t = torch.tensor([max(dt, dev_s), dev_s], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -304,11 +313,12 @@ def main():
 
     # value arm: frames resident in HBM
     sampler.start()
-    res_dev, t_dev, t_dev_events, tm_dev = timed(lambda: ctx.match_frames_bgr8_device(dev.data_ptr(), args.frames, FRAME_W, FRAME_H))
+    res_dev, t_dev, t_dev_events, tm_dev = timed(lambda: ctx.submit_frames_bgr8_device(dev.data_ptr(), args.frames, FRAME_W, FRAME_H))
     clocks = sampler.stop()
     # e2e arm: the public host-buffer call, H2D of every frame + D2H of the results inside the timed region
-    res_e2e, t_e2e, _, tm_e2e = timed(lambda: ctx.match_frames_bgr8_ptr(pin.ptr, args.frames, FRAME_W, FRAME_H))
+    res_e2e, t_e2e, _, tm_e2e = timed(lambda: ctx.submit_frames_bgr8_ptr(pin.ptr, args.frames, FRAME_W, FRAME_H))
     assert np.array_equal(res_dev, res_e2e), "device-resident and host-buffer arms disagree"
+    assert np.array_equal(res_dev, ctx.match_frames_bgr8_ptr(pin.ptr, args.frames, FRAME_W, FRAME_H)), "submit/collect and the synchronous call disagree"
 
     total_frames = args.frames * world * args.steps
     value = total_frames / t_dev
@@ -355,7 +365,7 @@ def main():
     # ---- extra (rank 0, N=1): the same step with the reference's complete decision tail switched on (SURVEY 8(f) ranks 1-2:
     #      RANSAC rating gate lib.rs:284-333 + warp/similarity gate lib.rs:335-389) ----
     verify_detail = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_extras:
         try:
             vctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=args.max_batch, geometric_verification=2))
             for p in range(args.pages):
@@ -383,7 +393,7 @@ def main():
     # ---- extra (rank 0, N=1): the SIFT-128 / L2 variant of the same path (north_star; BASELINE configs[3] geometry at this run's
     #      page count): K11 SIFT on the GPU for pages and frames -> K10 tcgen05 L2 k-NN -> vote, on a bounded sample of the frames ----
     sift_detail = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_extras:
         try:
             ns = min(args.frames, 64)
             sctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=16, descriptor_kind=slideo_b200.ffi.DESC_SIFT128))

@@ -173,6 +173,13 @@ int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx);
  * call with received != 0 after filling it (before pool_commit) to declare the coordinates valid. */
 int32_t slideo_b200_pool_points_device_view(slideo_b200_ctx* ctx, void** d_pt, size_t* bytes, int32_t* has_points, int32_t received);
 
+/* Small gray images of the pages (slide.small_img, lib.rs:105; the warp + similarity gate of cfg.geometric_verification == 2).  On
+ * the rank that built the pool: *page_w / *page_h = the uniform page size (0 when the pages differ in size or came without images)
+ * and *d_small = n_pages small images.  On a reserved ctx: pass the sender's page size as set_w / set_h to size the buffer and
+ * get the pointer to receive into (before pool_commit). */
+int32_t slideo_b200_pool_pages_device_view(slideo_b200_ctx* ctx, void** d_small, size_t* bytes, int32_t* page_w, int32_t* page_h,
+                                           int32_t set_w, int32_t set_h);
+
 /* ---- the per-frame hot path  (replaces match_images_with_frame lib.rs:249-295, head of the ranking) ------- */
 /* n BGR 8UC3 frames (what VideoCapture::retrieve yields, video_capture.rs:45-53), HOST memory, frame i at
  * frames + i*frame_stride; rows `stride` bytes apart.  Copies to the device, extracts ORB (or SIFT for a SIFT128 ctx),

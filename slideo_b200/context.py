@@ -147,6 +147,14 @@ class Context:
         self._ck(self._lib.slideo_b200_pool_points_device_view(self._h, ctypes.byref(d), ctypes.byref(b), ctypes.byref(h), int(received)))
         return d.value or 0, b.value, bool(h.value)
 
+    def pool_pages_device_view(self, set_w: int = 0, set_h: int = 0):
+        """(d_small ptr, bytes, page_w, page_h) of the pages' small images (warp + similarity gate across GPUs); on a reserved ctx
+        pass the sender's page size to allocate the receiving buffer."""
+        d, b, w, h = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self._lib.slideo_b200_pool_pages_device_view(self._h, ctypes.byref(d), ctypes.byref(b), ctypes.byref(w), ctypes.byref(h),
+                                                              set_w, set_h))
+        return d.value or 0, b.value, w.value, h.value
+
     def pool_commit(self) -> None:
         self._ck(self._lib.slideo_b200_pool_commit(self._h))
 

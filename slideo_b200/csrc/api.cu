@@ -275,7 +275,7 @@ struct slideo_b200_ctx {
                 st = 3 * w;
                 fst = img_bytes;
             }
-            const bool trace = getenv("SLIDEO_TRACE") != nullptr;
+            static const bool trace = getenv("SLIDEO_TRACE") != nullptr;   // developer knob, read once per process
             auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
             const double h0 = trace ? now() : 0;
             EventPair t = begin_timing(0, stream);
@@ -409,6 +409,7 @@ struct slideo_b200_ctx {
     int page_w = 0, page_h = 0;
     bool page_geom_ok = true;
     bool page_small_ready = false;              // d_page_small holds the small image of every page (built here or replicated)
+    bool page_small_received = false;           // a reserved pool got its page images through pool_pages_device_view
     DevBuf<uint8_t> d_page_small, d_all_frames;
     AreaTables page_area;
     DevBuf<int32_t> d_v_best_it, d_v_surv_cand;
@@ -1151,7 +1152,8 @@ int32_t slideo_b200_pool_import(slideo_b200_ctx* ctx, const void* desc, int32_t 
         arg(page_offsets[0] == 0 && page_offsets[n_pages] == n_desc, "page_offsets must start at 0 and end at n_desc");
         for (int p = 0; p < n_pages; ++p) arg(page_offsets[p] <= page_offsets[p + 1], "page_offsets must be non-decreasing");
         ctx->check_pool_limits(n_desc, n_pages);
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->drain();
+        ctx->close_epoch();
         ctx->h_pool.assign((const uint8_t*)desc, (const uint8_t*)desc + (size_t)n_desc * ctx->desc_bytes);
         ctx->h_pool_pt.clear();
         ctx->pool_pts_valid = n_desc == 0;
@@ -1166,7 +1168,8 @@ int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n
     return guarded(ctx, [&] {
         arg(n_desc >= 0 && n_pages >= 0, "negative size");
         ctx->check_pool_limits(n_desc, n_pages);
-        SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->drain();
+        ctx->close_epoch();
         ctx->finalized = false;
         ctx->reserved = true;
         ctx->nt = n_desc;
@@ -1175,6 +1178,10 @@ int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n
         ctx->h_pool_pt.clear();
         ctx->pool_pts_valid = n_desc == 0;
         ctx->pts_received = false;
+        ctx->page_small_received = false;
+        ctx->page_small_ready = false;
+        ctx->page_geom_ok = false;
+        ctx->h_page_small.clear();
         ctx->page_off.assign((size_t)n_pages + 1, 0);
         if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) ctx->d_pool.reserve((size_t)std::max(n_desc, 1) * 32 + 64);
         else ctx->d_pool_f32.reserve((size_t)std::max(n_desc, 1) * 512);
@@ -1209,6 +1216,27 @@ int32_t slideo_b200_pool_points_device_view(slideo_b200_ctx* ctx, void** d_pt, s
     });
 }
 
+int32_t slideo_b200_pool_pages_device_view(slideo_b200_ctx* ctx, void** d_small, size_t* bytes, int32_t* page_w, int32_t* page_h,
+                                           int32_t set_w, int32_t set_h) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        if (!ctx->finalized && !ctx->reserved) throw StateError("no device pool yet (finalize_pool or pool_reserve first)");
+        if (ctx->reserved && set_w > 0 && set_h > 0) {   // the receiving side: size the buffer for the sender's page geometry
+            ctx->page_w = set_w;
+            ctx->page_h = set_h;
+            ctx->page_area.build(set_w, set_h);
+            ctx->d_page_small.reserve((size_t)std::max(ctx->n_pages, 1) * ctx->page_area.dw * ctx->page_area.dh);
+            ctx->page_geom_ok = true;
+            ctx->page_small_received = true;
+        }
+        const bool have = ctx->reserved ? ctx->page_small_received : (ctx->page_geom_ok && ctx->page_small_ready);
+        if (d_small) *d_small = have ? (void*)ctx->d_page_small.p : nullptr;
+        if (bytes) *bytes = have ? (size_t)ctx->n_pages * ctx->page_area.dw * ctx->page_area.dh : 0;
+        if (page_w) *page_w = have ? ctx->page_w : 0;
+        if (page_h) *page_h = have ? ctx->page_h : 0;
+    });
+}
+
 int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
@@ -1227,6 +1255,7 @@ int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx) {
         }
         ctx->build_page_of();              // (no host copy of the coordinates on this rank: the device copy filled by the caller stays)
         if (got_pts) ctx->pool_pts_valid = true;
+        if (ctx->page_small_received) ctx->page_small_ready = true;
         ctx->reserved = false;
         ctx->finalized = true;
     });

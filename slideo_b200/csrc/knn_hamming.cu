@@ -502,10 +502,8 @@ KnnPlan knn_hamming_plan(int nq, int nt, int k, int num_sms, int ctas_per_sm_req
     // queries per thread: 8 amortises the pooled-row loads best, 4 gives twice as many tiles -> fewer, longer stream-K
     // segments per tile (every segment re-warms its selection thresholds from scratch)
     int ctas_per_sm = ctas_per_sm_req >= 1 && ctas_per_sm_req <= KNN_CTAS_PER_SM ? ctas_per_sm_req : KNN_CTAS_PER_SM;
-    if (const char* e = getenv("SLIDEO_KNN_CTAS")) { if (atoi(e) >= 1 && atoi(e) <= KNN_CTAS_PER_SM) ctas_per_sm = atoi(e); }
     const long long target0 = (long long)num_sms * ctas_per_sm;
     p.qr = (long long)cdiv(nq, KNN_THREADS * 8) * 2 >= target0 * 3 ? 8 : 4;
-    if (const char* e = getenv("SLIDEO_KNN_QR")) { if (atoi(e) == 4 || atoi(e) == 8) p.qr = atoi(e); }
     const int KNN_TILE = KNN_THREADS * p.qr;
     p.tile = KNN_TILE;
     p.n_tiles = cdiv(nq, KNN_TILE);
@@ -550,14 +548,12 @@ void knn_hamming_launch(const KnnPlan& plan, const void* d_q, const void* d_pool
     if (vote) P.vote = *vote;
     else P.vote = VoteArgs{nullptr, nullptr, nullptr, 0, 0.f};
     const size_t smem = (size_t)KNN_STAGES * KNN_CHUNK * KNN_ROW_U4 * 16 + KNN_STAGES * sizeof(uint64_t) + 2 * plan.tile * sizeof(int);
-    static bool configured = false;
-    if (!configured) {
+    {   // function attributes are per device: set on every launch (cheap) so that ctxs on several GPUs of one process all get them
         const int max_smem = (int)((size_t)KNN_STAGES * KNN_CHUNK * KNN_ROW_U4 * 16 + KNN_STAGES * sizeof(uint64_t) + 2 * KNN_THREADS * KNN_QR_MAX * sizeof(int));
         SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         SLIDEO_CUDA(cudaFuncSetAttribute(knn_hamming_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
     }
     if (plan.qr == 8) knn_hamming_kernel<8><<<plan.grid, KNN_THREADS, smem, stream>>>(P);
     else knn_hamming_kernel<4><<<plan.grid, KNN_THREADS, smem, stream>>>(P);

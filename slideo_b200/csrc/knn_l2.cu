@@ -607,6 +607,23 @@ void l2_prepare_launch(const float* d_src, int n, bool is_query, void* d_main, v
     SLIDEO_CUDA(cudaGetLastError());
 }
 
+namespace {
+// developer knobs (profiling counters, split / trigger experiments): read from the environment ONCE per process, never on the
+// launch path
+struct L2Env { bool no_split, prof; int trigger, dbg; };
+const L2Env& l2_env() {
+    static const L2Env e = [] {
+        L2Env v;
+        v.no_split = getenv("SLIDEO_L2_NO_SPLIT") != nullptr;
+        v.prof = getenv("SLIDEO_L2_PROF") != nullptr;
+        v.trigger = getenv("SLIDEO_L2_TRIGGER") ? std::min(L2_TRIGGER, std::max(1, atoi(getenv("SLIDEO_L2_TRIGGER")))) : 26;
+        v.dbg = getenv("SLIDEO_L2_DEBUG") ? atoi(getenv("SLIDEO_L2_DEBUG")) : 0;
+        return v;
+    }();
+    return e;
+}
+}  // namespace
+
 void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool_main, const void* d_pool_tail, int nt, int k,
                    int32_t* d_idx, float* d_dist, int num_sms, cudaStream_t stream, int* launches) {
     if (nq <= 0) return;
@@ -627,7 +644,7 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.mt_a = P.n_mtiles; P.ns_a = 1; P.ns_b = 1;
     if (P.n_mtiles < num_sms) {
         P.ns_a = std::min(P.n_ntiles, std::max(1, num_sms / P.n_mtiles));
-    } else if (!getenv("SLIDEO_L2_NO_SPLIT")) {
+    } else if (!l2_env().no_split) {
         const int r = P.n_mtiles % num_sms;
         const int c = r > 0 ? std::min(std::min(4, P.n_ntiles), num_sms / r) : 1;
         if (c >= 2) { P.mt_a = P.n_mtiles - r; P.ns_b = c; }
@@ -641,9 +658,9 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.partial = (uint64_t*)ws.d_part;
     P.idx_out = d_idx;
     P.dist_out = d_dist;
-    P.trigger = getenv("SLIDEO_L2_TRIGGER") ? std::min(L2_TRIGGER, std::max(1, atoi(getenv("SLIDEO_L2_TRIGGER")))) : 26;
+    P.trigger = l2_env().trigger;
     P.prof = nullptr;
-    P.dbg = getenv("SLIDEO_L2_DEBUG") ? atoi(getenv("SLIDEO_L2_DEBUG")) : 0;
+    P.dbg = l2_env().dbg;
 
     const int q_pad = l2_rows_padded(nq), t_pad = l2_rows_padded(nt);
     const CUtensorMap tq_main = make_map(ws.d_q_main, L2_DIM, q_pad, 64, L2_BM, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -651,13 +668,10 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     const CUtensorMap tt_main = make_map(d_pool_main, L2_DIM, t_pad, 64, L2_BN, CU_TENSOR_MAP_SWIZZLE_128B);
     const CUtensorMap tt_tail = make_map(d_pool_tail, L2_TAIL, t_pad, L2_TAIL, L2_BN, CU_TENSOR_MAP_SWIZZLE_32B);
 
-    static bool configured = false;
-    if (!configured) {
-        SLIDEO_CUDA(cudaFuncSetAttribute(knn_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-        configured = true;
-    }
+    // function attributes are per device: set on every launch (cheap) so that ctxs on several GPUs of one process all get them
+    SLIDEO_CUDA(cudaFuncSetAttribute(knn_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
     static unsigned long long* d_prof = nullptr;
-    if (getenv("SLIDEO_L2_PROF")) {
+    if (l2_env().prof) {
         if (!d_prof) SLIDEO_CUDA(cudaMalloc(&d_prof, 8 * sizeof(unsigned long long)));
         SLIDEO_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), stream));
         P.prof = d_prof;

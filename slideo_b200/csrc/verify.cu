@@ -518,11 +518,8 @@ void verify_launch(const VerifyArgs& a, cudaStream_t stream, int* launches) {
     gather_matches_kernel<<<dim3(VERIFY_TOP_SLIDES, a.n_frames), V_THREADS, 0, stream>>>(a.d_keys, a.k, a.d_frame_q0, a.d_page_of, a.d_cand_page,
                                                                                      a.d_cand_votes, a.d_n_cand, a.ratio, (uint2*)a.d_corr);
     const size_t smem = (size_t)V_SMEM_PTS * sizeof(float4) + (size_t)VERIFY_MAX_ITERS * sizeof(uint2);
-    static bool configured = false;
-    if (!configured) {
-        SLIDEO_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // function attributes are per device: set on every launch (cheap) so that ctxs on several GPUs of one process all get them
+    SLIDEO_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ransac_kernel<<<dim3(VERIFY_TOP_SLIDES, a.n_frames), V_THREADS, smem, stream>>>((const uint2*)a.d_corr, a.d_frame_q0, a.k, a.d_cand_votes,
                                                                                   a.d_n_cand, a.d_frame_pt, a.d_pool_pt, 3.0f, VERIFY_MAX_ITERS,
                                                                                   0.99, a.d_rating, a.d_best_it);

@@ -80,6 +80,7 @@ SYMBOLS = {
                                              ctypes.POINTER(c_sz)]),
     "slideo_b200_pool_commit": (c_i32, [c_vp]),
     "slideo_b200_pool_points_device_view": (c_i32, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_sz), c_i32p, c_i32]),
+    "slideo_b200_pool_pages_device_view": (c_i32, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_sz), c_i32p, c_i32p, c_i32, c_i32]),
     "slideo_b200_match_frames_bgr8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_vp]),
     "slideo_b200_match_frames_bgr8_device": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, c_vp]),
     "slideo_b200_submit_frames_bgr8": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_sz, ctypes.POINTER(ctypes.c_int64)]),

@@ -59,12 +59,13 @@ def broadcast_pool_device(ctx, src: int = 0) -> None:
     import torch.distributed as dist
     rank = dist.get_rank()
     dev = torch.device("cuda", torch.cuda.current_device())
-    hdr = torch.zeros(3, dtype=torch.int64, device=dev)
+    hdr = torch.zeros(5, dtype=torch.int64, device=dev)
     if rank == src:
         n, p = ctx.pool_info()
-        hdr[0], hdr[1], hdr[2] = n, p, int(ctx.pool_points_device_view()[2])
+        _, _, pw, ph = ctx.pool_pages_device_view()
+        hdr[0], hdr[1], hdr[2], hdr[3], hdr[4] = n, p, int(ctx.pool_points_device_view()[2]), pw, ph
     dist.broadcast(hdr, src)
-    n, p, has_pts = int(hdr[0].item()), int(hdr[1].item()), bool(hdr[2].item())
+    n, p, has_pts, pw, ph = int(hdr[0].item()), int(hdr[1].item()), bool(hdr[2].item()), int(hdr[3].item()), int(hdr[4].item())
     if rank != src:
         ctx.pool_reserve(n, p)
     d_desc, desc_bytes, d_off, off_bytes = ctx.pool_device_view()
@@ -78,6 +79,9 @@ def broadcast_pool_device(ctx, src: int = 0) -> None:
             dist.broadcast(torch.as_tensor(_DevView(d_pt, pt_bytes), device=dev), src)
             if rank != src:
                 ctx.pool_points_device_view(received=True)
+    if pw > 0 and ph > 0 and p > 0:                   # the pages' small images, only needed by the warp + similarity gate
+        d_sm, sm_bytes, _, _ = ctx.pool_pages_device_view(pw, ph) if rank != src else ctx.pool_pages_device_view()
+        dist.broadcast(torch.as_tensor(_DevView(d_sm, sm_bytes), device=dev), src)
     torch.cuda.synchronize()
     if rank != src:
         ctx.pool_commit()

@@ -191,6 +191,11 @@ def _replicate_device(a, b):
         assert dpbytes == pbytes
         torch.as_tensor(_DevView(dp, pbytes), device=dev).copy_(torch.as_tensor(_DevView(sp, pbytes), device=dev))
         b.pool_points_device_view(received=True)
+    ss, sm_bytes, pw, ph = a.pool_pages_device_view()
+    if pw > 0 and sm_bytes:
+        ds, dsm_bytes, _, _ = b.pool_pages_device_view(pw, ph)
+        assert dsm_bytes == sm_bytes
+        torch.as_tensor(_DevView(ds, sm_bytes), device=dev).copy_(torch.as_tensor(_DevView(ss, sm_bytes), device=dev))
     torch.cuda.synchronize()
     b.pool_commit()
 
@@ -204,7 +209,7 @@ def test_pool_replication_gives_identical_results(scene, kind):
         frames = np.ascontiguousarray(frames[:4, :400, :600])
         cfg = dict(descriptor_kind=slideo_b200.ffi.DESC_SIFT128, max_batch=2)
     else:
-        cfg = dict(max_batch=4, geometric_verification=1)
+        cfg = dict(max_batch=4, geometric_verification=2)
     with slideo_b200.Context(slideo_b200.default_config(**cfg)) as a, slideo_b200.Context(slideo_b200.default_config(**cfg)) as b, \
             slideo_b200.Context(slideo_b200.default_config(**{**cfg, "geometric_verification": 0})) as c:
         for p in pages:
@@ -217,6 +222,9 @@ def test_pool_replication_gives_identical_results(scene, kind):
         assert np.array_equal(b.match_frames_bgr8(frames), ra)
         if kind == "orb":
             assert a.get_verification(0, len(frames)) == b.get_verification(0, len(frames))
+            da, db = a.get_decisions(0, len(frames)), b.get_decisions(0, len(frames))
+            assert [d["image"] for d in da] == [d["image"] for d in db] and any(d["image"] >= 0 for d in da)
+            assert repr(da) == repr(db)            # rated pages, similarities and refined matrices bit for bit
         desc, offs = a.pool_export()
         c.pool_import(desc, offs)
         assert c.pool_info() == a.pool_info()
