@@ -5,17 +5,26 @@ Workload (config.workload): configs[1] = 1k synthetic 1080p BGR frames x 50 rend
 256-bit Hamming brute-force k-NN (k=30) + the reference's 1.05-ratio vote -> (best_slide, votes) per frame.
 A "step" is one pass of the hot path over this rank's 1000 frames.  At N>1 every rank gets its own 1000 frames
 (frames shard with no data-path collective; the pool is replicated by one NCCL broadcast before the timed region)
--> "scaling": "weak".
+-> "scaling": "weak".  The K steps are software-pipelined through the library's asynchronous entry points
+(slideo_b200_submit_frames_bgr8[_device] / slideo_b200_collect): step s+1 is submitted before step s is collected.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Prints ONE JSON line (rank 0).  `value` = frames/s with the frames already resident in HBM; `e2e` = the same through
-slideo_b200_match_frames_bgr8 with HOST (pinned) frames, H2D + D2H inside the timed region.  `roofline` describes the
-dominant kernel (K8, brute-force Hamming k-NN): it is integer-pipe bound, not HBM bound,
-so the binding fraction is against the measured POPC-pipe ceiling and the HBM fraction is reported beside it.
-`cpu_baseline` / `--impl reference` time the reference's CPU path (OpenCV ORB + BFMatcher + vote through cv2, the
-library the reference calls) on this box's host cores -- the only place this file touches `oracle/`.
+the host-buffer entry point with HOST (pinned) frames, H2D + D2H inside the timed region.  `roofline` describes the
+dominant kernel (K8 v5, bit-sliced brute-force Hamming k-NN): it is integer-pipe (ALU / LOP3) bound, not HBM bound
+(DESIGN.md), so the binding fraction is against the measured LOP3 ceiling of its formulation and the
+HBM fraction is reported beside it.  `cpu_baseline` / `--impl reference` time the reference's CPU path (OpenCV ORB +
+matcher + vote through cv2, the library the reference calls) on this box's host cores -- the only place this file
+touches `oracle/` -- with BOTH matchers: exact BFMatcher (like-for-like, the headline arm) and the FLANN-LSH matcher
+the reference really builds (flann.rs:15-23; approximate, timing only).
+
+detail blocks (rank 0 prints them; torchrun-safe):
+  with_geometric_verification : the same step with the reference's full decision tail (RANSAC + warp/similarity gates)
+  sift128_variant             : BASELINE configs[3] geometry (SIFT-128 / L2 on tcgen05, 200 pages) on a stated sample
+  configs2_strong             : BASELINE configs[2]: 10 000 frames x 500 pages STRONG-sharded over the N ranks, timed from the
+                                first add_page through the pool all-gather to the last result
 """
 from __future__ import annotations
 
@@ -37,6 +46,9 @@ sys.path.insert(0, ROOT)
 FRAME_W, FRAME_H = 1920, 1080
 FRAME_BYTES = FRAME_W * FRAME_H * 3
 KNN_K = 30
+C2_FRAMES, C2_PAGES = 10_000, 500      # BASELINE configs[2]
+C3_PAGES = 200                         # BASELINE configs[3]
+LOP3_PER_PAIR_V5 = 1070.0 / 128.0      # thread-level LOP3 per descriptor pair of K8 v5 (1070 per lane and 128 rows)
 
 # ----------------------------------------------------------------------------------------------------------------
 # worker-process helpers (fork()ed before any CUDA initialisation)
@@ -58,14 +70,18 @@ def _gen_page(p):
     return p, synth.make_page(p)
 
 
-def _cpu_init(page_descs):
+def _cpu_init(page_descs, matcher):
     import cv2
     cv2.setNumThreads(1)                       # frame-level parallelism like the reference's rayon scope (lib.rs:174-221)
     from oracle import cv2_oracle as co
     _CPU["orb"] = co.make_orb(2000)
-    m = cv2.BFMatcher(cv2.NORM_HAMMING)
-    m.add([d for d in page_descs if len(d)])
-    _CPU["bf"] = m
+    nonempty = [d for d in page_descs if len(d)]
+    if matcher == "lsh":                       # what the reference builds per worker thread (flann.rs:15-23, lib.rs:255-262)
+        _CPU["m"] = co.make_lsh_matcher(nonempty)
+    else:
+        m = cv2.BFMatcher(cv2.NORM_HAMMING)
+        m.add(nonempty)
+        _CPU["m"] = m
     _CPU["nonempty"] = [i for i, d in enumerate(page_descs) if len(d)]
     _CPU["npages"] = len(page_descs)
     _CPU["co"] = co
@@ -81,13 +97,13 @@ def _cpu_page_desc(p):
 
 
 def _cpu_match_frame(args):
-    """The reference's per-frame path on the CPU: ORB -> exact BF knn(30) -> vote (lib.rs:264-282)."""
+    """The reference's per-frame path on the CPU: ORB -> knn(30) -> vote (lib.rs:264-282)."""
     f, npages = args
     _, frame = _gen_frame((f, npages))
     co = _CPU["co"]
     t0 = time.perf_counter()
     _, _, desc = co.orb_canonical(frame, orb=_CPU["orb"])
-    rows = _CPU["bf"].knnMatch(np.ascontiguousarray(desc), KNN_K)
+    rows = _CPU["m"].knnMatch(np.ascontiguousarray(desc), KNN_K)
     v = co.vote_rows(rows, len(_CPU["nonempty"]))
     votes = np.zeros(_CPU["npages"], np.int64)
     votes[_CPU["nonempty"]] = v
@@ -95,16 +111,52 @@ def _cpu_match_frame(args):
     return f, best, int(votes[best]) if best >= 0 else 0, len(desc), time.perf_counter() - t0
 
 
+def _cpu_sift_frame(args):
+    """cv2.SIFT_create() + BFMatcher(NORM_L2) knn(30) on one frame; the L2 matcher runs on the first `nq_sample` query rows and is
+    scaled linearly to the frame's descriptor count (brute force is linear in the number of queries)."""
+    f, npages, nq_sample = args
+    import cv2
+    cv2.setNumThreads(1)
+    _, frame = _gen_frame((f, npages))
+    sift = _CPU.setdefault("sift", cv2.SIFT_create())
+    t0 = time.perf_counter()
+    _, desc = sift.detectAndCompute(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), None)
+    t_sift = time.perf_counter() - t0
+    n = 0 if desc is None else len(desc)
+    t_knn = 0.0
+    if n:
+        t0 = time.perf_counter()
+        _CPU["sift_m"].knnMatch(np.ascontiguousarray(desc[:nq_sample]), KNN_K)
+        t_knn = (time.perf_counter() - t0) * n / min(n, nq_sample)
+    return f, n, t_sift, t_knn
+
+
+def _cpu_sift_init(pool, offs):
+    import cv2
+    cv2.setNumThreads(1)
+    m = cv2.BFMatcher(cv2.NORM_L2)
+    # one train Mat per page, like the reference adds its pages (flann.rs:64-71); OpenCV also caps a Mat at 2^18 rows here
+    m.add([np.ascontiguousarray(pool[offs[i]:offs[i + 1]]) for i in range(len(offs) - 1) if offs[i + 1] > offs[i]])
+    _CPU["sift_m"] = m
+
+
+def _cpu_noop(i):
+    time.sleep(0.05)
+    return i
+
+
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(npages: int, frame_ids, cores: int, steps: int = 1, warmup: int = 0):
+def cpu_reference_rate(npages: int, frame_ids, cores: int, steps: int = 1, warmup: int = 0, matcher: str = "bf", page_descs=None):
     """frames/s of the CPU path on `cores` worker processes; each step matches `frame_ids` once."""
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        page_descs = [None] * npages
-        for p, d in pool.imap_unordered(_cpu_page_desc, range(npages)):
-            page_descs[p] = d
+    if page_descs is None:
+        with ctx.Pool(cores) as pool:
+            page_descs = [None] * npages
+            for p, d in pool.imap_unordered(_cpu_page_desc, range(npages)):
+                page_descs[p] = d
     times, results = [], None
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(page_descs,)) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(page_descs, matcher)) as pool:
+        pool.map(_cpu_noop, range(cores))      # every worker has built its matcher (LSH: index training) before the clock starts
         for s in range(warmup + steps):
             t0 = time.perf_counter()
             out = pool.map(_cpu_match_frame, [(f, npages) for f in frame_ids], chunksize=1)
@@ -112,8 +164,13 @@ def cpu_reference_rate(npages: int, frame_ids, cores: int, steps: int = 1, warmu
             if s >= warmup:
                 times.append(dt)
             results = out
-    # (the wall time also contains the synthetic generation of each sampled frame, ~0.3 % of a CPU frame)
+    # (the wall time also contains the synthetic generation of each sampled frame, ~1 % of a CPU frame)
     return len(frame_ids) * len(times) / sum(times), times, results, page_descs
+
+
+def cpu_sample_ids(n_frames: int, cores: int):
+    """>= 32 frames; here also >= 2 frames per core so that the rate is not cores / single-frame latency."""
+    return list(range(min(n_frames, max(32, 2 * cores))))
 
 
 class ClockSampler:
@@ -172,8 +229,9 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = list(range(min(args.frames, max(cores, 8))))
-    rate, times, results, _ = cpu_reference_rate(args.pages, sample, cores, steps=args.steps, warmup=args.warmup)
+    sample = cpu_sample_ids(args.frames, cores)
+    rate, times, results, page_descs = cpu_reference_rate(args.pages, sample, cores, steps=args.steps, warmup=args.warmup)
+    lsh_rate, lsh_times, _, _ = cpu_reference_rate(args.pages, sample, cores, steps=1, warmup=0, matcher="lsh", page_descs=page_descs)
     import cv2
     line = {
         "impl": "reference", "metric": "1080p frames matched/s", "value": rate, "unit": "frames/s", "n_gpus": args.gpus,
@@ -183,7 +241,11 @@ def run_reference(args, rank: int, world: int):
         "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{len(sample)} frames/step of the {args.frames}-frame workload, cv2 {cv2.__version__} "
                                    f"(OpenCV, the library the reference calls; it pins 4.5.2) ORB(2000)+BFMatcher(HAMMING).knnMatch(30)+vote, "
-                                   f"one process per core, 1 OpenCV thread each (mirrors rayon per-frame parallelism)"},
+                                   f"one process per core, 1 OpenCV thread each (mirrors rayon per-frame parallelism)",
+                         "flann_lsh": {"value": lsh_rate, "unit": "frames/s",
+                                       "what": "the same sample with the matcher the reference really builds: FlannBasedMatcher LSH(6,12,1), "
+                                               "checks 32 (flann.rs:15-23), one index per worker, index training outside the clock; "
+                                               "approximate and non-deterministic -> timing only, the headline value stays the exact BF arm"}},
         "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,6 +257,7 @@ def workload_config(args, world):
                         f"256-bit Hamming BF-knn k=30 + 1.05-ratio vote, per GPU",
             "frames_per_gpu": args.frames, "pages": args.pages, "nfeatures": 2000, "knn_k": KNN_K, "max_batch": args.max_batch,
             "parallelism": f"frames sharded over {world} GPU(s), pool replicated (1 NCCL broadcast)" if world > 1 else "1 GPU",
+            "pipelining": "steps are submitted one ahead of the collect (slideo_b200_submit_frames_bgr8 / _collect)",
             "l2_policy": f"inputs larger than L2 ({args.frames * FRAME_BYTES / 1e9:.1f} GB of frames per step vs 126 MB)"}
 
 
@@ -207,9 +270,11 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (configs[1]: 1000)")
     ap.add_argument("--pages", type=int, default=50, help="slide pages in the pool (configs[1]: 50)")
     ap.add_argument("--max-batch", type=int, default=64,
-                    help="frames per detection batch (K8 runs on chunks of the pooled query stream, independent of this)")
+                    help="frames per detection batch (K8 runs on whole waves of the pooled query stream, independent of this)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the detail blocks (decision tail, SIFT variant, configs[2])")
+    ap.add_argument("--c2-frames", type=int, default=C2_FRAMES, help="total frames of the configs[2] strong-scaling block")
+    ap.add_argument("--c2-pages", type=int, default=C2_PAGES)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -228,18 +293,25 @@ def main():
     cpu_results = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import cv2
-        sample = list(range(min(args.frames, max(cores, 8))))
-        rate, times, cpu_results, _ = cpu_reference_rate(args.pages, sample, cores)
+        sample = cpu_sample_ids(args.frames, cores)
+        rate, times, cpu_results, page_descs = cpu_reference_rate(args.pages, sample, cores)
+        lsh_rate, lsh_times, _, _ = cpu_reference_rate(args.pages, sample, cores, matcher="lsh", page_descs=page_descs)
         cpu_baseline = {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": f"first {len(sample)} frames of the workload (one pass, {times[0]:.1f} s), cv2 {cv2.__version__} "
-                                  f"ORB(2000)+BFMatcher(HAMMING).knnMatch(30)+vote, one process per core, 1 OpenCV thread each"}
+                                  f"ORB(2000)+BFMatcher(HAMMING).knnMatch(30)+vote, one process per core, 1 OpenCV thread each",
+                        "flann_lsh": {"value": lsh_rate, "unit": "frames/s",
+                                      "what": f"same sample ({lsh_times[0]:.1f} s) with the reference's real matcher, FlannBasedMatcher "
+                                              "LSH(6,12,1) checks 32 (flann.rs:15-23), index training outside the clock; approximate, "
+                                              "timing only -- the headline ratio stays on the exact BF arm (like for like)"}}
 
     # ---- host-side input generation in fork()ed workers, BEFORE CUDA is initialised in this process ----------
     gen_procs = max(1, min(32, cores // max(world, 1)))
     f_lo = rank * args.frames
     fork = mp.get_context("fork")
     gen_pool = fork.Pool(gen_procs)
-    pages_async = gen_pool.map_async(_gen_page, range(args.pages)) if rank == 0 else None
+    extras = not args.no_extras
+    n_pages_gen = max(args.pages, args.c2_pages if extras else 0, C3_PAGES if extras else 0)
+    pages_async = gen_pool.map_async(_gen_page, range(n_pages_gen))   # every rank renders the deck (the configs[2] block shards its extraction)
     frames_iter = gen_pool.imap(_gen_frame, [(f_lo + i, args.pages) for i in range(args.frames)], chunksize=4)
 
     import torch
@@ -250,18 +322,34 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allgather_int(x: int):
+        if world == 1:
+            return [int(x)]
+        t = torch.tensor([x], dtype=torch.int64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [int(o[0]) for o in out]
+
     ctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=args.max_batch))
 
     # ---- page pool: built on rank 0 by the library's own ORB, replicated by one broadcast --------------------
+    pages = dict(pages_async.get())
     t0 = time.perf_counter()
     if rank == 0:
-        pages = dict(pages_async.get())
         for p in range(args.pages):
             ctx.add_page_gray8(pages[p])
         ctx.finalize_pool()
@@ -288,13 +376,13 @@ def main():
         and K8 launches enqueued) before the results of step s are collected, so the GPU never drains between steps.  Every
         step's work, its H2D copies and the D2H of its results lie inside the bracket."""
         def run(k):
-            res, prev = None, submit()
+            prev = submit()
             for _ in range(k - 1):
                 nxt = submit()
-                res = ctx.collect(prev, args.frames)
+                ctx.collect(prev, args.frames)
                 prev = nxt
             return ctx.collect(prev, args.frames)
-        res = run(args.warmup)
+        run(args.warmup)
         ctx.timings(reset=True)
         barrier()
         t0 = time.perf_counter()
@@ -318,54 +406,69 @@ def main():
     # e2e arm: the public host-buffer call, H2D of every frame + D2H of the results inside the timed region
     res_e2e, t_e2e, _, tm_e2e = timed(lambda: ctx.submit_frames_bgr8_ptr(pin.ptr, args.frames, FRAME_W, FRAME_H))
     assert np.array_equal(res_dev, res_e2e), "device-resident and host-buffer arms disagree"
-    assert np.array_equal(res_dev, ctx.match_frames_bgr8_ptr(pin.ptr, args.frames, FRAME_W, FRAME_H)), "submit/collect and the synchronous call disagree"
+    assert np.array_equal(res_dev, ctx.match_frames_bgr8_ptr(pin.ptr, args.frames, FRAME_W, FRAME_H)), \
+        "submit/collect and the synchronous call disagree"
+    ctx.timings(reset=True)
 
     total_frames = args.frames * world * args.steps
     value = total_frames / t_dev
     e2e = total_frames / t_e2e
+    truth_ok = sum(1 for i in range(args.frames) if _truth_ok(res_dev, f_lo + i, i, args.pages))
+    truth_per_rank = allgather_int(truth_ok)
 
-    # ---- roofline of the dominant kernel (K8) -----------------------------------------------------------------
+    # ---- roofline of the dominant kernel (K8 v5) ----------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    popc_rate = ctx.microbench(1)       # thread-level POPC/s over the whole GPU, measured now on this device
-    lop3_rate = ctx.microbench(0)
-    mix_rate = ctx.microbench(2)
+    lop3_rate = ctx.microbench(0)       # thread-level LOP3/s over the whole GPU, measured now on this device
+    popc_rate = ctx.microbench(1)
+    mix_rate = ctx.microbench(3)        # the v5 inner loop alone (no selection, no slab reloads), pairs/s
     knn_s = tm_dev["ms_knn"] * 1e-3
     launches = max(int(tm_dev["knn_launches"]), 1)
     pairs = float(tm_dev["knn_pairs"])
     nq_total = pairs / max(pool_n, 1)
     alg_bytes = 32.0 * (nq_total + pool_n * launches) + 8.0 * KNN_K * nq_total     # 32(Nq+Nt) + 8 k Nq per launch
     ach_pairs = pairs / knn_s / 1e9
-    # two-pipe integer roofline of the carry-save formulation: 4 POPC per pair on the XU pipe, 13 LOP3 per
-    # pair on the ALU pipe; both rates measured now on this GPU by the library's own micro-benchmarks
-    peak_pairs = min(popc_rate / 4.0, lop3_rate / 13.0) / 1e9
-    roofline = {
-        "bound": "int-pipe", "kernel": "knn_hamming_kernel (K8, + split merge)", "achieved": ach_pairs, "peak": peak_pairs,
-        "unit": "Gpair/s", "frac": ach_pairs / peak_pairs,
-        "peak_source": "measured now on this GPU: min(POPC thread-ops/s / 4 POPC per pair, LOP3 thread-ops/s / 13 LOP3 per pair); "
-                       "K8 is integer-pipe bound, not HBM- or tensor-bound (SURVEY.md 8d); SURVEY's naive 8-POPC ceiling would be popc/8",
-        "naive_popc8_ceiling_gpairs": popc_rate / 8.0 / 1e9,
-        "avg_launch_ms": 1e3 * knn_s / launches, "pairs_per_launch": pairs / launches, "share_of_step": knn_s / max(t_dev_events, 1e-9),
-        "lop3_ops_per_s": lop3_rate, "popc_ops_per_s": popc_rate, "mix_ceiling_gpairs": mix_rate / 1e9,
-        "hbm": {"bound": "hbm", "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
-        "traffic": None,
-    }
+    peak_pairs = lop3_rate / LOP3_PER_PAIR_V5 / 1e9
+    traffic = None
+    traffic_note = "not measured in this run"
     prof = os.path.join(ROOT, "profiles", "k8_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            # dram bytes scale with 32 (Nq + Nt): the capture's per-launch figure is rescaled to this run's launch shape
+            cap_alg = 32.0 * (tj["nq"] + tj["nt"])
+            traffic = tj["dram_bytes_per_launch"] * (32.0 * (nq_total / launches + pool_n)) / cap_alg
+            traffic_note = (f"constant from the committed ncu capture {tj.get('source', 'profiles/k8_traffic.json')} "
+                            f"({tj['dram_bytes_per_launch'] / 1e6:.1f} MB at {tj['nq']} x {tj['nt']}, "
+                            f"{tj['dram_bytes_per_launch'] / cap_alg:.2f} x its 32 (Nq + Nt) bytes), rescaled to this launch shape; "
+                            "NOT measured in this run")
         except Exception:
             pass
+    roofline = {
+        "bound": "int-pipe", "kernel": "knn5_kernel (K8 v5, bit-sliced Hamming k-NN + fused vote)", "achieved": ach_pairs,
+        "peak": peak_pairs, "unit": "Gpair/s", "frac": ach_pairs / peak_pairs,
+        "peak_source": f"measured now on this GPU: LOP3 thread-ops/s / {LOP3_PER_PAIR_V5:.2f} LOP3 per pair (1070 per lane and 128 pooled "
+                       "rows: 8 x 15 + 7 full adders x 2 x 4 words, one half adder, the 10-plane compare); K8 is ALU-pipe bound, not "
+                       "HBM- or tensor-bound (SURVEY.md 8d).  The POPC formulation of round 1 (4 POPC + 13 LOP3 per pair) had its "
+                       "ceiling at popc/4: see r1_popc_ceiling_gpairs",
+        "r1_popc_ceiling_gpairs": min(popc_rate / 4.0, lop3_rate / 13.0) / 1e9,
+        "naive_popc8_ceiling_gpairs": popc_rate / 8.0 / 1e9,
+        "avg_launch_ms": 1e3 * knn_s / launches, "pairs_per_launch": pairs / launches, "share_of_step": knn_s / max(t_dev_events, 1e-9),
+        "share_note": "avg_launch_ms is bracketed by events on the K8 stream and contains the time K8 CTAs wait for SMs held by K1-K7",
+        "lop3_ops_per_s": lop3_rate, "popc_ops_per_s": popc_rate, "mix_ceiling_gpairs": mix_rate / 1e9,
+        "hbm": {"bound": "hbm", "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+        "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": alg_bytes / launches,
+    }
 
     # ---- extra (rank 0, N=1): the same step with the reference's complete decision tail switched on (SURVEY 8(f) ranks 1-2:
     #      RANSAC rating gate lib.rs:284-333 + warp/similarity gate lib.rs:335-389) ----
     verify_detail = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    if rank == 0 and world == 1 and extras:
         try:
             vctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=args.max_batch, geometric_verification=2))
             for p in range(args.pages):
@@ -390,43 +493,28 @@ def main():
         except Exception as ex:  # the extra must never break the contract line
             verify_detail = {"error": str(ex)}
 
-    # ---- extra (rank 0, N=1): the SIFT-128 / L2 variant of the same path (north_star; BASELINE configs[3] geometry at this run's
-    #      page count): K11 SIFT on the GPU for pages and frames -> K10 tcgen05 L2 k-NN -> vote, on a bounded sample of the frames ----
+    # ---- extra (every rank; rank 0 prints): BASELINE configs[3] -- the SIFT-128 / L2 variant of the same path at 200 pages:
+    #      K11 SIFT on the GPU for pages and frames -> K10 tcgen05 L2 k-NN -> vote, on a stated sample of the 5000 / N frames ----
     sift_detail = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    if extras:
         try:
-            ns = min(args.frames, 64)
-            sctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=16, descriptor_kind=slideo_b200.ffi.DESC_SIFT128))
-            t0 = time.perf_counter()
-            for p in range(args.pages):
-                sctx.add_page_gray8(pages[p])
-            sctx.finalize_pool()
-            t_spool = time.perf_counter() - t0
-            s_n, _ = sctx.pool_info()
-            sctx.match_frames_bgr8_device(dev.data_ptr(), ns, FRAME_W, FRAME_H)   # warm-up: workspaces grow to this sample's sizes
-            sctx.timings(reset=True)
-            s_sampler = ClockSampler(local_rank)
-            s_sampler.start()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                rs = sctx.match_frames_bgr8_device(dev.data_ptr(), ns, FRAME_W, FRAME_H)
-            dts = (time.perf_counter() - t0) / 3
-            s_clocks = s_sampler.stop()
-            tms = sctx.timings(reset=True)
-            for key in ("ms_detect", "ms_knn", "knn_pairs"):
-                tms[key] = tms[key] / 3
-            bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1368.2)))
-            k10_tflops = 2.0 * 144.0 * float(tms["knn_pairs"]) / max(tms["ms_knn"], 1e-9) / 1e9
-            sift_detail = {"frames": ns, "frames_per_s": ns / dts, "pool_descriptors": s_n, "pool_build_s": t_spool,
-                           "keypoints_per_frame": float(np.mean(rs[:, 2])), "ms_k11_per_frame": tms["ms_detect"] / ns,
-                           "ms_k10_per_frame": tms["ms_knn"] / ns,
-                           "k10_roofline": {"bound": "tensor", "achieved": k10_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
-                                            "frac": k10_tflops / bf16_peak, "flops": "2*(128+16)*Nq*Nt per launch"},
-                           "frames_with_truth_match": int(sum(1 for i in range(ns) if _truth_ok(rs, f_lo + i, i, args.pages))),
-                           "clocks": {"sm_mhz": s_clocks["sm_mhz"], "reasons": s_clocks["reasons"], "power_w_max": s_clocks["power_w_max"]}}
-            sctx.close()
-        except Exception as ex:  # the extra must never break the contract line
+            sift_detail = sift_block(slideo_b200, args, rank, world, local_rank, pages, dev, f_lo, peaks, cores, allmax, allgather_int,
+                                     barrier)
+        except Exception as ex:
             sift_detail = {"error": str(ex)}
+            if world > 1:
+                raise                  # a rank that dropped out of a collective block must not leave the others hanging
+
+    # ---- extra (every rank; rank 0 prints): BASELINE configs[2] strong scaling ------------------------------------------------
+    c2_detail = None
+    if extras:
+        try:
+            c2_detail = configs2_block(slideo_b200, sharding, torch, dist, args, rank, world, local_rank, pages, dev, f_lo, allmax,
+                                       allgather_int, barrier)
+        except Exception as ex:
+            c2_detail = {"error": str(ex)}
+            if world > 1:
+                raise
 
     if rank == 0:
         parity = None
@@ -447,15 +535,149 @@ def main():
             "detail": {"device_ms_per_step_events": 1e3 * t_dev_events / args.steps, "ms_detect_per_step": tm_dev["ms_detect"] / args.steps,
                        "ms_knn_per_step": tm_dev["ms_knn"] / args.steps, "pool_descriptors": pool_n, "pool_pages": pool_pages,
                        "pool_build_s": t_pool, "keypoints_per_frame": float(np.mean(res_dev[:, 2])),
-                       "frames_with_truth_match": int(sum(1 for i in range(args.frames) if _truth_ok(res_dev, f_lo + i, i, args.pages))),
+                       "frames_with_truth_match": truth_per_rank[0], "frames_with_truth_match_per_rank": truth_per_rank,
                        "cpu_sample_matches_gpu": parity, "descriptor_pairs_per_s": pairs * world / t_dev,
-                       "with_geometric_verification": verify_detail, "sift128_variant": sift_detail},
+                       "with_geometric_verification": verify_detail, "sift128_variant": sift_detail, "configs2_strong": c2_detail},
         }
         print(json.dumps(line), flush=True)
     pin.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _cycle_submit(dev_ptr, n_resident, n_total, chunk, submit_device):
+    """Submits n_total frames as chunks that cycle through the rank's n_resident device-resident frames.  Every frame is fully
+    re-processed (nothing is cached); returns [(ticket, n, first_resident_index)]."""
+    out, done = [], 0
+    while done < n_total:
+        i0 = done % n_resident
+        n = min(chunk, n_total - done, n_resident - i0)
+        out.append((submit_device(dev_ptr + i0 * FRAME_BYTES, n), n, i0))
+        done += n
+    return out
+
+
+def configs2_block(slideo_b200, sharding, torch, dist, args, rank, world, local_rank, pages, dev, f_lo, allmax, allgather_int, barrier):
+    """BASELINE configs[2]: 10 000 frames x 500 pages, ORB / Hamming, frames STRONG-sharded over the N ranks.  Timed from the first
+    add_page to the last result: every rank extracts its contiguous share of the pages (the reference extracts pages in a rayon
+    par_iter, lib.rs:45-56), the pool is assembled on every rank by an all-gather of the page-sharded descriptors (issued as one
+    in-place NCCL broadcast per source rank straight between the library's device buffers), then every rank matches its
+    10 000 / N frames.  The frames cycle through the rank's resident synthetic frames (their true pages are pages 0..49 of the
+    500-page deck); every frame is fully processed."""
+    F, P = args.c2_frames, args.c2_pages
+    lo, hi = sharding.shard_range(F, rank, world)
+    n_mine = hi - lo
+    p_lo, p_hi = sharding.shard_range(P, rank, world)
+    barrier()
+    t_start = time.perf_counter()
+    builder = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=1))
+    for p in range(p_lo, p_hi):
+        builder.add_page_gray8(pages[p])
+    builder.finalize_pool()
+    c2 = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=args.max_batch))
+    coll = sharding.allgather_pool_device(builder, c2, dist if world > 1 else None)
+    torch.cuda.synchronize()
+    t_pool = time.perf_counter() - t_start
+    builder.close()
+    n_desc, n_pages = c2.pool_info()
+    # untimed warm-up on a few frames (workspaces, first-touch allocations)
+    t_w0 = time.perf_counter()
+    c2.match_frames_bgr8_device(dev.data_ptr(), min(64, args.frames), FRAME_W, FRAME_H)
+    t_warm = time.perf_counter() - t_w0
+    c2.timings(reset=True)
+    barrier()
+    t_match0 = time.perf_counter()
+    tickets = _cycle_submit(dev.data_ptr(), args.frames, n_mine, args.frames,
+                            lambda ptr, n: c2.submit_frames_bgr8_device(ptr, n, FRAME_W, FRAME_H))
+    good = 0
+    for t, n, i0 in tickets:
+        r = c2.collect(t, n)
+        good += sum(1 for i in range(n) if _truth_ok(r, f_lo + i0 + i, i, args.pages))
+    c2.synchronize()
+    torch.cuda.synchronize()
+    t_match = time.perf_counter() - t_match0
+    tm = c2.timings(reset=True)
+    c2.close()
+    t_pool_max, t_match_max = allmax(t_pool), allmax(t_match)
+    goods = allgather_int(good)
+    frames_rank = allgather_int(n_mine)
+    return {"workload": f"configs[2]: {F} frames x {P} pages strong-sharded over {world} GPU(s): {n_mine} frames on rank 0; frames cycle "
+                        f"through each rank's {args.frames} resident synthetic frames (every frame fully processed), device-resident",
+            "frames_total": F, "pages": P, "n_gpus": world, "pool_descriptors": n_desc, "pool_pages": n_pages,
+            "seconds_pool_phase": t_pool_max, "seconds_match_phase": t_match_max, "seconds_total": t_pool_max + t_match_max,
+            "frames_per_s_total": F / (t_pool_max + t_match_max), "frames_per_s_match_only": F / t_match_max,
+            "untimed_warmup_s": t_warm,
+            "pool_phase": {"pages_per_rank": p_hi - p_lo, "collective": coll},
+            "k8_gpairs_per_s_rank0": tm["knn_pairs"] / max(tm["ms_knn"], 1e-9) / 1e6,
+            "frames_per_rank": frames_rank, "frames_with_truth_match_per_rank": goods,
+            "strong_scaling_note": "efficiency at N GPUs = seconds_total(N=1) / (N x seconds_total(N)); both phases are inside seconds_total"}
+
+
+def sift_block(slideo_b200, args, rank, world, local_rank, pages, dev, f_lo, peaks, cores, allmax, allgather_int, barrier):
+    """BASELINE configs[3]: 5000 frames x 200 pages, SIFT-128 / L2 through the bf16 tcgen05 path, frames sharded over the N ranks.
+    Measured on a stated sample of each rank's share; every rank builds the 200-page SIFT pool itself (no collective in the block)."""
+    F_total = 5000
+    n_share = -(-F_total // world)
+    ns = min(n_share, args.frames, 96)
+    sctx = slideo_b200.Context(slideo_b200.default_config(device=local_rank, max_batch=16, descriptor_kind=slideo_b200.ffi.DESC_SIFT128))
+    t0 = time.perf_counter()
+    for p in range(C3_PAGES):
+        sctx.add_page_gray8(pages[p])
+    sctx.finalize_pool()
+    t_spool = time.perf_counter() - t0
+    s_n, _ = sctx.pool_info()
+    sctx.match_frames_bgr8_device(dev.data_ptr(), min(ns, 16), FRAME_W, FRAME_H)   # warm-up: workspaces grow to this sample's sizes
+    sctx.timings(reset=True)
+    s_sampler = ClockSampler(local_rank)
+    barrier()
+    s_sampler.start()
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rs = sctx.match_frames_bgr8_device(dev.data_ptr(), ns, FRAME_W, FRAME_H)
+    dts = (time.perf_counter() - t0) / reps
+    s_clocks = s_sampler.stop()
+    tms = sctx.timings(reset=True)
+    for key in ("ms_detect", "ms_knn", "knn_pairs"):
+        tms[key] = tms[key] / reps
+    dts_max = allmax(dts)
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1368.2)))
+    k10_tflops = (2.0 * 128.0 + 3.0) * float(tms["knn_pairs"]) / max(tms["ms_knn"], 1e-9) / 1e9   # SURVEY 8d: 2*128 + 3 FLOP per pair
+    good = int(sum(1 for i in range(ns) if _truth_ok(rs, f_lo + i, i, args.pages)))
+    goods = allgather_int(good)
+    # CPU baseline of the variant (rank 0, N=1 only): cv2.SIFT_create() + BFMatcher(NORM_L2) on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            pool_host, pool_offs = sctx.pool_export()
+            n_cpu = min(cores, 16)
+            with mp.get_context("fork").Pool(n_cpu, initializer=_cpu_sift_init, initargs=(pool_host, pool_offs)) as wp:
+                t0 = time.perf_counter()
+                out = wp.map(_cpu_sift_frame, [(f_lo + i, args.pages, 64) for i in range(n_cpu)], chunksize=1)
+                wall = time.perf_counter() - t0
+            per_frame = statistics.mean(ts + tk for _, _, ts, tk in out)
+            import cv2
+            cpu = {"value": n_cpu / per_frame, "unit": "frames/s", "cores": n_cpu, "kind": "port",
+                   "sample": f"{n_cpu} frames, one per worker process (1 OpenCV thread each), cv2 {cv2.__version__} SIFT_create().detectAndCompute "
+                             f"in full ({statistics.mean(ts for _, _, ts, _ in out):.2f} s/frame) + BFMatcher(NORM_L2).knnMatch(30) against the "
+                             f"{s_n}-descriptor pool timed on the first 64 query rows of each frame and scaled linearly to its "
+                             f"{statistics.mean(n for _, n, _, _ in out):.0f} descriptors ({statistics.mean(tk for _, _, _, tk in out):.1f} s/frame "
+                             f"extrapolated); sample wall time {wall:.1f} s"}
+        except Exception as ex:
+            cpu = {"error": str(ex)}
+    sctx.close()
+    return {"workload": f"configs[3]: {F_total} frames x {C3_PAGES} pages, SIFT-128 / L2, {world} GPU(s): sample of {ns} of the {n_share} frames "
+                        f"of each rank, device-resident, {reps} repetitions",
+            "n_gpus": world, "frames_sampled_per_rank": ns, "frames_per_s_per_gpu": ns / dts_max, "frames_per_s_total": world * ns / dts_max,
+            "seconds_for_5000_frames_extrapolated": n_share / (ns / dts_max),
+            "pool_descriptors": s_n, "pool_build_s": t_spool,
+            "keypoints_per_frame": float(np.mean(rs[:, 2])), "ms_k11_per_frame": tms["ms_detect"] / ns, "ms_k10_per_frame": tms["ms_knn"] / ns,
+            "k10_roofline": {"bound": "tensor", "achieved": k10_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
+                             "frac": k10_tflops / bf16_peak, "flops": "(2*128 + 3) * Nq * Nt per launch (SURVEY.md 8d)",
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1368.2"},
+            "frames_with_truth_match_per_rank": goods, "cpu_baseline": cpu,
+            "clocks": {"sm_mhz": s_clocks["sm_mhz"], "reasons": s_clocks["reasons"], "power_w_max": s_clocks["power_w_max"]}}
 
 
 def _truth_ok(res, f_global, i, npages):

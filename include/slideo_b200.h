@@ -273,8 +273,9 @@ int32_t slideo_b200_bf_knn_l2_device(slideo_b200_ctx* ctx, const void* d_q, int3
 int32_t slideo_b200_host_alloc(void** out, size_t bytes); /* pinned host memory */
 int32_t slideo_b200_host_free(void* p);
 int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, int32_t reset);
-/* Integer-pipe micro-benchmark used as the K8 roofline denominator: which = 0 LOP3, 1 POPC, 2 the K8 inner-loop
- * instruction mix; returns thread-level ops (or descriptor pairs for which=2) per second over the whole GPU. */
+/* Integer-pipe micro-benchmarks used as the K8 roofline denominators: which = 0 LOP3, 1 POPC (thread-level ops per second over
+ * the whole GPU), 2 the inner-loop instruction mix of K8 v4 (XOR/POPC), 3 the inner loop of K8 v5 (bit-sliced: list walk +
+ * carry-save tree + compare on synthetic shared-memory contents) -- both in descriptor pairs per second. */
 int32_t slideo_b200_microbench(slideo_b200_ctx* ctx, int32_t which, double* out_per_second);
 int32_t slideo_b200_synchronize(slideo_b200_ctx* ctx);
 

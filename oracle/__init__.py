@@ -30,7 +30,7 @@ VOTE_RATIO = 1.05     # crates/matching-opencv/src/lib.rs:275
 def build() -> str:
     """Compile liboracle.so (gcc) if missing or stale."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c", "ransac_oracle.c", "area_oracle.c", "sift_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "bf_oracle.c", "ransac_oracle.c", "area_oracle.c", "sift_oracle.c", "libm_port.c")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so

@@ -1908,9 +1908,9 @@ int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, 
 int32_t slideo_b200_microbench(slideo_b200_ctx* ctx, int32_t which, double* out_per_second) {
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
-        arg(which >= 0 && which <= 2, "which must be 0, 1 or 2");
+        arg(which >= 0 && which <= 3, "which must be 0, 1, 2 or 3");
         arg(out_per_second != nullptr, "out_per_second must not be NULL");
-        *out_per_second = microbench_run(which, ctx->num_sms, ctx->stream);
+        *out_per_second = which == 3 ? knn5_microbench_run(ctx->num_sms, ctx->stream) : microbench_run(which, ctx->num_sms, ctx->stream);
     });
 }
 

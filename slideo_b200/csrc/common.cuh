@@ -115,6 +115,7 @@ size_t knn5_dyn_partial_bytes(int num_sms, int k);
 void knn5_plan_launch(KnnStream* d_state, KnnDyn* d_dyn, int nt, int num_sms, int flush, cudaStream_t stream);
 void knn5_launch_dyn(const KnnDyn* d_dyn, int nq_max, int nt, int k, int num_sms, const void* d_q_base, const void* d_slabs,
                      uint32_t* d_keys_base, uint32_t* d_partial, const VoteArgs* vote_base, cudaStream_t stream, int* launches);
+double knn5_microbench_run(int num_sms, cudaStream_t stream);   // pairs/s of the v5 inner loop alone
 // frames of the stream whose queries are all matched -> (best_slide, votes, n_keypoints) rows in a host-mapped ring + progress word
 void stream_finalize_launch(KnnStream* d_state, const KnnDyn* d_dyn, const int32_t* d_frame_q0, const int32_t* d_votes, int n_pages,
                             const int32_t* d_frame_nkp, int32_t* h_ring, int ring_mask, long long seq_base, int32_t* d_results,

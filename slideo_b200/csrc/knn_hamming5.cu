@@ -100,6 +100,86 @@ __device__ __forceinline__ void k5_set_meta(uint32_t* meta, int lane, int A, boo
     else if (lane == 13) meta[13] = (uint32_t)tau;
 }
 
+struct K5Planes { V4 pl0, ones, twos, fours, eights, s16, s32, s64, s128, s256; };   // s = 2c + pt' as bit planes 0..9
+
+// one query against the slab in shared memory: walks the query's list of bit rows (128 entries, padded with the zero row) and
+// adds the words of those rows for this lane's 128 pooled rows.  Harley-Seal: 15 full adders per 16 inputs, a second level over
+// the 8 weight-16 carries; the accumulators are seeded with pt' >> 1, so the total is s = 2c + pt'.
+__device__ __forceinline__ void k5_scan(const uint4* lst, int lanebase, K5Planes& P) {
+    V4 ones = lds4(lanebase + (K5_ROW_PT + 1) * K5_ROWB), twos = lds4(lanebase + (K5_ROW_PT + 2) * K5_ROWB),
+       fours = lds4(lanebase + (K5_ROW_PT + 3) * K5_ROWB), eights = lds4(lanebase + (K5_ROW_PT + 4) * K5_ROWB),
+       s16 = lds4(lanebase + (K5_ROW_PT + 5) * K5_ROWB), s32 = lds4(lanebase + (K5_ROW_PT + 6) * K5_ROWB),
+       s64 = lds4(lanebase + (K5_ROW_PT + 7) * K5_ROWB), s128 = lds4(lanebase + (K5_ROW_PT + 8) * K5_ROWB);
+    V4 s256, o_prev, t32a, u64a;
+#pragma unroll
+    for (int w = 0; w < K5_W; ++w) s256.v[w] = o_prev.v[w] = t32a.v[w] = u64a.v[w] = 0;
+#pragma unroll
+    for (int blk = 0; blk < 8; ++blk) {
+        const uint4 e0 = lst[blk * 4], e1 = lst[blk * 4 + 1], e2 = lst[blk * 4 + 2], e3 = lst[blk * 4 + 3];
+        const uint32_t ent[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+        V4 x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = lds4((uint32_t)imad((int)ent[i], K5_ROWB, lanebase));
+        V4 ta, tb, fa, fb, ea, eb, o;
+        csa(ones, ta, ones, x[0], x[1]);
+        csa(ones, tb, ones, x[2], x[3]);
+        csa(twos, fa, twos, ta, tb);
+        csa(ones, ta, ones, x[4], x[5]);
+        csa(ones, tb, ones, x[6], x[7]);
+        csa(twos, fb, twos, ta, tb);
+        csa(fours, ea, fours, fa, fb);
+        csa(ones, ta, ones, x[8], x[9]);
+        csa(ones, tb, ones, x[10], x[11]);
+        csa(twos, fa, twos, ta, tb);
+        csa(ones, ta, ones, x[12], x[13]);
+        csa(ones, tb, ones, x[14], x[15]);
+        csa(twos, fb, twos, ta, tb);
+        csa(fours, eb, fours, fa, fb);
+        csa(eights, o, eights, ea, eb);
+        if (blk & 1) {
+            V4 t;
+            csa(s16, t, s16, o_prev, o);
+            if ((blk & 3) == 3) {
+                V4 u;
+                csa(s32, u, s32, t32a, t);
+                if (blk == 7) {
+                    V4 v;
+                    csa(s64, v, s64, u64a, u);
+#pragma unroll
+                    for (int w = 0; w < K5_W; ++w) { s256.v[w] = s128.v[w] & v.v[w]; s128.v[w] ^= v.v[w]; }
+                } else u64a = u;
+            } else t32a = t;
+        } else o_prev = o;
+    }
+    P.pl0 = lds4(lanebase + K5_ROW_PT * K5_ROWB);
+    P.ones = ones; P.twos = twos; P.fours = fours; P.eights = eights; P.s16 = s16; P.s32 = s32; P.s64 = s64; P.s128 = s128; P.s256 = s256;
+}
+
+// survivors of the test d < tau: the carry out of s + C + cin over the 10 planes, inverted for a complemented list, masked by
+// the slab's valid rows.  Returns the OR of the four result words.
+__device__ __forceinline__ uint32_t k5_compare(const K5Planes& P, const uint32_t* meta, int lanebase, uint32_t (&res)[K5_W]) {
+    const V4 valid = lds4(lanebase + K5_ROW_VALID * K5_ROWB);
+    const uint4 m0 = *reinterpret_cast<const uint4*>(meta), m1 = *reinterpret_cast<const uint4*>(meta + 4),
+                m2 = *reinterpret_cast<const uint4*>(meta + 8);
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < K5_W; ++w) {
+        uint32_t cy = knn_lop3<KNN_LUT_MAJ>(P.pl0.v[w], m0.x, m2.z);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.ones.v[w], m0.y, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.twos.v[w], m0.z, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.fours.v[w], m0.w, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.eights.v[w], m1.x, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.s16.v[w], m1.y, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.s32.v[w], m1.z, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.s64.v[w], m1.w, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.s128.v[w], m2.x, cy);
+        cy = knn_lop3<KNN_LUT_MAJ>(P.s256.v[w], m2.y, cy);
+        res[w] = (cy ^ m2.w) & valid.v[w];
+        any |= res[w];
+    }
+    return any;
+}
+
 __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + K5_OFF_LIST);   // [tile][128] bit-row indices
@@ -180,77 +260,14 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
             for (int qi = 0; qi < K5_QPW; ++qi) {
                 const int ql = warp * K5_QPW + qi;
                 if (qbase + ql >= nq) break;   // warp-uniform
-                const uint4* lst = reinterpret_cast<const uint4*>(s_list + ql * K5_LIST);
-                // Harley-Seal accumulators seeded with pt' >> 1 (planes 1..8 of pt'): the total is s = 2c + pt'
-                V4 ones = lds4(lanebase + (K5_ROW_PT + 1) * K5_ROWB), twos = lds4(lanebase + (K5_ROW_PT + 2) * K5_ROWB),
-                   fours = lds4(lanebase + (K5_ROW_PT + 3) * K5_ROWB), eights = lds4(lanebase + (K5_ROW_PT + 4) * K5_ROWB),
-                   s16 = lds4(lanebase + (K5_ROW_PT + 5) * K5_ROWB), s32 = lds4(lanebase + (K5_ROW_PT + 6) * K5_ROWB),
-                   s64 = lds4(lanebase + (K5_ROW_PT + 7) * K5_ROWB), s128 = lds4(lanebase + (K5_ROW_PT + 8) * K5_ROWB);
-                V4 s256, o_prev, t32a, u64a;
-#pragma unroll
-                for (int w = 0; w < K5_W; ++w) s256.v[w] = o_prev.v[w] = t32a.v[w] = u64a.v[w] = 0;
-#pragma unroll
-                for (int blk = 0; blk < 8; ++blk) {
-                    const uint4 e0 = lst[blk * 4], e1 = lst[blk * 4 + 1], e2 = lst[blk * 4 + 2], e3 = lst[blk * 4 + 3];
-                    const uint32_t ent[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
-                    V4 x[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) x[i] = lds4((uint32_t)imad((int)ent[i], K5_ROWB, lanebase));
-                    V4 ta, tb, fa, fb, ea, eb, o;
-                    csa(ones, ta, ones, x[0], x[1]);
-                    csa(ones, tb, ones, x[2], x[3]);
-                    csa(twos, fa, twos, ta, tb);
-                    csa(ones, ta, ones, x[4], x[5]);
-                    csa(ones, tb, ones, x[6], x[7]);
-                    csa(twos, fb, twos, ta, tb);
-                    csa(fours, ea, fours, fa, fb);
-                    csa(ones, ta, ones, x[8], x[9]);
-                    csa(ones, tb, ones, x[10], x[11]);
-                    csa(twos, fa, twos, ta, tb);
-                    csa(ones, ta, ones, x[12], x[13]);
-                    csa(ones, tb, ones, x[14], x[15]);
-                    csa(twos, fb, twos, ta, tb);
-                    csa(fours, eb, fours, fa, fb);
-                    csa(eights, o, eights, ea, eb);
-                    // second level over the 8 weight-16 carries
-                    if (blk & 1) {
-                        V4 t;
-                        csa(s16, t, s16, o_prev, o);
-                        if ((blk & 3) == 3) {
-                            V4 u;
-                            csa(s32, u, s32, t32a, t);
-                            if (blk == 7) {
-                                V4 v;
-                                csa(s64, v, s64, u64a, u);
-#pragma unroll
-                                for (int w = 0; w < K5_W; ++w) { s256.v[w] = s128.v[w] & v.v[w]; s128.v[w] ^= v.v[w]; }
-                            } else u64a = u;
-                        } else t32a = t;
-                    } else o_prev = o;
-                }
-                // s as planes {pt'0, ones, twos, fours, eights, s16, s32, s64, s128, s256}; survivors: carry out of s + C + cin
-                const V4 pl0 = lds4(lanebase + K5_ROW_PT * K5_ROWB);
-                const V4 valid = lds4(lanebase + K5_ROW_VALID * K5_ROWB);
+                K5Planes pl_;
+                k5_scan(reinterpret_cast<const uint4*>(s_list + ql * K5_LIST), lanebase, pl_);
                 uint32_t* meta = s_meta + ql * K5_META;
-                const uint4 m0 = *reinterpret_cast<const uint4*>(meta), m1 = *reinterpret_cast<const uint4*>(meta + 4),
-                            m2 = *reinterpret_cast<const uint4*>(meta + 8);
                 uint32_t res[K5_W];
-                uint32_t any = 0;
-#pragma unroll
-                for (int w = 0; w < K5_W; ++w) {
-                    uint32_t cy = knn_lop3<KNN_LUT_MAJ>(pl0.v[w], m0.x, m2.z);
-                    cy = knn_lop3<KNN_LUT_MAJ>(ones.v[w], m0.y, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(twos.v[w], m0.z, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(fours.v[w], m0.w, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(eights.v[w], m1.x, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(s16.v[w], m1.y, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(s32.v[w], m1.z, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(s64.v[w], m1.w, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(s128.v[w], m2.x, cy);
-                    cy = knn_lop3<KNN_LUT_MAJ>(s256.v[w], m2.y, cy);
-                    res[w] = (cy ^ m2.w) & valid.v[w];
-                    any |= res[w];
-                }
+                const uint32_t any = k5_compare(pl_, meta, lanebase, res);
+                const V4 &pl0 = pl_.pl0, &ones = pl_.ones, &twos = pl_.twos, &fours = pl_.fours, &eights = pl_.eights, &s16 = pl_.s16,
+                         &s32 = pl_.s32, &s64 = pl_.s64, &s128 = pl_.s128, &s256 = pl_.s256;
+                const uint4 m2 = *reinterpret_cast<const uint4*>(meta + 8);
                 if (!__any_sync(KNN_FULL, any != 0)) continue;
 
                 // ---- slow path: exact distances of the survivors, inserted into the query's sorted top-k --------------------
@@ -480,9 +497,40 @@ __global__ void stream_publish_kernel(KnnStream* st, const KnnDyn* dyn, const in
     *h_progress = seq_base + f_new;
 }
 
+// The v5 inner loop (list walk + carry-save tree + compare) on synthetic shared-memory contents, no selection, no slab reloads:
+// the ceiling of this formulation in descriptor pairs per second (slideo_b200_microbench which = 3).
+__global__ void __launch_bounds__(K5_THREADS, 1) knn5_microbench_kernel(uint32_t* out, int iters) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    uint32_t* s_words = reinterpret_cast<uint32_t*>(s_raw);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + K5_OFF_LIST);
+    uint32_t* s_meta = reinterpret_cast<uint32_t*>(s_raw + K5_OFF_META);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t h = (blockIdx.x * K5_THREADS + tid) * 2654435761u + 12345u;
+    for (int i = tid; i < 267 * K5_ROWB / 4; i += K5_THREADS) { h = h * 1664525u + 1013904223u; s_words[i] = h ^ (h >> 13); }
+    for (int i = tid; i < KNN5_TILE * K5_LIST; i += K5_THREADS) { h = h * 1664525u + 1013904223u; s_list[i] = (h >> 8) & 255u; }
+    __syncthreads();
+    for (int ql = warp * K5_QPW; ql < (warp + 1) * K5_QPW; ++ql) k5_set_meta(s_meta + ql * K5_META, lane, 128, false, 40);
+    __syncthreads();
+    const int lanebase = (int)knn_smem_u32(s_raw) + lane * 16;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+        for (int qi = 0; qi < K5_QPW; ++qi) {
+            const int ql = warp * K5_QPW + qi;
+            K5Planes pl;
+            k5_scan(reinterpret_cast<const uint4*>(s_list + ql * K5_LIST), lanebase, pl);
+            uint32_t res[K5_W];
+            const uint32_t any = k5_compare(pl, s_meta + ql * K5_META, lanebase, res);
+            if (__any_sync(KNN_FULL, any != 0)) acc += __popc(any);
+        }
+    }
+    out[blockIdx.x * K5_THREADS + tid] = acc;
+}
+
 void k5_configure() {
     // per device and cheap: set on every launch (a process may drive several GPUs from several ctxs)
     SLIDEO_CUDA(cudaFuncSetAttribute(knn5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM));
+    SLIDEO_CUDA(cudaFuncSetAttribute(knn5_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM));
 }
 
 }  // namespace
@@ -566,6 +614,30 @@ void knn5_launch_dyn(const KnnDyn* d_dyn, int nq_max, int nt, int k, int num_sms
         d_partial, d_dyn, 0, 1, k, d_keys_base, P.vote);
     SLIDEO_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
+}
+
+double knn5_microbench_run(int num_sms, cudaStream_t stream) {
+    const int iters = 64;
+    uint32_t* d_out = nullptr;
+    SLIDEO_CUDA(cudaMalloc(&d_out, (size_t)num_sms * K5_THREADS * 4));
+    cudaEvent_t e0, e1;
+    SLIDEO_CUDA(cudaEventCreate(&e0));
+    SLIDEO_CUDA(cudaEventCreate(&e1));
+    k5_configure();
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        SLIDEO_CUDA(cudaEventRecord(e0, stream));
+        knn5_microbench_kernel<<<num_sms, K5_THREADS, K5_SMEM, stream>>>(d_out, iters);
+        SLIDEO_CUDA(cudaEventRecord(e1, stream));
+        SLIDEO_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SLIDEO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return (double)num_sms * iters * KNN5_TILE * KNN5_SLAB_ROWS / (best * 1e-3);
 }
 
 }  // namespace slideo

@@ -16,9 +16,11 @@
 //   sift_bucket_*         descriptor threads are scheduled by window radius (counting sort), so warps run equal-length loops
 //   sift_descriptor_kernel S.10 4x4x8 histogram, one thread per keypoint with its 360 bins in shared memory
 //
-// The only operations not bit-defined by the oracle's source are libm's cosf / sinf / exp2f (keypoint size, descriptor
-// rotation): the device evaluates them in double and rounds once, which agrees with glibc except for results within ~1e-9
-// relative of a rounding boundary.
+// The oracle calls libm for three values (exp2f for the keypoint size, cosf / sinf for the descriptor rotation); OpenCV calls the
+// same libm.  glibc evaluates them as short double-precision polynomials with one final rounding (flt-32/e_exp2f.c,
+// s_sincosf.h -- the ARM optimized-routines algorithms); glibc_exp2f / glibc_sinf / glibc_cosf below restate exactly those
+// algorithms, so the device returns the same bits (checked against glibc 2.39 over every 7th float of [0, 1.6] and every 5th of
+// [0, 6.4], with and without FMA contraction: 0 differences; tests/test_gpu_sift.py checks the device against the host libm).
 #include "sift.cuh"
 
 #include <math.h>
@@ -27,6 +29,72 @@
 namespace slideo {
 
 namespace {
+
+// ---- glibc's float exp2 / sin / cos, restated (see the header comment) -----------------------------------------------------------
+// 2^(i/32) as doubles with the exponent contribution of i removed (glibc's __exp2f_data.tab)
+__device__ const unsigned long long GLIBC_EXP2F_TAB[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull, 0x3fef54873168b9aaull,
+    0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull,
+    0x3feea11473eb0187ull, 0x3feea589994cce13ull, 0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
+    0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+
+// exp2f for |x| < 128 (the keypoint size uses x in (0, 1.2))
+__device__ __forceinline__ float glibc_exp2f(float x) {
+    const double SHIFT = 211106232532992.0;   // 0x1.8p+52 / 32
+    const double C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1;
+    const double xd = (double)x;
+    double kd = __dadd_rn(xd, SHIFT);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, SHIFT);
+    const double r = __dsub_rn(xd, kd);
+    const unsigned long long t = GLIBC_EXP2F_TAB[ki & 31] + (ki << 47);
+    const double sc = __longlong_as_double((long long)t);
+    const double z = __dadd_rn(__dmul_rn(C0, r), C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+    y = __dadd_rn(__dmul_rn(z, r2), y);
+    return (float)__dmul_rn(y, sc);
+}
+
+// sinf / cosf for 0 <= |y| < 120: reduce_fast + sinf_poly of glibc's s_sincosf.h.  want_cos selects the polynomial like cosf does.
+__device__ __forceinline__ float glibc_sincosf(float yf, bool want_cos) {
+    const double HPI_INV = 0x1.45F306DC9C883p+23, HPI = 0x1.921FB54442D18p0;
+    const double c0 = 1.0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    double x = (double)yf;
+    const unsigned top = (__float_as_uint(yf) >> 20) & 0x7ffu;
+    int n = 0;
+    double sgn = 1.0, flip = 1.0;
+    if (top < ((0x3f490fdbu >> 20) & 0x7ffu)) {           // |y| < pi/4 (abstop12 comparison)
+        if (top < ((0x39800000u >> 20) & 0x7ffu)) return want_cos ? 1.0f : yf;   // |y| < 2^-12
+    } else {
+        const double r = __dmul_rn(x, HPI_INV);
+        n = (__double2int_rz(r) + 0x800000) >> 24;
+        x = __dsub_rn(x, __dmul_rn((double)n, HPI));
+        sgn = (n & 3) == 1 || (n & 3) == 2 ? -1.0 : 1.0;   // sign[] = {1, -1, -1, 1}
+        if (n & 2) flip = -1.0;                             // __sincosf_table[1]: the cosine coefficients negated
+    }
+    const int sel = want_cos ? (n ^ 1) : n;
+    const double x2 = __dmul_rn(x, x);
+    const double xs = __dmul_rn(x, sgn);
+    if ((sel & 1) == 0) {
+        const double x3 = __dmul_rn(xs, x2);
+        const double t1 = __dadd_rn(s2, __dmul_rn(x2, s3));
+        const double x7 = __dmul_rn(x3, x2);
+        const double s = __dadd_rn(xs, __dmul_rn(x3, s1));
+        return (float)__dadd_rn(s, __dmul_rn(x7, t1));
+    }
+    const double x4 = __dmul_rn(x2, x2);
+    const double q2 = __dadd_rn(flip * c3, __dmul_rn(x2, flip * c4));
+    const double q1 = __dadd_rn(flip * c1, __dmul_rn(x2, flip * c2));
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __dadd_rn(flip * c0, __dmul_rn(x2, q1));
+    return (float)__dadd_rn(c, __dmul_rn(x6, q2));
+}
+__device__ __forceinline__ float glibc_sinf(float y) { return glibc_sincosf(y, false); }
+__device__ __forceinline__ float glibc_cosf(float y) { return glibc_sincosf(y, true); }
 
 constexpr int TW = 64, TH = 64;      // blur tile
 constexpr int EX_TX = 32, EX_TY = 16;  // extrema tile
@@ -382,7 +450,7 @@ __global__ void __launch_bounds__(128) sift_refine_kernel(const float* __restric
     rc.kx = ((float)c + xc) * (float)(1 << octv);
     rc.ky = ((float)r + xr) * (float)(1 << octv);
     rc.koct = octv + (l << 8) + (__double2int_rn(((double)xi + 0.5) * 255) << 16);
-    rc.ksize = (float)1.6 * (float)exp2((double)(((float)l + xi) / SIFT_LAYERS)) * (float)(1 << octv) * 2;
+    rc.ksize = (float)1.6 * glibc_exp2f(((float)l + xi) / SIFT_LAYERS) * (float)(1 << octv) * 2;
     rc.kresp = fabsf(contr);
     rc.packed = (int)(((uint32_t)octv << 28) | ((uint32_t)l << 26) | ((uint32_t)r << 13) | (uint32_t)c);
     const int slot = atomicAdd(refined_cnt + img, 1);
@@ -699,7 +767,7 @@ __global__ void __launch_bounds__(DESC_THREADS) sift_descriptor_kernel(const flo
         const int d = 4, n = 8;
         const int px = __float2int_rn(ptx), py = __float2int_rn(pty);
         const float ang = ori * (float)(3.14159265358979323846 / 180);
-        float cos_t = (float)cos((double)ang), sin_t = (float)sin((double)ang);
+        float cos_t = glibc_cosf(ang), sin_t = glibc_sinf(ang);
         const float bins_per_rad = n / 360.f;
         const float exp_scale = -1.f / (d * d * 0.5f);
         const float hist_width = 3.f * scl;

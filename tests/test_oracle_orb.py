@@ -14,7 +14,7 @@ import oracle
 import synth
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-REF_FIX = "/root/reference/data/matchings/test1"
+REF_FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fixtures")   # copies of the reference's data/matchings/test1/*.png (test infrastructure)
 
 try:
     import cv2

@@ -136,3 +136,16 @@ def test_sift_edge_sizes_equal_cv2(shape):
     flat = np.full(shape, 123, np.uint8)
     kf, oc, de = oracle.sift_detect_and_compute(flat)
     assert len(kf) == 0 and len(mg.cv2_sift(flat)[0]) == 0
+
+
+def test_libm_port_equals_libm():
+    """The three libm values of SIFT (exp2f for the size, cosf / sinf for the descriptor rotation) are evaluated on the GPU with glibc's
+    own algorithms (sift.cu).  oracle/libm_port.c restates them in C; here the restatement is pinned against this machine's libm on a
+    sweep of the ranges SIFT uses (size exponent in (0, 1.2), angles in [0, 2 pi])."""
+    import ctypes
+    L = oracle.lib()
+    L.libm_port_mismatches.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_uint32]
+    L.libm_port_mismatches.restype = ctypes.c_long
+    assert L.libm_port_mismatches(0, 0.0, 1.6, 61) == 0
+    assert L.libm_port_mismatches(1, 0.0, 6.4, 53) == 0
+    assert L.libm_port_mismatches(2, 0.0, 6.4, 53) == 0

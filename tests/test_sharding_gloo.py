@@ -137,3 +137,42 @@ def test_two_rank_sift_pool_equals_single_process(tmp_path):
     want = np.array([_sift_match(_sift_frame(desc, offs, f), desc, offs) for f in range(n_frames)], np.int32)
     assert np.array_equal(got, want)
     assert list(want[:, 0]) == [0, 1, 3, 0, 1]
+
+
+def _ag_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sizes = (120, 0, 90, 200, 33)                      # 5 pages over 2 ranks: 3 + 2, one of them empty
+        lo, hi = sharding.shard_range(len(sizes), rank, world)
+        mine = [synth.hamming_pool(n, seed=700 + i, dup_frac=0.0) for i, n in enumerate(sizes)][lo:hi]
+        desc = np.concatenate(mine) if mine else np.zeros((0, 32), np.uint8)
+        offs = np.zeros(len(mine) + 1, np.int32)
+        offs[1:] = np.cumsum([len(p) for p in mine])
+        full, offsets = sharding.allgather_pool_host(desc, offs)
+        np.savez(out_path % rank, desc=full, offs=offsets)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_page_sharded_pool_allgather_world2(tmp_path):
+    """The configs[2] pool phase: pages sharded over ranks, pool assembled everywhere by a ragged all-gather."""
+    import multiprocessing as mp
+    import synth
+    port = _free_port()
+    out = str(tmp_path / "ag_%d.npz")
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_ag_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    sizes = (120, 0, 90, 200, 33)
+    want = np.concatenate([synth.hamming_pool(n, seed=700 + i, dup_frac=0.0) for i, n in enumerate(sizes)])
+    want_offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    for r in range(2):
+        got = np.load(out % r)
+        assert np.array_equal(got["desc"], want) and np.array_equal(got["offs"], want_offs)
