@@ -273,6 +273,12 @@ int32_t slideo_b200_bf_knn_l2_device(slideo_b200_ctx* ctx, const void* d_q, int3
 int32_t slideo_b200_host_alloc(void** out, size_t bytes); /* pinned host memory */
 int32_t slideo_b200_host_free(void* p);
 int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, int32_t reset);
+/* Optional progress callback, the C form of ProgressReporter (crates/matching/src/progress.rs:3-17: Fn(u64, u64, &str)): while a
+ * match_frames_* / collect call waits for the GPU it reports (frames of this call finished, frames of this call, message) from
+ * the calling thread, once per finished k-NN launch group.  fn = NULL switches it off.  The message pointer is only valid during
+ * the callback. */
+typedef void (*slideo_b200_progress_fn)(uint64_t processed, uint64_t total, const char* message, void* user);
+int32_t slideo_b200_set_progress_callback(slideo_b200_ctx* ctx, slideo_b200_progress_fn fn, void* user);
 /* Integer-pipe micro-benchmarks used as the K8 roofline denominators: which = 0 LOP3, 1 POPC (thread-level ops per second over
  * the whole GPU), 2 the inner-loop instruction mix of K8 v4 (XOR/POPC), 3 the inner loop of K8 v5 (bit-sliced: list walk +
  * carry-save tree + compare on synthetic shared-memory contents) -- both in descriptor pairs per second. */

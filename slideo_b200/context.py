@@ -377,6 +377,15 @@ class Context:
         self._ck(self._lib.slideo_b200_get_timings(self._h, ctypes.byref(t), int(reset)))
         return {f: getattr(t, f) for f, _ in ffi.Timings._fields_}
 
+    def set_progress_callback(self, handler=None) -> None:
+        """handler(processed, total, message) or None -- the C form of crates/matching/src/progress.rs:3-17."""
+        if handler is None:
+            self._progress_cb = None
+            self._ck(self._lib.slideo_b200_set_progress_callback(self._h, None, None))
+            return
+        self._progress_cb = ffi.PROGRESS_FN(lambda a, b, m, _u: handler(int(a), int(b), (m or b"").decode()))   # keep the thunk alive
+        self._ck(self._lib.slideo_b200_set_progress_callback(self._h, ctypes.cast(self._progress_cb, ctypes.c_void_p), None))
+
     def microbench(self, which: int) -> float:
         v = ctypes.c_double()
         self._ck(self._lib.slideo_b200_microbench(self._h, which, ctypes.byref(v)))

@@ -426,6 +426,9 @@ struct slideo_b200_ctx {
     DevBuf<unsigned long long> d_sumsq;
     bool have_prev_small = false;
 
+    slideo_b200_progress_fn progress_fn = nullptr;   // optional (processed, total, message) callback, matching/src/progress.rs:3-17
+    void* progress_user = nullptr;
+
     bool want_keys() const { return cfg.keep_matches != 0 || cfg.geometric_verification != 0; }
     size_t kp_per_frame_cap(int w, int h) { return extractor(w, h, cfg.max_batch).kp_cap() / (size_t)cfg.max_batch; }
 
@@ -597,12 +600,16 @@ struct slideo_b200_ctx {
     }
 
     // waits until the results of frames [.., seq_end) are in the host ring; flushes the stream when its tail sits in a partial wave
-    void wait_progress(long long seq_end, bool check_flags) {
+    void wait_progress(long long seq_end, bool check_flags, long long seq_begin = -1) {
         bool flushed = false;
         while (*h_progress < seq_end) {
             if (launch_synced < launch_seq) {
                 SLIDEO_CUDA(cudaEventSynchronize(ev_knn[launch_synced % DYN_SLOTS]));
                 ++launch_synced;
+                if (progress_fn && seq_begin >= 0) {
+                    const long long done = std::min(std::max(*h_progress - seq_begin, 0LL), seq_end - seq_begin);
+                    progress_fn((uint64_t)done, (uint64_t)(seq_end - seq_begin), "Processing frames...", progress_user);
+                }
                 continue;
             }
             if (!ep_open || flushed) {   // everything has run and the frames are still missing: a capacity bit dropped them
@@ -639,7 +646,7 @@ struct slideo_b200_ctx {
         const Ticket t = tickets[i];
         const int n = (int)(t.seq1 - t.seq0);
         if (out && cap < n) throw ArgError("cap smaller than the number of frames of the ticket");
-        wait_progress(t.seq1, true);
+        wait_progress(t.seq1, true, t.seq0);
         if (out)
             for (int f = 0; f < n; ++f) {
                 const int32_t* r = h_ring + (size_t)((t.seq0 + f) & (RING - 1)) * 3;
@@ -679,7 +686,7 @@ struct slideo_b200_ctx {
             enqueue_frames(frames + (size_t)s0 * frame_stride, on_device, ns, w, h, stride, frame_stride, keep_frames ? d_all_frames.p : nullptr);
             const int set = cur_ep;
             close_epoch();
-            wait_progress(seq_submitted, true);
+            wait_progress(seq_submitted, true, seq0);
             SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
             for (int f = 0; f < ns; ++f) {
                 const int32_t* r = h_ring + (size_t)((seq0 + f) & (RING - 1)) * 3;
@@ -1877,6 +1884,14 @@ int32_t slideo_b200_host_alloc(void** out, size_t bytes) {
 int32_t slideo_b200_host_free(void* p) {
     if (!p) return SLIDEO_B200_OK;
     return cudaFreeHost(p) == cudaSuccess ? SLIDEO_B200_OK : SLIDEO_B200_E_CUDA;
+}
+
+int32_t slideo_b200_set_progress_callback(slideo_b200_ctx* ctx, slideo_b200_progress_fn fn, void* user) {
+    REQUIRE_CTX(ctx);
+    return guarded(ctx, [&] {
+        ctx->progress_fn = fn;
+        ctx->progress_user = user;
+    });
 }
 
 int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, int32_t reset) {

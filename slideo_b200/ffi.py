@@ -103,9 +103,12 @@ SYMBOLS = {
     "slideo_b200_host_alloc": (c_i32, [ctypes.POINTER(c_vp), c_sz]),
     "slideo_b200_host_free": (c_i32, [c_vp]),
     "slideo_b200_get_timings": (c_i32, [c_vp, ctypes.POINTER(Timings), c_i32]),
+    "slideo_b200_set_progress_callback": (c_i32, [c_vp, c_vp, c_vp]),
     "slideo_b200_microbench": (c_i32, [c_vp, c_i32, ctypes.POINTER(ctypes.c_double)]),
     "slideo_b200_synchronize": (c_i32, [c_vp]),
 }
+
+PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_void_p)
 
 _LIB = None
 

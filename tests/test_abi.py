@@ -43,14 +43,16 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_c(tmp_path):
     from slideo_b200 import ffi
     c = tmp_path / "sz.c"
-    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "slideo_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %d\\n",'
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "slideo_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %d %zu %zu %zu\\n",'
                  "sizeof(slideo_b200_config), sizeof(slideo_b200_frame_result), sizeof(slideo_b200_match), sizeof(slideo_b200_timings),"
-                 "offsetof(slideo_b200_config, vote_ratio), offsetof(slideo_b200_timings, knn_pairs), SLIDEO_B200_ABI_VERSION);return 0;}\n")
+                 "offsetof(slideo_b200_config, vote_ratio), offsetof(slideo_b200_timings, knn_pairs), SLIDEO_B200_ABI_VERSION,"
+                 "sizeof(slideo_b200_verify_result), sizeof(slideo_b200_decision), offsetof(slideo_b200_decision, refined_matrix));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
     vals = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
     assert vals == [ctypes.sizeof(ffi.Config), ctypes.sizeof(ffi.FrameResult), ctypes.sizeof(ffi.Match), ctypes.sizeof(ffi.Timings),
-                    ffi.Config.vote_ratio.offset, ffi.Timings.knn_pairs.offset, ffi.ABI_VERSION]
+                    ffi.Config.vote_ratio.offset, ffi.Timings.knn_pairs.offset, ffi.ABI_VERSION,
+                    ctypes.sizeof(ffi.VerifyResult), ctypes.sizeof(ffi.Decision), ffi.Decision.refined_matrix.offset]
 
 
 def test_default_config_is_the_reference_literals():
@@ -105,3 +107,96 @@ def test_tools_and_bench_compile():
     assert len(files) > 5
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+# ---- the Rust binding source (integration/matching-b200/src/ffi.rs) against the header ----------------------------------------------
+FFI_RS = os.path.join(ROOT, "integration", "matching-b200", "src", "ffi.rs")
+
+
+def _c_functions():
+    """name -> number of parameters, from the header."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int32_t|const char\*)\s+(slideo_b200_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def _c_structs():
+    """name -> [(field, C type, array dims)] from the header."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"typedef struct (slideo_b200_[a-z_]+) \{(.*?)\} \1;", src, flags=re.S):
+        fields = []
+        for decl in m.group(2).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            fm = re.match(r"([a-z0-9_]+)\s+([a-z0-9_]+)((?:\[[A-Z0-9_]+\])*)$", decl)
+            assert fm, decl
+            fields.append((fm.group(2), fm.group(1), re.findall(r"\[([A-Z0-9_]+)\]", fm.group(3))))
+        out[m.group(1)] = fields
+    return out
+
+
+def _rs_functions():
+    src = re.sub(r"//[^\n]*", "", open(FFI_RS).read())
+    out = {}
+    for m in re.finditer(r"pub fn (slideo_b200_[a-z0-9_]+)\s*\((.*?)\)\s*->", src, flags=re.S):
+        args = [a for a in m.group(2).split(",") if a.strip()]
+        out[m.group(1)] = len(args)
+    return out
+
+
+def _rs_structs():
+    src = re.sub(r"//[^\n]*", "", open(FFI_RS).read())
+    out = {}
+    for m in re.finditer(r"#\[repr\(C\)\]\s*(?:#\[derive\([^)]*\)\]\s*)?pub struct (slideo_b200_[a-z_]+) \{(.*?)\n\}", src, flags=re.S):
+        fields = []
+        for fm in re.finditer(r"pub ([a-z0-9_]+):\s*([^,\n]+),", m.group(2)):
+            fields.append((fm.group(1), fm.group(2).strip()))
+        out[m.group(1)] = fields
+    return out
+
+
+def test_rust_binding_declares_every_function_with_the_same_arity():
+    c, rs = _c_functions(), _rs_functions()
+    assert sorted(c) == _declared()
+    assert sorted(rs) == sorted(c), "ffi.rs and the header declare different functions"
+    for name, n in c.items():
+        assert rs[name] == n, f"{name}: {rs[name]} parameters in ffi.rs, {n} in the header"
+
+
+def test_rust_binding_structs_match_the_header():
+    consts = {"SLIDEO_B200_TOP_SLIDES": 40, "SLIDEO_B200_TOP_RATED": 10}
+    ctype = {"int32_t": "i32", "float": "f32", "double": "f64", "int64_t": "i64"}
+    c, rs = _c_structs(), _rs_structs()
+    assert sorted(c) == sorted(rs) and len(c) == 6
+    for name, fields in c.items():
+        assert [f for f, _, _ in fields] == [f for f, _ in rs[name]], name
+        for (fname, t, dims), (_, rtype) in zip(fields, rs[name]):
+            want = ctype[t]
+            for d in reversed(dims):                      # C a[X][Y] == Rust [[T; Y]; X]
+                want = f"[{want}; {d if d in consts else int(d)}]"
+            got = rtype
+            for k, v in consts.items():
+                want, got = want.replace(k, str(v)), got.replace(k, str(v))
+            assert got.replace(" ", "") == want.replace(" ", ""), f"{name}.{fname}: {rtype} vs {t}{dims}"
+    src = open(FFI_RS).read()
+    for k, v in consts.items():
+        assert re.search(rf"pub const {k}: usize = {v};", src)
+    # status codes and kinds
+    hdr = open(HEADER).read()
+    for name, val in re.findall(r"(SLIDEO_B200_(?:OK|E_[A-Z_]+|DESC_[A-Z0-9]+)) = (-?\d+)", hdr):
+        assert re.search(rf"pub const {name}: i32 = {val};", src), name
+
+
+def test_rust_crate_uses_the_decision_tail():
+    """the crate must decide like the reference (gate chain), not by min_votes."""
+    lib_rs = open(os.path.join(ROOT, "integration", "matching-b200", "src", "lib.rs")).read()
+    assert "geometric_verification = 2" in lib_rs and "slideo_b200_get_decisions" in lib_rs and "slideo_b200_mark_changed_bgr8" in lib_rs
+    assert "min_votes" not in lib_rs
+    for mod in re.findall(r"^mod ([a-z_]+);", lib_rs, flags=re.M):
+        assert os.path.exists(os.path.join(ROOT, "integration", "matching-b200", "src", mod + ".rs")), f"mod {mod} has no source file"
+    assert os.path.exists(os.path.join(ROOT, "integration", "matching-b200", "build.rs"))
