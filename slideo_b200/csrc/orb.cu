@@ -75,35 +75,66 @@ __global__ void __launch_bounds__(128) gray_kernel(const uint8_t* __restrict__ s
 // ---- K2 -----------------------------------------------------------------------------------------------------
 // resize INTER_LINEAR_EXACT, 8-bit: horizontal 8.8 fixed point then vertical, (v + 2^15) >> 16   
 // tables (host-built in double precision, identical to the oracle): xofs[dw], xc1[dw], yofs[dh], yc1[dh]
+// A thread owns 4 destination columns and walks down a strip of RS_H destination rows: its x tables stay in registers, and
+// the horizontally interpolated source row shared by two consecutive destination rows (scale 1.2: the lower source row of row y
+// is usually the upper source row of row y + 1) is computed once.
+constexpr int RS_H = 30;
+
 __global__ void __launch_bounds__(128) resize_kernel(uint8_t* __restrict__ pyr, size_t pyr_img_bytes, size_t src_off,
                                                      int sw, int sh, int spitch, size_t dst_off, int dw, int dh,
                                                      int dpitch, const int32_t* __restrict__ tab) {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y, img = blockIdx.z;
     if (x0 >= dw) return;
+    const int y0 = blockIdx.y * RS_H, y1 = min(y0 + RS_H, dh), img = blockIdx.z;
     const int32_t* xofs = tab;
     const int32_t* xc1 = tab + dw;
     const int32_t* yofs = tab + 2 * dw;
     const int32_t* yc1 = tab + 2 * dw + dh;
-    const int oy = __ldg(yofs + y), fy = __ldg(yc1 + y);
-    const uint8_t* base = pyr + (size_t)img * pyr_img_bytes;
-    const uint8_t* s0 = base + src_off + (size_t)oy * spitch;
-    const uint8_t* s1 = base + src_off + (size_t)min(oy + 1, sh - 1) * spitch;
-    uint8_t o[4] = {0, 0, 0, 0};
+    int ox[4], ox1[4];
+    uint32_t c0[4], c1[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int x = x0 + i;
-        if (x < dw) {
-            const int ox = __ldg(xofs + x), fx = __ldg(xc1 + x);
-            const int ox1 = min(ox + 1, sw - 1);
-            const uint32_t a = (uint32_t)s0[ox] * (uint32_t)(256 - fx) + (uint32_t)s0[ox1] * (uint32_t)fx;
-            const uint32_t b = (uint32_t)s1[ox] * (uint32_t)(256 - fx) + (uint32_t)s1[ox1] * (uint32_t)fx;
-            uint32_t v = (a * (uint32_t)(256 - fy) + b * (uint32_t)fy + (1u << 15)) >> 16;
-            o[i] = (uint8_t)min(v, 255u);
-        }
+        const int x = min(x0 + i, dw - 1);
+        ox[i] = __ldg(xofs + x);
+        c1[i] = (uint32_t)__ldg(xc1 + x);
+        c0[i] = 256u - c1[i];
+        ox1[i] = min(ox[i] + 1, sw - 1);
     }
-    *reinterpret_cast<uchar4*>(pyr + (size_t)img * pyr_img_bytes + dst_off + (size_t)y * dpitch + x0) =
-        make_uchar4(o[0], o[1], o[2], o[3]);
+    const uint8_t* base = pyr + (size_t)img * pyr_img_bytes + src_off;
+    uint8_t* dbase = pyr + (size_t)img * pyr_img_bytes + dst_off;
+    auto hrow = [&](int r, uint32_t (&o)[4]) {   // horizontal 8.8 fixed-point pass of source row r at this thread's 4 columns
+        const uint8_t* sr = base + (size_t)r * spitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = (uint32_t)sr[ox[i]] * c0[i] + (uint32_t)sr[ox1[i]] * c1[i];
+    };
+    int prev_row = -1;
+    uint32_t prev[4] = {0, 0, 0, 0};
+    for (int y = y0; y < y1; ++y) {
+        const int oy = __ldg(yofs + y), oy1 = min(oy + 1, sh - 1);
+        const uint32_t fy = (uint32_t)__ldg(yc1 + y);
+        uint32_t a[4], b[4];
+        if (oy == prev_row) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = prev[i];
+        } else {
+            hrow(oy, a);
+        }
+        if (oy1 == oy) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = a[i];
+        } else {
+            hrow(oy1, b);
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            prev[i] = b[i];
+            const uint32_t v = (a[i] * (256u - fy) + b[i] * fy + (1u << 15)) >> 16;
+            if (x0 + i < dw) o |= min(v, 255u) << (8 * i);
+        }
+        prev_row = oy1;
+        *reinterpret_cast<uint32_t*>(dbase + (size_t)y * dpitch + x0) = o;
+    }
 }
 
 // ---- K3 -----------------------------------------------------------------------------------------------------
@@ -413,62 +444,76 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Geo* __restrict__ gp
 // GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) as ORB invokes it: the generic float separable filter
 // (row: acc = k0*p0; acc = fma(k_i, p_i, acc) left to right; column: acc = k3*r3; acc = fma(k_{3+j}, r_{3+j} + r_{3-j},
 // acc); round-half-even, saturate) -- SURVEY A.7.
-__global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
-                                                   const Geo* __restrict__ gp, const FastMaps* __restrict__ maps) {
-    constexpr int PH = TILE_H + 6;            // 3-px halo above and below
-    constexpr int PWW = (TILE_W + 8) / 4;     // 18 words per row: columns tx0-4 .. tx0+67 (the filter needs tx0-3 .. tx0+66)
-    // staged as the same 96 x 40 byte box FAST loads (columns tx0-16 .., rows ty0-4 ..), so interior tiles arrive by TMA through
-    // the level's tensor map; the filter's rows / words sit at offset (OY, OX) inside the box
-    constexpr int BH = TILE_H + 8, BWW = (TILE_W + 32) / 4, OY = 1, OX = 3;
-    __shared__ __align__(128) uint32_t s_px[BH][BWW];
-    __shared__ float4 s_row[PH][TILE_W / 4];
+// Tile = BT_W x BT_H pixels, one warp per strip of BS_H rows, one lane per 4 columns.  The whole box (tile + halo, rounded to the
+// 16-byte alignment TMA needs in x) arrives by ONE tensor copy; elements outside the level arrive as zeros and the (at most 3)
+// halo rows / columns that BORDER_REFLECT_101 defines are then written in place from their mirror positions inside the box.
+// Every thread walks down its strip: the row pass of a new input row stays in registers (4 floats), the column pass reads
+// the last 7 of them -- no shared-memory round trip for the intermediate, every input row converted and filtered once per strip.
+constexpr int BT_W = 128, BT_H = 64, BS_H = 16, BT_THREADS = (BT_W / 4) * (BT_H / BS_H);
+constexpr int BB_W = BT_W + 32, BB_H = BT_H + 8;   // box: columns tx0 - 16 .. tx0 + 143, rows ty0 - 4 .. ty0 + 67
+
+__global__ void __launch_bounds__(BT_THREADS) blur_kernel(uint8_t* __restrict__ blur, const Geo* __restrict__ gp,
+                                                          const FastMaps* __restrict__ maps) {
+    __shared__ __align__(128) uint8_t s_box[BB_H][BB_W];
     __shared__ __align__(8) uint64_t s_bar;
 
     const Geo& g = *gp;
     int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].tile_base) ++l;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].btile_base) ++l;
     const OrbLevelGeom L = g.lv[l];
-    const int t = blockIdx.x - L.tile_base;
-    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    const int t = blockIdx.x - L.btile_base;
+    const int tx0 = (t % L.btiles_x) * BT_W, ty0 = (t / L.btiles_x) * BT_H;
     const int img = blockIdx.y;
-    const uint8_t* src = pyr + (size_t)img * g.pyr_img_bytes + L.img_off;
     uint8_t* dst = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
 
-    const bool interior = tx0 >= 16 && tx0 + TILE_W + 16 <= L.w && ty0 >= 4 && ty0 + TILE_H + 4 <= L.h;   // box inside the level: no reflection
-    if (interior) {
-        if (threadIdx.x == 0) {
-            tma_mbar_init(&s_bar, 1);
-            tma_mbar_expect_tx(&s_bar, BH * BWW * 4);
-            tma_load_3d(&s_px[0][0], &maps->lv[l], tx0 - 16, ty0 - 4, img, &s_bar);
-        }
-        __syncthreads();
-        tma_mbar_wait(&s_bar, 0);
-    } else {
-        // border tiles, 4 pixels per thread and step: whole words where they lie inside the image, reflected bytes at the borders
-        for (int i = threadIdx.x; i < PH * PWW; i += blockDim.x) {
-            const int py = i / PWW, pw = i - py * PWW;
-            const int gx = tx0 - 4 + 4 * pw, gy = reflect101(ty0 + py - 3, L.h);
-            const uint8_t* row = src + (size_t)gy * L.pitch;
-            uint32_t w;
-            if (gx >= 0 && gx + 3 < L.w) {
-                w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-            } else {
-                w = (uint32_t)row[reflect101(gx, L.w)] | ((uint32_t)row[reflect101(gx + 1, L.w)] << 8) |
-                    ((uint32_t)row[reflect101(gx + 2, L.w)] << 16) | ((uint32_t)row[reflect101(gx + 3, L.w)] << 24);
-            }
-            s_px[py + OY][pw + OX] = w;
+    if (threadIdx.x == 0) {
+        tma_mbar_init(&s_bar, 1);
+        tma_mbar_expect_tx(&s_bar, BB_H * BB_W);
+        tma_load_3d(&s_box[0][0], &maps->lv[l], tx0 - 16, ty0 - 4, img, &s_bar);
+    }
+    __syncthreads();
+    tma_mbar_wait(&s_bar, 0);
+
+    // BORDER_REFLECT_101 on the tiles that touch the level's border: rows first (all columns), then columns (all rows)
+    const bool top = ty0 == 0, bottom = ty0 + BT_H + 3 > L.h, left = tx0 == 0, right = tx0 + BT_W + 3 > L.w;
+    if (top || bottom) {
+        for (int i = threadIdx.x; i < 6 * (BB_W / 4); i += BT_THREADS) {
+            const int k = i / (BB_W / 4), cw = i - k * (BB_W / 4);
+            int y, ys;   // image row to fill, its mirror
+            if (k < 3) { y = -1 - k; ys = 1 + k; if (!top) continue; }
+            else { y = L.h + (k - 3); ys = L.h - 2 - (k - 3); if (!bottom) continue; }
+            const int r = y - (ty0 - 4), rs = ys - (ty0 - 4);
+            if (r < 0 || r >= BB_H || rs < 0 || rs >= BB_H) continue;
+            reinterpret_cast<uint32_t*>(&s_box[r][0])[cw] = reinterpret_cast<const uint32_t*>(&s_box[rs][0])[cw];
         }
         __syncthreads();
     }
+    if (left || right) {
+        for (int i = threadIdx.x; i < 6 * BB_H; i += BT_THREADS) {
+            const int k = i / BB_H, r = i - k * BB_H;
+            int x, xs;
+            if (k < 3) { x = -1 - k; xs = 1 + k; if (!left) continue; }
+            else { x = L.w + (k - 3); xs = L.w - 2 - (k - 3); if (!right) continue; }
+            const int c = x - (tx0 - 16), cs = xs - (tx0 - 16);
+            if (c < 0 || c >= BB_W || cs < 0 || cs >= BB_W) continue;
+            s_box[r][c] = s_box[r][cs];
+        }
+        __syncthreads();
+    }
+
+    const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
+    const int gx = tx0 + 4 * lane, gy0 = ty0 + strip * BS_H;
+    if (gx >= L.w || gy0 >= L.h) return;
     // getGaussianKernel(7, 2, CV_32F) as exact bit patterns
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
-    // row pass: 4 outputs per thread from 3 words (12 pixels: outputs x..x+3 use smem columns x+1 .. x+10)
-    for (int i = threadIdx.x; i < PH * (TILE_W / 4); i += blockDim.x) {
-        const int py = i / (TILE_W / 4), x4 = i - py * (TILE_W / 4);
-        const uint32_t w0 = s_px[py + OY][x4 + OX], w1 = s_px[py + OY][x4 + OX + 1], w2 = s_px[py + OY][x4 + OX + 2];
+    float h[7][4];   // row-pass results of the last 7 input rows (rotating window; all indices are compile-time after unrolling)
+#pragma unroll
+    for (int i = 0; i < BS_H + 6; ++i) {
+        // input row gy0 - 3 + i == box row strip * BS_H + 1 + i; the thread's 12 bytes start at box column 4 * lane + 12
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&s_box[strip * BS_H + 1 + i][0]) + lane + 3;
+        const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
         // u8 -> fp32 without the conversion pipe: byte b | 0x4B000000 is the float 2^23 + b, exactly; subtract 2^23
-        // (one PRMT on the ALU pipe + one FADD instead of shift, mask and I2F on the quarter-rate XU pipe)
         float p[12];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -476,7 +521,6 @@ __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ p
             p[4 + b] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7540 + b)) - 8388608.f;
             p[8 + b] = __uint_as_float(__byte_perm(w2, 0x4B000000u, 0x7540 + b)) - 8388608.f;
         }
-        float o[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             float acc = __fmul_rn(k0, p[b + 1]);
@@ -486,33 +530,25 @@ __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ p
             acc = __fmaf_rn(k2, p[b + 5], acc);
             acc = __fmaf_rn(k1, p[b + 6], acc);
             acc = __fmaf_rn(k0, p[b + 7], acc);
-            o[b] = acc;
+            h[i % 7][b] = acc;
         }
-        s_row[py][x4] = make_float4(o[0], o[1], o[2], o[3]);
-    }
-    __syncthreads();
-    // column pass: 4 outputs per thread, one 32-bit store (bytes beyond the level width stay inside the row padding)
-    for (int i = threadIdx.x; i < TILE_H * (TILE_W / 4); i += blockDim.x) {
-        const int y = i / (TILE_W / 4), x4 = i - y * (TILE_W / 4);
-        const int gx = tx0 + 4 * x4, gy = ty0 + y;
-        if (gx >= L.w || gy >= L.h) continue;
-        const float4 r0 = s_row[y][x4], r1 = s_row[y + 1][x4], r2 = s_row[y + 2][x4], r3 = s_row[y + 3][x4], r4 = s_row[y + 4][x4],
-                     r5 = s_row[y + 5][x4], r6 = s_row[y + 6][x4];
-        const float c0[4] = {r0.x, r0.y, r0.z, r0.w}, c1[4] = {r1.x, r1.y, r1.z, r1.w}, c2[4] = {r2.x, r2.y, r2.z, r2.w},
-                    c3[4] = {r3.x, r3.y, r3.z, r3.w}, c4[4] = {r4.x, r4.y, r4.z, r4.w}, c5[4] = {r5.x, r5.y, r5.z, r5.w},
-                    c6[4] = {r6.x, r6.y, r6.z, r6.w};
-        uint32_t out = 0;
+        if (i >= 6) {
+            const int j = i - 6, gy = gy0 + j;   // output row j: input rows j .. j + 6 of the strip = window slots (j + m) % 7
+            if (gy < L.h) {
+                uint32_t out = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            float acc = __fmul_rn(k3, c3[b]);
-            acc = __fmaf_rn(k2, __fadd_rn(c4[b], c2[b]), acc);
-            acc = __fmaf_rn(k1, __fadd_rn(c5[b], c1[b]), acc);
-            acc = __fmaf_rn(k0, __fadd_rn(c6[b], c0[b]), acc);
-            // round-half-even without F2I: acc + 1.5 * 2^23 has the rounded integer in its low mantissa bits (0 <= acc < 2^22)
-            const int v = __float_as_int(__fadd_rn(acc, 12582912.f)) - 0x4B400000;
-            out |= (uint32_t)min(max(v, 0), 255) << (8 * b);
+                for (int b = 0; b < 4; ++b) {
+                    float acc = __fmul_rn(k3, h[(j + 3) % 7][b]);
+                    acc = __fmaf_rn(k2, __fadd_rn(h[(j + 4) % 7][b], h[(j + 2) % 7][b]), acc);
+                    acc = __fmaf_rn(k1, __fadd_rn(h[(j + 5) % 7][b], h[(j + 1) % 7][b]), acc);
+                    acc = __fmaf_rn(k0, __fadd_rn(h[(j + 6) % 7][b], h[j % 7][b]), acc);
+                    // round-half-even without F2I: acc + 1.5 * 2^23 has the rounded integer in its low mantissa bits (0 <= acc < 2^22)
+                    const int v = __float_as_int(__fadd_rn(acc, 12582912.f)) - 0x4B400000;
+                    out |= (uint32_t)min(max(v, 0), 255) << (8 * b);
+                }
+                *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
+            }
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
     }
 }
 
@@ -677,7 +713,7 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
         lv_[L - 1].quota = cfg.nfeatures - sum > 0 ? cfg.nfeatures - sum : 0;
     }
     size_t img_off = 0, cand_off = 0, sel_off = 0, tab_off = 0;
-    int tile_base = 0;
+    int tile_base = 0, btile_base = 0;
     std::vector<int32_t> tables;
     for (int l = 0; l < L; ++l) {
         OrbLevelGeom& g = lv_[l];
@@ -700,6 +736,10 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
         g.tiles_y = cdiv(g.h, TILE_H);
         g.tile_base = tile_base;
         tile_base += g.tiles_x * g.tiles_y;
+        g.btiles_x = cdiv(g.w, BT_W);
+        g.btiles_y = cdiv(g.h, BT_H);
+        g.btile_base = btile_base;
+        btile_base += g.btiles_x * g.btiles_y;
         g.tab_off = tab_off;
         if (l > 0) {
             tables.resize(tab_off + 2 * (size_t)(g.w + g.h));
@@ -709,6 +749,7 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
         }
     }
     total_tiles_ = tile_base;
+    total_btiles_ = btile_base;
     pyr_img_bytes_ = img_off;
     cand_img_words_ = cand_off;
     sel_img_words_ = sel_off;
@@ -770,6 +811,11 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
                                   (uint64_t)lv_[l].pitch, (uint64_t)pyr_img_bytes_, TILE_W + 32, TILE_H + 8);
         SLIDEO_CUDA(cudaMalloc(&fast_maps_, sizeof fm));   // the maps live in global memory (64-byte aligned by cudaMalloc)
         SLIDEO_CUDA(cudaMemcpy(fast_maps_, &fm, sizeof fm, cudaMemcpyHostToDevice));
+        for (int l = 0; l < L; ++l)                        // the blur's boxes: BB_W x BB_H of the same tensors
+            fm.lv[l] = tma_map_3d(CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, d_pyr_ + lv_[l].img_off, (uint64_t)lv_[l].pitch, (uint64_t)lv_[l].h, (uint64_t)batch_cap,
+                                  (uint64_t)lv_[l].pitch, (uint64_t)pyr_img_bytes_, BB_W, BB_H);
+        SLIDEO_CUDA(cudaMalloc(&blur_maps_, sizeof fm));
+        SLIDEO_CUDA(cudaMemcpy(blur_maps_, &fm, sizeof fm, cudaMemcpyHostToDevice));
     }
     {
         Geo g;
@@ -790,6 +836,7 @@ OrbExtractor::~OrbExtractor() {
     cudaFree(d_q_frame_); cudaFree(d_kp_i_); cudaFree(d_kp_f_); cudaFree(d_desc_); cudaFree(d_tables_);
     cudaFree(d_pattern_); cudaFree(d_geom_);
     cudaFree(fast_maps_);
+    cudaFree(blur_maps_);
     cudaFreeHost(h_pinned_);
 }
 
@@ -810,7 +857,7 @@ void OrbExtractor::enqueue(const uint8_t* d_src, int n, int stride, size_t frame
     }
     for (int l = 1; l < L; ++l) {
         const OrbLevelGeom &s = lv_[l - 1], &d = lv_[l];
-        dim3 grid(cdiv(cdiv(d.w, 4), 128), d.h, n);
+        dim3 grid(cdiv(cdiv(d.w, 4), 128), cdiv(d.h, RS_H), n);
         resize_kernel<<<grid, 128, 0, stream>>>(d_pyr_, pyr_img_bytes_, s.img_off, s.w, s.h, s.pitch, d.img_off, d.w, d.h,
                                                 d.pitch, d_tables_ + d.tab_off);
         ++nl;
@@ -832,7 +879,7 @@ void OrbExtractor::enqueue(const uint8_t* d_src, int n, int stride, size_t frame
     scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_, d_info_,
                                                    sink ? sink->q_frame : nullptr);
     ++nl;
-    blur_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(d_pyr_, d_blur_, g, static_cast<const FastMaps*>(fast_maps_));
+    blur_kernel<<<dim3(total_btiles_, n), BT_THREADS, 0, stream>>>(d_blur_, g, static_cast<const FastMaps*>(blur_maps_));
     ++nl;
     {
         // the keypoint total of the batch lives on the device: a fixed grid of warps strides over it

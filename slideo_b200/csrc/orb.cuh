@@ -25,6 +25,7 @@ struct OrbLevelGeom {
     int sel_cap;          // selected keypoints per image (power of two, sort width)
     int tiles_x, tiles_y; // 64x32 tiles
     int tile_base;        // first flat tile index of this level
+    int btiles_x, btiles_y, btile_base;   // the blur's own (larger) tiles
     float scale, inv_scale;
     size_t img_off;       // byte offset of the level inside one image's pyramid
     size_t cand_off;      // uint32 offset inside one image's candidate area
@@ -88,7 +89,7 @@ private:
     bool safe_ = false;          // see describe_kernel<SAFE> (orb.cu)
     int w_, h_, batch_cap_;
     std::vector<OrbLevelGeom> lv_;
-    int total_tiles_ = 0;
+    int total_tiles_ = 0, total_btiles_ = 0;
     size_t pyr_img_bytes_ = 0, cand_img_words_ = 0, sel_img_words_ = 0, kp_cap_ = 0;
     uint8_t *d_pyr_ = nullptr, *d_blur_ = nullptr, *d_desc_ = nullptr;
     uint32_t *d_cand_ = nullptr, *d_sel_ = nullptr, *d_kp_src_ = nullptr;
@@ -97,7 +98,8 @@ private:
             *d_info_ = nullptr;   // batch header {total, stream query base, stream frame base, flags}
     float* d_kp_f_ = nullptr;
     void* d_geom_ = nullptr;     // OrbLevelGeom[nlevels] on the device
-    void* fast_maps_ = nullptr;  // per-level TMA tensor maps of the pyramid (device memory)
+    void* fast_maps_ = nullptr;  // per-level TMA tensor maps of the pyramid (device memory): FAST's boxes
+    void* blur_maps_ = nullptr;  // the same tensors with the blur's boxes
     int8_t* d_pattern_ = nullptr;  // 512 x 2 int8
     int32_t* h_pinned_ = nullptr;  // [0] total, [1] flags, [2..] frame offsets
     std::vector<int32_t> h_frame_off_;
