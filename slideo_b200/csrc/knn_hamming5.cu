@@ -313,9 +313,11 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
                         if (res[w] != 0) {
                             const int r = __ffs(res[w]) - 1;
                             res[w] &= res[w] - 1;
+                            // bit r of the 10 planes; AND on the ALU pipe, POPC on the (idle) XU pipe, shift-add on the FMA pipe
+                            const uint32_t bit = 1u << r;
                             int s = 0;
 #pragma unroll
-                            for (int p = 0; p < 10; ++p) s |= (int)((pl[p]->v[w] >> r) & 1u) << p;
+                            for (int p = 0; p < 10; ++p) s = imad(__popc(pl[p]->v[w] & bit), 1 << p, s);
                             const int d = invm ? A - 256 + s : A + 256 - s;
                             key = ((uint32_t)d << KEY_IDX_BITS) | (row0 + (uint32_t)(w * 32 + r));
                         }

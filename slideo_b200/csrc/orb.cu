@@ -176,7 +176,8 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k127) {
 struct FastMaps { CUtensorMap lv[ORB_MAX_LEVELS]; };   // one rank-3 u8 tensor {x, y, image} per pyramid level
 
 __global__ void __launch_bounds__(256) fast_kernel(const FastMaps* __restrict__ maps, const Geo* __restrict__ gp,
-                                                   uint32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+                                                   const uint32_t* __restrict__ tiles, uint32_t* __restrict__ cand,
+                                                   int32_t* __restrict__ cand_cnt) {
     // pixel tile: 40 rows x 20 words = columns tx0-8 .. tx0+71; score tile: 34 rows x 72 columns = tx0-4 .. tx0+67, i.e. the
     // 64 x 32 pixels of the tile plus the halo the 3x3 NMS needs, rounded to whole words so every thread handles 4 pixels
     constexpr int PH = TILE_H + 8, PWW = (TILE_W + 32) / 4, PWB = PWW * 4, PX0 = 2;   // the staged rows start 16 B-aligned at tx0 - 16 (TMA): PX0 words before tx0 - 8
@@ -188,11 +189,9 @@ __global__ void __launch_bounds__(256) fast_kernel(const FastMaps* __restrict__ 
     __shared__ int s_n;
 
     const Geo& g = *gp;
-    int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].tile_base) ++l;
-    const OrbLevelGeom L = g.lv[l];
-    const int t = blockIdx.x - L.tile_base;
-    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    const uint32_t tref = __ldg(tiles + blockIdx.x);   // level | tx0 << 4 | ty0 << 16, precomputed on the host: no per-CTA search / division
+    const int l = tref & 15, tx0 = (tref >> 4) & 0xFFF, ty0 = tref >> 16;
+    const OrbLevelGeom& L = g.lv[l];
     const int img = blockIdx.y;
     // keypoints survive only edge pixels inside the level (runByImageBorder): tiles that lie entirely in that band do nothing,
     // and inside a tile scores are only needed for rows / columns [edge - 1, size - edge] (the 3x3 NMS looks one pixel out)
@@ -453,16 +452,14 @@ constexpr int BT_W = 128, BT_H = 64, BS_H = 16, BT_THREADS = (BT_W / 4) * (BT_H 
 constexpr int BB_W = BT_W + 32, BB_H = BT_H + 8;   // box: columns tx0 - 16 .. tx0 + 143, rows ty0 - 4 .. ty0 + 67
 
 __global__ void __launch_bounds__(BT_THREADS) blur_kernel(uint8_t* __restrict__ blur, const Geo* __restrict__ gp,
-                                                          const FastMaps* __restrict__ maps) {
+                                                          const FastMaps* __restrict__ maps, const uint32_t* __restrict__ tiles) {
     __shared__ __align__(128) uint8_t s_box[BB_H][BB_W];
     __shared__ __align__(8) uint64_t s_bar;
 
     const Geo& g = *gp;
-    int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].btile_base) ++l;
-    const OrbLevelGeom L = g.lv[l];
-    const int t = blockIdx.x - L.btile_base;
-    const int tx0 = (t % L.btiles_x) * BT_W, ty0 = (t / L.btiles_x) * BT_H;
+    const uint32_t tref = __ldg(tiles + blockIdx.x);   // level | tx0 << 4 | ty0 << 16
+    const int l = tref & 15, tx0 = (tref >> 4) & 0xFFF, ty0 = tref >> 16;
+    const OrbLevelGeom& L = g.lv[l];
     const int img = blockIdx.y;
     uint8_t* dst = blur + (size_t)img * g.pyr_img_bytes + L.img_off;
 
@@ -750,6 +747,19 @@ OrbExtractor::OrbExtractor(const OrbConfig& cfg, int w, int h, int batch_cap) : 
     }
     total_tiles_ = tile_base;
     total_btiles_ = btile_base;
+    {   // flat tile index -> level | tx0 << 4 | ty0 << 16 for FAST's and the blur's tilings
+        std::vector<uint32_t> tf, tb;
+        for (int l = 0; l < L; ++l) {
+            for (int ty = 0; ty < lv_[l].tiles_y; ++ty)
+                for (int tx = 0; tx < lv_[l].tiles_x; ++tx) tf.push_back((uint32_t)l | (uint32_t)(tx * TILE_W) << 4 | (uint32_t)(ty * TILE_H) << 16);
+            for (int ty = 0; ty < lv_[l].btiles_y; ++ty)
+                for (int tx = 0; tx < lv_[l].btiles_x; ++tx) tb.push_back((uint32_t)l | (uint32_t)(tx * BT_W) << 4 | (uint32_t)(ty * BT_H) << 16);
+        }
+        SLIDEO_CUDA(cudaMalloc(&d_tiles_fast_, tf.size() * 4));
+        SLIDEO_CUDA(cudaMemcpy(d_tiles_fast_, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
+        SLIDEO_CUDA(cudaMalloc(&d_tiles_blur_, tb.size() * 4));
+        SLIDEO_CUDA(cudaMemcpy(d_tiles_blur_, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice));
+    }
     pyr_img_bytes_ = img_off;
     cand_img_words_ = cand_off;
     sel_img_words_ = sel_off;
@@ -837,6 +847,8 @@ OrbExtractor::~OrbExtractor() {
     cudaFree(d_pattern_); cudaFree(d_geom_);
     cudaFree(fast_maps_);
     cudaFree(blur_maps_);
+    cudaFree(d_tiles_fast_);
+    cudaFree(d_tiles_blur_);
     cudaFreeHost(h_pinned_);
 }
 
@@ -862,7 +874,7 @@ void OrbExtractor::enqueue(const uint8_t* d_src, int n, int stride, size_t frame
                                                 d.pitch, d_tables_ + d.tab_off);
         ++nl;
     }
-    fast_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(static_cast<const FastMaps*>(fast_maps_), g, d_cand_, d_cand_cnt_);
+    fast_kernel<<<dim3(total_tiles_, n), 256, 0, stream>>>(static_cast<const FastMaps*>(fast_maps_), g, d_tiles_fast_, d_cand_, d_cand_cnt_);
     ++nl;
     {
         int max_sel = 0;
@@ -879,7 +891,7 @@ void OrbExtractor::enqueue(const uint8_t* d_src, int n, int stride, size_t frame
     scatter_kernel<<<dim3(L, n), 256, 0, stream>>>(g, d_sel_, d_sel_cnt_, d_kp_off_, d_kp_src_, d_q_frame_, d_kp_i_, kp_cap_, d_info_,
                                                    sink ? sink->q_frame : nullptr);
     ++nl;
-    blur_kernel<<<dim3(total_btiles_, n), BT_THREADS, 0, stream>>>(d_blur_, g, static_cast<const FastMaps*>(blur_maps_));
+    blur_kernel<<<dim3(total_btiles_, n), BT_THREADS, 0, stream>>>(d_blur_, g, static_cast<const FastMaps*>(blur_maps_), d_tiles_blur_);
     ++nl;
     {
         // the keypoint total of the batch lives on the device: a fixed grid of warps strides over it

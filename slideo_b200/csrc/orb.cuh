@@ -100,6 +100,7 @@ private:
     void* d_geom_ = nullptr;     // OrbLevelGeom[nlevels] on the device
     void* fast_maps_ = nullptr;  // per-level TMA tensor maps of the pyramid (device memory): FAST's boxes
     void* blur_maps_ = nullptr;  // the same tensors with the blur's boxes
+    uint32_t *d_tiles_fast_ = nullptr, *d_tiles_blur_ = nullptr;   // flat tile index -> level | tx0 << 4 | ty0 << 16
     int8_t* d_pattern_ = nullptr;  // 512 x 2 int8
     int32_t* h_pinned_ = nullptr;  // [0] total, [1] flags, [2..] frame offsets
     std::vector<int32_t> h_frame_off_;
