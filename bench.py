@@ -410,6 +410,31 @@ def main():
         "submit/collect and the synchronous call disagree"
     ctx.timings(reset=True)
 
+    # ---- what the host -> device fabric of this box can deliver when all ranks copy at once (context for `e2e` at N > 1) ----
+    h2d_probe = None
+    try:
+        probe_bytes = min(args.frames * FRAME_BYTES, 2 << 30)
+        src_t = torch.from_numpy(pin.array[:probe_bytes])
+        dst_t = dev[:probe_bytes]
+        dst_t.copy_(src_t, non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dst_t.copy_(src_t, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        gbs = 3 * probe_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        t = torch.tensor([gbs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_probe = {"aggregate_gbs": float(t[0]), "per_gpu_gbs_rank0": gbs,
+                     "what": f"plain cudaMemcpyAsync pinned host -> device of {probe_bytes / 1e9:.1f} GB x 3 on all {world} rank(s) at the same time "
+                             "(sum of the per-rank rates): the ceiling of any e2e arm that uploads BGR frames"}
+        dev.copy_(torch.from_numpy(pin.array), non_blocking=False)   # (the probe overwrote nothing: same bytes, but keep it obvious)
+    except Exception as ex:
+        h2d_probe = {"error": str(ex)}
+
     total_frames = args.frames * world * args.steps
     value = total_frames / t_dev
     e2e = total_frames / t_e2e
@@ -526,7 +551,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": args.frames * FRAME_BYTES,
-                    "d2h_bytes_per_step": args.frames * 12, "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "d2h_bytes_per_step": args.frames * 12, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "h2d_gbs_used": e2e * FRAME_BYTES / 1e9, "h2d_fabric_probe": h2d_probe},
             "gpu_launches": int(tm_dev["kernel_launches"]),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "power_w_max": clocks["power_w_max"], "samples": clocks["samples"]},

@@ -7,8 +7,9 @@ ranks, pool replicated: no data-path collective).  Data as SURVEY.md 8(d) states
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/matcher_sweep.py
 
 Rank 0 prints one JSON line per point: time = max over ranks of the device time (CUDA events inside the library),
-rates are whole-job (all ranks).  Fractions: K8 against the two-pipe integer roofline measured on this GPU by the library's
-micro-benchmark (min(POPC/4, LOP3/13) pairs/s), K10 against MEASURED_PEAKS.json's sustained bf16 peak."""
+rates are whole-job (all ranks).  Fractions: K8 (v5, bit-sliced) against the ALU-pipe roofline of its formulation measured on this
+GPU by the library's micro-benchmark (LOP3 thread-ops/s / 8.36 LOP3 per pair), K10 against MEASURED_PEAKS.json's sustained bf16
+peak with SURVEY.md 8(d)'s algorithmic (2*128 + 3) FLOP per pair."""
 import json
 import os
 import sys
@@ -33,7 +34,7 @@ try:
 except Exception:
     pass
 bf16_peak = float(peaks.get("bf16_tflops_sustained", 1368.2))
-int_peak = min(ctx.microbench(1) / 4.0, ctx.microbench(0) / 13.0) / 1e9      # Gpair/s per GPU
+int_peak = ctx.microbench(0) / (1070.0 / 128.0) / 1e9      # Gpair/s per GPU: K8 v5 spends 1070 LOP3 per lane and 128 pooled rows
 
 
 def hamming_rows(n, seed):
@@ -80,7 +81,7 @@ for nt in (1000, 10000, 100000, 1000000):
         if rank == 0:
             pairs = float(nq) * world * nt
             gp_h, gp_l = pairs / ms_h / 1e6, pairs / ms_l / 1e6
-            tf_l = 2.0 * 144.0 * pairs / ms_l / 1e9
+            tf_l = (2.0 * 128.0 + 3.0) * pairs / ms_l / 1e9
             print(json.dumps({"n_gpus": world, "nq": nq * world, "nt": nt, "k": K,
                               "hamming": {"ms": round(ms_h, 4), "gpairs_per_s": round(gp_h, 1), "frac_int_pipe_roofline": round(gp_h / (int_peak * world), 4),
                                           "hbm_bytes_algorithmic": 32 * (nq * world + nt * world) + 8 * K * nq * world},
