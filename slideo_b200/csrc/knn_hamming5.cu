@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
                 s_topk[ql * 32 + lane] = cur;
                 const uint32_t kth = __shfl_sync(KNN_FULL, cur, P.k - 1);
                 const int tau_new = kth == KEY_EMPTY ? 512 : (int)(kth >> KEY_IDX_BITS);
+                __syncwarp();   // every lane has read this query's masks / threshold before they are rewritten
                 if (tau_new != tau) k5_set_meta(meta, lane, A, invm != 0, tau_new);
                 __syncwarp();
             }
