@@ -229,3 +229,43 @@ def test_pool_replication_gives_identical_results(scene, kind):
         c.pool_import(desc, offs)
         assert c.pool_info() == a.pool_info()
         assert np.array_equal(c.match_frames_bgr8(frames), ra)
+
+
+def test_stream_geometry_change_progress_callback_and_dropped_ticket(scene):
+    """Two geometries in flight at once (the stream closes its epoch and opens a new one), a ticket collected into NULL, and the
+    progress callback (crates/matching/src/progress.rs:3-17 as a C function pointer)."""
+    import ctypes
+    import slideo_b200
+    from slideo_b200 import ffi
+    pages, frames, expect = scene
+    small_pages = [np.ascontiguousarray(p[200:680, 300:940]) for p in pages]
+    small = np.ascontiguousarray(frames[:6, 200:680, 300:940])
+    with slideo_b200.Context(slideo_b200.default_config(max_batch=4)) as c:
+        for p in pages:
+            c.add_page_gray8(p)
+        c.finalize_pool()
+        want_small = c.match_frames_bgr8(small)
+        seen = []
+        c.set_progress_callback(lambda a, b, m: seen.append((a, b, m)))
+        big = np.ascontiguousarray(frames)
+        t1 = c.submit_frames_bgr8(big)
+        t2 = c.submit_frames_bgr8(small)
+        t3 = c.submit_frames_bgr8(big)
+        assert np.array_equal(c.collect(t1, len(big)), expect)
+        assert seen and all(b == len(big) and a <= b for a, b, _ in seen) and seen[-1][2].startswith("Processing")
+        # drop ticket 2 (out = NULL), then ticket 3 must still be right
+        got = ctypes.c_int32()
+        c._ck(c._lib.slideo_b200_collect(c._h, t2, None, 0, ctypes.byref(got)))
+        assert got.value == len(small)
+        c.set_progress_callback(None)
+        n_seen = len(seen)
+        assert np.array_equal(c.collect(t3, len(big)), expect)
+        assert len(seen) == n_seen
+        assert np.array_equal(c.match_frames_bgr8(small), want_small)
+    # the small crops equal the oracle too (votes may be low: the check is parity, not recognition)
+    page_desc = [oracle.orb_detect_and_compute(p)[2] for p in pages]
+    for i in (0, 5):
+        d = oracle.orb_detect_and_compute(oracle.gray_from_bgr(small[i]))[2]
+        best, votes, _ = oracle.match_frame(d, page_desc)
+        assert tuple(want_small[i]) == (best, votes, len(d))
+    del small_pages
