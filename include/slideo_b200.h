@@ -275,7 +275,7 @@ int32_t slideo_b200_host_free(void* p);
 int32_t slideo_b200_get_timings(slideo_b200_ctx* ctx, slideo_b200_timings* out, int32_t reset);
 /* Optional progress callback, the C form of ProgressReporter (crates/matching/src/progress.rs:3-17: Fn(u64, u64, &str)): while a
  * match_frames_* / collect call waits for the GPU it reports (frames of this call finished, frames of this call, message) from
- * the calling thread, once per finished k-NN launch group.  fn = NULL switches it off.  The message pointer is only valid during
+ * the calling thread, once per finished k-NN launch group and once when the call's frames are complete.  fn = NULL switches it off.  The message pointer is only valid during
  * the callback. */
 typedef void (*slideo_b200_progress_fn)(uint64_t processed, uint64_t total, const char* message, void* user);
 int32_t slideo_b200_set_progress_callback(slideo_b200_ctx* ctx, slideo_b200_progress_fn fn, void* user);

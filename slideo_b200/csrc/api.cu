@@ -83,7 +83,9 @@ struct slideo_b200_ctx {
     DevBuf<uint8_t> d_pool5;             // ORB: the pool as bit-sliced slabs, what K8 v5 streams (knn5_pool_prepare_launch)
     DevBuf<uint8_t> d_t5;                // bit-sliced copy of a caller-provided pool (stage-level k-NN)
     DevBuf<uint8_t> d_t48;               // 48 B expanded copy of a caller-provided pool (stage-level k-NN, cfg.knn_impl == 4)
-    DevBuf<uint32_t> d_partial5;         // K8 v5 partial rows (split tiles)
+    DevBuf<uint32_t> d_partial5;         // K8 v5 partial rows (split tiles): static launches on `stream`
+    DevBuf<uint32_t> d_partial5_stream;  // ... and the frame path's launches on `knn_stream` (the two may be in flight together)
+    DevBuf<uint8_t> d_mark_frames;       // upload buffer of mark_changed_bgr8 (never the staging ring: tickets may be in flight)
     DevBuf<uint8_t> d_pool_tail;         // SIFT: bf16 norm tails of the pool (knn_l2.cu)
     DevBuf<uint8_t> d_pool_f32;          // SIFT: the pooled descriptors as fp32 (what the NCCL broadcast moves; bf16 operands are derived)
     DevBuf<uint16_t> d_page_of;          // nt
@@ -452,7 +454,7 @@ struct slideo_b200_ctx {
         }
         SLIDEO_CUDA(cudaEventCreate(&ev_span0));
         SLIDEO_CUDA(cudaEventCreate(&ev_span1));
-        d_partial5.reserve(knn5_dyn_partial_bytes(num_sms, KNN_MAX_K) / 4);
+        d_partial5_stream.reserve(knn5_dyn_partial_bytes(num_sms, KNN_MAX_K) / 4);
     }
     void engine_destroy() {
         if (d_dyn) cudaFree(d_dyn);
@@ -483,7 +485,7 @@ struct slideo_b200_ctx {
         VoteArgs va{e.q_frame.p, d_page_of.p, e.votes.p, n_pages, cfg.vote_ratio};
         EventPair t = begin_timing(1, knn_stream);
         int nl = 0;
-        knn5_launch_dyn(d_dyn + slot, e.q_cap, nt, cfg.knn_k, num_sms, e.desc.p, d_pool5.p, want_keys() ? e.keys.p : nullptr, d_partial5.p,
+        knn5_launch_dyn(d_dyn + slot, e.q_cap, nt, cfg.knn_k, num_sms, e.desc.p, d_pool5.p, want_keys() ? e.keys.p : nullptr, d_partial5_stream.p,
                         &va, knn_stream, &nl);
         end_timing(t, knn_stream);
         stream_finalize_launch(e.d_state, d_dyn + slot, e.frame_q0.p, e.votes.p, n_pages, e.frame_nkp.p, h_ring, RING - 1, e.seq_base,
@@ -619,6 +621,8 @@ struct slideo_b200_ctx {
             launch_group(true);
             flushed = true;
         }
+        if (progress_fn && seq_begin >= 0 && *h_progress >= seq_end)   // always one final report, also when nothing had to be waited for
+            progress_fn((uint64_t)(seq_end - seq_begin), (uint64_t)(seq_end - seq_begin), "Processing frames...", progress_user);
         if (!check_flags) return;
         const int fl = *h_flags;
         if (fl) {
@@ -1592,14 +1596,15 @@ int32_t slideo_b200_mark_changed_bgr8(slideo_b200_ctx* ctx, const uint8_t* frame
         arg(stride >= 3 * w, "stride < 3*w");
         arg(frame_stride >= (size_t)stride * (h - 1) + (size_t)3 * w, "frame_stride too small");
         const size_t img_bytes = (size_t)3 * w * h;
-        ctx->d_frames[0].reserve((size_t)std::min(ctx->cfg.max_batch, n) * img_bytes);
+        if ((size_t)std::min(ctx->cfg.max_batch, n) * img_bytes > ctx->d_mark_frames.cap) SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->d_mark_frames.reserve((size_t)std::min(ctx->cfg.max_batch, n) * img_bytes);
         mark_changed_impl(ctx, n, w, h, reset != 0, out_changed, out_similarity, [&](int f0, int nb, int* st, size_t* fst) -> const uint8_t* {
             EventPair t = ctx->begin_timing(2, ctx->stream);
-            ctx->upload_images(ctx->d_frames[0].p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride, ctx->stream);
+            ctx->upload_images(ctx->d_mark_frames.p, frames + (size_t)f0 * frame_stride, nb, 3 * w, h, stride, frame_stride, ctx->stream);
             ctx->end_timing(t, ctx->stream);
             *st = 3 * w;
             *fst = img_bytes;
-            return ctx->d_frames[0].p;
+            return ctx->d_mark_frames.p;
         });
     });
 }

@@ -253,6 +253,7 @@ def test_stream_geometry_change_progress_callback_and_dropped_ticket(scene):
         t3 = c.submit_frames_bgr8(big)
         assert np.array_equal(c.collect(t1, len(big)), expect)
         assert seen and all(b == len(big) and a <= b for a, b, _ in seen) and seen[-1][2].startswith("Processing")
+        assert seen[-1][0] == len(big)
         # drop ticket 2 (out = NULL), then ticket 3 must still be right
         got = ctypes.c_int32()
         c._ck(c._lib.slideo_b200_collect(c._h, t2, None, 0, ctypes.byref(got)))
