@@ -57,7 +57,7 @@ constexpr uint32_t B_TAIL_BYTES = L2_BN * 32;
 constexpr uint32_t A_BYTES = 2 * A_MAIN_BYTES + A_TAIL_BYTES;   // 36 KB
 constexpr uint32_t B_BYTES = 2 * B_MAIN_BYTES + B_TAIL_BYTES;   // 72 KB
 constexpr uint32_t SMEM_OPERANDS = A_BYTES + L2_STAGES * B_BYTES;   // 180 KB
-constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 128 + 4 * L2_BM * 4 + 1024;   // + barriers/tmem ptr + tau / half-rank exchange + alignment slack
+constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 128 + 6 * L2_BM * 4 + 1024;   // + barriers/tmem ptr + tau / half-rank / pre-pass exchange + alignment slack
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,6 +113,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// the smallest float above x (x finite or +inf, never NaN; +inf stays): branch-free nextafterf(x, +inf)
+__device__ __forceinline__ float next_up(float x) {
+    const int b = __float_as_int(x);
+    const int up = b >= 0 ? b + 1 : (b == (int)0x80000000 ? 1 : b - 1);
+    return b == 0x7F800000 ? x : __int_as_float(up);
+}
+__device__ __forceinline__ float lds_volatile(uint32_t saddr) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
@@ -163,6 +174,8 @@ struct L2Params {
     int mt_a, ns_a, ns_b;  // query tiles [0, mt_a) are split ns_a ways over the pool, tiles [mt_a, n_mtiles) ns_b ways; partial rows have ns_max slots
     int ns_max;
     int trigger;           // new candidates of a list that schedule its cut-back (1..L2_TRIGGER)
+    int pre_tiles;         // threshold pre-pass: pool tiles at the head of a work item whose accumulators are only reduced to group
+    int pre_min;           //   minima (see l2_npre); items with fewer than pre_min tiles have no pre-pass
     unsigned long long* prof;  // developer instrument (SLIDEO_L2_PROF): cycles of epilogue warps in {acc wait, drain, cut-back, item tail}, MMA warp in {acc_empty wait, b_full wait}
     int dbg;               // developer switch (SLIDEO_L2_DEBUG): 1 = epilogue skips the TMEM drain, 2 = drains but never selects
     uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
@@ -191,6 +204,14 @@ __device__ __forceinline__ L2Item l2_item(const L2Params& P, int item) {
     return w;
 }
 
+// Threshold pre-pass.  A work item first runs its leading `pre_tiles` pool tiles through the tensor pipe WITHOUT selecting: every
+// epilogue thread (= query row) only folds the accumulator columns it drains into ceil(k/2) group minima (a group = a fixed number
+// of consecutive 32-column chunks).  The 2 * ceil(k/2) >= k minima of a row (both column halves) are k distinct pooled descriptors, so
+// their maximum t0 bounds the row's k-th distance from above: the item then restarts at its first tile and selects with that
+// threshold from the first column on, instead of appending whole tiles until its lists have filled and tightened (about half of
+// all candidates a row ever appends fall into its first ~2000 columns).  Cost: pre_tiles extra tiles of pure MMA + min tree.
+__device__ __forceinline__ int l2_npre(const L2Params& P, int j0, int j1) { return j1 - j0 >= P.pre_min ? P.pre_tiles : 0; }
+
 __device__ __forceinline__ void emit_l2_row(uint64_t key, int lane, int q, int k, int32_t* idx_out, float* dist_out) {
     if (lane < k) {
         const bool ok = key != KEY64_EMPTY;
@@ -217,6 +238,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
     volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 16);   // [2][L2_BM]: running k-th distance of each (group, row) list
     volatile float* s_half = s_tau + 2 * L2_BM;                             // [2][L2_BM]: its ceil(k/2)-th distance
+    volatile float* s_pre = s_half + 2 * L2_BM;                             // [2][L2_BM]: pre-pass bound of each column half (l2_npre)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -251,7 +273,9 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 tma_load_2d(sA, &tm_q_main, 0, mt * L2_BM, a_full);
                 tma_load_2d(sA + A_MAIN_BYTES, &tm_q_main, 64, mt * L2_BM, a_full);
                 tma_load_2d(sA + 2 * A_MAIN_BYTES, &tm_q_tail, 0, mt * L2_BM, a_full);
-                for (int j = j0; j < j1; ++j, ++bcount) {
+                const int npre = l2_npre(P, j0, j1);
+                for (int t = -npre; t < j1 - j0; ++t, ++bcount) {
+                    const int j = j0 + (t < 0 ? t + npre : t);       // the pre-pass tiles, then the whole item from its first tile
                     const int s = bcount % L2_STAGES;
                     mbar_wait(&b_empty[s], ((bcount / L2_STAGES) & 1) ^ 1);
                     uint8_t* dst = sB + (size_t)s * B_BYTES;
@@ -272,8 +296,9 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 const L2Item w = l2_item(P, item);
                 const int j0 = w.j0, j1 = w.j1;
                 mbar_wait(a_full, it & 1);
-                for (int j = j0; j < j1; ++j, ++bcount) {
-                    const int b = (j - j0) & 1;
+                const int n_seq = l2_npre(P, j0, j1) + j1 - j0;
+                for (int t = 0; t < n_seq; ++t, ++bcount) {
+                    const int b = t & 1;
                     const int s = bcount % L2_STAGES;
                     const long long m0 = P.prof ? clock64() : 0;
                     mbar_wait(&acc_empty[b], (acc_use[b] & 1) ^ 1);   // both epilogue groups drained this TMEM buffer
@@ -305,7 +330,9 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         const int row = quarter * 32 + lane;         // query row within the tile
         uint64_t* my_buf = P.scratch + (((size_t)blockIdx.x * 2 + g) * L2_BM + row) * L2_SLOTS;
         const uint32_t taddr_group = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * L2_BNH;
-        uint32_t acc_seen[2] = {0, 0};
+        uint32_t acc_phase = 0;                      // bit b: parity of the next completion of acc_full[b] this thread waits for
+        const uint32_t sa_tau_other = smem_u32(const_cast<float*>(s_tau)) + (uint32_t)((g ^ 1) * L2_BM + row) * 4;
+        const uint32_t sa_half0 = smem_u32(const_cast<float*>(s_half)) + (uint32_t)row * 4;
         long long pw = 0, pd = 0, pc = 0, pt = 0;
 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -354,28 +381,75 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 __syncwarp();
             };
 
+            // ---- threshold pre-pass (l2_npre): group minima only, nothing is appended
+            const int npre = l2_npre(P, j0, j1);
+            if (npre) {
+                const float inf = __int_as_float(0x7F800000);
+                const int n_groups = (P.k + 1) / 2;
+                const int per_group = npre * (L2_BNH / 32) / n_groups;   // 32-column chunks folded into one minimum (>= 1: host)
+                float gmin = inf, t0 = -inf;
+                int in_group = 0, groups = 0;
+                for (int t = 0; t < npre; ++t) {
+                    const int b = t & 1;
+                    mbar_wait(&acc_full[b], (acc_phase >> b) & 1);
+                    acc_phase ^= 1u << b;
+                    tc_fence_after();
+                    const uint32_t taddr_base = taddr_group + (uint32_t)b * L2_BN;
+                    uint32_t va[32], vb[32];
+                    tc_ld32(taddr_base, va);
+#pragma unroll 1
+                    for (int c = 0; c < L2_BNH / 32; c += 2) {
+                        tc_ld_wait();
+                        tc_ld32(taddr_base + (uint32_t)(c + 1) * 32, vb);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            uint32_t (&v)[32] = half == 0 ? va : vb;
+                            if (half == 1) {
+                                tc_ld_wait();
+                                if (c + 2 < L2_BNH / 32) tc_ld32(taddr_base + (uint32_t)(c + 2) * 32, va);
+                            }
+                            float m = inf;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                m = fminf(m, fminf(fminf(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                                   fminf(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]))));
+                            if (groups < n_groups) {
+                                gmin = fminf(gmin, m);
+                                if (++in_group == per_group) { t0 = fmaxf(t0, gmin); gmin = inf; in_group = 0; ++groups; }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[b]);
+                }
+                s_pre[g * L2_BM + row] = t0;
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // the next write of s_pre lies behind the two barriers of the item tail
+                // k distinct pooled descriptors of this item lie at or below the larger half bound: candidates above it are never needed
+                if (q < P.nq) tau = next_up(fmaxf(s_pre[row], s_pre[L2_BM + row]));
+            }
+
             for (int j = j0; j < j1; ++j) {
                 // both groups drain EVERY tile, half of its columns each: the accumulator goes back to the tensor pipe after
                 // half a drain, and the MMA of tile j + 2 never queues behind a whole-tile epilogue
-                const int b = (j - j0) & 1;
+                const int b = (npre + j - j0) & 1;
                 const long long t0 = P.prof ? clock64() : 0;
-                mbar_wait(&acc_full[b], acc_seen[b] & 1);
-                ++acc_seen[b];
+                mbar_wait(&acc_full[b], (acc_phase >> b) & 1);
+                acc_phase ^= 1u << b;
                 tc_fence_after();
                 const long long t1 = P.prof ? clock64() : 0;
                 const int col0 = j * L2_BN + g * L2_BNH;
                 const uint32_t taddr_base = taddr_group + (uint32_t)b * L2_BN;
                 // effective threshold: own k-th distance (strict) or the other group's (non-strict: an equal distance
                 // with a smaller index could still displace its k-th entry), whichever is tighter
-                float thr = tau;
+                // (next_up: non-strict bounds; three shared loads in flight together, no branches -- this runs once per tile per thread)
+                float thr;
                 {
-                    const float inf = __int_as_float(0x7F800000);
-                    const float other = s_tau[(g ^ 1) * L2_BM + row];
-                    if (other < thr) thr = fminf(thr, nextafterf(other, inf));
+                    const float other = lds_volatile(sa_tau_other);
+                    const float h0 = lds_volatile(sa_half0), h1 = lds_volatile(sa_half0 + L2_BM * 4);
                     // both lists hold >= ceil(k/2) entries at or below the larger of their ceil(k/2)-th distances, so k entries of
                     // the union do: anything above it cannot reach the final k (ties may, hence non-strict)
-                    const float hx = fmaxf(s_half[row], s_half[L2_BM + row]);
-                    if (hx < thr) thr = fminf(thr, nextafterf(hx, inf));
+                    thr = fminf(tau, fminf(next_up(other), next_up(fmaxf(h0, h1))));
                 }
                 const int n_chunks = P.dbg == 1 ? 0 : L2_BNH / 32;
                 uint32_t va[32], vb[32];
@@ -610,7 +684,7 @@ void l2_prepare_launch(const float* d_src, int n, bool is_query, void* d_main, v
 namespace {
 // developer knobs (profiling counters, split / trigger experiments): read from the environment ONCE per process, never on the
 // launch path
-struct L2Env { bool no_split, prof; int trigger, dbg; };
+struct L2Env { bool no_split, prof; int trigger, dbg, pre; };
 const L2Env& l2_env() {
     static const L2Env e = [] {
         L2Env v;
@@ -618,6 +692,7 @@ const L2Env& l2_env() {
         v.prof = getenv("SLIDEO_L2_PROF") != nullptr;
         v.trigger = getenv("SLIDEO_L2_TRIGGER") ? std::min(L2_TRIGGER, std::max(1, atoi(getenv("SLIDEO_L2_TRIGGER")))) : 26;
         v.dbg = getenv("SLIDEO_L2_DEBUG") ? atoi(getenv("SLIDEO_L2_DEBUG")) : 0;
+        v.pre = getenv("SLIDEO_L2_PRE") ? std::max(0, atoi(getenv("SLIDEO_L2_PRE"))) : 32;
         return v;
     }();
     return e;
@@ -659,6 +734,9 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.idx_out = d_idx;
     P.dist_out = d_dist;
     P.trigger = l2_env().trigger;
+    // pre-pass of pre_tiles tiles for items of at least 6 x as many; every group minimum must cover at least one chunk
+    P.pre_tiles = std::max(l2_env().pre, (k + 1) / 2 / (L2_BNH / 32) + 1);
+    P.pre_min = l2_env().pre > 0 ? 6 * P.pre_tiles : 0x7FFFFFFF;
     P.prof = nullptr;
     P.dbg = l2_env().dbg;
 
