@@ -41,12 +41,16 @@ constexpr int L2_TAIL = 16;
 constexpr int L2_BM = 128;              // queries per tile (TMEM lanes)
 constexpr int L2_BN = 256;              // pooled descriptors per tile (TMEM columns)
 constexpr int L2_STAGES = 2;            // B stages in shared memory
-constexpr int L2_THREADS = 320;
+constexpr int L2_THREADS = 448;         // TMA warp, MMA warp, 8 drain warps, 4 sorter warps
 constexpr int L2_BNH = L2_BN / 2;       // pooled columns of a tile drained by one epilogue group
-constexpr int L2_TRIGGER = 64;          // upper bound of L2Params::trigger (new candidates of a list that schedule a cut-back)
-// candidate keys per (group, row): slots [0, 32) hold the sorted k best of the last cut-back, new candidates are appended from
-// slot 32 on; a whole half tile can be appended past the trigger without a check
-constexpr int L2_SLOTS = 32 + L2_TRIGGER + L2_BNH;
+constexpr int L2_TRIGGER = 32;          // upper bound of L2Params::trigger (new candidates of a list that schedule a cut-back)
+// candidate keys per (group, row): slots [0, 32) hold the sorted k best of the last cut-back (written by the sorter warps only);
+// new candidates are appended by the drain thread to one of two regions of L2_REGION slots.  When a region passes the trigger
+// the thread hands it to a sorter warp and goes on appending to the other one; a region takes a whole half tile past the trigger.
+constexpr int L2_REGION = L2_TRIGGER + L2_BNH;
+constexpr int L2_SLOTS = 32 + 2 * L2_REGION;
+constexpr int L2_RQ = 64;               // request ring of a drain warp (at most one request per list + the end marker in flight)
+constexpr uint32_t L2_REQ_END = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint64_t KEY64_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 
@@ -57,7 +61,8 @@ constexpr uint32_t B_TAIL_BYTES = L2_BN * 32;
 constexpr uint32_t A_BYTES = 2 * A_MAIN_BYTES + A_TAIL_BYTES;   // 36 KB
 constexpr uint32_t B_BYTES = 2 * B_MAIN_BYTES + B_TAIL_BYTES;   // 72 KB
 constexpr uint32_t SMEM_OPERANDS = A_BYTES + L2_STAGES * B_BYTES;   // 180 KB
-constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + 128 + 6 * L2_BM * 4 + 1024;   // + barriers/tmem ptr + tau / half-rank / pre-pass exchange + alignment slack
+constexpr uint32_t SMEM_CTRL = 128 + 6 * L2_BM * 4 + 8 * L2_RQ * 4 + 8 * 32 * 4 + 64;   // barriers/tmem ptr, tau / half-rank / pre-pass exchange, request rings, done counters, ring tails
+constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + SMEM_CTRL + 1024;   // + alignment slack
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,6 +127,11 @@ __device__ __forceinline__ float next_up(float x) {
 __device__ __forceinline__ float lds_volatile(uint32_t saddr) {
     float v;
     asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
     return v;
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -221,6 +231,7 @@ __device__ __forceinline__ void emit_l2_row(uint64_t key, int lane, int q, int k
     }
 }
 
+template <bool DEV>   // DEV: developer instruments (cycle counters, drain-only switches) compiled in
 __global__ void __launch_bounds__(L2_THREADS, 1)
 knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_tail,
               const __grid_constant__ CUtensorMap tm_t_main, const __grid_constant__ CUtensorMap tm_t_tail, const L2Params P) {
@@ -239,6 +250,9 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 16);   // [2][L2_BM]: running k-th distance of each (group, row) list
     volatile float* s_half = s_tau + 2 * L2_BM;                             // [2][L2_BM]: its ceil(k/2)-th distance
     volatile float* s_pre = s_half + 2 * L2_BM;                             // [2][L2_BM]: pre-pass bound of each column half (l2_npre)
+    volatile uint32_t* s_req = reinterpret_cast<volatile uint32_t*>(s_pre + 2 * L2_BM);   // [8][L2_RQ]: cut-back requests of a drain warp
+    volatile uint32_t* s_done = s_req + 8 * L2_RQ;                          // [8][32]: requests the sorter has completed, per list
+    volatile uint32_t* s_req_tail = s_done + 8 * 32;                        // [8]: requests a drain warp has posted
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -250,6 +264,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 4 * L2_BM; i += L2_THREADS) s_tau[i] = __int_as_float(0x7F800000);   // s_tau and s_half
+    for (int i = tid; i < 8 * 32 + 8; i += L2_THREADS) s_done[i] = 0;                           // s_done and s_req_tail
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -300,12 +315,12 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 for (int t = 0; t < n_seq; ++t, ++bcount) {
                     const int b = t & 1;
                     const int s = bcount % L2_STAGES;
-                    const long long m0 = P.prof ? clock64() : 0;
+                    const long long m0 = DEV && P.prof ? clock64() : 0;
                     mbar_wait(&acc_empty[b], (acc_use[b] & 1) ^ 1);   // both epilogue groups drained this TMEM buffer
                     ++acc_use[b];
-                    const long long m1 = P.prof ? clock64() : 0;
+                    const long long m1 = DEV && P.prof ? clock64() : 0;
                     mbar_wait(&b_full[s], (bcount / L2_STAGES) & 1);
-                    if (P.prof) { mw_acc += m1 - m0; mw_b += clock64() - m1; }
+                    if (DEV && P.prof) { mw_acc += m1 - m0; mw_b += clock64() - m1; }
                     tc_fence_after();
                     const uint32_t b0 = smem_u32(sB + (size_t)s * B_BYTES), b1 = b0 + B_MAIN_BYTES, bt = b0 + 2 * B_MAIN_BYTES;
                     const uint32_t d = tmem_base + (uint32_t)b * L2_BN;
@@ -321,64 +336,123 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 }
                 tc_commit(a_empty);
             }
-            if (P.prof) { atomicAdd(P.prof + 4, (unsigned long long)mw_acc); atomicAdd(P.prof + 5, (unsigned long long)mw_b); }
+            if (DEV && P.prof) { atomicAdd(P.prof + 4, (unsigned long long)mw_acc); atomicAdd(P.prof + 5, (unsigned long long)mw_b); }
         }
+    } else if (warp >= 10) {
+        // ===================== sorter warps =====================
+        // Sorter s serves the two drain warps of one TMEM lane quarter (s: columns 0..127, s + 4: columns 128..255).  A request
+        // names a list, the region holding its new candidates and their number: the sorted k best of the last cut-back (slots
+        // 0..31) are merged with the candidates, 32 at a time -- chunk sorted descending, lane-wise min with the ascending best =
+        // the 32 smallest as a bitonic sequence -- written back, and the list's k-th and ceil(k/2)-th distances are published.
+        // The drain warps never sort: the tensor pipe does not wait for a cut-back.
+        const int s = warp - 10;
+        uint32_t head[2] = {0, 0};
+        long long ps_busy = 0;
+        unsigned ps_req = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            unsigned ended = 0;
+            while (ended != 3u) {
+                bool worked = false;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (ended >> i & 1u) continue;
+                    const int e = s + 4 * i;                     // drain warp e: group i, lane quarter (e + 2) & 3
+                    const uint32_t tail = s_req_tail[e];
+                    if (head[i] == tail) continue;
+                    __threadfence_block();                       // the candidates of every posted request are visible from here on
+                    const long long tb0 = DEV && P.prof ? clock64() : 0;
+                    worked = true;
+                    while (head[i] != tail) {
+                        const uint32_t r = s_req[e * L2_RQ + (head[i] & (L2_RQ - 1))];
+                        ++head[i];
+                        if (r == L2_REQ_END) { ended |= 1u << i; break; }
+                        const int rl = (int)(r & 31u), region = (int)(r >> 5 & 1u), n = (int)(r >> 8);
+                        const bool hb = (r >> 6 & 1u) != 0;
+                        const int row = ((e + 2) & 3) * 32 + rl;
+                        uint64_t* buf = P.scratch + (((size_t)blockIdx.x * 2 + i) * L2_BM + row) * L2_SLOTS;
+                        const uint64_t* cand = buf + 32 + region * L2_REGION;
+                        uint64_t top = hb ? __ldcg(buf + lane) : KEY64_EMPTY;                   // all three loads in flight together
+                        uint64_t x0 = lane < n ? __ldcg(cand + lane) : KEY64_EMPTY;
+                        uint64_t x1 = 32 + lane < n ? __ldcg(cand + 32 + lane) : KEY64_EMPTY;
+                        if (n > 0) top = warp_merge32_asc(min(top, warp_sort32_desc(x0, lane)), lane);
+                        if (n > 32) top = warp_merge32_asc(min(top, warp_sort32_desc(x1, lane)), lane);
+                        for (int c0 = 64; c0 < n; c0 += 32) {
+                            const uint64_t x = c0 + lane < n ? __ldcg(cand + c0 + lane) : KEY64_EMPTY;
+                            top = warp_merge32_asc(min(top, warp_sort32_desc(x, lane)), lane);
+                        }
+                        if (lane >= P.k) top = KEY64_EMPTY;
+                        buf[lane] = top;
+                        const uint64_t kth = __shfl_sync(FULL, top, P.k - 1);
+                        const uint64_t hth = __shfl_sync(FULL, top, (P.k + 1) / 2 - 1);
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (kth != KEY64_EMPTY) s_tau[i * L2_BM + row] = __uint_as_float((uint32_t)(kth >> 32));
+                            if (hth != KEY64_EMPTY) s_half[i * L2_BM + row] = __uint_as_float((uint32_t)(hth >> 32));
+                            s_done[e * 32 + rl] = s_done[e * 32 + rl] + 1;
+                        }
+                        ++ps_req;
+                    }
+                    if (DEV && P.prof) ps_busy += clock64() - tb0;
+                }
+                if (!worked) __nanosleep(40);
+            }
+        }
+        if (DEV && P.prof && lane == 0) { atomicAdd(P.prof + 6, (unsigned long long)ps_busy); atomicAdd(P.prof + 7, (unsigned long long)ps_req); }
     } else {
-        // ===================== epilogue groups =====================
-        const int g = (warp - 2) >> 2;               // 0: columns 0..127 of every tile, 1: columns 128..255
+        // ===================== drain warps (epilogue groups) =====================
+        const int e = warp - 2;                      // drain warp
+        const int g = e >> 2;                        // 0: columns 0..127 of every tile, 1: columns 128..255
         const int quarter = warp & 3;                // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;         // query row within the tile
         uint64_t* my_buf = P.scratch + (((size_t)blockIdx.x * 2 + g) * L2_BM + row) * L2_SLOTS;
         const uint32_t taddr_group = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * L2_BNH;
         uint32_t acc_phase = 0;                      // bit b: parity of the next completion of acc_full[b] this thread waits for
+        const uint32_t sa_tau_own = smem_u32(const_cast<float*>(s_tau)) + (uint32_t)(g * L2_BM + row) * 4;
         const uint32_t sa_tau_other = smem_u32(const_cast<float*>(s_tau)) + (uint32_t)((g ^ 1) * L2_BM + row) * 4;
         const uint32_t sa_half0 = smem_u32(const_cast<float*>(s_half)) + (uint32_t)row * 4;
+        const uint32_t sa_done = smem_u32(const_cast<uint32_t*>(s_done)) + (uint32_t)(e * 32 + lane) * 4;
+        uint32_t n_posted = 0;                       // requests posted for this thread's list (s_done counts the completed ones)
+        uint32_t req_tail = 0;                       // requests posted by this warp (warp-uniform)
         long long pw = 0, pd = 0, pc = 0, pt = 0;
 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const L2Item w = l2_item(P, item);
             const int mt = w.mt, sp = w.sp, j0 = w.j0, j1 = w.j1;
             const int q = mt * L2_BM + row;
-            float tau = q < P.nq ? __int_as_float(0x7F800000) : -1.f;   // +inf / never
-            int cnt = 32;              // next free slot of this row's list
+            float bound = q < P.nq ? __int_as_float(0x7F800000) : -1.f;   // pre-pass bound: +inf / never
+            int region = 0;            // region of the list this thread appends to
+            int cnt = 0;               // candidates in it
             bool have_base = false;    // slots 0..31 hold a sorted cut-back of this item
 
-            auto compact = [&](bool force) {
-                // warp-cooperative cut-back of the lists that passed the trigger (all lists at the end of an item): the sorted k
-                // best of the last cut-back (slots 0..31) are merged with the new candidates (slot 32 on), 32 at a time:
-                // chunk sorted descending, lane-wise min with the ascending best = the 32 smallest as a bitonic sequence
-                unsigned need = force ? FULL : __ballot_sync(FULL, cnt > 32 + P.trigger);
-                while (need) {
-                    const int L = __ffs(need) - 1;
-                    need &= need - 1;
-                    uint64_t* buf = my_buf + ((ptrdiff_t)L - lane) * L2_SLOTS;
-                    const int n = __shfl_sync(FULL, cnt, L);
-                    const bool hb = __shfl_sync(FULL, (int)have_base, L) != 0;
-                    uint64_t top = hb ? __ldcg(buf + lane) : KEY64_EMPTY;                   // all three loads in flight together
-                    uint64_t x0 = 32 + lane < n ? __ldcg(buf + 32 + lane) : KEY64_EMPTY;
-                    uint64_t x1 = 64 + lane < n ? __ldcg(buf + 64 + lane) : KEY64_EMPTY;
-                    if (n > 32) top = warp_merge32_asc(min(top, warp_sort32_desc(x0, lane)), lane);
-                    if (n > 64) top = warp_merge32_asc(min(top, warp_sort32_desc(x1, lane)), lane);
-                    for (int c0 = 96; c0 < n; c0 += 32) {
-                        const uint64_t x = c0 + lane < n ? __ldcg(buf + c0 + lane) : KEY64_EMPTY;
-                        top = warp_merge32_asc(min(top, warp_sort32_desc(x, lane)), lane);
-                    }
-                    if (lane >= P.k) top = KEY64_EMPTY;
-                    __syncwarp();
-                    buf[lane] = top;
-                    const uint64_t kth = __shfl_sync(FULL, top, P.k - 1);
-                    const uint64_t hth = __shfl_sync(FULL, top, (P.k + 1) / 2 - 1);
-                    if (lane == L) {
-                        if (kth != KEY64_EMPTY) {
-                            tau = __uint_as_float((uint32_t)(kth >> 32));
-                            s_tau[g * L2_BM + row] = tau;   // the other group may prune against it (non-strictly)
-                        }
-                        if (hth != KEY64_EMPTY) s_half[g * L2_BM + row] = __uint_as_float((uint32_t)(hth >> 32));
-                        cnt = 32;
-                        have_base = true;
-                    }
+            // hands the regions that passed the trigger (force: every region that holds anything, and every list that has no
+            // sorted base yet) to the sorter warp and switches the thread to the other region
+            auto post = [&](bool force) {
+                bool want = force ? (cnt > 0 || !have_base) : cnt > P.trigger;
+                if (want && lds_volatile_u32(sa_done) != n_posted) {
+                    // the previous cut-back of this list is still in the sorter's queue: wait only if the region cannot take another
+                    // half tile (or at the end of the item), else try again after the next tile
+                    if (force || cnt > L2_TRIGGER) { while (lds_volatile_u32(sa_done) != n_posted) {} }
+                    else want = false;
                 }
+                const unsigned m = __ballot_sync(FULL, want);
+                if (m == 0 && !force) return;
+                if (want) {
+                    s_req[e * L2_RQ + ((req_tail + __popc(m & ((1u << lane) - 1u))) & (L2_RQ - 1))] =
+                        (uint32_t)lane | (uint32_t)region << 5 | (have_base ? 64u : 0u) | (uint32_t)cnt << 8;
+                    ++n_posted;
+                    region ^= 1;
+                    cnt = 0;
+                    have_base = true;
+                }
+                req_tail += __popc(m);
+                if (force) {
+                    if (lane == 0) s_req[e * L2_RQ + (req_tail & (L2_RQ - 1))] = L2_REQ_END;
+                    ++req_tail;
+                }
+                __threadfence_block();     // this thread's appended candidates and its request before the tail moves
                 __syncwarp();
+                if (lane == 0) s_req_tail[e] = req_tail;
             };
 
             // ---- threshold pre-pass (l2_npre): group minima only, nothing is appended
@@ -410,9 +484,9 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                             }
                             float m = inf;
 #pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                m = fminf(m, fminf(fminf(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
-                                                   fminf(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]))));
+                            for (int i = 0; i < 8; ++i)
+                                m = fminf(m, fminf(fminf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
+                                                   fminf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]))));
                             if (groups < n_groups) {
                                 gmin = fminf(gmin, m);
                                 if (++in_group == per_group) { t0 = fmaxf(t0, gmin); gmin = inf; in_group = 0; ++groups; }
@@ -426,32 +500,33 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 s_pre[g * L2_BM + row] = t0;
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // the next write of s_pre lies behind the two barriers of the item tail
                 // k distinct pooled descriptors of this item lie at or below the larger half bound: candidates above it are never needed
-                if (q < P.nq) tau = next_up(fmaxf(s_pre[row], s_pre[L2_BM + row]));
+                if (q < P.nq) bound = next_up(fmaxf(s_pre[row], s_pre[L2_BM + row]));
             }
 
             for (int j = j0; j < j1; ++j) {
                 // both groups drain EVERY tile, half of its columns each: the accumulator goes back to the tensor pipe after
                 // half a drain, and the MMA of tile j + 2 never queues behind a whole-tile epilogue
                 const int b = (npre + j - j0) & 1;
-                const long long t0 = P.prof ? clock64() : 0;
+                const long long t0 = DEV && P.prof ? clock64() : 0;
                 mbar_wait(&acc_full[b], (acc_phase >> b) & 1);
                 acc_phase ^= 1u << b;
                 tc_fence_after();
-                const long long t1 = P.prof ? clock64() : 0;
+                const long long t1 = DEV && P.prof ? clock64() : 0;
                 const int col0 = j * L2_BN + g * L2_BNH;
                 const uint32_t taddr_base = taddr_group + (uint32_t)b * L2_BN;
-                // effective threshold: own k-th distance (strict) or the other group's (non-strict: an equal distance
-                // with a smaller index could still displace its k-th entry), whichever is tighter
-                // (next_up: non-strict bounds; three shared loads in flight together, no branches -- this runs once per tile per thread)
+                // effective threshold: the pre-pass bound, the k-th distance of the own list as of its last cut-back (strict: a later
+                // column of this half has a larger index) or the other group's (non-strict: an equal distance with a smaller index
+                // could still displace its k-th entry), whichever is tighter.  Both lists hold >= ceil(k/2) entries at or below the
+                // larger of their ceil(k/2)-th distances, so k entries of the union do: anything above it cannot reach the final k
+                // (ties may, hence non-strict).  Four shared loads in flight together, no branches: once per tile per thread.
                 float thr;
                 {
-                    const float other = lds_volatile(sa_tau_other);
+                    const float own = lds_volatile(sa_tau_own), other = lds_volatile(sa_tau_other);
                     const float h0 = lds_volatile(sa_half0), h1 = lds_volatile(sa_half0 + L2_BM * 4);
-                    // both lists hold >= ceil(k/2) entries at or below the larger of their ceil(k/2)-th distances, so k entries of
-                    // the union do: anything above it cannot reach the final k (ties may, hence non-strict)
-                    thr = fminf(tau, fminf(next_up(other), next_up(fmaxf(h0, h1))));
+                    thr = fminf(fminf(bound, own), fminf(next_up(other), next_up(fmaxf(h0, h1))));
                 }
-                const int n_chunks = P.dbg == 1 ? 0 : L2_BNH / 32;
+                uint64_t* app = my_buf + 32 + region * L2_REGION;
+                const int n_chunks = DEV && P.dbg == 1 ? 0 : L2_BNH / 32;
                 uint32_t va[32], vb[32];
                 if (n_chunks) tc_ld32(taddr_base, va);
 #pragma unroll 1
@@ -470,26 +545,26 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                         bool hit[8];
                         bool any = false;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float m = fminf(fminf(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
-                                                  fminf(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
-                            hit[q] = m < thr;
-                            any |= hit[q];
+                        for (int i = 0; i < 8; ++i) {
+                            const float m = fminf(fminf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
+                                                  fminf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                            hit[i] = m < thr;
+                            any |= hit[i];
                         }
-                        if (P.dbg == 2) any = any && v[0] == 0x12345678u;
+                        if (DEV && P.dbg == 2) any = any && v[0] == 0x12345678u;
                         if (any) {
                             const uint32_t cbase = (uint32_t)(col0 + (c + half) * 32);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                if (!hit[q]) continue;
+                            for (int i = 0; i < 8; ++i) {
+                                if (!hit[i]) continue;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {   // straight-line, predicated stores: a sparse hit must not cost a branch per element
-                                    const float val = __uint_as_float(v[4 * q + i]);
+                                for (int u = 0; u < 4; ++u) {   // straight-line, predicated stores: a sparse hit must not cost a branch per element
+                                    const float val = __uint_as_float(v[4 * i + u]);
                                     asm volatile(
                                         "{\n\t.reg .pred p;\n\t"
                                         "setp.lt.f32 p, %0, %1;\n\t"
                                         "@p st.global.v2.u32 [%2], {%3, %4};\n\t}"
-                                        ::"f"(val), "f"(thr), "l"(my_buf + cnt), "r"(cbase + (uint32_t)(4 * q + i)), "r"(v[4 * q + i])
+                                        ::"f"(val), "f"(thr), "l"(app + cnt), "r"(cbase + (uint32_t)(4 * i + u)), "r"(v[4 * i + u])
                                         : "memory");
                                     cnt += val < thr ? 1 : 0;
                                 }
@@ -500,20 +575,21 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[b]);
-                const long long t2 = P.prof ? clock64() : 0;
-                // lists are cut back only now, after the accumulator has been handed back: the tensor pipe refills this TMEM
-                // buffer while the warp sorts (a list can take a whole tile of appends past the trigger: L2_SLOTS)
-                if (__any_sync(FULL, cnt > 32 + P.trigger)) compact(false);
-                if (P.prof && lane == 0) {
+                const long long t2 = DEV && P.prof ? clock64() : 0;
+                // the accumulator is back with the tensor pipe: hand the regions that passed the trigger to the sorter
+                post(false);
+                if (DEV && P.prof && lane == 0) {
                     const long long t3 = clock64();
                     pw += t1 - t0; pd += t2 - t1; pc += t3 - t2;
                 }
             }
 
-            // end of item: every list sorted and cut to k, then group 0 merges both lists of a row and emits it
-            const long long t4 = P.prof ? clock64() : 0;
+            // end of item: every list sorted and cut to k by the sorter, then group 0 merges both lists of a row and emits it
+            const long long t4 = DEV && P.prof ? clock64() : 0;
             __syncwarp();
-            compact(true);
+            post(true);
+            while (lds_volatile_u32(sa_done) != n_posted) {}
+            __threadfence_block();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             s_tau[g * L2_BM + row] = __int_as_float(0x7F800000);   // next item starts unpruned (nobody reads it until the 2nd barrier)
             s_half[g * L2_BM + row] = __int_as_float(0x7F800000);
@@ -533,9 +609,9 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (P.prof && lane == 0) pt += clock64() - t4;
+            if (DEV && P.prof && lane == 0) pt += clock64() - t4;
         }
-        if (P.prof && lane == 0) {
+        if (DEV && P.prof && lane == 0) {
             atomicAdd(P.prof + 0, (unsigned long long)pw); atomicAdd(P.prof + 1, (unsigned long long)pd);
             atomicAdd(P.prof + 2, (unsigned long long)pc); atomicAdd(P.prof + 3, (unsigned long long)pt);
         }
@@ -747,22 +823,24 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     const CUtensorMap tt_tail = make_map(d_pool_tail, L2_TAIL, t_pad, L2_TAIL, L2_BN, CU_TENSOR_MAP_SWIZZLE_32B);
 
     // function attributes are per device: set on every launch (cheap) so that ctxs on several GPUs of one process all get them
-    SLIDEO_CUDA(cudaFuncSetAttribute(knn_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    const bool dev = l2_env().prof || l2_env().dbg != 0;
+    SLIDEO_CUDA(cudaFuncSetAttribute(dev ? knn_l2_kernel<true> : knn_l2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
     static unsigned long long* d_prof = nullptr;
     if (l2_env().prof) {
         if (!d_prof) SLIDEO_CUDA(cudaMalloc(&d_prof, 8 * sizeof(unsigned long long)));
         SLIDEO_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), stream));
         P.prof = d_prof;
     }
-    knn_l2_kernel<<<grid, L2_THREADS, SMEM_TOTAL, stream>>>(tq_main, tq_tail, tt_main, tt_tail, P);
+    if (dev) knn_l2_kernel<true><<<grid, L2_THREADS, SMEM_TOTAL, stream>>>(tq_main, tq_tail, tt_main, tt_tail, P);
+    else knn_l2_kernel<false><<<grid, L2_THREADS, SMEM_TOTAL, stream>>>(tq_main, tq_tail, tt_main, tt_tail, P);
     SLIDEO_CUDA(cudaGetLastError());
     if (P.prof) {
         unsigned long long h[8];
         SLIDEO_CUDA(cudaStreamSynchronize(stream));
         SLIDEO_CUDA(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
         const double ew = 8.0 * grid, mw = 1.0 * grid;   // epilogue warps, MMA warps
-        fprintf(stderr, "[l2 prof] per epilogue warp (Mcycles): acc wait %.2f drain %.2f cut-back %.2f tail %.2f | per MMA warp: acc_empty wait %.2f b_full wait %.2f\n",
-                h[0] / ew / 1e6, h[1] / ew / 1e6, h[2] / ew / 1e6, h[3] / ew / 1e6, h[4] / mw / 1e6, h[5] / mw / 1e6);
+        fprintf(stderr, "[l2 prof] per drain warp (Mcycles): acc wait %.2f drain %.2f post %.2f tail %.2f | per MMA warp: acc_empty wait %.2f b_full wait %.2f | per sorter warp: busy %.2f, %.0f requests\n",
+                h[0] / ew / 1e6, h[1] / ew / 1e6, h[2] / ew / 1e6, h[3] / ew / 1e6, h[4] / mw / 1e6, h[5] / mw / 1e6, h[6] / (4.0 * grid) / 1e6, h[7] / (4.0 * grid));
     }
     if (launches) ++*launches;
     // merge of the partial rows of the split tiles (one warp per query)
