@@ -61,7 +61,7 @@ constexpr uint32_t B_TAIL_BYTES = L2_BN * 32;
 constexpr uint32_t A_BYTES = 2 * A_MAIN_BYTES + A_TAIL_BYTES;   // 36 KB
 constexpr uint32_t B_BYTES = 2 * B_MAIN_BYTES + B_TAIL_BYTES;   // 72 KB
 constexpr uint32_t SMEM_OPERANDS = A_BYTES + L2_STAGES * B_BYTES;   // 180 KB
-constexpr uint32_t SMEM_CTRL = 128 + 6 * L2_BM * 4 + 8 * L2_RQ * 4 + 8 * 32 * 4 + 64;   // barriers/tmem ptr, tau / half-rank / pre-pass exchange, request rings, done counters, ring tails
+constexpr uint32_t SMEM_CTRL = 128 + 3 * L2_BM * 4 + 8 * L2_RQ * 4 + 8 * 32 * 4 + 64;   // barriers/tmem ptr, tau / pre-pass exchange, request rings, done counters, ring tails + items done
 constexpr uint32_t SMEM_TOTAL = SMEM_OPERANDS + SMEM_CTRL + 1024;   // + alignment slack
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
@@ -247,12 +247,12 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     uint64_t* acc_full = bars + 6;               // [2]: TMEM buffer = tile parity, 256 columns each
     uint64_t* acc_empty = bars + 10;             // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
-    volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 16);   // [2][L2_BM]: running k-th distance of each (group, row) list
-    volatile float* s_half = s_tau + 2 * L2_BM;                             // [2][L2_BM]: its ceil(k/2)-th distance
-    volatile float* s_pre = s_half + 2 * L2_BM;                             // [2][L2_BM]: pre-pass bound of each column half (l2_npre)
+    volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 16);   // [L2_BM]: k-th distance of each row's list as of its last cut-back
+    volatile float* s_pre = s_tau + L2_BM;                                  // [2][L2_BM]: pre-pass bound of each column half (l2_npre)
     volatile uint32_t* s_req = reinterpret_cast<volatile uint32_t*>(s_pre + 2 * L2_BM);   // [8][L2_RQ]: cut-back requests of a drain warp
     volatile uint32_t* s_done = s_req + 8 * L2_RQ;                          // [8][32]: requests the sorter has completed, per list
     volatile uint32_t* s_req_tail = s_done + 8 * 32;                        // [8]: requests a drain warp has posted
+    volatile uint32_t* s_items_done = s_req_tail + 8;                       // [4]: work items a sorter warp has emitted
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -263,8 +263,8 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 4 * L2_BM; i += L2_THREADS) s_tau[i] = __int_as_float(0x7F800000);   // s_tau and s_half
-    for (int i = tid; i < 8 * 32 + 8; i += L2_THREADS) s_done[i] = 0;                           // s_done and s_req_tail
+    for (int i = tid; i < L2_BM; i += L2_THREADS) s_tau[i] = __int_as_float(0x7F800000);
+    for (int i = tid; i < 8 * 32 + 8 + 4; i += L2_THREADS) s_done[i] = 0;                       // s_done, s_req_tail, s_items_done
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -340,23 +340,27 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         }
     } else if (warp >= 10) {
         // ===================== sorter warps =====================
-        // Sorter s serves the two drain warps of one TMEM lane quarter (s: columns 0..127, s + 4: columns 128..255).  A request
-        // names a list, the region holding its new candidates and their number: the sorted k best of the last cut-back (slots
-        // 0..31) are merged with the candidates, 32 at a time -- chunk sorted descending, lane-wise min with the ascending best =
-        // the 32 smallest as a bitonic sequence -- written back, and the list's k-th and ceil(k/2)-th distances are published.
-        // The drain warps never sort: the tensor pipe does not wait for a cut-back.
+        // Sorter s owns the lists of one TMEM lane quarter: ONE sorted list of the k best per query row (slots 0..31 of the row's
+        // column-half-0 buffer), fed by the two drain warps of the quarter (s: columns 0..127 of every tile, s + 4: columns
+        // 128..255).  A request names a row, the region holding new candidates and their number: the list is merged with the
+        // candidates, 32 at a time -- chunk sorted descending, lane-wise min with the ascending list = the 32 smallest as a bitonic
+        // sequence -- written back, and its k-th distance published for both drain threads of the row.  At the end of a work item
+        // the sorter emits the rows.  The drain warps never sort and never wait for an emission: the tensor pipe does not either.
         const int s = warp - 10;
+        const int row0 = ((s + 2) & 3) * 32;             // first row of the quarter
         uint32_t head[2] = {0, 0};
+        uint32_t items_done = 0;
         long long ps_busy = 0;
         unsigned ps_req = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            unsigned ended = 0;
+            const L2Item w = l2_item(P, item);
+            unsigned ended = 0, has_list = 0;            // bit r: row row0 + r has a sorted list in this item
             while (ended != 3u) {
                 bool worked = false;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     if (ended >> i & 1u) continue;
-                    const int e = s + 4 * i;                     // drain warp e: group i, lane quarter (e + 2) & 3
+                    const int e = s + 4 * i;                     // drain warp e: column half i of this quarter
                     const uint32_t tail = s_req_tail[e];
                     if (head[i] == tail) continue;
                     __threadfence_block();                       // the candidates of every posted request are visible from here on
@@ -367,11 +371,9 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                         ++head[i];
                         if (r == L2_REQ_END) { ended |= 1u << i; break; }
                         const int rl = (int)(r & 31u), region = (int)(r >> 5 & 1u), n = (int)(r >> 8);
-                        const bool hb = (r >> 6 & 1u) != 0;
-                        const int row = ((e + 2) & 3) * 32 + rl;
-                        uint64_t* buf = P.scratch + (((size_t)blockIdx.x * 2 + i) * L2_BM + row) * L2_SLOTS;
-                        const uint64_t* cand = buf + 32 + region * L2_REGION;
-                        uint64_t top = hb ? __ldcg(buf + lane) : KEY64_EMPTY;                   // all three loads in flight together
+                        uint64_t* list = P.scratch + ((size_t)blockIdx.x * 2 * L2_BM + row0 + rl) * L2_SLOTS;
+                        const uint64_t* cand = P.scratch + (((size_t)blockIdx.x * 2 + i) * L2_BM + row0 + rl) * L2_SLOTS + 32 + region * L2_REGION;
+                        uint64_t top = has_list >> rl & 1u ? __ldcg(list + lane) : KEY64_EMPTY;   // all three loads in flight together
                         uint64_t x0 = lane < n ? __ldcg(cand + lane) : KEY64_EMPTY;
                         uint64_t x1 = 32 + lane < n ? __ldcg(cand + 32 + lane) : KEY64_EMPTY;
                         if (n > 0) top = warp_merge32_asc(min(top, warp_sort32_desc(x0, lane)), lane);
@@ -381,15 +383,12 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                             top = warp_merge32_asc(min(top, warp_sort32_desc(x, lane)), lane);
                         }
                         if (lane >= P.k) top = KEY64_EMPTY;
-                        buf[lane] = top;
+                        list[lane] = top;
+                        has_list |= 1u << rl;
                         const uint64_t kth = __shfl_sync(FULL, top, P.k - 1);
-                        const uint64_t hth = __shfl_sync(FULL, top, (P.k + 1) / 2 - 1);
-                        __threadfence_block();
-                        __syncwarp();
                         if (lane == 0) {
-                            if (kth != KEY64_EMPTY) s_tau[i * L2_BM + row] = __uint_as_float((uint32_t)(kth >> 32));
-                            if (hth != KEY64_EMPTY) s_half[i * L2_BM + row] = __uint_as_float((uint32_t)(hth >> 32));
-                            s_done[e * 32 + rl] = s_done[e * 32 + rl] + 1;
+                            if (kth != KEY64_EMPTY) s_tau[row0 + rl] = __uint_as_float((uint32_t)(kth >> 32));
+                            s_done[e * 32 + rl] = s_done[e * 32 + rl] + 1;   // the region may be appended to again
                         }
                         ++ps_req;
                     }
@@ -397,6 +396,20 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 }
                 if (!worked) __nanosleep(40);
             }
+            // both drain warps have finished the item: emit the rows (oracle order: the list is sorted by (distance, index))
+            for (int L = 0; L < 32; ++L) {
+                const int qq = w.mt * L2_BM + row0 + L;
+                if (qq >= P.nq) break;   // warp-uniform
+                const uint64_t* list = P.scratch + ((size_t)blockIdx.x * 2 * L2_BM + row0 + L) * L2_SLOTS;
+                const uint64_t m = has_list >> L & 1u ? __ldcg(list + lane) : KEY64_EMPTY;
+                if (w.ns == 1) emit_l2_row(m, lane, qq, P.k, P.idx_out, P.dist_out);
+                else if (lane < P.k) P.partial[((size_t)qq * P.ns_max + w.sp) * P.k + lane] = m;
+            }
+            s_tau[row0 + lane] = __int_as_float(0x7F800000);   // the next item starts unpruned
+            __threadfence_block();
+            __syncwarp();
+            ++items_done;
+            if (lane == 0) s_items_done[s] = items_done;       // the drain warps may read s_tau for the next item
         }
         if (DEV && P.prof && lane == 0) { atomicAdd(P.prof + 6, (unsigned long long)ps_busy); atomicAdd(P.prof + 7, (unsigned long long)ps_req); }
     } else {
@@ -408,29 +421,28 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
         uint64_t* my_buf = P.scratch + (((size_t)blockIdx.x * 2 + g) * L2_BM + row) * L2_SLOTS;
         const uint32_t taddr_group = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * L2_BNH;
         uint32_t acc_phase = 0;                      // bit b: parity of the next completion of acc_full[b] this thread waits for
-        const uint32_t sa_tau_own = smem_u32(const_cast<float*>(s_tau)) + (uint32_t)(g * L2_BM + row) * 4;
-        const uint32_t sa_tau_other = smem_u32(const_cast<float*>(s_tau)) + (uint32_t)((g ^ 1) * L2_BM + row) * 4;
-        const uint32_t sa_half0 = smem_u32(const_cast<float*>(s_half)) + (uint32_t)row * 4;
+        const uint32_t sa_tau = smem_u32(const_cast<float*>(s_tau)) + (uint32_t)row * 4;
+        const uint32_t sa_items_done = smem_u32(const_cast<uint32_t*>(s_items_done)) + (uint32_t)(e & 3) * 4;
+        uint32_t items_begun = 0;                    // work items this warp has started before the current one
         const uint32_t sa_done = smem_u32(const_cast<uint32_t*>(s_done)) + (uint32_t)(e * 32 + lane) * 4;
-        uint32_t n_posted = 0;                       // requests posted for this thread's list (s_done counts the completed ones)
+        uint32_t n_posted = 0;                       // requests posted by this thread (s_done counts the completed ones)
+        int region = 0;                              // region this thread appends to (survives work items: the other one may still be queued)
         uint32_t req_tail = 0;                       // requests posted by this warp (warp-uniform)
         long long pw = 0, pd = 0, pc = 0, pt = 0;
 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const L2Item w = l2_item(P, item);
-            const int mt = w.mt, sp = w.sp, j0 = w.j0, j1 = w.j1;
+            const int mt = w.mt, j0 = w.j0, j1 = w.j1;
             const int q = mt * L2_BM + row;
             float bound = q < P.nq ? __int_as_float(0x7F800000) : -1.f;   // pre-pass bound: +inf / never
-            int region = 0;            // region of the list this thread appends to
-            int cnt = 0;               // candidates in it
-            bool have_base = false;    // slots 0..31 hold a sorted cut-back of this item
+            int cnt = 0;               // candidates in the region this thread appends to
 
-            // hands the regions that passed the trigger (force: every region that holds anything, and every list that has no
-            // sorted base yet) to the sorter warp and switches the thread to the other region
+            // hands the regions that passed the trigger (force: every region that holds anything, then the end-of-item marker) to
+            // the sorter warp and switches the thread to its other region
             auto post = [&](bool force) {
-                bool want = force ? (cnt > 0 || !have_base) : cnt > P.trigger;
+                bool want = force ? cnt > 0 : cnt > P.trigger;
                 if (want && lds_volatile_u32(sa_done) != n_posted) {
-                    // the previous cut-back of this list is still in the sorter's queue: wait only if the region cannot take another
+                    // the thread's previous request is still in the sorter's queue: wait only if the region cannot take another
                     // half tile (or at the end of the item), else try again after the next tile
                     if (force || cnt > L2_TRIGGER) { while (lds_volatile_u32(sa_done) != n_posted) {} }
                     else want = false;
@@ -439,11 +451,10 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 if (m == 0 && !force) return;
                 if (want) {
                     s_req[e * L2_RQ + ((req_tail + __popc(m & ((1u << lane) - 1u))) & (L2_RQ - 1))] =
-                        (uint32_t)lane | (uint32_t)region << 5 | (have_base ? 64u : 0u) | (uint32_t)cnt << 8;
+                        (uint32_t)lane | (uint32_t)region << 5 | (uint32_t)cnt << 8;
                     ++n_posted;
                     region ^= 1;
                     cnt = 0;
-                    have_base = true;
                 }
                 req_tail += __popc(m);
                 if (force) {
@@ -503,6 +514,10 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 if (q < P.nq) bound = next_up(fmaxf(s_pre[row], s_pre[L2_BM + row]));
             }
 
+            // s_tau belongs to the previous item until the sorter has emitted it (it is a pre-pass or a whole item behind at most)
+            while (lds_volatile_u32(sa_items_done) != items_begun) {}
+            ++items_begun;
+
             for (int j = j0; j < j1; ++j) {
                 // both groups drain EVERY tile, half of its columns each: the accumulator goes back to the tensor pipe after
                 // half a drain, and the MMA of tile j + 2 never queues behind a whole-tile epilogue
@@ -514,17 +529,10 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 const long long t1 = DEV && P.prof ? clock64() : 0;
                 const int col0 = j * L2_BN + g * L2_BNH;
                 const uint32_t taddr_base = taddr_group + (uint32_t)b * L2_BN;
-                // effective threshold: the pre-pass bound, the k-th distance of the own list as of its last cut-back (strict: a later
-                // column of this half has a larger index) or the other group's (non-strict: an equal distance with a smaller index
-                // could still displace its k-th entry), whichever is tighter.  Both lists hold >= ceil(k/2) entries at or below the
-                // larger of their ceil(k/2)-th distances, so k entries of the union do: anything above it cannot reach the final k
-                // (ties may, hence non-strict).  Four shared loads in flight together, no branches: once per tile per thread.
-                float thr;
-                {
-                    const float own = lds_volatile(sa_tau_own), other = lds_volatile(sa_tau_other);
-                    const float h0 = lds_volatile(sa_half0), h1 = lds_volatile(sa_half0 + L2_BM * 4);
-                    thr = fminf(fminf(bound, own), fminf(next_up(other), next_up(fmaxf(h0, h1))));
-                }
+                // effective threshold: the pre-pass bound or the k-th distance of the row's list as of its last cut-back, whichever is
+                // tighter -- non-strict (next_up): the list holds candidates of both column halves, an equal distance with a smaller
+                // index could still displace its k-th entry; the sorter decides on the full (distance, index) key
+                const float thr = fminf(bound, next_up(lds_volatile(sa_tau)));
                 uint64_t* app = my_buf + 32 + region * L2_REGION;
                 const int n_chunks = DEV && P.dbg == 1 ? 0 : L2_BNH / 32;
                 uint32_t va[32], vb[32];
@@ -584,31 +592,11 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                 }
             }
 
-            // end of item: every list sorted and cut to k by the sorter, then group 0 merges both lists of a row and emits it
+            // end of item: the rest of the candidates and the end marker go to the sorter, which emits the rows; the drain warps
+            // go straight on to the next item
             const long long t4 = DEV && P.prof ? clock64() : 0;
             __syncwarp();
             post(true);
-            while (lds_volatile_u32(sa_done) != n_posted) {}
-            __threadfence_block();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            s_tau[g * L2_BM + row] = __int_as_float(0x7F800000);   // next item starts unpruned (nobody reads it until the 2nd barrier)
-            s_half[g * L2_BM + row] = __int_as_float(0x7F800000);
-            if (g == 0) {
-                const uint64_t* base0 = P.scratch + (((size_t)blockIdx.x * 2 + 0) * L2_BM + quarter * 32) * L2_SLOTS;
-                const uint64_t* base1 = P.scratch + (((size_t)blockIdx.x * 2 + 1) * L2_BM + quarter * 32) * L2_SLOTS;
-                // every list holds its k best keys in slots 0..31, sorted, padded with empty keys
-                for (int L = 0; L < 32; ++L) {
-                    const int qq = mt * L2_BM + quarter * 32 + L;
-                    if (qq >= P.nq) break;   // warp-uniform
-                    // list 0 ascending, list 1 read back to front (descending): lane-wise min = the 32 smallest, bitonic
-                    const uint64_t a = __ldcg(base0 + (size_t)L * L2_SLOTS + lane);
-                    const uint64_t b = __ldcg(base1 + (size_t)L * L2_SLOTS + (31 - lane));
-                    const uint64_t m = warp_merge32_asc(a < b ? a : b, lane);
-                    if (w.ns == 1) emit_l2_row(m, lane, qq, P.k, P.idx_out, P.dist_out);
-                    else if (lane < P.k) P.partial[((size_t)qq * P.ns_max + sp) * P.k + lane] = m;
-                }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (DEV && P.prof && lane == 0) pt += clock64() - t4;
         }
         if (DEV && P.prof && lane == 0) {
