@@ -561,22 +561,31 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                         }
                         if (DEV && P.dbg == 2) any = any && v[0] == 0x12345678u;
                         if (any) {
+                            // slow path (a fifth of the chunks, two threads of the warp on average): ONE divergent region; the hit
+                            // group's four values are picked by a select tree instead of a branch per group
+                            unsigned hm = 0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) hm |= hit[i] ? 1u << i : 0u;
                             const uint32_t cbase = (uint32_t)(col0 + (c + half) * 32);
+                            do {
+                                const int gi = __ffs(hm) - 1;
+                                hm &= hm - 1;
+                                const uint32_t col = cbase + 4u * (uint32_t)gi;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                if (!hit[i]) continue;
+                                for (int u = 0; u < 4; ++u) {
+                                    uint32_t x = v[28 + u];
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) {   // straight-line, predicated stores: a sparse hit must not cost a branch per element
-                                    const float val = __uint_as_float(v[4 * i + u]);
+                                    for (int i = 6; i >= 0; --i) x = gi == i ? v[4 * i + u] : x;
+                                    const float val = __uint_as_float(x);
                                     asm volatile(
                                         "{\n\t.reg .pred p;\n\t"
                                         "setp.lt.f32 p, %0, %1;\n\t"
                                         "@p st.global.v2.u32 [%2], {%3, %4};\n\t}"
-                                        ::"f"(val), "f"(thr), "l"(app + cnt), "r"(cbase + (uint32_t)(4 * i + u)), "r"(v[4 * i + u])
+                                        ::"f"(val), "f"(thr), "l"(app + cnt), "r"(col + (uint32_t)u), "r"(x)
                                         : "memory");
                                     cnt += val < thr ? 1 : 0;
                                 }
-                            }
+                            } while (hm);
                         }
                     }
                 }
