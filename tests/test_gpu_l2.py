@@ -114,3 +114,67 @@ def test_l2_full_size_properties(ctx):
         d = np.sqrt(((q[i][None, :] - t) ** 2).sum(-1)).astype(np.float32)
         order = np.lexsort((np.arange(len(t)), d))[:30]
         assert np.array_equal(order.astype(np.int32), gi[i])
+
+
+def _exact_knn_rows(q, t, k, rows):
+    """(distance, index)-ordered k nearest pooled rows of the given query rows: exact integer arithmetic in numpy (the oracle's
+    definition, oracle/bf_oracle.c, restated for a handful of rows of a pool too large for the C loop in a test)."""
+    out_i, out_d = [], []
+    tt = t.astype(np.int64)
+    for r in rows:
+        d2 = ((tt - q[r].astype(np.int64)[None, :]) ** 2).sum(-1)
+        order = np.lexsort((np.arange(len(t)), d2))[:k]
+        out_i.append(order.astype(np.int32))
+        out_d.append(np.sqrt(d2[order].astype(np.float32)))
+    return np.stack(out_i), np.stack(out_d)
+
+
+def test_l2_long_work_items_take_the_threshold_pre_pass(ctx):
+    """Work items of >= 192 pool tiles run the threshold pre-pass (knn_l2.cu, l2_npre) and start selecting against a bound derived
+    from group minima; 149 query tiles also put one tile into the split last wave (no pre-pass there).  Exactness is checked row by
+    row against integer arithmetic on 64 rows (first, last, split-wave rows, random rows); every row is checked for order, range and
+    for reporting the exact distance of the index it names; duplicates inside the pool decide ties by index."""
+    import torch
+    nq, nt, k = 149 * 128 - 5, 50_000, 30
+    t = sift_like(nt, 300)
+    t[40_000:40_016] = t[100:116]                 # exact duplicates far apart: ties broken by index
+    q = sift_like(nq, 301, dup_from=t)
+    gi, gd = ctx.bf_knn_l2(q, t, k)
+    assert gi.min() >= 0 and gi.max() < nt
+    assert (np.diff(gd, axis=1) >= 0).all()
+    # the reported distance is the exact distance of the reported index, for every row (float64 on the GPU box's torch, integers)
+    tq, tt = torch.from_numpy(q).cuda().double(), torch.from_numpy(t).cuda().double()
+    for a in range(0, nq, 2048):
+        sel = torch.from_numpy(gi[a:a + 2048].astype(np.int64)).cuda()
+        d2 = ((tq[a:a + 2048, None, :] - tt[sel]) ** 2).sum(-1)
+        assert np.array_equal(gd[a:a + 2048], np.sqrt(d2.cpu().numpy().astype(np.float32)))
+    # no row misses a neighbour: the k-th reported distance equals the true k-th smallest distance (all rows, chunked on the GPU)
+    tn = (tt * tt).sum(1)
+    for a in range(0, nq, 1024):
+        d2 = (tq[a:a + 1024] ** 2).sum(1, keepdim=True) + tn[None, :] - 2.0 * tq[a:a + 1024] @ tt.T
+        kth = torch.topk(d2, k, dim=1, largest=False).values[:, -1].cpu().numpy()
+        assert np.array_equal(gd[a:a + 1024, -1], np.sqrt(kth.astype(np.float32)))
+    rng = np.random.default_rng(5)
+    rows = np.unique(np.concatenate([[0, 1, 127, 128, nq - 1, nq - 2, 148 * 128, 148 * 128 + 60], rng.integers(0, nq, 56)]))
+    oi, od = _exact_knn_rows(q, t, k, rows)
+    assert np.array_equal(gi[rows], oi)
+    assert np.array_equal(gd[rows].view(np.uint32), od.view(np.uint32))
+
+
+def test_l2_pre_pass_with_float_descriptors(ctx):
+    """The same long work items with general float rows: the pre-pass bound must hold for inexact accumulations too (tolerance as in
+    test_l2_float_descriptors_within_tolerance: 1e-4 relative against the bf16-rounded inputs, the figure north_star states)."""
+    import torch
+    rng = np.random.default_rng(9)
+    nq, nt, k = 148 * 128, 50_000, 30
+    t = rng.normal(0, 1, (nt, 128)).astype(np.float32)
+    q = (t[rng.integers(0, nt, nq)] + rng.normal(0, 0.3, (nq, 128))).astype(np.float32)
+    gi, gd = ctx.bf_knn_l2(q, t, k)
+    assert (np.diff(gd, axis=1) >= 0).all()
+    tq = torch.from_numpy(q).cuda().to(torch.bfloat16).double()      # the rounding the kernel applies
+    tt = torch.from_numpy(t).cuda().to(torch.bfloat16).double()
+    tn = (tt * tt).sum(1)
+    for a in range(0, nq, 1024):
+        d2 = ((tq[a:a + 1024] ** 2).sum(1, keepdim=True) + tn[None, :] - 2.0 * tq[a:a + 1024] @ tt.T).clamp_(min=0)
+        true = torch.topk(d2, k, dim=1, largest=False).values.sqrt().cpu().numpy()
+        assert np.allclose(gd[a:a + 1024], true, rtol=1e-4, atol=1e-5)
