@@ -10,17 +10,22 @@
 // (cv2 SIFT emits integers 0..255: exactly representable in bf16, every product and partial sum an integer < 2^24)
 // the fp32 accumulator in TMEM holds the exact squared distance, so sqrtf() of it is cv2's distance bit for bit.
 //
-// Kernel anatomy (persistent, one CTA per SM, 320 threads):
-//     warp 0      TMA producer      cp.async.bulk.tensor.2d (SWIZZLE_128B main blocks, SWIZZLE_32B norm tail) + mbarriers
-//     warp 1      MMA issuer        tcgen05.mma.cta_group::1.kind::f16, M = 128 queries x N = 256 pooled rows, 9 K-steps,
-//                                   fp32 accumulators in TMEM (2 x 256 columns = all 512), tcgen05.commit -> mbarriers
-//     warps 2-5   epilogue group 0  tcgen05.ld.32x32b.x32: thread = query row, 32 pooled columns per load; the epilogue of
-//     warps 6-9   epilogue group 1  a pair is a 3-input-min tree + ONE fp32 compare per 4 columns against the row's running k-th distance; survivors are
-//                                   appended as 64-bit keys (d2 bits << 32 | index) to a 128-slot per-(group,row) buffer in
-//                                   L2 scratch, cut back to its k best by a warp-cooperative streaming bitonic top-32 AFTER the
-//                                   accumulator has been released (the tensor pipe never waits for a sort)
-// Both groups drain every tile, half of its columns each (TMEM buffer = tile parity), so an accumulator is back with the tensor
-// pipe after half a drain; at the end of a work item both lists are merged and the row is emitted in oracle order.
+// Kernel anatomy (persistent, one CTA per SM, 448 threads):
+//     warp 0       TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B main blocks, SWIZZLE_32B norm tail) + mbarriers
+//     warp 1       MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M = 128 queries x N = 256 pooled rows, 9 K-steps,
+//                                 fp32 accumulators in TMEM (2 x 256 columns = all 512), tcgen05.commit -> mbarriers
+//     warps 2-9    drain warps    tcgen05.ld.32x32b.x32: thread = query row, 32 pooled columns per load.  Fast path of a chunk: a
+//                                 3-input-min tree and ONE fp32 compare against the row's threshold.  Slow path (a fifth of the
+//                                 chunks at a 1 M pool): the hit 4-column group is picked by a select tree and its survivors are
+//                                 appended as 64-bit keys (d2 bits << 32 | index) to the thread's region in L2 scratch.  Warps
+//                                 2-5 drain columns 0..127 of EVERY tile, warps 6-9 columns 128..255 (TMEM buffer = tile
+//                                 parity): an accumulator is back with the tensor pipe after half a drain.
+//     warps 10-13  sorter warps   one per TMEM lane quarter: own ONE sorted list of the k best per query row, merge the regions
+//                                 the drain threads hand over (streaming bitonic top-32), publish the row's k-th distance, and
+//                                 emit the rows at the end of a work item.  The drain warps never sort and never wait for an
+//                                 emission, so the tensor pipe does not either.
+// A work item (query tile x pool range) of >= 4 tiles starts with a threshold pre-pass (l2_npre): a sixth of its tiles (4..32)
+// run through the tensor pipe once only to bound every row's k-th distance by the maximum of k group minima.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -144,12 +149,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
-// Measured alternatives of the epilogue (65 k x 1 M, this file's version 923 TFLOP/s): four groups of 4 warps on 64-column
-// slices with x16 loads 907; the same with one x64 load per slice 731 (96 registers, spills) -- a drain without any selection
-// takes ~945 cycles per 128 x 256 fp32 tile however many warps share it, i.e. TMEM reads deliver ~139 B/clk per SM: that, not
-// the warp count, is the floor under the epilogue.
-// (N = 128 MMAs with four 128-column TMEM buffers were measured: the tensor ceiling drops from 1354 to 1131 TFLOP/s -- the A operand
-//  is re-read from shared memory twice as often -- so the tile stays at N = 256 with two buffers)
+// Measured (65 k x 1 M, profiles/r2_k10_steps.txt): without any selection the kernel runs at 1354 TFLOP/s on (2 * 128 + 3) FLOP per
+// pair, i.e. the drain + min tree alone keeps up with the tensor pipe; everything below that is the slow path and the coupling it
+// causes (a tile is released by ALL drain warps, so one warp's detour stalls the MMA of the tile after next).  Hence: cut-backs on
+// their own warps, one divergent region per slow-path visit, a branch-free threshold set-up per tile, and a small instruction
+// footprint (the sort network exists once, out of line: inlining it four more times cost 5 % on every shape).  Rejected after
+// measuring: N = 128 MMAs with four TMEM buffers (tensor ceiling 1354 -> 1131: the A operand is re-read from shared memory twice as
+// often), four epilogue groups on 64-column slices / x64 loads (round 1), three column parts per lane quarter with setmaxnreg (640
+// threads), parking hit chunks in a shared-memory ring, a jump table over the union of hit groups, batching or software-pipelining
+// the sorter's requests.
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L2_BN >> 3) << 17) | ((uint32_t)(L2_BM >> 4) << 24);
 
 // 32 keys, one per lane.  warp_sort32_desc: full bitonic sort, descending in lane order.  warp_merge32_asc: the last 5
@@ -178,6 +186,11 @@ __device__ __forceinline__ uint64_t warp_merge32_asc(uint64_t v, int lane) {
     return v;
 }
 
+// one out-of-line copy for the sorter warps (the kernel's instruction footprint is shared with the drain warps' hot loop)
+__device__ __noinline__ uint64_t warp_top32_merge(uint64_t top, uint64_t x, int lane) {
+    return warp_merge32_asc(min(top, warp_sort32_desc(x, lane)), lane);
+}
+
 struct L2Params {
     int nq, nt, k;
     int n_mtiles, n_ntiles;
@@ -185,7 +198,7 @@ struct L2Params {
     int ns_max;
     int trigger;           // new candidates of a list that schedule its cut-back (1..L2_TRIGGER)
     int pre_tiles;         // threshold pre-pass: pool tiles at the head of a work item whose accumulators are only reduced to group
-    int pre_min;           //   minima (see l2_npre); items with fewer than pre_min tiles have no pre-pass
+    int pre_min, pre_floor; //   minima (see l2_npre); items with fewer than pre_min tiles have no pre-pass
     unsigned long long* prof;  // developer instrument (SLIDEO_L2_PROF): cycles of epilogue warps in {acc wait, drain, cut-back, item tail}, MMA warp in {acc_empty wait, b_full wait}
     int dbg;               // developer switch (SLIDEO_L2_DEBUG): 1 = epilogue skips the TMEM drain, 2 = drains but never selects
     uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
@@ -220,7 +233,12 @@ __device__ __forceinline__ L2Item l2_item(const L2Params& P, int item) {
 // their maximum t0 bounds the row's k-th distance from above: the item then restarts at its first tile and selects with that
 // threshold from the first column on, instead of appending whole tiles until its lists have filled and tightened (about half of
 // all candidates a row ever appends fall into its first ~2000 columns).  Cost: pre_tiles extra tiles of pure MMA + min tree.
-__device__ __forceinline__ int l2_npre(const L2Params& P, int j0, int j1) { return j1 - j0 >= P.pre_min ? P.pre_tiles : 0; }
+// Shorter items get a shorter pre-pass: a sixth of their tiles, at least pre_floor (every group minimum must cover a chunk);
+// pre_min == pre_floor <= n, so the pre-pass never exceeds the item.
+__device__ __forceinline__ int l2_npre(const L2Params& P, int j0, int j1) {
+    const int n = j1 - j0;
+    return n >= P.pre_min ? min(P.pre_tiles, max(P.pre_floor, n / 6)) : 0;
+}
 
 __device__ __forceinline__ void emit_l2_row(uint64_t key, int lane, int q, int k, int32_t* idx_out, float* dist_out) {
     if (lane < k) {
@@ -376,11 +394,11 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                         uint64_t top = has_list >> rl & 1u ? __ldcg(list + lane) : KEY64_EMPTY;   // all three loads in flight together
                         uint64_t x0 = lane < n ? __ldcg(cand + lane) : KEY64_EMPTY;
                         uint64_t x1 = 32 + lane < n ? __ldcg(cand + 32 + lane) : KEY64_EMPTY;
-                        if (n > 0) top = warp_merge32_asc(min(top, warp_sort32_desc(x0, lane)), lane);
-                        if (n > 32) top = warp_merge32_asc(min(top, warp_sort32_desc(x1, lane)), lane);
+                        if (n > 0) top = warp_top32_merge(top, x0, lane);
+                        if (n > 32) top = warp_top32_merge(top, x1, lane);
                         for (int c0 = 64; c0 < n; c0 += 32) {
                             const uint64_t x = c0 + lane < n ? __ldcg(cand + c0 + lane) : KEY64_EMPTY;
-                            top = warp_merge32_asc(min(top, warp_sort32_desc(x, lane)), lane);
+                            top = warp_top32_merge(top, x, lane);
                         }
                         if (lane >= P.k) top = KEY64_EMPTY;
                         list[lane] = top;
@@ -498,7 +516,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                             for (int i = 0; i < 8; ++i)
                                 m = fminf(m, fminf(fminf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                                                    fminf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]))));
-                            if (groups < n_groups) {
+                            if (groups < n_groups && m < inf) {   // (a chunk of nothing but padding columns does not count)
                                 gmin = fminf(gmin, m);
                                 if (++in_group == per_group) { t0 = fmaxf(t0, gmin); gmin = inf; in_group = 0; ++groups; }
                             }
@@ -508,7 +526,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[b]);
                 }
-                s_pre[g * L2_BM + row] = t0;
+                s_pre[g * L2_BM + row] = groups == n_groups ? t0 : inf;   // too few real columns: no bound
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // the next write of s_pre lies behind the two barriers of the item tail
                 // k distinct pooled descriptors of this item lie at or below the larger half bound: candidates above it are never needed
                 if (q < P.nq) bound = next_up(fmaxf(s_pre[row], s_pre[L2_BM + row]));
@@ -789,12 +807,16 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     // selection per part (measured: 921 -> 855 TFLOP/s when every tile is split in two), so tiles are split only
     //  * when there are too few of them to fill the machine (all tiles, ns_a ways), or
     //  * in the LAST wave: the n_mtiles % SMs tiles that would leave most SMs idle are split so that their parts fill one wave.
+    // A part keeps at least pre_floor tiles where the pool allows it, so that it can run the threshold pre-pass: without a bound
+    // the first tiles of an item append every column and the item is paced by its sorter warps.
+    P.pre_floor = ((k + 1) / 2 + L2_BNH / 32 - 1) / (L2_BNH / 32);
+    const int max_parts = std::max(1, P.n_ntiles / P.pre_floor);
     P.mt_a = P.n_mtiles; P.ns_a = 1; P.ns_b = 1;
     if (P.n_mtiles < num_sms) {
-        P.ns_a = std::min(P.n_ntiles, std::max(1, num_sms / P.n_mtiles));
+        P.ns_a = std::min(max_parts, std::max(1, num_sms / P.n_mtiles));
     } else if (!l2_env().no_split) {
         const int r = P.n_mtiles % num_sms;
-        const int c = r > 0 ? std::min(std::min(4, P.n_ntiles), num_sms / r) : 1;
+        const int c = r > 0 ? std::min(std::min(4, max_parts), num_sms / r) : 1;
         if (c >= 2) { P.mt_a = P.n_mtiles - r; P.ns_b = c; }
     }
     P.ns_max = std::max(P.ns_a, P.ns_b);
@@ -807,9 +829,11 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     P.idx_out = d_idx;
     P.dist_out = d_dist;
     P.trigger = l2_env().trigger;
-    // pre-pass of pre_tiles tiles for items of at least 6 x as many; every group minimum must cover at least one chunk
-    P.pre_tiles = std::max(l2_env().pre, (k + 1) / 2 / (L2_BNH / 32) + 1);
-    P.pre_min = l2_env().pre > 0 ? 6 * P.pre_tiles : 0x7FFFFFFF;
+    // pre-pass: a sixth of an item's tiles, pre_floor..pre_tiles of them, for items of at least pre_floor tiles (a 4-tile item runs
+    // twice: the tensor pipe is not what bounds it); every group minimum must cover at least one 32-column chunk (a thread drains
+    // L2_BNH / 32 chunks of a tile)
+    P.pre_tiles = std::max(l2_env().pre, P.pre_floor);
+    P.pre_min = l2_env().pre > 0 ? P.pre_floor : 0x7FFFFFFF;
     P.prof = nullptr;
     P.dbg = l2_env().dbg;
 

@@ -6,7 +6,7 @@ for round in 1 2; do
   for v in A B; do
     cp tools/scratch/ab/lib$v.so slideo_b200/libslideo_b200.so
     echo "== $v (round $round)"
-    timeout 100 python tools/k10_probe.py "$@" 2>&1 | cut -c1-110
+    timeout 40 python tools/k10_probe.py "$@" 2>&1 | cut -c1-110
   done
 done
 cp /tmp/lib_keep.so slideo_b200/libslideo_b200.so
