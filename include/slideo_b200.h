@@ -174,7 +174,8 @@ int32_t slideo_b200_pool_commit(slideo_b200_ctx* ctx);
 int32_t slideo_b200_pool_points_device_view(slideo_b200_ctx* ctx, void** d_pt, size_t* bytes, int32_t* has_points, int32_t received);
 
 /* Small gray images of the pages (slide.small_img, lib.rs:105; the warp + similarity gate of cfg.geometric_verification == 2).  On
- * the rank that built the pool: *page_w / *page_h = the uniform page size (0 when the pages differ in size or came without images)
+ * the rank that built the pool: *page_w / *page_h = the uniform page size (0 when the pages differ in size or came without images:
+ * the gates themselves handle mixed page sizes, as the reference does per slide -- only this replication view carries one size)
  * and *d_small = n_pages small images.  On a reserved ctx: pass the sender's page size as set_w / set_h to size the buffer and
  * get the pointer to receive into (before pool_commit). */
 int32_t slideo_b200_pool_pages_device_view(slideo_b200_ctx* ctx, void** d_small, size_t* bytes, int32_t* page_w, int32_t* page_h,

@@ -407,13 +407,20 @@ struct slideo_b200_ctx {
     std::vector<VerifyRecord> verify_results;   // one per frame of the last match_frames_* call
     // photometric stage (K14, cfg.geometric_verification == 2)
     std::vector<slideo_b200_decision> decisions;
-    std::vector<uint8_t> h_page_small;          // gray small image of every page (uniform page geometry)
-    int page_w = 0, page_h = 0;
-    bool page_geom_ok = true;
+    std::vector<uint8_t> h_page_small;          // gray small image of every page, back to back (page p at h_page_small_off[p])
+    // page geometry: one class per distinct page size (the reference warps the frame to each slide's own size, lib.rs:339-348)
+    struct PageClass { int w = 0, h = 0; AreaTables area; };
+    std::vector<std::unique_ptr<PageClass>> page_classes;
+    std::vector<int32_t> h_page_class;               // [n_pages]
+    std::vector<unsigned long long> h_page_small_off; // [n_pages]
+    DevBuf<PageGeom> d_page_geom;
+    DevBuf<int32_t> d_page_class;
+    DevBuf<unsigned long long> d_page_small_off;
+    int max_small_w = 0, max_small_h = 0;
+    bool page_geom_ok = true;                   // every page came with its image (add_page_gray8) or the images were replicated
     bool page_small_ready = false;              // d_page_small holds the small image of every page (built here or replicated)
     bool page_small_received = false;           // a reserved pool got its page images through pool_pages_device_view
     DevBuf<uint8_t> d_page_small, d_all_frames;
-    AreaTables page_area;
     DevBuf<int32_t> d_v_best_it, d_v_surv_cand;
     DevBuf<double> d_v_refined;
     DevBuf<unsigned long long> d_v_sumsq;
@@ -762,7 +769,7 @@ struct slideo_b200_ctx {
     // K14 on the survivors of a finished epoch (lib.rs:335-389); appends one decision per frame
     void photometric_epoch(const VerifyArgs& va, int n_frames, size_t base) {
         if (!page_geom_ok || !page_small_ready)
-            throw StateError("the warp + similarity gate needs every page as an image (add_page_gray8) and one page size");
+            throw StateError("the warp + similarity gate needs every page as an image (add_page_gray8, or replicated page images)");
         if (!photo_frames) throw StateError("frames are not resident for the warp + similarity gate");
         const size_t F = (size_t)n_frames;
         d_v_refined.reserve(F * VERIFY_TOP_RATED * 4);
@@ -773,9 +780,8 @@ struct slideo_b200_ctx {
         p.d_corr = va.d_corr; p.d_frame_q0 = va.d_frame_q0; p.d_frame_pt = va.d_frame_pt; p.d_pool_pt = va.d_pool_pt;
         p.d_frames = photo_frames; p.frame_w = photo_w; p.frame_h = photo_h; p.frame_stride_row = photo_row_stride;
         p.frame_stride = photo_frame_stride;
-        p.page_w = page_w; p.page_h = page_h; p.small_w = page_area.dw; p.small_h = page_area.dh;
-        p.d_xoff = page_area.d_xoff; p.d_xsi = page_area.d_xsi; p.d_xa = page_area.d_xa;
-        p.d_yoff = page_area.d_yoff; p.d_ysi = page_area.d_ysi; p.d_ya = page_area.d_ya;
+        p.d_geom = d_page_geom.p; p.d_page_class = d_page_class.p; p.d_page_small_off = d_page_small_off.p;
+        p.max_small_w = max_small_w; p.max_small_h = max_small_h;
         p.d_page_small = d_page_small.p; p.d_refined = d_v_refined.p; p.d_sumsq = d_v_sumsq.p;
         EventPair t = begin_timing(5, knn_stream);
         int nl = 0;
@@ -787,8 +793,6 @@ struct slideo_b200_ctx {
         SLIDEO_CUDA(cudaMemcpyAsync(ss.data(), d_v_sumsq.p, ss.size() * 8, cudaMemcpyDeviceToHost, knn_stream));
         SLIDEO_CUDA(cudaMemcpyAsync(ref.data(), d_v_refined.p, ref.size() * 8, cudaMemcpyDeviceToHost, knn_stream));
         SLIDEO_CUDA(cudaStreamSynchronize(knn_stream));
-        const int pcount = page_area.dw * page_area.dh;
-        const float max_error = sqrtf((255.0f * 255.0f * 3.0f) * (float)pcount);   // image_utils.rs:24-25
         decisions.resize(base + F);
         for (size_t f = 0; f < F; ++f) {
             const VerifyRecord& r = verify_results[base + f];
@@ -798,6 +802,8 @@ struct slideo_b200_ctx {
             std::vector<Rated> rated;
             for (int j = 0; j < r.n_survivors; ++j) {
                 const double error_l2 = sqrt((double)ss[f * VERIFY_TOP_RATED + j]);
+                const AreaTables& ar = page_classes[(size_t)h_page_class[(size_t)r.survivor_page[j]]]->area;
+                const float max_error = sqrtf((255.0f * 255.0f * 3.0f) * (float)(ar.dw * ar.dh));   // image_utils.rs:24-25
                 const float sim = 1.0f - (float)error_l2 / max_error;               // image_utils.rs:26
                 rated.push_back({r.survivor_page[j], sim});
                 for (int c = 0; c < 4; ++c) d.refined_matrix[j][c] = ref[(f * VERIFY_TOP_RATED + j) * 4 + c];
@@ -812,6 +818,38 @@ struct slideo_b200_ctx {
                     ++d.n_rated;
                 }
             if (d.n_rated) d.image = d.rated_page[0];
+        }
+    }
+
+    // the size class of a page (created on first use)
+    int page_class_index(int w, int h) {
+        for (size_t c = 0; c < page_classes.size(); ++c)
+            if (page_classes[c]->w == w && page_classes[c]->h == h) return (int)c;
+        page_classes.emplace_back(new PageClass());
+        page_classes.back()->w = w;
+        page_classes.back()->h = h;
+        page_classes.back()->area.build(w, h);
+        return (int)page_classes.size() - 1;
+    }
+    // device tables of the page geometry (classes, class and small-image offset of every page)
+    void upload_page_geometry() {
+        std::vector<PageGeom> g(page_classes.size());
+        max_small_w = max_small_h = 0;
+        for (size_t c = 0; c < page_classes.size(); ++c) {
+            const PageClass& pc = *page_classes[c];
+            g[c].page_w = pc.w; g[c].page_h = pc.h; g[c].small_w = pc.area.dw; g[c].small_h = pc.area.dh;
+            g[c].d_xoff = pc.area.d_xoff; g[c].d_xsi = pc.area.d_xsi; g[c].d_xa = pc.area.d_xa;
+            g[c].d_yoff = pc.area.d_yoff; g[c].d_ysi = pc.area.d_ysi; g[c].d_ya = pc.area.d_ya;
+            max_small_w = std::max(max_small_w, pc.area.dw);
+            max_small_h = std::max(max_small_h, pc.area.dh);
+        }
+        d_page_geom.reserve(std::max<size_t>(g.size(), 1));
+        d_page_class.reserve(std::max<size_t>(h_page_class.size(), 1));
+        d_page_small_off.reserve(std::max<size_t>(h_page_small_off.size(), 1));
+        if (!g.empty()) SLIDEO_CUDA(cudaMemcpy(d_page_geom.p, g.data(), g.size() * sizeof(PageGeom), cudaMemcpyHostToDevice));
+        if (!h_page_class.empty()) {
+            SLIDEO_CUDA(cudaMemcpy(d_page_class.p, h_page_class.data(), h_page_class.size() * 4, cudaMemcpyHostToDevice));
+            SLIDEO_CUDA(cudaMemcpy(d_page_small_off.p, h_page_small_off.data(), h_page_small_off.size() * 8, cudaMemcpyHostToDevice));
         }
     }
 
@@ -839,9 +877,10 @@ struct slideo_b200_ctx {
         d_page_off.reserve((size_t)n_pages + 1);
         if (nt > 0) SLIDEO_CUDA(cudaMemcpyAsync(d_page_of.p, po.data(), (size_t)nt * 2, cudaMemcpyHostToDevice, stream));
         SLIDEO_CUDA(cudaMemcpyAsync(d_page_off.p, page_off.data(), ((size_t)n_pages + 1) * 4, cudaMemcpyHostToDevice, stream));
-        if (cfg.geometric_verification >= 2 && page_geom_ok && !h_page_small.empty()) {
+        if (cfg.geometric_verification >= 2 && page_geom_ok && !h_page_small.empty() && (int)h_page_class.size() == n_pages) {
             d_page_small.reserve(h_page_small.size());
             SLIDEO_CUDA(cudaMemcpyAsync(d_page_small.p, h_page_small.data(), h_page_small.size(), cudaMemcpyHostToDevice, stream));
+            upload_page_geometry();
             page_small_ready = true;
         }
         pool_pts_valid = pool_pts_valid && h_pool_pt.size() == (size_t)nt * 2;
@@ -1047,23 +1086,18 @@ int32_t slideo_b200_add_page_gray8(slideo_b200_ctx* ctx, const uint8_t* px, int3
         }
         SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->cfg.geometric_verification >= 2) {   // slide.small_img (lib.rs:105): to_small_image of the gray page replicated to BGR
-            if (ctx->page_w == 0) {
-                ctx->page_w = w;
-                ctx->page_h = h;
-                ctx->page_area.build(w, h);
-            }
-            if (w != ctx->page_w || h != ctx->page_h) {
-                ctx->page_geom_ok = false;
-            } else {
-                const size_t sb = (size_t)ctx->page_area.dw * ctx->page_area.dh;
-                ctx->d_page_small_tmp.reserve(sb);
-                area_small_launch(ctx->page_area, ctx->d_img.p, 1, w, (size_t)w * h, ctx->d_page_small_tmp.p, ctx->stream, 1);
-                const size_t b0 = ctx->h_page_small.size();
-                ctx->h_page_small.resize(b0 + sb);
-                SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_page_small.data() + b0, ctx->d_page_small_tmp.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
-                SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
-                ctx->tm.kernel_launches += 1;
-            }
+            const int pc = ctx->page_class_index(w, h);
+            const AreaTables& ar = ctx->page_classes[(size_t)pc]->area;
+            const size_t sb = (size_t)ar.dw * ar.dh;
+            ctx->d_page_small_tmp.reserve(sb);
+            area_small_launch(ar, ctx->d_img.p, 1, w, (size_t)w * h, ctx->d_page_small_tmp.p, ctx->stream, 1);
+            const size_t b0 = ctx->h_page_small.size();
+            ctx->h_page_small.resize(b0 + sb);
+            SLIDEO_CUDA(cudaMemcpyAsync(ctx->h_page_small.data() + b0, ctx->d_page_small_tmp.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+            SLIDEO_CUDA(cudaStreamSynchronize(ctx->stream));
+            ctx->tm.kernel_launches += 1;
+            ctx->h_page_class.push_back(pc);
+            ctx->h_page_small_off.push_back((unsigned long long)b0);
         }
         for (int i = 0; i < total; ++i) {   // KeyPoint.pt of the slide keypoints (lib.rs:299)
             ctx->h_pool_pt.push_back(kpf[(size_t)i * 4]);
@@ -1193,6 +1227,9 @@ int32_t slideo_b200_pool_reserve(slideo_b200_ctx* ctx, int32_t n_desc, int32_t n
         ctx->page_small_ready = false;
         ctx->page_geom_ok = false;
         ctx->h_page_small.clear();
+        ctx->page_classes.clear();
+        ctx->h_page_class.clear();
+        ctx->h_page_small_off.clear();
         ctx->page_off.assign((size_t)n_pages + 1, 0);
         if (ctx->cfg.descriptor_kind == SLIDEO_B200_DESC_ORB256) ctx->d_pool.reserve((size_t)std::max(n_desc, 1) * 32 + 64);
         else ctx->d_pool_f32.reserve((size_t)std::max(n_desc, 1) * 512);
@@ -1232,19 +1269,27 @@ int32_t slideo_b200_pool_pages_device_view(slideo_b200_ctx* ctx, void** d_small,
     REQUIRE_CTX(ctx);
     return guarded(ctx, [&] {
         if (!ctx->finalized && !ctx->reserved) throw StateError("no device pool yet (finalize_pool or pool_reserve first)");
-        if (ctx->reserved && set_w > 0 && set_h > 0) {   // the receiving side: size the buffer for the sender's page geometry
-            ctx->page_w = set_w;
-            ctx->page_h = set_h;
-            ctx->page_area.build(set_w, set_h);
-            ctx->d_page_small.reserve((size_t)std::max(ctx->n_pages, 1) * ctx->page_area.dw * ctx->page_area.dh);
+        if (ctx->reserved && set_w > 0 && set_h > 0) {   // the receiving side: size the buffer for the sender's (uniform) page geometry
+            ctx->page_classes.clear();
+            const int pc = ctx->page_class_index(set_w, set_h);
+            const AreaTables& ar = ctx->page_classes[(size_t)pc]->area;
+            const size_t sb = (size_t)ar.dw * ar.dh;
+            ctx->d_page_small.reserve((size_t)std::max(ctx->n_pages, 1) * sb);
+            ctx->h_page_class.assign((size_t)ctx->n_pages, 0);
+            ctx->h_page_small_off.resize((size_t)ctx->n_pages);
+            for (int p = 0; p < ctx->n_pages; ++p) ctx->h_page_small_off[(size_t)p] = (unsigned long long)p * sb;
+            ctx->upload_page_geometry();
             ctx->page_geom_ok = true;
             ctx->page_small_received = true;
         }
-        const bool have = ctx->reserved ? ctx->page_small_received : (ctx->page_geom_ok && ctx->page_small_ready);
+        // replication moves ONE page size: a deck of mixed page sizes reports 0 x 0 here and keeps its gates on the rank that built it
+        const bool uniform = ctx->page_classes.size() == 1;
+        const bool have = uniform && (ctx->reserved ? ctx->page_small_received : (ctx->page_geom_ok && ctx->page_small_ready));
+        const AreaTables* ar = uniform ? &ctx->page_classes[0]->area : nullptr;
         if (d_small) *d_small = have ? (void*)ctx->d_page_small.p : nullptr;
-        if (bytes) *bytes = have ? (size_t)ctx->n_pages * ctx->page_area.dw * ctx->page_area.dh : 0;
-        if (page_w) *page_w = have ? ctx->page_w : 0;
-        if (page_h) *page_h = have ? ctx->page_h : 0;
+        if (bytes) *bytes = have ? (size_t)ctx->n_pages * ar->dw * ar->dh : 0;
+        if (page_w) *page_w = have ? ctx->page_classes[0]->w : 0;
+        if (page_h) *page_h = have ? ctx->page_classes[0]->h : 0;
     });
 }
 

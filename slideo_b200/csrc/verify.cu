@@ -459,23 +459,26 @@ __global__ void __launch_bounds__(128) photometric_kernel(const PhotoArgs A) {
     const int f = blockIdx.z / VERIFY_TOP_RATED, j = blockIdx.z - f * VERIFY_TOP_RATED;
     const VerifyRecord& rec = A.d_records[f];
     if (j >= rec.n_survivors) return;
+    const int page = rec.survivor_page[j];
+    const PageGeom G = A.d_geom[A.d_page_class[page]];   // the slide's own size (the reference warps to slide_info.img.size())
     const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+    if (dy >= G.small_h) return;                          // block-uniform: the grid covers the largest small image of the deck
     unsigned long long acc = 0;
-    if (dx < A.small_w) {
+    if (dx < G.small_w) {
         const double* h = A.d_refined + ((size_t)f * VERIFY_TOP_RATED + j) * 4;
         const double M0 = h[0], M1 = -h[1], M2 = h[2], M3 = h[1], M4 = h[0], M5 = h[3];
         const uint8_t* frame = A.d_frames + (size_t)f * A.frame_stride;
-        const int x0 = A.d_xoff[dx], x1 = A.d_xoff[dx + 1], y0 = A.d_yoff[dy], y1 = A.d_yoff[dy + 1];
+        const int x0 = G.d_xoff[dx], x1 = G.d_xoff[dx + 1], y0 = G.d_yoff[dy], y1 = G.d_yoff[dy + 1];
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         for (int jj = y0; jj < y1; ++jj) {
-            const int sy = A.d_ysi[jj];
-            const float beta = A.d_ya[jj];
+            const int sy = G.d_ysi[jj];
+            const float beta = G.d_ya[jj];
             const int X0 = __double2int_rn((M1 * (double)sy + M2) * 1024.) + 512;
             const int Y0 = __double2int_rn((M4 * (double)sy + M5) * 1024.) + 512;
             float b0 = 0.f, b1 = 0.f, b2 = 0.f;
             for (int kk = x0; kk < x1; ++kk) {
-                const int sx = A.d_xsi[kk];
-                const float al = A.d_xa[kk];
+                const int sx = G.d_xsi[kk];
+                const float al = G.d_xa[kk];
                 const int X = (X0 + __double2int_rn(M0 * (double)sx * 1024.)) >> 10;
                 const int Y = (Y0 + __double2int_rn(M3 * (double)sx * 1024.)) >> 10;
                 float p0 = 0.f, p1 = 0.f, p2 = 0.f;   // BORDER_CONSTANT 0
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(128) photometric_kernel(const PhotoArgs A) {
                 s0 = __fadd_rn(s0, __fmul_rn(beta, b0)); s1 = __fadd_rn(s1, __fmul_rn(beta, b1)); s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
             }
         }
-        const int g = A.d_page_small[((size_t)rec.survivor_page[j] * A.small_h + dy) * A.small_w + dx];
+        const int g = A.d_page_small[A.d_page_small_off[page] + (size_t)dy * G.small_w + dx];
         const int v0 = min(max(__float2int_rn(s0), 0), 255) - g, v1 = min(max(__float2int_rn(s1), 0), 255) - g,
                   v2 = min(max(__float2int_rn(s2), 0), 255) - g;
         acc = (unsigned long long)(v0 * v0 + v1 * v1 + v2 * v2);
@@ -536,7 +539,7 @@ void photometric_launch(const PhotoArgs& a, cudaStream_t stream, int* launches) 
     if (a.n_frames <= 0) return;
     SLIDEO_CUDA(cudaMemsetAsync(a.d_sumsq, 0, (size_t)a.n_frames * VERIFY_TOP_RATED * sizeof(unsigned long long), stream));
     lm_refine_kernel<<<dim3(VERIFY_TOP_RATED, a.n_frames), 128, 0, stream>>>(a);
-    photometric_kernel<<<dim3(cdiv(a.small_w, 128), a.small_h, a.n_frames * VERIFY_TOP_RATED), 128, 0, stream>>>(a);
+    photometric_kernel<<<dim3(cdiv(a.max_small_w, 128), a.max_small_h, a.n_frames * VERIFY_TOP_RATED), 128, 0, stream>>>(a);
     SLIDEO_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
 }

@@ -33,6 +33,14 @@ struct VerifyArgs {
 
 // K14: photometric verification of the survivors (lib.rs:335-389): LM-refined matrix -> warpAffine(WARP_INVERSE_MAP, nearest)
 // of the frame into the slide's geometry -> INTER_AREA small image -> sum of squared differences to the slide's small image
+// geometry of one page size: the slide image size the frame is warped to (lib.rs:339-348, slide_info.img.size()) and the area tables
+// of to_small_image for it (image_utils.rs:8-19)
+struct PageGeom {
+    int page_w, page_h, small_w, small_h;
+    const int32_t *d_xoff, *d_xsi, *d_yoff, *d_ysi;
+    const float *d_xa, *d_ya;
+};
+
 struct PhotoArgs {
     int n_frames, k;
     const VerifyRecord* d_records;     // [n_frames]
@@ -46,10 +54,11 @@ struct PhotoArgs {
     const uint8_t* d_frames;           // BGR8 frames of the group
     int frame_w, frame_h, frame_stride_row;
     size_t frame_stride;
-    int page_w, page_h, small_w, small_h;          // uniform page geometry
-    const int32_t *d_xoff, *d_xsi, *d_yoff, *d_ysi; // area tables of (page_w, page_h) -> (small_w, small_h)
-    const float *d_xa, *d_ya;
-    const uint8_t* d_page_small;       // [n_pages][small_h * small_w] gray
+    const PageGeom* d_geom;            // one entry per distinct page size of the deck
+    const int32_t* d_page_class;       // [n_pages] index into d_geom
+    const unsigned long long* d_page_small_off;   // [n_pages] byte offset of the page's small image in d_page_small
+    int max_small_w, max_small_h;      // over the deck's page sizes (launch geometry)
+    const uint8_t* d_page_small;       // gray small images, page p at d_page_small_off[p], small_h * small_w bytes of its size class
     double* d_refined;                 // [n_frames][10][4]  (a, b, tx, ty)
     unsigned long long* d_sumsq;       // [n_frames][10]
 };

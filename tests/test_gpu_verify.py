@@ -128,3 +128,42 @@ def test_photometric_gate_equals_oracle(scene):
             assert np.allclose(dec[f]["refined"][j], [m[0, 0], m[1, 0], m[0, 2], m[1, 2]], rtol=0, atol=1e-9)
         truth = synth.frame_truth(f, NPAGES)
         assert dec[f]["image"] == (truth if truth >= 0 else -1)
+
+
+def test_photometric_gate_with_mixed_page_sizes():
+    """A deck whose pages differ in size: the reference warps the frame to each slide's own size and compares small images of that
+    slide's geometry (lib.rs:339-351, slide_info.img.size()); the library keeps one geometry class per page size.  Decisions,
+    survivors and similarities against the oracle chain on the same pages; replication (one page size per deck) reports 0 x 0."""
+    import cv2
+    import slideo_b200
+    from oracle import photometric as ph
+    npages = 4
+    base = [synth.make_page(p) for p in range(npages)]
+    sizes = [None, (1600, 900), None, (1440, 810)]
+    pages = [b if s is None else cv2.resize(b, s, interpolation=cv2.INTER_AREA) for b, s in zip(base, sizes)]
+    frames = np.stack([synth.make_frame(f, npages, base) for f in range(6)])   # frames show the full-size renderings
+    feats = [oracle.orb_detect_and_compute(p) for p in pages]
+    pool = np.concatenate([f[2] for f in feats])
+    pool_pts = np.concatenate([f[1][:, :2] for f in feats])
+    offs = np.zeros(npages + 1, np.int32)
+    offs[1:] = np.cumsum([len(f[2]) for f in feats])
+    with slideo_b200.Context(slideo_b200.default_config(geometric_verification=2, max_batch=4)) as c:
+        for p in pages:
+            c.add_page_gray8(p)
+        c.finalize_pool()
+        c.match_frames_bgr8(frames)
+        ver = c.get_verification(0, len(frames))
+        dec = c.get_decisions(0, len(frames))
+        assert c.pool_pages_device_view()[2:] == (0, 0)
+    seen = set()
+    for f in range(len(frames)):
+        ki, kf, dd = oracle.orb_detect_and_compute(oracle.gray_from_bgr(frames[f]))
+        idx, dist = oracle.bf_knn_hamming(dd, pool, 30)
+        want = ph.decide_frame(idx, dist.astype(np.float32), offs, kf[:, :2], pool_pts, frames[f], pages)
+        assert ver[f]["survivors"] == [tuple(int(v) for v in x) for x in want["survivors"]]
+        assert dec[f]["image"] == want["image"], f"frame {f}"
+        assert [p for p, _ in dec[f]["rated"]] == [p for p, _ in want["rated"]]
+        for (_, s), (_, ws) in zip(dec[f]["rated"], want["rated"]):
+            assert abs(float(s) - float(ws)) <= 1e-6
+        seen.add(dec[f]["image"])
+    assert len({pages[i].shape for i in seen if i >= 0}) == 3          # pages of all three sizes were decided for
