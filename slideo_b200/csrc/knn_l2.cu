@@ -811,12 +811,26 @@ void l2_knn_launch(L2Workspace& ws, const float* d_q, int nq, const void* d_pool
     // the first tiles of an item append every column and the item is paced by its sorter warps.
     P.pre_floor = ((k + 1) / 2 + L2_BNH / 32 - 1) / (L2_BNH / 32);
     const int max_parts = std::max(1, P.n_ntiles / P.pre_floor);
+    // parts per tile for `tiles` query tiles that share the machine: rounds x (pool / parts + the fixed cost of a part) is
+    // minimised.  The fixed cost -- pre-pass, restarted selection, the sorters' end-of-item requests, emission -- is worth ~350
+    // tiles (calibrated: 79 tiles x 3907 gain nothing from 9 parts, 98 tiles run 18 % faster as 294 thirds in two rounds than
+    // as one round that leaves 50 SMs idle, 79 x 391 lose 70 % when cut in five)
+    auto choose_parts = [&](int tiles, int limit) {
+        int best = 1;
+        double best_cost = 1e300;
+        for (int c = 1; c <= std::min(limit, max_parts); ++c) {
+            const double rounds = (double)cdiv(tiles * c, num_sms);
+            const double cost = rounds * ((double)P.n_ntiles / c + std::min(32.0, std::max(4.0, P.n_ntiles / (6.0 * c))) + 350.0);
+            if (cost < best_cost * 0.97) { best_cost = cost; best = c; }   // a finer split must pay for restarting the selection
+        }
+        return best;
+    };
     P.mt_a = P.n_mtiles; P.ns_a = 1; P.ns_b = 1;
     if (P.n_mtiles < num_sms) {
-        P.ns_a = std::min(max_parts, std::max(1, num_sms / P.n_mtiles));
+        P.ns_a = choose_parts(P.n_mtiles, 64);
     } else if (!l2_env().no_split) {
         const int r = P.n_mtiles % num_sms;
-        const int c = r > 0 ? std::min(std::min(4, max_parts), num_sms / r) : 1;
+        const int c = r > 0 ? choose_parts(r, 8) : 1;
         if (c >= 2) { P.mt_a = P.n_mtiles - r; P.ns_b = c; }
     }
     P.ns_max = std::max(P.ns_a, P.ns_b);
