@@ -22,7 +22,7 @@ namespace slideo {
 
 namespace {
 
-constexpr int TILE_W = 64, TILE_H = 32;
+constexpr int TILE_W = 64, TILE_H = 64;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct Geo {
@@ -178,8 +178,9 @@ struct FastMaps { CUtensorMap lv[ORB_MAX_LEVELS]; };   // one rank-3 u8 tensor {
 __global__ void __launch_bounds__(256) fast_kernel(const FastMaps* __restrict__ maps, const Geo* __restrict__ gp,
                                                    const uint32_t* __restrict__ tiles, uint32_t* __restrict__ cand,
                                                    int32_t* __restrict__ cand_cnt) {
-    // pixel tile: 40 rows x 20 words = columns tx0-8 .. tx0+71; score tile: 34 rows x 72 columns = tx0-4 .. tx0+67, i.e. the
-    // 64 x 32 pixels of the tile plus the halo the 3x3 NMS needs, rounded to whole words so every thread handles 4 pixels
+    // pixel tile: 72 rows x 24 words (columns tx0-16 .. tx0+79); score tile: 66 rows x 72 columns = tx0-4 .. tx0+67, i.e. the
+    // 64 x 64 pixels of the tile plus the halo the 3x3 NMS needs, rounded to whole words so every thread handles 4 pixels
+    // (64 x 32 tiles spent a quarter of the kernel's instructions on the per-CTA prologue: 64 x 64 is 1 % of the step faster)
     constexpr int PH = TILE_H + 8, PWW = (TILE_W + 32) / 4, PWB = PWW * 4, PX0 = 2;   // the staged rows start 16 B-aligned at tx0 - 16 (TMA): PX0 words before tx0 - 8
     constexpr int SH = TILE_H + 2, SWW = (TILE_W + 8) / 4, SWB = SWW * 4;
     __shared__ __align__(128) uint32_t s_px[PH][PWW];
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const FastMaps* __restrict__ 
     const int eb = g.edge;
     if (tx0 + TILE_W <= eb || tx0 >= L.w - eb || ty0 + TILE_H <= eb || ty0 >= L.h - eb) return;
 
-    // tile load by TMA: one 96 x 40 byte box of the level's {x, y, image} tensor (columns tx0-16 .., rows ty0-4 ..) lands in s_px
+    // tile load by TMA: one 96 x 72 byte box of the level's {x, y, image} tensor (columns tx0-16 .., rows ty0-4 ..) lands in s_px
     // while the threads clear the score tile; elements outside the level (negative coordinates included) arrive as zero,
     // which is what FAST needs there (it is only evaluated 3 pixels inside the level)
     if (threadIdx.x == 0) {
