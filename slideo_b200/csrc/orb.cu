@@ -40,36 +40,43 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 
 // ---- K1 -----------------------------------------------------------------------------------------------------
 // cvtColor BGR2GRAY 8u: (B*3735 + G*19235 + R*9798 + 2^14) >> 15   
+__device__ __forceinline__ uint32_t gray_of(uint32_t B, uint32_t G, uint32_t R) { return (B * 3735u + G * 19235u + R * 9798u + 16384u) >> 15; }
+
+// A thread converts 16 pixels: three 16-byte loads in flight, one 16-byte store (the kernel is bound by memory latency, not by the
+// arithmetic: with 4 pixels per thread 60 % of its stall samples sat on the first use of the loaded word).
 __global__ void __launch_bounds__(128) gray_kernel(const uint8_t* __restrict__ src, int stride, size_t frame_stride,
                                                    int channels, uint8_t* __restrict__ pyr, size_t pyr_img_bytes, int w,
                                                    int h, int pitch) {
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int y = blockIdx.y, img = blockIdx.z;
     if (x >= w) return;
     const uint8_t* row = src + (size_t)img * frame_stride + (size_t)y * stride;
-    uint8_t g[4] = {0, 0, 0, 0};
+    uint8_t* dst = pyr + (size_t)img * pyr_img_bytes + (size_t)y * pitch + x;   // pitch and x are multiples of 16
     if (channels == 3) {
         const uint8_t* p = row + 3 * x;
-        if (x + 4 <= w && (((uintptr_t)p) & 3) == 0) {
-            const uint32_t* p32 = reinterpret_cast<const uint32_t*>(p);
-            const uint32_t a = __ldg(p32), b = __ldg(p32 + 1), c = __ldg(p32 + 2);
-            const uint32_t B0 = a & 255, G0 = (a >> 8) & 255, R0 = (a >> 16) & 255, B1 = a >> 24;
-            const uint32_t G1 = b & 255, R1 = (b >> 8) & 255, B2 = (b >> 16) & 255, G2 = b >> 24;
-            const uint32_t R2 = c & 255, B3 = (c >> 8) & 255, G3 = (c >> 16) & 255, R3 = c >> 24;
-            g[0] = (uint8_t)((B0 * 3735u + G0 * 19235u + R0 * 9798u + 16384u) >> 15);
-            g[1] = (uint8_t)((B1 * 3735u + G1 * 19235u + R1 * 9798u + 16384u) >> 15);
-            g[2] = (uint8_t)((B2 * 3735u + G2 * 19235u + R2 * 9798u + 16384u) >> 15);
-            g[3] = (uint8_t)((B3 * 3735u + G3 * 19235u + R3 * 9798u + 16384u) >> 15);
+        if (x + 16 <= w && (((uintptr_t)p) & 15) == 0) {
+            const uint4* p128 = reinterpret_cast<const uint4*>(p);
+            const uint4 v0 = __ldg(p128), v1 = __ldg(p128 + 1), v2 = __ldg(p128 + 2);
+            const uint32_t wds[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            uint32_t out[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {   // 4 pixels = 3 words: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+                const uint32_t a = wds[3 * q], bb = wds[3 * q + 1], c = wds[3 * q + 2];
+                const uint32_t g0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+                const uint32_t g1 = gray_of(a >> 24, bb & 255, (bb >> 8) & 255);
+                const uint32_t g2 = gray_of((bb >> 16) & 255, bb >> 24, c & 255);
+                const uint32_t g3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+                out[q] = g0 | g1 << 8 | g2 << 16 | g3 << 24;
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
         } else {
-            for (int i = 0; i < 4 && x + i < w; ++i)
-                g[i] = (uint8_t)(((uint32_t)p[3 * i] * 3735u + (uint32_t)p[3 * i + 1] * 19235u +
-                                  (uint32_t)p[3 * i + 2] * 9798u + 16384u) >> 15);
+            for (int i = 0; i < 16 && x + i < w; ++i) dst[i] = (uint8_t)gray_of(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
         }
+    } else if (x + 16 <= w && (((uintptr_t)(row + x)) & 15) == 0) {
+        *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(row + x));
     } else {
-        for (int i = 0; i < 4 && x + i < w; ++i) g[i] = row[x + i];
+        for (int i = 0; i < 16 && x + i < w; ++i) dst[i] = row[x + i];
     }
-    uchar4 o = make_uchar4(g[0], g[1], g[2], g[3]);
-    *reinterpret_cast<uchar4*>(pyr + (size_t)img * pyr_img_bytes + (size_t)y * pitch + x) = o;
 }
 
 // ---- K2 -----------------------------------------------------------------------------------------------------
@@ -864,7 +871,7 @@ void OrbExtractor::enqueue(const uint8_t* d_src, int n, int stride, size_t frame
     SLIDEO_CUDA(cudaMemsetAsync(d_cand_cnt_, 0, (size_t)n * L * 4, stream));
     SLIDEO_CUDA(cudaMemsetAsync(d_flags_, 0, 4, stream));
     {
-        dim3 grid(cdiv(cdiv(w_, 4), 128), h_, n);
+        dim3 grid(cdiv(cdiv(w_, 16), 128), h_, n);
         gray_kernel<<<grid, 128, 0, stream>>>(d_src, stride, frame_stride, channels, d_pyr_, pyr_img_bytes_, w_, h_, lv_[0].pitch);
         ++nl;
     }
