@@ -274,18 +274,27 @@ __global__ void __launch_bounds__(256) sift_extrema_kernel(const float* __restri
     const int x0 = (t % oc.tiles_x) * EX_TX, y0 = (t / oc.tiles_x) * EX_TY;
     const int W = oc.w, H = oc.h;
     const float* base = pyr + (size_t)img * g.img_floats + oc.off;
-    for (int e = threadIdx.x; e < PH * PW; e += 256) {
+    // staging is bound by load latency (a thread stages two or three positions): the loop is unrolled completely and all loads of
+    // a thread are issued before the first difference is formed
+    constexpr int NE = (PH * PW + 255) / 256;
+    float gv[NE][SIFT_GAUSS];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = min((int)threadIdx.x + k * 256, PH * PW - 1);
         const int ly = e / PW, lx = e - ly * PW;
         int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
         gy = gy < 0 ? 0 : gy > H - 1 ? H - 1 : gy;
         gx = gx < 0 ? 0 : gx > W - 1 ? W - 1 : gx;
         const float* p = base + (size_t)gy * oc.pitch + gx;
-        float a = p[0];
 #pragma unroll
-        for (int l = 1; l < SIFT_GAUSS; ++l) {
-            const float b = p[(size_t)l * oc.layer_stride];
-            s_dog[l - 1][e] = b - a;
-            a = b;
+        for (int l = 0; l < SIFT_GAUSS; ++l) gv[k][l] = __ldg(p + (size_t)l * oc.layer_stride);
+    }
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = (int)threadIdx.x + k * 256;
+        if (e < PH * PW) {
+#pragma unroll
+            for (int l = 1; l < SIFT_GAUSS; ++l) s_dog[l - 1][e] = gv[k][l] - gv[k][l - 1];
         }
     }
     __syncthreads();
@@ -486,13 +495,25 @@ __global__ void __launch_bounds__(128) sift_orient_kernel(const float* __restric
         if (y <= 0 || y >= H - 1) continue;
         // four window samples per iteration from 16-byte aligned loads of the three rows (a quarter of the L1 lookups that
         // per-sample scalar loads cost, and 4-way ILP); samples outside [j_lo, j_hi] are computed and dropped
+        // The loads of the next four columns are issued before the current four are worked on (one thread per keypoint: nothing
+        // else covers the load latency).
         const float* rowm = im + (size_t)y * pitch;
-        for (int c4 = (c + j_lo) & ~3; c4 <= c + j_hi; c4 += 4) {
-            const float4 up = __ldg(reinterpret_cast<const float4*>(rowm - pitch + c4));
-            const float4 mid = __ldg(reinterpret_cast<const float4*>(rowm + c4));
-            const float4 dn = __ldg(reinterpret_cast<const float4*>(rowm + pitch + c4));
-            const float left = c4 > 0 ? __ldg(rowm + c4 - 1) : 0.f;
-            const float right = c4 + 4 < pitch ? __ldg(rowm + c4 + 4) : 0.f;
+        const int c4_end = c + j_hi;
+        int c4 = (c + j_lo) & ~3;
+        float4 up_n = make_float4(0.f, 0.f, 0.f, 0.f), mid_n = up_n, dn_n = up_n;
+        float left_n = 0.f, right_n = 0.f;
+        auto fetch = [&](int cc) {
+            up_n = __ldg(reinterpret_cast<const float4*>(rowm - pitch + cc));
+            mid_n = __ldg(reinterpret_cast<const float4*>(rowm + cc));
+            dn_n = __ldg(reinterpret_cast<const float4*>(rowm + pitch + cc));
+            left_n = cc > 0 ? __ldg(rowm + cc - 1) : 0.f;
+            right_n = cc + 4 < pitch ? __ldg(rowm + cc + 4) : 0.f;
+        };
+        if (c4 <= c4_end) fetch(c4);
+        for (; c4 <= c4_end; c4 += 4) {
+            const float4 up = up_n, mid = mid_n, dn = dn_n;
+            const float left = left_n, right = right_n;
+            if (c4 + 4 <= c4_end) fetch(c4 + 4);
             const float dxs[4] = {mid.y - left, mid.z - mid.x, mid.w - mid.y, right - mid.z};
             const float dys[4] = {up.x - dn.x, up.y - dn.y, up.z - dn.z, up.w - dn.w};
             float wm[4], num[4], den[4], q[4], sq[4];
