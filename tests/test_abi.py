@@ -200,3 +200,30 @@ def test_rust_crate_uses_the_decision_tail():
     for mod in re.findall(r"^mod ([a-z_]+);", lib_rs, flags=re.M):
         assert os.path.exists(os.path.join(ROOT, "integration", "matching-b200", "src", mod + ".rs")), f"mod {mod} has no source file"
     assert os.path.exists(os.path.join(ROOT, "integration", "matching-b200", "build.rs"))
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (what bench.py printed on the GPU box) carry every key the driver's contract names, and
+    their derived figures are consistent (frac = achieved / peak, value = frames per step / step time)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("r2_bench_n.json", "r2_bench_o_8gpu.json"):
+        d = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert k in d, (name, k)
+        assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert "workload" in d["config"] and "model" not in d["config"]
+        for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert k in d["e2e"], (name, k)
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.001
+        r = d["roofline"]
+        for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert k in r, (name, k)
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["n_gpus"] == 1:
+            c = d["cpu_baseline"]
+            for k in ("value", "unit", "cores", "kind", "sample"):
+                assert k in c, (name, k)
+            assert c["kind"] in ("reference", "port") and "flann_lsh" in c
