@@ -49,9 +49,10 @@ constexpr int L2_STAGES = 2;            // B stages in shared memory
 constexpr int L2_THREADS = 448;         // TMA warp, MMA warp, 8 drain warps, 4 sorter warps
 constexpr int L2_BNH = L2_BN / 2;       // pooled columns of a tile drained by one epilogue group
 constexpr int L2_TRIGGER = 32;          // upper bound of L2Params::trigger (new candidates of a list that schedule a cut-back)
-// candidate keys per (group, row): slots [0, 32) hold the sorted k best of the last cut-back (written by the sorter warps only);
-// new candidates are appended by the drain thread to one of two regions of L2_REGION slots.  When a region passes the trigger
-// the thread hands it to a sorter warp and goes on appending to the other one; a region takes a whole half tile past the trigger.
+// scratch per (column half, row): slots [0, 32) of the half-0 buffer hold the row's sorted k best as of the last cut-back (written
+// by the row's sorter warp only; unused in the half-1 buffer); new candidates are appended by the drain thread of (half, row) to one
+// of its two regions of L2_REGION slots.  When a region passes the trigger the thread hands it to the sorter warp and goes on
+// appending to the other one; a region takes a whole half tile past the trigger.
 constexpr int L2_REGION = L2_TRIGGER + L2_BNH;
 constexpr int L2_SLOTS = 32 + 2 * L2_REGION;
 constexpr int L2_RQ = 64;               // request ring of a drain warp (at most one request per list + the end marker in flight)
@@ -199,7 +200,7 @@ struct L2Params {
     int trigger;           // new candidates of a list that schedule its cut-back (1..L2_TRIGGER)
     int pre_tiles;         // threshold pre-pass: pool tiles at the head of a work item whose accumulators are only reduced to group
     int pre_min, pre_floor; //   minima (see l2_npre); items with fewer than pre_min tiles have no pre-pass
-    unsigned long long* prof;  // developer instrument (SLIDEO_L2_PROF): cycles of epilogue warps in {acc wait, drain, cut-back, item tail}, MMA warp in {acc_empty wait, b_full wait}
+    unsigned long long* prof;  // developer instrument (SLIDEO_L2_PROF): cycles of drain warps in {acc wait, drain, request posting, item tail}, of the MMA warp in {acc_empty wait, b_full wait}, of the sorter warps (busy, requests)
     int dbg;               // developer switch (SLIDEO_L2_DEBUG): 1 = epilogue skips the TMEM drain, 2 = drains but never selects
     uint64_t* scratch;     // [grid][2][L2_BM][L2_SLOTS]
     uint64_t* partial;     // [nq][ns_max][k]   (only rows of split tiles are used)
@@ -267,7 +268,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
     volatile float* s_tau = reinterpret_cast<volatile float*>(bars + 16);   // [L2_BM]: k-th distance of each row's list as of its last cut-back
     volatile float* s_pre = s_tau + L2_BM;                                  // [2][L2_BM]: pre-pass bound of each column half (l2_npre)
-    volatile uint32_t* s_req = reinterpret_cast<volatile uint32_t*>(s_pre + 2 * L2_BM);   // [8][L2_RQ]: cut-back requests of a drain warp
+    volatile uint32_t* s_req = reinterpret_cast<volatile uint32_t*>(s_pre + 2 * L2_BM);   // [8][L2_RQ]: cut-back requests of a drain warp (row | region << 5 | candidates << 8)
     volatile uint32_t* s_done = s_req + 8 * L2_RQ;                          // [8][32]: requests the sorter has completed, per list
     volatile uint32_t* s_req_tail = s_done + 8 * 32;                        // [8]: requests a drain warp has posted
     volatile uint32_t* s_items_done = s_req_tail + 8;                       // [4]: work items a sorter warp has emitted
@@ -334,7 +335,7 @@ knn_l2_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_consta
                     const int b = t & 1;
                     const int s = bcount % L2_STAGES;
                     const long long m0 = DEV && P.prof ? clock64() : 0;
-                    mbar_wait(&acc_empty[b], (acc_use[b] & 1) ^ 1);   // both epilogue groups drained this TMEM buffer
+                    mbar_wait(&acc_empty[b], (acc_use[b] & 1) ^ 1);   // all eight drain warps are done with this TMEM buffer
                     ++acc_use[b];
                     const long long m1 = DEV && P.prof ? clock64() : 0;
                     mbar_wait(&b_full[s], (bcount / L2_STAGES) & 1);
