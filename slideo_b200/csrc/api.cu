@@ -403,6 +403,8 @@ struct slideo_b200_ctx {
     // verification state of the last match call
     DevBuf<int32_t> d_v_cand_page, d_v_cand_votes, d_v_n_cand, d_v_rating;
     DevBuf<uint8_t> d_v_corr;
+    DevBuf<uint8_t> d_v_pairs;                  // RANSAC sample pairs of every small correspondence count (built once, verify.cuh)
+    bool v_pairs_built = false;
     DevBuf<VerifyRecord> d_v_out;
     std::vector<VerifyRecord> verify_results;   // one per frame of the last match_frames_* call
     // photometric stage (K14, cfg.geometric_verification == 2)
@@ -747,6 +749,13 @@ struct slideo_b200_ctx {
         a.d_frame_pt = e.pt.p; a.d_pool_pt = d_pool_pt.p;
         a.d_cand_page = d_v_cand_page.p; a.d_cand_votes = d_v_cand_votes.p; a.d_n_cand = d_v_n_cand.p; a.d_rating = d_v_rating.p;
         a.d_corr = d_v_corr.p; a.d_out = d_v_out.p;
+        if (!v_pairs_built) {
+            d_v_pairs.reserve(verify_pairs_bytes());
+            verify_pairs_build(d_v_pairs.p, knn_stream);
+            v_pairs_built = true;
+            tm.kernel_launches += 1;
+        }
+        a.d_pairs = reinterpret_cast<const uint2*>(d_v_pairs.p);
         const bool photo = cfg.geometric_verification >= 2;
         if (photo) {
             d_v_best_it.reserve(F * VERIFY_TOP_SLIDES);

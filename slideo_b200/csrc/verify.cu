@@ -129,16 +129,35 @@ __device__ int update_num_iters(double p, double ep, int max_iters) {
     return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : __double2int_rn(num / denom);
 }
 
+// The sample sequence of cv::RNG((uint64)-1) -- two distinct indices per iteration (getSubset; checkSubset never rejects a 2-point
+// sample) -- is a pure function of the correspondence count n.  It is inherently serial (a multiply-with-carry generator and a
+// rejection loop), and one thread spelling out 2000 pairs while its CTA waits used to be most of a small candidate's time.  The
+// sequences of every n <= VERIFY_PAIRS_N (the wrong pages of a frame: a few dozen correspondences, never terminating early) are
+// therefore built ONCE per context, one thread per n.
+__global__ void __launch_bounds__(64) ransac_pairs_kernel(uint2* __restrict__ pairs, int max_iters) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 3 || n > VERIFY_PAIRS_N) return;
+    unsigned long long s = 0xFFFFFFFFFFFFFFFFull;
+    uint2* out = pairs + (size_t)n * max_iters;
+    for (int it = 0; it < max_iters; ++it) {
+        const uint32_t i0 = rng_next(s) % (uint32_t)n;
+        uint32_t i1;
+        do { i1 = rng_next(s) % (uint32_t)n; } while (i1 == i0);
+        out[it] = make_uint2(i0, i1);
+    }
+}
+
 __global__ void __launch_bounds__(V_THREADS) ransac_kernel(const uint2* __restrict__ corr, const int32_t* __restrict__ frame_q0, int k,
                                                            const int32_t* __restrict__ cand_votes, const int32_t* __restrict__ n_cand,
                                                            const float2* __restrict__ frame_pt, const float2* __restrict__ pool_pt,
                                                            float thr, int max_iters, double confidence, int32_t* __restrict__ rating,
-                                                           int32_t* __restrict__ best_it_out) {
+                                                           int32_t* __restrict__ best_it_out, const uint2* __restrict__ pair_table) {
     extern __shared__ __align__(16) uint8_t v_smem[];
     float4* s_pts = reinterpret_cast<float4*>(v_smem);                                        // [V_SMEM_PTS] (fx, fy, tx, ty)
-    uint2* s_pairs = reinterpret_cast<uint2*>(v_smem + (size_t)V_SMEM_PTS * sizeof(float4));  // [max_iters] sample indices
-    __shared__ int s_good[V_CHUNK];
+    uint2* s_pairs = reinterpret_cast<uint2*>(v_smem + (size_t)V_SMEM_PTS * sizeof(float4));  // [V_CHUNK] sample indices of the current round (large n)
+    __shared__ int s_good[V_THREADS];
     __shared__ int s_state[3];   // niters, max_good, iteration of the best model
+    __shared__ unsigned long long s_rng;   // generator state behind the pairs spelled out so far (large n)
 
     const int c = blockIdx.x, f = blockIdx.y;
     if (threadIdx.x == 0 && best_it_out) best_it_out[(size_t)f * VERIFY_TOP_SLIDES + c] = -1;
@@ -167,16 +186,9 @@ __global__ void __launch_bounds__(V_THREADS) ransac_kernel(const uint2* __restri
             s_pts[i] = make_float4(fr.x, fr.y, to.x, to.y);
         }
     }
+    const bool small = n <= VERIFY_PAIRS_N && pair_table != nullptr;
     if (threadIdx.x == 0) {
-        // the sample sequence of cv::RNG((uint64)-1): two distinct indices per iteration (getSubset; checkSubset never
-        // rejects a 2-point sample), a pure function of n
-        unsigned long long s = 0xFFFFFFFFFFFFFFFFull;
-        for (int it = 0; it < max_iters; ++it) {
-            const uint32_t i0 = rng_next(s) % (uint32_t)n;
-            uint32_t i1;
-            do { i1 = rng_next(s) % (uint32_t)n; } while (i1 == i0);
-            s_pairs[it] = make_uint2(i0, i1);
-        }
+        s_rng = 0xFFFFFFFFFFFFFFFFull;
         s_state[0] = max_iters > 1 ? max_iters : 1;
         s_state[1] = 0;
         s_state[2] = -1;
@@ -192,54 +204,94 @@ __global__ void __launch_bounds__(V_THREADS) ransac_kernel(const uint2* __restri
         return make_float4(fr.x, fr.y, to.x, to.y);
     };
 
+    // closed-form model of a sample (AffinePartial2DEstimatorCallback::runKernel, double) and its inlier count over points [i0, n)
+    // with stride `step` (Affine2DEstimatorCallback::computeError + findInliers: fp32, no contraction, err <= thr^2)
+    auto count_inliers = [&](const uint2 pr, int i0, int step) {
+        const float4 p0 = point((int)pr.x), p1 = point((int)pr.y);
+        const double x1 = p0.x, y1 = p0.y, x2 = p1.x, y2 = p1.y, X1 = p0.z, Y1 = p0.w, X2 = p1.z, Y2 = p1.w;
+        const double d = 1. / ((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+        const double S0 = d * ((X1 - X2) * (x1 - x2) + (Y1 - Y2) * (y1 - y2));
+        const double S1 = d * ((Y1 - Y2) * (x1 - x2) - (X1 - X2) * (y1 - y2));
+        const double S2 = d * ((Y1 - Y2) * (x1 * y2 - x2 * y1) - (X1 * y2 - X2 * y1) * (y1 - y2) - (X1 * x2 - X2 * x1) * (x1 - x2));
+        const double S3 = d * (-(X1 - X2) * (x1 * y2 - x2 * y1) - (Y1 * x2 - Y2 * x1) * (x1 - x2) - (Y1 * y2 - Y2 * y1) * (y1 - y2));
+        const float F0 = (float)S0, F1 = (float)(-S1), F2 = (float)S2, F3 = (float)S1, F4 = (float)S0, F5 = (float)S3;
+        int good = 0;
+        for (int i = i0; i < n; i += step) {
+            const float4 p = point(i);
+            const float a = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F0, p.x), __fmul_rn(F1, p.y)), F2), p.z);
+            const float b = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F3, p.x), __fmul_rn(F4, p.y)), F5), p.w);
+            const float e = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+            good += e <= t ? 1 : 0;
+        }
+        return good;
+    };
+    // replay of the sequential loop over the hypotheses [it0, it0 + cnt) whose inlier counts sit in s_good: a hypothesis only
+    // counts if the loop would still be running
+    auto replay = [&](int it0, int cnt) {
+        int ni = s_state[0], mg = s_state[1], bi = s_state[2];
+        for (int h = 0; h < cnt; ++h) {
+            const int it = it0 + h;
+            if (it >= ni) break;
+            const int good = s_good[h];
+            if (good > (mg > 1 ? mg : 1)) {
+                mg = good;
+                bi = it;
+                ni = update_num_iters(confidence, (double)(n - good) / n, ni);
+            }
+        }
+        s_state[0] = ni;
+        s_state[1] = mg;
+        s_state[2] = bi;
+    };
+
+    if (small) {
+        // few correspondences (the wrong pages among a frame's 40 candidates; the loop never terminates early for them): one
+        // THREAD per hypothesis -- its own model, all n points from shared memory (broadcast reads) -- 256 hypotheses per round,
+        // samples from the table
+        const uint2* pairs = pair_table + (size_t)n * max_iters;
+        for (int it0 = 0; ; it0 += V_THREADS) {
+            const int niters = s_state[0];
+            if (it0 >= niters) break;
+            const int it = it0 + (int)threadIdx.x;
+            s_good[threadIdx.x] = it < niters ? count_inliers(__ldg(pairs + it), 0, 1) : 0;
+            __syncthreads();
+            if (threadIdx.x == 0) replay(it0, V_THREADS);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            *out = s_state[1];
+            if (best_it_out) best_it_out[(size_t)f * VERIFY_TOP_SLIDES + c] = s_state[2];
+        }
+        return;
+    }
+
     for (int it0 = 0; ; it0 += V_CHUNK) {
         const int niters = s_state[0];
         if (it0 >= niters) break;
+        // many correspondences (the page the frame shows: the loop ends after a handful of hypotheses): one WARP per hypothesis,
+        // lanes over the points; the samples of this round are spelled out now (not all max_iters up front)
+        if (threadIdx.x == 0) {
+            unsigned long long s = s_rng;
+            for (int h = 0; h < V_CHUNK; ++h) {
+                const uint32_t i0 = rng_next(s) % (uint32_t)n;
+                uint32_t i1;
+                do { i1 = rng_next(s) % (uint32_t)n; } while (i1 == i0);
+                s_pairs[h] = make_uint2(i0, i1);
+            }
+            s_rng = s;
+        }
+        __syncthreads();
         for (int h = warp; h < V_CHUNK; h += V_WARPS) {
-            const int it = it0 + h;
             int good = 0;
-            if (it < niters) {
-                const uint2 pr = s_pairs[it];
-                const float4 p0 = point((int)pr.x), p1 = point((int)pr.y);
-                // AffinePartial2DEstimatorCallback::runKernel (double, closed form)
-                const double x1 = p0.x, y1 = p0.y, x2 = p1.x, y2 = p1.y, X1 = p0.z, Y1 = p0.w, X2 = p1.z, Y2 = p1.w;
-                const double d = 1. / ((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
-                const double S0 = d * ((X1 - X2) * (x1 - x2) + (Y1 - Y2) * (y1 - y2));
-                const double S1 = d * ((Y1 - Y2) * (x1 - x2) - (X1 - X2) * (y1 - y2));
-                const double S2 = d * ((Y1 - Y2) * (x1 * y2 - x2 * y1) - (X1 * y2 - X2 * y1) * (y1 - y2) - (X1 * x2 - X2 * x1) * (x1 - x2));
-                const double S3 = d * (-(X1 - X2) * (x1 * y2 - x2 * y1) - (Y1 * x2 - Y2 * x1) * (x1 - x2) - (Y1 * y2 - Y2 * y1) * (y1 - y2));
-                const float F0 = (float)S0, F1 = (float)(-S1), F2 = (float)S2, F3 = (float)S1, F4 = (float)S0, F5 = (float)S3;
-                // Affine2DEstimatorCallback::computeError + findInliers (fp32, no contraction, err <= thr^2)
-                for (int i = lane; i < n; i += 32) {
-                    const float4 p = point(i);
-                    const float a = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F0, p.x), __fmul_rn(F1, p.y)), F2), p.z);
-                    const float b = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(F3, p.x), __fmul_rn(F4, p.y)), F5), p.w);
-                    const float e = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
-                    good += e <= t ? 1 : 0;
-                }
+            if (it0 + h < niters) {
+                good = count_inliers(s_pairs[h], lane, 32);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(FULL, good, o);
             }
             if (lane == 0) s_good[h] = good;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // replay of the sequential loop over this chunk: a hypothesis only counts if the loop would still be running
-            int ni = s_state[0], mg = s_state[1], bi = s_state[2];
-            for (int h = 0; h < V_CHUNK; ++h) {
-                const int it = it0 + h;
-                if (it >= ni) break;
-                const int good = s_good[h];
-                if (good > (mg > 1 ? mg : 1)) {
-                    mg = good;
-                    bi = it;
-                    ni = update_num_iters(confidence, (double)(n - good) / n, ni);
-                }
-            }
-            s_state[0] = ni;
-            s_state[1] = mg;
-            s_state[2] = bi;
-        }
+        if (threadIdx.x == 0) replay(it0, V_CHUNK);
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -513,6 +565,12 @@ __global__ void __launch_bounds__(128) photometric_kernel(const PhotoArgs A) {
 
 }  // namespace
 
+size_t verify_pairs_bytes() { return (size_t)(VERIFY_PAIRS_N + 1) * VERIFY_MAX_ITERS * sizeof(uint2); }
+void verify_pairs_build(void* d_pairs, cudaStream_t stream) {
+    ransac_pairs_kernel<<<cdiv(VERIFY_PAIRS_N + 1, 64), 64, 0, stream>>>((uint2*)d_pairs, VERIFY_MAX_ITERS);
+    SLIDEO_CUDA(cudaGetLastError());
+}
+
 size_t verify_corr_bytes(long long total_entries) { return (size_t)(total_entries > 0 ? total_entries : 1) * sizeof(uint2); }
 
 void verify_launch(const VerifyArgs& a, cudaStream_t stream, int* launches) {
@@ -520,12 +578,12 @@ void verify_launch(const VerifyArgs& a, cudaStream_t stream, int* launches) {
     select_candidates_kernel<<<a.n_frames, 128, 0, stream>>>(a.d_votes, a.n_pages, a.d_cand_page, a.d_cand_votes, a.d_n_cand);
     gather_matches_kernel<<<dim3(VERIFY_TOP_SLIDES, a.n_frames), V_THREADS, 0, stream>>>(a.d_keys, a.k, a.d_frame_q0, a.d_page_of, a.d_cand_page,
                                                                                      a.d_cand_votes, a.d_n_cand, a.ratio, (uint2*)a.d_corr);
-    const size_t smem = (size_t)V_SMEM_PTS * sizeof(float4) + (size_t)VERIFY_MAX_ITERS * sizeof(uint2);
+    const size_t smem = (size_t)V_SMEM_PTS * sizeof(float4) + (size_t)V_CHUNK * sizeof(uint2);
     // function attributes are per device: set on every launch (cheap) so that ctxs on several GPUs of one process all get them
     SLIDEO_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ransac_kernel<<<dim3(VERIFY_TOP_SLIDES, a.n_frames), V_THREADS, smem, stream>>>((const uint2*)a.d_corr, a.d_frame_q0, a.k, a.d_cand_votes,
                                                                                   a.d_n_cand, a.d_frame_pt, a.d_pool_pt, 3.0f, VERIFY_MAX_ITERS,
-                                                                                  0.99, a.d_rating, a.d_best_it);
+                                                                                  0.99, a.d_rating, a.d_best_it, a.d_pairs);
     gate_kernel<<<cdiv(a.n_frames, 128), 128, 0, stream>>>(a.d_cand_page, a.d_cand_votes, a.d_rating, a.d_n_cand, a.n_frames, a.d_out, a.d_survivor_cand);
     SLIDEO_CUDA(cudaGetLastError());
     if (launches) *launches += 4;

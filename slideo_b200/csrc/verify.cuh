@@ -29,7 +29,11 @@ struct VerifyArgs {
     VerifyRecord* d_out;          // [n_frames]
     int32_t* d_best_it;           // [n_frames][40] RANSAC iteration whose model won (photometric stage), may be null
     int32_t* d_survivor_cand;     // [n_frames][10] candidate slot of each survivor (photometric stage), may be null
+    const uint2* d_pairs = nullptr;   // verify_pairs_bytes(): RANSAC sample pairs of every correspondence count n <= VERIFY_PAIRS_N (built once)
 };
+constexpr int VERIFY_PAIRS_N = 256;
+size_t verify_pairs_bytes();
+void verify_pairs_build(void* d_pairs, cudaStream_t stream);
 
 // K14: photometric verification of the survivors (lib.rs:335-389): LM-refined matrix -> warpAffine(WARP_INVERSE_MAP, nearest)
 // of the frame into the slide's geometry -> INTER_AREA small image -> sum of squared differences to the slide's small image
