@@ -207,7 +207,7 @@ def test_committed_bench_lines_follow_the_contract():
     their derived figures are consistent (frac = achieved / peak, value = frames per step / step time)."""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for name in ("r2_bench_p.json", "r2_bench_n.json", "r2_bench_o_8gpu.json"):
+    for name in ("r2_bench_q.json", "r2_bench_p.json", "r2_bench_o_8gpu.json"):
         d = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                   "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
