@@ -40,7 +40,18 @@ constexpr int K5_OFF_LIST = 267 * K5_ROWB;
 constexpr int K5_OFF_META = K5_OFF_LIST + KNN5_TILE * K5_LIST * 4;
 constexpr int K5_OFF_TOPK = K5_OFF_META + KNN5_TILE * K5_META * 4;
 constexpr int K5_OFF_BAR = K5_OFF_TOPK + KNN5_TILE * 32 * 4;
-constexpr int K5_SMEM = K5_OFF_BAR + 16;
+constexpr int K5_OFF_PERM = K5_OFF_BAR + 16;
+constexpr int K5_SMEM = K5_OFF_PERM + KNN5_TILE * 4;
+constexpr int K5_META_NH = 14;                   // meta word 14: the query's list length in half blocks of 8 entries
+// K5_GRAN: granularity at which the list walk stops at the end of a query's list: 0 = never (always 128 entries),
+// 1 = whole blocks of 16 entries, 2 = half blocks of 8.  K5_FLIP: pool rows and queries are XORed with the pool's majority vector.
+#ifndef K5_GRAN
+#define K5_GRAN 2
+#endif
+#ifndef K5_FLIP
+#define K5_FLIP 1
+#endif
+constexpr int K5_FLIP_SAMPLE = 8192;             // rows of the pool the majority vector is counted on
 constexpr int K5_RADIX_ABOVE = 64;               // survivors of one (query, slab) above which the radix select runs first
 static_assert(K5_SLAB_BYTES == KNN5_SLAB_BYTES, "slab size");
 static_assert(K5_W * 1024 == KNN5_SLAB_ROWS, "slab rows");
@@ -102,10 +113,28 @@ __device__ __forceinline__ void k5_set_meta(uint32_t* meta, int lane, int A, boo
 
 struct K5Planes { V4 pl0, ones, twos, fours, eights, s16, s32, s64, s128, s256; };   // s = 2c + pt' as bit planes 0..9
 
-// one query against the slab in shared memory: walks the query's list of bit rows (128 entries, padded with the zero row) and
-// adds the words of those rows for this lane's 128 pooled rows.  Harley-Seal: 15 full adders per 16 inputs, a second level over
-// the 8 weight-16 carries; the accumulators are seeded with pt' >> 1, so the total is s = 2c + pt'.
-__device__ __forceinline__ void k5_scan(const uint4* lst, int lanebase, K5Planes& P) {
+// one query against the slab in shared memory: walks the query's list of bit rows (nh half blocks of 8 entries, padded with the
+// zero row up to the next block boundary) and adds the words of those rows for this lane's 128 pooled rows.  Harley-Seal: 15 full
+// adders per 16 inputs, a second level over the 8 weight-16 carries; the accumulators are seeded with pt' >> 1, so the total is
+// s = 2c + pt'.  ORB descriptors of slides are far from balanced (mean list length 80-90 of 128 after the majority flip), so the walk
+// stops at the end of the list: nh is warp-uniform.
+__device__ __forceinline__ void k5_half(const uint4* lst, int lanebase, V4& ones, V4& twos, V4& fours, V4& e) {
+    const uint4 e0 = lst[0], e1 = lst[1];
+    const uint32_t ent[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    V4 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = lds4((uint32_t)imad((int)ent[i], K5_ROWB, lanebase));
+    V4 ta, tb, fa, fb;
+    csa(ones, ta, ones, x[0], x[1]);
+    csa(ones, tb, ones, x[2], x[3]);
+    csa(twos, fa, twos, ta, tb);
+    csa(ones, ta, ones, x[4], x[5]);
+    csa(ones, tb, ones, x[6], x[7]);
+    csa(twos, fb, twos, ta, tb);
+    csa(fours, e, fours, fa, fb);
+}
+
+__device__ __forceinline__ void k5_scan(const uint4* lst, int lanebase, int nh, K5Planes& P) {
     V4 ones = lds4(lanebase + (K5_ROW_PT + 1) * K5_ROWB), twos = lds4(lanebase + (K5_ROW_PT + 2) * K5_ROWB),
        fours = lds4(lanebase + (K5_ROW_PT + 3) * K5_ROWB), eights = lds4(lanebase + (K5_ROW_PT + 4) * K5_ROWB),
        s16 = lds4(lanebase + (K5_ROW_PT + 5) * K5_ROWB), s32 = lds4(lanebase + (K5_ROW_PT + 6) * K5_ROWB),
@@ -115,27 +144,42 @@ __device__ __forceinline__ void k5_scan(const uint4* lst, int lanebase, K5Planes
     for (int w = 0; w < K5_W; ++w) s256.v[w] = o_prev.v[w] = t32a.v[w] = u64a.v[w] = 0;
 #pragma unroll
     for (int blk = 0; blk < 8; ++blk) {
-        const uint4 e0 = lst[blk * 4], e1 = lst[blk * 4 + 1], e2 = lst[blk * 4 + 2], e3 = lst[blk * 4 + 3];
-        const uint32_t ent[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
-        V4 x[16];
+        V4 o;
+        if (K5_GRAN == 0 || 2 * blk < nh) {
+            if (K5_GRAN != 2 || 2 * blk + 1 < nh) {
+                // whole block: all 16 loads are in flight before the first adder
+                const uint4 e0 = lst[blk * 4], e1 = lst[blk * 4 + 1], e2 = lst[blk * 4 + 2], e3 = lst[blk * 4 + 3];
+                const uint32_t ent[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+                V4 x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = lds4((uint32_t)imad((int)ent[i], K5_ROWB, lanebase));
-        V4 ta, tb, fa, fb, ea, eb, o;
-        csa(ones, ta, ones, x[0], x[1]);
-        csa(ones, tb, ones, x[2], x[3]);
-        csa(twos, fa, twos, ta, tb);
-        csa(ones, ta, ones, x[4], x[5]);
-        csa(ones, tb, ones, x[6], x[7]);
-        csa(twos, fb, twos, ta, tb);
-        csa(fours, ea, fours, fa, fb);
-        csa(ones, ta, ones, x[8], x[9]);
-        csa(ones, tb, ones, x[10], x[11]);
-        csa(twos, fa, twos, ta, tb);
-        csa(ones, ta, ones, x[12], x[13]);
-        csa(ones, tb, ones, x[14], x[15]);
-        csa(twos, fb, twos, ta, tb);
-        csa(fours, eb, fours, fa, fb);
-        csa(eights, o, eights, ea, eb);
+                for (int i = 0; i < 16; ++i) x[i] = lds4((uint32_t)imad((int)ent[i], K5_ROWB, lanebase));
+                V4 ta, tb, fa, fb, ea, eb;
+                csa(ones, ta, ones, x[0], x[1]);
+                csa(ones, tb, ones, x[2], x[3]);
+                csa(twos, fa, twos, ta, tb);
+                csa(ones, ta, ones, x[4], x[5]);
+                csa(ones, tb, ones, x[6], x[7]);
+                csa(twos, fb, twos, ta, tb);
+                csa(fours, ea, fours, fa, fb);
+                csa(ones, ta, ones, x[8], x[9]);
+                csa(ones, tb, ones, x[10], x[11]);
+                csa(twos, fa, twos, ta, tb);
+                csa(ones, ta, ones, x[12], x[13]);
+                csa(ones, tb, ones, x[14], x[15]);
+                csa(twos, fb, twos, ta, tb);
+                csa(fours, eb, fours, fa, fb);
+                csa(eights, o, eights, ea, eb);
+            } else {
+                // the list ends in the first half of this block: 8 entries, the weight-8 carry meets no partner
+                V4 ea;
+                k5_half(lst + blk * 4, lanebase, ones, twos, fours, ea);
+#pragma unroll
+                for (int w = 0; w < K5_W; ++w) { o.v[w] = eights.v[w] & ea.v[w]; eights.v[w] ^= ea.v[w]; }
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < K5_W; ++w) o.v[w] = 0;
+        }
         if (blk & 1) {
             V4 t;
             csa(s16, t, s16, o_prev, o);
@@ -186,6 +230,7 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
     uint32_t* s_meta = reinterpret_cast<uint32_t*>(s_raw + K5_OFF_META);   // [tile][16]
     uint32_t* s_topk = reinterpret_cast<uint32_t*>(s_raw + K5_OFF_TOPK);   // [tile][32] sorted keys
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_raw + K5_OFF_BAR);
+    uint32_t* s_perm = reinterpret_cast<uint32_t*>(s_raw + K5_OFF_PERM);   // [warp][K5_QPW] queries of the tile, dealt by list length
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int q_off = 0, nq = P.nq, n_tiles = P.n_tiles, splits = P.splits;
@@ -205,20 +250,33 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
     const uint32_t sbase = knn_smem_u32(s_raw);
     const int lanebase = (int)sbase + lane * 16;
     uint32_t parity = 0;
+#if K5_FLIP
+    // the pool's majority vector (knn5_flip_kernel) sits behind the last slab; Hamming distances do not change when both sides are
+    // XORed with the same vector, the set-bit lists get shorter
+    const uint32_t flip = reinterpret_cast<const uint32_t*>(P.slabs + (size_t)P.n_slabs * K5_SLAB_BYTES)[lane & 7];
+#else
+    const uint32_t flip = 0;
+#endif
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item / splits, split = item - tile * splits;
         const int slab0 = (int)((long long)P.n_slabs * split / splits), slab1 = (int)((long long)P.n_slabs * (split + 1) / splits);
-        const int qbase = tile * KNN5_TILE;
+        // query ql of tile t is row ql * n_tiles + t of the launch: every tile is an even sample of the whole query range, so that
+        // tiles (and with them the CTAs of a wave) cost the same although the walk of a query costs what its list is long and
+        // neighbouring keypoints have lists of similar length (tile-to-tile spread of contiguous tiles: 10-17 %)
 
-        // ---- tile prologue: set-bit lists, compare masks, empty top-k of this warp's queries --------------------------------
+        __syncthreads();   // the previous item is emitted: its lists, masks and top-k rows may be overwritten by any warp
+        // ---- tile prologue: set-bit lists, compare masks, empty top-k of queries warp * 8 .. warp * 8 + 7 -------------------
 #pragma unroll 1
         for (int qi = 0; qi < K5_QPW; ++qi) {
-            const int ql = warp * K5_QPW + qi, q = qbase + ql;
+            const int ql = warp * K5_QPW + qi, q = ql * n_tiles + tile;
             uint32_t* lst = s_list + ql * K5_LIST;
             s_topk[ql * 32 + lane] = KEY_EMPTY;
-            if (q >= nq) continue;   // warp-uniform
-            const uint32_t word = reinterpret_cast<const uint32_t*>(P.q + (size_t)(q_off + q) * 2)[lane & 7];
+            if (q >= nq) {   // warp-uniform
+                if (lane == 0) s_meta[ql * K5_META + K5_META_NH] = 0;
+                continue;
+            }
+            const uint32_t word = reinterpret_cast<const uint32_t*>(P.q + (size_t)(q_off + q) * 2)[lane & 7] ^ flip;
             int A = __popc(word);
             A += __shfl_xor_sync(KNN_FULL, A, 1);
             A += __shfl_xor_sync(KNN_FULL, A, 2);
@@ -244,10 +302,26 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
             const int n = __shfl_sync(KNN_FULL, incl, 31);
             for (int i = n + lane; i < K5_LIST; i += 32) lst[i] = K5_ROW_ZERO;
             k5_set_meta(s_meta + ql * K5_META, lane, A, inv, 512);
+            if (lane == 0) s_meta[ql * K5_META + K5_META_NH] = K5_GRAN == 2 ? (uint32_t)((n + 7) >> 3) : (uint32_t)(((n + 15) >> 4) << 1);
+        }
+        // ---- the tile's queries are dealt to the warps by list length (descending, boustrophedon), so that the warps of the CTA
+        //      reach the per-slab barrier together although a query's walk costs what its list is long ----------------------------
+        __syncthreads();
+        if (tid < KNN5_TILE) {
+            const uint32_t mine = s_meta[tid * K5_META + K5_META_NH];
+            int rank = 0;
+#pragma unroll 8
+            for (int j = 0; j < KNN5_TILE; ++j) {
+                const uint32_t o = s_meta[j * K5_META + K5_META_NH];
+                rank += (o > mine || (o == mine && j < tid)) ? 1 : 0;
+            }
+            const int round = rank / K5_WARPS, j = rank - round * K5_WARPS;
+            s_perm[((round & 1) ? K5_WARPS - 1 - j : j) * K5_QPW + round] = (uint32_t)tid;
         }
 
+        if (slab0 >= slab1) __syncthreads();   // empty pool: the emission below still reads the dealing
         for (int slab = slab0; slab < slab1; ++slab) {
-            __syncthreads();   // every warp is done with the previous slab; the lists of this tile are written
+            __syncthreads();   // every warp is done with the previous slab; the lists and the dealing of this tile are written
             if (tid == 0) {
                 knn_mbar_expect_tx(s_bar, K5_SLAB_BYTES);
                 knn_bulk_g2s(s_raw, P.slabs + (size_t)slab * K5_SLAB_BYTES, K5_SLAB_BYTES, s_bar);
@@ -258,11 +332,11 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
 
 #pragma unroll 1
             for (int qi = 0; qi < K5_QPW; ++qi) {
-                const int ql = warp * K5_QPW + qi;
-                if (qbase + ql >= nq) break;   // warp-uniform
-                K5Planes pl_;
-                k5_scan(reinterpret_cast<const uint4*>(s_list + ql * K5_LIST), lanebase, pl_);
+                const int ql = (int)s_perm[warp * K5_QPW + qi];
+                if (ql * n_tiles + tile >= nq) continue;   // warp-uniform
                 uint32_t* meta = s_meta + ql * K5_META;
+                K5Planes pl_;
+                k5_scan(reinterpret_cast<const uint4*>(s_list + ql * K5_LIST), lanebase, (int)meta[K5_META_NH], pl_);
                 uint32_t res[K5_W];
                 const uint32_t any = k5_compare(pl_, meta, lanebase, res);
                 const V4 &pl0 = pl_.pl0, &ones = pl_.ones, &twos = pl_.twos, &fours = pl_.fours, &eights = pl_.eights, &s16 = pl_.s16,
@@ -347,8 +421,8 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_kernel(const Knn5Params P)
         __syncwarp();
 #pragma unroll 1
         for (int qi = 0; qi < K5_QPW; ++qi) {
-            const int ql = warp * K5_QPW + qi, q = qbase + ql;
-            if (q >= nq) break;
+            const int ql = (int)s_perm[warp * K5_QPW + qi], q = ql * n_tiles + tile;   // the rows this warp owned during the scan
+            if (q >= nq) continue;
             const uint32_t key = s_topk[ql * 32 + lane];
             if (splits == 1) {
                 knn_emit_row(key, lane, q_off + q, P.k, P.keys_out, P.vote);
@@ -365,11 +439,12 @@ __global__ void __launch_bounds__(128) knn5_merge_kernel(const uint32_t* __restr
                                                          int splits_s, int k, uint32_t* keys_out, const VoteArgs vote) {
     int q_off = 0, nq = nq_s, splits = splits_s;
     if (dyn != nullptr) { q_off = dyn->q0; nq = dyn->nq; splits = dyn->splits; }
+    const int n_tiles = (nq + KNN5_TILE - 1) / KNN5_TILE;
     if (splits <= 1) return;   // emitted by K8 itself
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
-    const int tile = q / KNN5_TILE, row = q - tile * KNN5_TILE;
+    const int row = q / n_tiles, tile = q - row * n_tiles;   // K8's query-to-tile map
     uint32_t k0 = KEY_EMPTY;
     for (int s = 0; s < splits; ++s) {
         uint32_t k1 = lane < k ? partial[(((size_t)tile * splits + s) * KNN5_TILE + row) * k + lane] : KEY_EMPTY;
@@ -378,8 +453,45 @@ __global__ void __launch_bounds__(128) knn5_merge_kernel(const uint32_t* __restr
     knn_emit_row(k0, lane, q_off + q, k, keys_out, vote);
 }
 
+// The pool's majority vector: bit b is set when more than half of (a fixed, evenly spaced sample of) the pooled rows have it set.
+// Any vector keeps the distances exact; this one makes the set-bit lists short (descriptors of slides share their bias).
+// One CTA of 32 warps; a warp reads 32 rows at a time and counts every bit column with a ballot.
+__global__ void __launch_bounds__(1024) knn5_flip_kernel(const uint4* __restrict__ src, int nt, uint32_t* __restrict__ flip) {
+    __shared__ int s_cnt[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 256) s_cnt[tid] = 0;
+    __syncthreads();
+    const int n_sample = nt < K5_FLIP_SAMPLE ? nt : K5_FLIP_SAMPLE;
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // lane i: rows of the sample with bit 32 k + i set
+    for (int i0 = (tid >> 5) * 32; i0 < n_sample; i0 += 1024) {   // warp-uniform
+        const int i = i0 + lane;
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (i < n_sample) {
+            const size_t row = (size_t)((long long)i * nt / n_sample);
+            const uint4 a = __ldg(src + row * 2), b = __ldg(src + row * 2 + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const int c = __popc(__ballot_sync(KNN_FULL, (w[k] >> b) & 1u));
+                if (lane == b) cnt[k] += c;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_cnt[32 * k + lane], cnt[k]);
+    __syncthreads();
+    if (tid < 256) {
+        const uint32_t word = __ballot_sync(KNN_FULL, 2 * s_cnt[tid] > n_sample);
+        if (lane == 0) flip[tid >> 5] = word;
+    }
+}
+
 // 32 B rows -> bit-sliced slabs.  One warp per 32 pooled rows (one word column of a slab).
-__global__ void __launch_bounds__(256) knn5_bitslice_kernel(const uint4* __restrict__ src, int nt, uint8_t* __restrict__ slabs, int n_cols) {
+__global__ void __launch_bounds__(256) knn5_bitslice_kernel(const uint4* __restrict__ src, int nt, uint8_t* __restrict__ slabs, int n_cols,
+                                                            const uint32_t* __restrict__ flip) {
     const int lane = threadIdx.x & 31;
     const int col_g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // global word column: rows 32 col_g ..
     if (col_g >= n_cols) return;
@@ -389,6 +501,8 @@ __global__ void __launch_bounds__(256) knn5_bitslice_kernel(const uint4* __restr
     if (row < nt) {
         const uint4 a = __ldg(src + (size_t)row * 2), b = __ldg(src + (size_t)row * 2 + 1);
         w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] ^= flip[k];
     }
     uint32_t* out = reinterpret_cast<uint32_t*>(slabs + (size_t)slab * K5_SLAB_BYTES) + j;
     int pc = 0;
@@ -523,7 +637,7 @@ __global__ void __launch_bounds__(K5_THREADS, 1) knn5_microbench_kernel(uint32_t
         for (int qi = 0; qi < K5_QPW; ++qi) {
             const int ql = warp * K5_QPW + qi;
             K5Planes pl;
-            k5_scan(reinterpret_cast<const uint4*>(s_list + ql * K5_LIST), lanebase, pl);
+            k5_scan(reinterpret_cast<const uint4*>(s_list + ql * K5_LIST), lanebase, 16, pl);
             uint32_t res[K5_W];
             const uint32_t any = k5_compare(pl, s_meta + ql * K5_META, lanebase, res);
             if (__any_sync(KNN_FULL, any != 0)) acc += __popc(any);
@@ -545,8 +659,12 @@ size_t knn5_pool_bytes(int nt) { return (size_t)knn5_slabs(nt) * K5_SLAB_BYTES; 
 
 void knn5_pool_prepare_launch(const void* d_pool32, int nt, void* d_slabs, cudaStream_t stream) {
     const int n_cols = knn5_slabs(nt) * (KNN5_SLAB_ROWS / 32);
+    // the majority vector lives behind the last slab (callers reserve knn5_pool_bytes(nt) + 64)
+    uint32_t* d_flip = reinterpret_cast<uint32_t*>((uint8_t*)d_slabs + knn5_pool_bytes(nt));
+    if (n_cols == 0 || !K5_FLIP) SLIDEO_CUDA(cudaMemsetAsync(d_flip, 0, 32, stream));
     if (n_cols == 0) return;   // empty pool: no slab, K8 emits empty rows
-    knn5_bitslice_kernel<<<cdiv(n_cols, 8), 256, 0, stream>>>((const uint4*)d_pool32, nt, (uint8_t*)d_slabs, n_cols);
+    if (K5_FLIP) knn5_flip_kernel<<<1, 1024, 0, stream>>>((const uint4*)d_pool32, nt, d_flip);
+    knn5_bitslice_kernel<<<cdiv(n_cols, 8), 256, 0, stream>>>((const uint4*)d_pool32, nt, (uint8_t*)d_slabs, n_cols, d_flip);
     SLIDEO_CUDA(cudaGetLastError());
 }
 
