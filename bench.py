@@ -473,6 +473,27 @@ def main():
                             "NOT measured in this run")
         except Exception:
             pass
+    # K8 walks a query's set-bit list only as far as it is long (whole blocks of 16 entries) after XORing pool and queries with the
+    # pool's majority vector: the LOP3 it executes per pair depend on the descriptors.  Estimated here on the host from the
+    # descriptors of a sample of this run's frames (the dense count 1070 per lane and 128 rows = 120 per block x 8 + 110).
+    walk = None
+    try:
+        pd, _ = ctx.pool_export()
+        n_s = min(len(pd), 8192)
+        maj = 2 * np.unpackbits(pd[(np.arange(n_s, dtype=np.int64) * len(pd)) // n_s], axis=1).sum(0) > n_s   # knn5_flip_kernel
+        sample = range(0, args.frames, max(1, args.frames // 16))
+        qd = np.concatenate([ctx.extract_orb(host[i])[2] for i in sample])
+        a = (np.unpackbits(qd, axis=1) ^ maj).sum(1)
+        blocks = float(((np.minimum(a, 256 - a) + 15) // 16).mean())
+        lpp = (120.0 * blocks + 110.0) / 128.0
+        walk = {"mean_list_entries": float(np.minimum(a, 256 - a).mean()), "mean_blocks_of_16": blocks, "lop3_per_pair_executed": lpp,
+                "peak_executed_gpairs": lop3_rate / lpp / 1e9, "frac_of_executed_peak": ach_pairs / (lop3_rate / lpp / 1e9),
+                "sample": f"{len(qd)} descriptors of {len(sample)} frames of this run, pool of {len(pd)}; host-side estimate",
+                "note": "`peak` / `frac` above use the data-independent dense count (8.36 LOP3 per pair, a list of 128 entries): the "
+                        "figure earlier lines of this repo were quoted on; frac_of_executed_peak divides by the ALU ceiling of the "
+                        "LOP3 this workload really executes"}
+    except Exception as ex:
+        walk = {"error": str(ex)}
     roofline = {
         "bound": "int-pipe", "kernel": "knn5_kernel (K8 v5, bit-sliced Hamming k-NN + fused vote)", "achieved": ach_pairs,
         "peak": peak_pairs, "unit": "Gpair/s", "frac": ach_pairs / peak_pairs,
@@ -484,7 +505,7 @@ def main():
         "naive_popc8_ceiling_gpairs": popc_rate / 8.0 / 1e9,
         "avg_launch_ms": 1e3 * knn_s / launches, "pairs_per_launch": pairs / launches, "share_of_step": knn_s / max(t_dev_events, 1e-9),
         "share_note": "avg_launch_ms is bracketed by events on the K8 stream and contains the time K8 CTAs wait for SMs held by K1-K7",
-        "lop3_ops_per_s": lop3_rate, "popc_ops_per_s": popc_rate, "mix_ceiling_gpairs": mix_rate / 1e9,
+        "lop3_ops_per_s": lop3_rate, "popc_ops_per_s": popc_rate, "mix_ceiling_gpairs": mix_rate / 1e9, "list_walk": walk,
         "hbm": {"bound": "hbm", "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
         "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": alg_bytes / launches,

@@ -46,10 +46,13 @@ constexpr int K5_META_NH = 14;                   // meta word 14: the query's li
 // K5_GRAN: granularity at which the list walk stops at the end of a query's list: 0 = never (always 128 entries),
 // 1 = whole blocks of 16 entries, 2 = half blocks of 8.  K5_FLIP: pool rows and queries are XORed with the pool's majority vector.
 #ifndef K5_GRAN
-#define K5_GRAN 2
+#define K5_GRAN 1
 #endif
 #ifndef K5_FLIP
 #define K5_FLIP 1
+#endif
+#ifndef K5_PREFETCH
+#define K5_PREFETCH 0
 #endif
 constexpr int K5_FLIP_SAMPLE = 8192;             // rows of the pool the majority vector is counted on
 constexpr int K5_RADIX_ABOVE = 64;               // survivors of one (query, slab) above which the radix select runs first
@@ -142,17 +145,29 @@ __device__ __forceinline__ void k5_scan(const uint4* lst, int lanebase, int nh, 
     V4 s256, o_prev, t32a, u64a;
 #pragma unroll
     for (int w = 0; w < K5_W; ++w) s256.v[w] = o_prev.v[w] = t32a.v[w] = u64a.v[w] = 0;
+#if K5_PREFETCH
+    uint4 en0 = lst[0], en1 = lst[1], en2 = lst[2], en3 = lst[3];
+#endif
 #pragma unroll
     for (int blk = 0; blk < 8; ++blk) {
         V4 o;
         if (K5_GRAN == 0 || 2 * blk < nh) {
             if (K5_GRAN != 2 || 2 * blk + 1 < nh) {
                 // whole block: all 16 loads are in flight before the first adder
+#if K5_PREFETCH
+                const uint4 e0 = en0, e1 = en1, e2 = en2, e3 = en3;
+#else
                 const uint4 e0 = lst[blk * 4], e1 = lst[blk * 4 + 1], e2 = lst[blk * 4 + 2], e3 = lst[blk * 4 + 3];
+#endif
                 const uint32_t ent[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
                 V4 x[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) x[i] = lds4((uint32_t)imad((int)ent[i], K5_ROWB, lanebase));
+#if K5_PREFETCH
+                // the entries of the next block (the list is padded to 128 entries, so they exist) are requested before this block's
+                // adders: a block that starts behind a branch then waits for one shared-memory round trip instead of two
+                if (blk < 7) { en0 = lst[blk * 4 + 4]; en1 = lst[blk * 4 + 5]; en2 = lst[blk * 4 + 6]; en3 = lst[blk * 4 + 7]; }
+#endif
                 V4 ta, tb, fa, fb, ea, eb;
                 csa(ones, ta, ones, x[0], x[1]);
                 csa(ones, tb, ones, x[2], x[3]);

@@ -2,7 +2,8 @@
 
 * K8 v5 (default) against K8 v4 (cfg.knn_impl = 4, the XOR/POPC kernel of round 1, itself bit-exact vs the oracle in
   test_gpu_knn.py) on shapes the CPU oracle cannot finish in seconds, and against the oracle on shapes that exercise v5's own edge
-  cases (pool sizes around the 4096-row slab, queries with > 128 set bits, all-zero / all-one descriptors, split tiles);
+  cases (pool sizes around the 4096-row slab, queries with > 128 set bits, all-zero / all-one descriptors, split tiles, every
+  list length on a biased pool);
 * submit / collect == match_frames, several tickets in flight, tickets collected out of order, blank frames (zero keypoints)
   inside a stream, a stream long enough to cross an epoch (2048 frames) on small frames;
 * the changed-frame chain across calls of growing size (ADVICE r1: slot 0 must survive a regrowth);
@@ -44,6 +45,28 @@ def test_v5_dense_sparse_and_constant_descriptors():
                         np.full((3, 32), 255, np.uint8), with_density(20, 129 / 256), with_density(20, 127 / 256), pool[::97]])
     with slideo_b200.Context() as c:
         for k in (30, 1, 32):
+            gi, gd = c.bf_knn_hamming(q, pool, k)
+            oi, od = oracle.bf_knn_hamming(q, pool, k)
+            assert np.array_equal(gd, od) and np.array_equal(gi, oi), k
+
+
+def test_v5_every_list_length_on_a_biased_pool():
+    """K8 v5 XORs pool and queries with the pool's majority vector and walks a query's list only as far as it is long: one query for
+    every list length 0..128 on either side of the complement switch (257 queries = three partly filled tiles whose rows are dealt
+    to the warps by length), on a pool whose bits are biased like descriptors of slides."""
+    import slideo_b200
+    rng = np.random.default_rng(11)
+    p_bit = rng.choice([0.03, 0.2, 0.5, 0.8, 0.97], 256)
+    pool_bits = rng.random((6000, 256)) < p_bit                     # <= 8192 rows: the kernel's sample is the whole pool
+    maj = 2 * pool_bits.sum(0) > len(pool_bits)
+    pool = np.packbits(pool_bits, axis=1)
+    q_bits = np.zeros((257, 256), bool)
+    for n in range(257):                                            # popcount n after the flip: list length min(n, 256 - n)
+        q_bits[n, rng.permutation(256)[:n]] = True
+    q = np.packbits(q_bits ^ maj, axis=1)
+    q = np.concatenate([q, pool[::501]])                            # and some exact hits (distance 0)
+    with slideo_b200.Context() as c:
+        for k in (30, 7):
             gi, gd = c.bf_knn_hamming(q, pool, k)
             oi, od = oracle.bf_knn_hamming(q, pool, k)
             assert np.array_equal(gd, od) and np.array_equal(gi, oi), k
