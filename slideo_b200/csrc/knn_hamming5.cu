@@ -12,10 +12,17 @@
 // also bit-sliced), so the tree delivers s = 2c + pt' directly and  d = A + 256 - s.  Queries with more than 128 set bits walk
 // the list of their CLEAR bits instead (c' = |~q & t| = pt - c,  d = A - 256 + s'), so a list never exceeds 128 entries.
 // The test d < tau (tau = the query's running k-th distance, warp-uniform) is a 10-bit ripple carry of s + (1024 - T) on the
-// planes: 10 LOP3 per 32 rows.  Total ~8.3 LOP3 per pair on the ALU pipe, nothing on the XU pipe.
+// planes: 10 LOP3 per 32 rows.  Total ~8.3 LOP3 per pair on the ALU pipe for a list of 128 entries, nothing on the XU pipe.
+//
+// The walk is as long as the list.  Descriptors of slides are far from balanced (the shorter list has ~90 entries on average), so
+// the walk stops at the end of the list in whole blocks of 16 entries, and pool rows and queries are first XORed with the pool's
+// majority vector (knn5_flip_kernel; distances are invariant, the lists shrink to ~82 entries).  A query then costs what its list
+// is long: the queries of a tile are dealt to the warps by list length, and tile t takes rows ql * n_tiles + t of the launch (an
+// even sample of the query range) so that the tiles of a wave cost the same.
 //
 // Structure.  One CTA of 16 warps per SM.  Shared memory: the current slab (136 KB, one 1-D TMA bulk copy), the set-bit lists of the
-// CTA's 128 queries (64 KB), per-query compare masks and the per-query sorted top-k keys (dist << 23 | index).  Survivors of the
+// CTA's 128 queries (64 KB), per-query compare masks + list length, the per-query sorted top-k keys (dist << 23 | index) and the
+// dealing of the tile's queries to the warps.  Survivors of the
 // test are rare after the first slabs; their exact distances are read off the planes and inserted into the sorted top-k by
 // warp ballots.  A slab that yields more than 64 survivors for a query (the first one always does) is first cut down to the k best
 // (+ ties) by a bit-sliced radix select.  Work items are (query tile x pool split); with more than one split per tile partial rows
@@ -51,6 +58,8 @@ constexpr int K5_META_NH = 14;                   // meta word 14: the query's li
 #ifndef K5_FLIP
 #define K5_FLIP 1
 #endif
+// K5_PREFETCH: the entries of the next block are requested before the adders of the current one (measured: +0.3 %, inside the
+// run-to-run spread; off).
 #ifndef K5_PREFETCH
 #define K5_PREFETCH 0
 #endif
