@@ -207,7 +207,7 @@ def test_committed_bench_lines_follow_the_contract():
     their derived figures are consistent (frac = achieved / peak, value = frames per step / step time)."""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for name in ("r2_bench_q.json", "r2_bench_p.json", "r2_bench_o_8gpu.json"):
+    for name in ("r2_bench_r.json", "r2_bench_q.json", "r2_bench_p.json", "r2_bench_o_8gpu.json"):
         d = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                   "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
@@ -227,3 +227,24 @@ def test_committed_bench_lines_follow_the_contract():
             for k in ("value", "unit", "cores", "kind", "sample"):
                 assert k in c, (name, k)
             assert c["kind"] in ("reference", "port") and "flann_lsh" in c
+
+
+def test_reference_arm_runs_on_the_host_and_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU path of the reference through cv2, no GPU, no repo kernels) at a tiny size: one JSON line
+    with the reference arm's keys (tier contract: impl, cpu_baseline describing this run, e2e with zero copied bytes)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--frames", "4", "--pages", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "1080p frames matched/s" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert "workload" in d["config"]
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and abs(c["value"] - d["value"]) < 1e-9 * max(1.0, d["value"])
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["unit"] == d["unit"]
+    assert "libslideo_b200" not in out.stderr
+
